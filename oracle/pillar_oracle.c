@@ -1,0 +1,353 @@
+/*
+ * pillar_oracle.c -- TEST INFRASTRUCTURE ONLY (the parity checker, never the product).
+ *
+ * Plain-C CPU restatement of the reference's dynamic pillar encoder,
+ *   /root/reference/pcdet/models/backbones_3d/vfe/dynamic_pillar_vfe.py
+ * (DynamicPillarVFE :49-142, DynamicPillarVFESimple2D :146-252 and its two radar
+ * subclasses :255-373, PFNLayerV2 :14-46), plus the two torch_scatter functions it
+ * calls (scatter_mean / scatter_max; torch-scatter==2.1.1, third-party, not in the
+ * reference tree -- semantics restated from the library's documentation, see
+ * oracle/ref_loader.py).
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+ * legs may load this library.  The product path (radardistill_b200/) never does.
+ *
+ * Parity status: the reference ships NO tests / golden vectors for this path
+ * (SURVEY.md section 4), so this oracle is pinned against outputs of the reference
+ * module itself, run in the build container through oracle/ref_loader.py and committed
+ * as the .npz files under tests/golden/ by oracle/gen_golden.py.
+ *
+ * Arithmetic modes (argument `mean_mode`):
+ *   ORC_MEAN_SEQ_F32 (0): scatter_mean exactly as torch_scatter's CPU kernel does it --
+ *       fp32 running sum in row order, fp32 divide by the count.  This is the
+ *       "reference CPU semantics" mode used to pin against the goldens.
+ *   ORC_MEAN_F64 (1): the CANONICAL order-independent definition the CUDA kernels
+ *       implement: sum in fp64 (exact for any realistic pillar), one rounding to fp32.
+ *       Differences to mode 0 are <= 1 ulp of the mean and are bounded in the tests.
+ * The linear layer is a sequential fmaf chain over k = 0..Cin-1 (the reference's sgemm
+ * has an unspecified summation order; results agree to fp32 tolerance, tests state it).
+ *
+ * Threads: the two per-point loops (features, linear) are split over pthreads
+ * (orc_set_threads; libgomp is not in the image).  Everything else is scalar.
+ *
+ * Build: see oracle/Makefile  (gcc -O2 -ffp-contract=off -pthread -shared -fPIC).
+ */
+#include <math.h>
+#include <pthread.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+/* ------------------------------------------------------------------ tiny parallel-for */
+static int g_threads = 1;
+void orc_set_threads(int t) { g_threads = t < 1 ? 1 : (t > 256 ? 256 : t); }
+int orc_get_threads(void) { return g_threads; }
+
+typedef void (*range_fn)(int64_t lo, int64_t hi, void *ctx);
+typedef struct { range_fn fn; void *ctx; int64_t lo, hi; } range_job;
+static void *range_tramp(void *p) { range_job *j = (range_job *)p; j->fn(j->lo, j->hi, j->ctx); return NULL; }
+static void parallel_for(int64_t n, range_fn fn, void *ctx) {
+    int t = g_threads;
+    if (t <= 1 || n < 4096) { fn(0, n, ctx); return; }
+    pthread_t th[256];
+    range_job jobs[256];
+    int64_t chunk = (n + t - 1) / t;
+    int started = 0;
+    for (int i = 0; i < t; ++i) {
+        int64_t lo = i * chunk, hi = lo + chunk > n ? n : lo + chunk;
+        if (lo >= hi) break;
+        jobs[i].fn = fn; jobs[i].ctx = ctx; jobs[i].lo = lo; jobs[i].hi = hi;
+        if (pthread_create(&th[i], NULL, range_tramp, &jobs[i]) != 0) { fn(lo, hi, ctx); th[i] = 0; jobs[i].fn = NULL; }
+        started = i + 1;
+    }
+    for (int i = 0; i < started; ++i) if (jobs[i].fn) pthread_join(th[i], NULL);
+}
+
+#define ORC_MEAN_SEQ_F32 0
+#define ORC_MEAN_F64 1
+
+#define ORC_LAYOUT_SIMPLE2D 0 /* dynamic_pillar_vfe.py:219-237 */
+#define ORC_LAYOUT_DYNPILLAR 1 /* dynamic_pillar_vfe.py:113-121 */
+
+typedef struct {
+    float lo[3];   /* point_cloud_range[0:3]                       (:189 / :85) */
+    float vsz[3];  /* voxel_size as fp32                           (:188 / :84) */
+    float off[3];  /* voxel/2 + lo, computed in double, cast once  (:180-182)   */
+    int32_t nx, ny; /* grid_size[0], grid_size[1]                  (:184-187)   */
+    int32_t cols;   /* 1 + C floats per row (batch idx first)                   */
+    int32_t layout, use_abs, use_cluster, use_relative, with_distance;
+    int32_t c_in, c_out;
+} orc_cfg;
+
+int orc_abi_version(void) { return 1; }
+
+/* ------------------------------------------------------------------ a1-a4: index part */
+
+/* LSD radix sort of (key, idx) pairs by key (keys are non-negative here). */
+static void radix_sort_pairs(uint32_t *key, int32_t *idx, int64_t n) {
+    uint32_t *k2 = (uint32_t *)malloc(sizeof(uint32_t) * (size_t)(n > 0 ? n : 1));
+    int32_t *i2 = (int32_t *)malloc(sizeof(int32_t) * (size_t)(n > 0 ? n : 1));
+    for (int pass = 0; pass < 4; ++pass) {
+        int64_t hist[257];
+        memset(hist, 0, sizeof(hist));
+        int sh = pass * 8;
+        for (int64_t i = 0; i < n; ++i) hist[((key[i] >> sh) & 255u) + 1]++;
+        for (int b = 0; b < 256; ++b) hist[b + 1] += hist[b];
+        for (int64_t i = 0; i < n; ++i) {
+            int64_t d = hist[(key[i] >> sh) & 255u]++;
+            k2[d] = key[i];
+            i2[d] = idx[i];
+        }
+        uint32_t *tk = key; key = k2; k2 = tk;
+        int32_t *ti = idx; idx = i2; i2 = ti;
+    }
+    /* 4 passes => data is back in the caller's buffers */
+    free(k2);
+    free(i2);
+}
+
+/*
+ * Quantise, mask, merged key, unique (sorted), inverse, counts, coords.
+ *   keep[j]   : original row of the j-th kept point (stable, input order)  (:203-206)
+ *   pcoord    : (n,2) int32 cx, cy of kept points                          (:201-202)
+ *   inv[j]    : pillar id of kept point j                                  (:212)
+ *   unq[p]    : merged key of pillar p, ascending                          (:208-212)
+ *   cnt[p]    : points in pillar p
+ *   coords    : (P, coord_cols) int32, [b,cy,cx] or [b,0,cy,cx]            (:243-248 / :132-138)
+ * Returns 0, or -1 if a kept row has a negative merged key (batch index < 0).
+ */
+int orc_index(const float *pts, int64_t n0, const orc_cfg *g, int coord_cols,
+              int32_t *keep, int32_t *pcoord, int32_t *inv, int32_t *unq, int32_t *cnt,
+              int32_t *coords, int64_t *n_out, int64_t *p_out) {
+    const int cols = g->cols;
+    int64_t n = 0;
+    for (int64_t i = 0; i < n0; ++i) {
+        const float *r = pts + i * cols;
+        /* torch: floor((x - lo) / vsz).int()   -- fp32 sub, IEEE fp32 divide, floor, cast */
+        float qx = floorf((r[1] - g->lo[0]) / g->vsz[0]);
+        float qy = floorf((r[2] - g->lo[1]) / g->vsz[1]);
+        /* NaN / +-inf / out-of-int32 values: torch's .int() yields INT_MIN on x86 => dropped */
+        int okx = (qx >= 0.0f) && (qx < (float)g->nx);
+        int oky = (qy >= 0.0f) && (qy < (float)g->ny);
+        if (okx && oky) {
+            keep[n] = (int32_t)i;
+            pcoord[2 * n] = (int32_t)qx;
+            pcoord[2 * n + 1] = (int32_t)qy;
+            ++n;
+        }
+    }
+    *n_out = n;
+    uint32_t *key = (uint32_t *)malloc(sizeof(uint32_t) * (size_t)(n > 0 ? n : 1));
+    int32_t *idx = (int32_t *)malloc(sizeof(int32_t) * (size_t)(n > 0 ? n : 1));
+    const int32_t sxy = g->nx * g->ny, sy = g->ny;
+    int bad = 0;
+    for (int64_t j = 0; j < n; ++j) {
+        int32_t b = (int32_t)pts[(int64_t)keep[j] * cols]; /* .int() truncates toward zero */
+        int32_t k = b * sxy + pcoord[2 * j] * sy + pcoord[2 * j + 1]; /* int32, :208-210 */
+        if (k < 0) bad = 1;
+        key[j] = (uint32_t)k;
+        idx[j] = (int32_t)j;
+    }
+    if (bad) { free(key); free(idx); return -1; }
+    radix_sort_pairs(key, idx, n); /* stable; ascending == torch.unique(sorted=True) */
+    int64_t p = -1;
+    for (int64_t s = 0; s < n; ++s) {
+        if (s == 0 || key[s] != key[s - 1]) {
+            ++p;
+            unq[p] = (int32_t)key[s];
+            cnt[p] = 0;
+        }
+        cnt[p]++;
+        inv[idx[s]] = (int32_t)p;
+    }
+    const int64_t P = p + 1;
+    *p_out = P;
+    for (int64_t q = 0; q < P; ++q) {
+        int32_t u = unq[q];
+        int32_t b = u / sxy, cx = (u % sxy) / sy, cy = u % sy;
+        if (coord_cols == 3) {
+            coords[3 * q] = b; coords[3 * q + 1] = cy; coords[3 * q + 2] = cx;
+        } else {
+            coords[4 * q] = b; coords[4 * q + 1] = 0; coords[4 * q + 2] = cy; coords[4 * q + 3] = cx;
+        }
+    }
+    free(key);
+    free(idx);
+    return 0;
+}
+
+/* ------------------------------------------------------------------ a5: scatter_mean */
+void orc_pillar_mean(const float *pts, const orc_cfg *g, const int32_t *keep, const int32_t *inv,
+                     const int32_t *cnt, int64_t n, int64_t P, int mean_mode, float *mean) {
+    const int cols = g->cols;
+    if (mean_mode == ORC_MEAN_SEQ_F32) {
+        /* torch_scatter CPU: out[index[i]] += src[i] in row order, then out / clamp(count,1) */
+        for (int64_t q = 0; q < 3 * P; ++q) mean[q] = 0.0f;
+        for (int64_t j = 0; j < n; ++j) {
+            const float *r = pts + (int64_t)keep[j] * cols;
+            float *m = mean + 3 * (int64_t)inv[j];
+            m[0] = m[0] + r[1]; m[1] = m[1] + r[2]; m[2] = m[2] + r[3];
+        }
+        for (int64_t q = 0; q < P; ++q) {
+            float c = (float)(cnt[q] < 1 ? 1 : cnt[q]);
+            mean[3 * q] = mean[3 * q] / c; mean[3 * q + 1] = mean[3 * q + 1] / c; mean[3 * q + 2] = mean[3 * q + 2] / c;
+        }
+    } else {
+        double *acc = (double *)calloc((size_t)(3 * P + 1), sizeof(double));
+        for (int64_t j = 0; j < n; ++j) {
+            const float *r = pts + (int64_t)keep[j] * cols;
+            double *m = acc + 3 * (int64_t)inv[j];
+            m[0] += (double)r[1]; m[1] += (double)r[2]; m[2] += (double)r[3];
+        }
+        for (int64_t q = 0; q < P; ++q) {
+            double c = (double)(cnt[q] < 1 ? 1 : cnt[q]);
+            mean[3 * q] = (float)(acc[3 * q] / c);
+            mean[3 * q + 1] = (float)(acc[3 * q + 1] / c);
+            mean[3 * q + 2] = (float)(acc[3 * q + 2] / c);
+        }
+        free(acc);
+    }
+}
+
+/* ------------------------------------------------------------------ a6-a8: decorated features */
+/* Writes the Cin features of one kept point (same op order / roundings as the reference). */
+static inline void point_features(const float *r, const int32_t *pc, const float *m, const orc_cfg *g, float *f) {
+    const int C = g->cols - 1;
+    const float x = r[1], y = r[2], z = r[3];
+    /* :215-217  x - (cx.float()*voxel_x + x_offset): separate mul, add, sub roundings */
+    float cen[3];
+    cen[0] = x - ((float)pc[0] * g->vsz[0] + g->off[0]);
+    cen[1] = y - ((float)pc[1] * g->vsz[1] + g->off[1]);
+    cen[2] = z - g->off[2];
+    int k = 0;
+    if (g->layout == ORC_LAYOUT_SIMPLE2D) {
+        f[k++] = cen[0]; f[k++] = cen[1]; f[k++] = cen[2];
+        for (int c = g->use_abs ? 1 : 4; c <= C; ++c) f[k++] = r[c];
+        if (g->use_cluster) { f[k++] = x - m[0]; f[k++] = y - m[1]; f[k++] = z - m[2]; }
+        if (g->with_distance) f[k++] = sqrtf(fmaf(z, z, fmaf(y, y, x * x)));
+        if (g->use_relative) { f[k++] = x - g->lo[0]; f[k++] = y - g->lo[1]; f[k++] = z - g->lo[2]; }
+    } else {
+        for (int c = g->use_abs ? 1 : 4; c <= C; ++c) f[k++] = r[c];
+        f[k++] = x - m[0]; f[k++] = y - m[1]; f[k++] = z - m[2];
+        f[k++] = cen[0]; f[k++] = cen[1]; f[k++] = cen[2];
+        if (g->with_distance) f[k++] = sqrtf(fmaf(z, z, fmaf(y, y, x * x)));
+    }
+}
+
+typedef struct { const float *pts; const orc_cfg *g; const int32_t *keep, *pcoord, *inv; const float *mean; float *f; } feat_ctx;
+static void feat_range(int64_t lo, int64_t hi, void *p) {
+    feat_ctx *c = (feat_ctx *)p;
+    const int cols = c->g->cols, cin = c->g->c_in;
+    for (int64_t j = lo; j < hi; ++j)
+        point_features(c->pts + (int64_t)c->keep[j] * cols, c->pcoord + 2 * j, c->mean + 3 * (int64_t)c->inv[j], c->g,
+                       c->f + j * cin);
+}
+void orc_features(const float *pts, const orc_cfg *g, const int32_t *keep, const int32_t *pcoord,
+                  const int32_t *inv, const float *mean, int64_t n, float *f) {
+    feat_ctx c = {pts, g, keep, pcoord, inv, mean, f};
+    parallel_for(n, feat_range, &c);
+}
+
+/* ------------------------------------------------------------------ a9: PFNLayerV2 */
+/* x[j][c] = sum_k W[c][k] f[j][k]  as a sequential fmaf chain (k ascending), (+ bias). */
+typedef struct { const float *f, *W; float *x; int cin, cout; } lin_ctx;
+static void lin_range(int64_t lo, int64_t hi, void *p) {
+    lin_ctx *c = (lin_ctx *)p;
+    const int cin = c->cin, cout = c->cout;
+    for (int64_t j = lo; j < hi; ++j) {
+        const float *fj = c->f + j * cin;
+        for (int o = 0; o < cout; ++o) {
+            float acc = 0.0f;
+            for (int k = 0; k < cin; ++k) acc = fmaf(c->W[o * cin + k], fj[k], acc);
+            c->x[j * cout + o] = acc;
+        }
+    }
+}
+void orc_linear(const float *f, int64_t n, int cin, const float *W, int cout, float *x) {
+    lin_ctx c = {f, W, x, cin, cout};
+    parallel_for(n, lin_range, &c);
+}
+
+/* Train-mode batch statistics over the n kept points: mean and BIASED variance, in fp64. */
+void orc_bn_batch_stats(const float *x, int64_t n, int cout, double *mean, double *var) {
+    for (int c = 0; c < cout; ++c) {
+        double s = 0.0, s2 = 0.0;
+        for (int64_t j = 0; j < n; ++j) {
+            double v = (double)x[j * cout + c];
+            s += v;
+            s2 += v * v;
+        }
+        double m = n > 0 ? s / (double)n : 0.0;
+        double vv = n > 0 ? s2 / (double)n - m * m : 0.0;
+        mean[c] = m;
+        var[c] = vv > 0.0 ? vv : 0.0;
+    }
+}
+
+/* y = x*scale + shift with scale = gamma/sqrt(var+eps), shift = beta - mean*scale (fp64, one rounding). */
+void orc_bn_fold(const float *gamma, const float *beta, const double *mean, const double *var, double eps,
+                 int cout, float *scale, float *shift) {
+    for (int c = 0; c < cout; ++c) {
+        double inv_std = 1.0 / sqrt(var[c] + eps);
+        double a = (double)gamma[c] * inv_std;
+        scale[c] = (float)a;
+        shift[c] = (float)((double)beta[c] - mean[c] * a);
+    }
+}
+
+/* z = relu(fma(x, scale, shift)); out[p][c] = max_j z ; arg = FIRST j attaining it (:39-40). */
+void orc_act_max(const float *x, int64_t n, int cout, const float *scale, const float *shift,
+                 const int32_t *inv, int64_t P, float *out, int32_t *arg) {
+    for (int64_t q = 0; q < P * cout; ++q) { out[q] = -1.0f; arg[q] = (int32_t)n; }
+    for (int64_t j = 0; j < n; ++j) {
+        float *o = out + (int64_t)inv[j] * cout;
+        int32_t *a = arg + (int64_t)inv[j] * cout;
+        for (int c = 0; c < cout; ++c) {
+            float y = fmaf(x[j * cout + c], scale[c], shift[c]);
+            float z = y > 0.0f ? y : 0.0f;
+            if (z > o[c]) { o[c] = z; a[c] = (int32_t)j; } /* strict '>' => first index wins */
+        }
+    }
+}
+
+/* ------------------------------------------------------------------ a12: backward (parameter grads)
+ * Given g (P,Cout): route to argmax rows, ReLU', BatchNorm backward (train: batch stats; eval:
+ * running stats => g_x = scale * g_y), dW = g_x^T f.  All reductions in fp64.
+ * use_norm == 0: linear has a bias, y = x + b: dbias -> dbeta slot, dgamma = 0.
+ */
+void orc_backward(const float *g, const float *f, const float *x, const float *out, const int32_t *arg,
+                  int64_t n, int64_t P, int cin, int cout, const float *gamma, const double *mean,
+                  const double *var, double eps, int train_bn, int use_norm,
+                  float *dW, float *dgamma, float *dbeta) {
+    double *gy = (double *)calloc((size_t)(n * cout + 1), sizeof(double));
+    for (int64_t q = 0; q < P; ++q)
+        for (int c = 0; c < cout; ++c)
+            if (out[q * cout + c] > 0.0f && arg[q * cout + c] < n)
+                gy[(int64_t)arg[q * cout + c] * cout + c] += (double)g[q * cout + c];
+    for (int c = 0; c < cout; ++c) {
+        double inv_std = use_norm ? 1.0 / sqrt(var[c] + eps) : 1.0;
+        double mu = use_norm ? mean[c] : 0.0;
+        double db = 0.0, dg = 0.0;
+        for (int64_t j = 0; j < n; ++j) {
+            double xh = ((double)x[j * cout + c] - mu) * inv_std;
+            db += gy[j * cout + c];
+            dg += gy[j * cout + c] * xh;
+        }
+        dbeta[c] = (float)db;
+        dgamma[c] = use_norm ? (float)dg : 0.0f;
+        double a = use_norm ? (double)gamma[c] * inv_std : 1.0;
+        for (int k = 0; k < cin; ++k) {
+            double acc = 0.0;
+            for (int64_t j = 0; j < n; ++j) {
+                double gx = gy[j * cout + c];
+                if (use_norm && train_bn) {
+                    double xh = ((double)x[j * cout + c] - mu) * inv_std;
+                    gx = gx - db / (double)n - xh * dg / (double)n;
+                }
+                acc += a * gx * (double)f[j * cin + k];
+            }
+            dW[c * cin + k] = (float)acc;
+        }
+    }
+    free(gy);
+}
