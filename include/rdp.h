@@ -1,0 +1,158 @@
+/*
+ * rdp.h -- C ABI of librdp.so: the B200 (sm_100a) dynamic pillar encoder.
+ *
+ * Drop-in boundary for RadarDistill's pillar-encoding front end.  Every entry point
+ * replaces a stretch of /root/reference/pcdet/models/backbones_3d/vfe/dynamic_pillar_vfe.py
+ * (cited per function).  Plain C: raw device pointers, sizes and a CUDA stream handle
+ * (passed as void* == cudaStream_t); no torch types.  All functions return an int status
+ * (RDP_OK == 0, negative = error), never throw, keep no global state, and are re-entrant
+ * per (stream, workspace).  The caller owns every buffer.  Nothing here synchronises the
+ * stream; the only host<->device traffic is what the caller does with `counters`.
+ *
+ * Calling sequence for one forward:
+ *     rdp_workspace_bytes -> (allocate ws, outputs at capacity n_points)
+ *     rdp_index_fwd       -> coords / inverse / counts, counters[N,P] on the device
+ *     rdp_pfn_fwd         -> features (+ argmax, pillar_mean, bn state in train mode)
+ *     (caller copies `counters` back once to learn N and P and narrows its views)
+ *     rdp_pfn_bwd         -> dW, dgamma, dbeta             (training only)
+ */
+#ifndef RDP_H_
+#define RDP_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RDP_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define RDP_API __attribute__((visibility("default")))
+#else
+#define RDP_API
+#endif
+
+enum rdp_status {
+    RDP_OK = 0,
+    RDP_ERR_INVALID_ARG = -1,  /* null pointer, non-positive size, misaligned buffer       */
+    RDP_ERR_WORKSPACE = -2,    /* workspace smaller than rdp_workspace_bytes says           */
+    RDP_ERR_CUDA = -3,         /* a CUDA runtime call failed (see rdp_last_cuda_error)      */
+    RDP_ERR_UNSUPPORTED = -4,  /* configuration outside what the kernels implement          */
+    RDP_ERR_KEYSPACE = -5      /* batch_size*nx*ny does not fit a non-negative int32 key    */
+};
+
+/* counters[] slots (int32, device memory, RDP_NUM_COUNTERS entries, written by rdp_index_fwd) */
+enum rdp_counter {
+    RDP_CNT_N = 0,       /* points kept by the range mask              (dynamic_pillar_vfe.py:203-206) */
+    RDP_CNT_P = 1,       /* pillars == rows of features / coords       (:212)                          */
+    RDP_CNT_ERRFLAGS = 2 /* bit0: a row's batch index was outside [0, batch_size)                      */
+};
+#define RDP_NUM_COUNTERS 16
+
+#define RDP_LAYOUT_SIMPLE2D 0  /* DynamicPillarVFESimple2D + radar subclasses (:219-237): [center|pts|cluster|dist|rel] */
+#define RDP_LAYOUT_DYNPILLAR 1 /* DynamicPillarVFE (:113-121):                            [pts|cluster|center|dist]    */
+
+/* Grid geometry: the constructor arguments of the reference classes (:73-85, :177-189). */
+typedef struct rdp_geom {
+    float lo[3];        /* point_cloud_range[0:3]                                            */
+    float vsz[3];       /* voxel_size, fp32                                                  */
+    float off[3];       /* voxel/2 + lo  (x_offset, y_offset, z_offset), rounded once to fp32 */
+    int32_t nx, ny;     /* grid_size[0], grid_size[1]                                        */
+    int32_t batch_size; /* frames in this call; rows carry their frame index in column 0     */
+    int32_t cols;       /* floats per row = 1 + num_point_features                           */
+} rdp_geom_t;
+
+/* Feature layout + PFN shape: model_cfg of the reference classes (:53-62, :150-166). */
+typedef struct rdp_layout {
+    int32_t layout;        /* RDP_LAYOUT_*                        */
+    int32_t use_abs;       /* USE_ABSLOTE_XYZ                     */
+    int32_t use_cluster;   /* USE_CLUSTER_XYZ (Simple2D only)     */
+    int32_t use_relative;  /* USE_RELATIVE_XYZ (Simple2D only)    */
+    int32_t with_distance; /* WITH_DISTANCE                       */
+    int32_t c_in, c_out;   /* PFNLayerV2 linear: (c_out, c_in)    */
+    int32_t coord_cols;    /* 3: [b,y,x]   4: [b,0,y,x]           */
+} rdp_layout_t;
+
+/* Batch-norm / linear parameters of the single PFNLayerV2 (:14-46).  Device pointers. */
+typedef struct rdp_pfn_params {
+    const float *weight;  /* (c_out, c_in) row-major, linear.weight                          */
+    const float *bias;    /* (c_out) linear.bias when USE_NORM is false, else NULL           */
+    const float *gamma;   /* (c_out) norm.weight, NULL when USE_NORM is false                */
+    const float *beta;    /* (c_out) norm.bias                                               */
+    float *running_mean;  /* (c_out) read in eval mode, updated in place in train mode       */
+    float *running_var;   /* (c_out)                                                         */
+    double eps;           /* 1e-3  (:29)                                                     */
+    double momentum;      /* 0.01  (:29)                                                     */
+    int32_t train_bn;     /* 1: batch statistics + running-stat update; 0: running stats     */
+} rdp_pfn_params_t;
+
+RDP_API int rdp_abi_version(void);
+RDP_API const char *rdp_status_string(int status);
+/* Text of the last CUDA error seen by the calling thread inside librdp ("" if none). */
+RDP_API const char *rdp_last_cuda_error(void);
+
+/* Bytes of scratch rdp_index_fwd / rdp_pfn_fwd / rdp_pfn_bwd need for up to n_points rows. */
+RDP_API int rdp_workspace_bytes(int64_t n_points, const rdp_geom_t *geom, const rdp_layout_t *layout, size_t *bytes);
+
+/*
+ * Quantise -> range mask -> merged key -> sorted unique -> inverse / counts / coords.
+ * Replaces dynamic_pillar_vfe.py:201-212 and :243-248 (also :93-103, :132-138).
+ *   points   (n_points, cols) fp32, row-major, 16-byte aligned
+ *   coords   (cap n_points, coord_cols) int32   rows [0,P) valid, ascending merged key
+ *   inverse  (cap n_points) int32               entries [0,N) valid: pillar of the j-th KEPT point
+ *   counts   (cap n_points) int32               entries [0,P) valid
+ *   counters (RDP_NUM_COUNTERS) int32 device
+ */
+RDP_API int rdp_index_fwd(const float *points, int64_t n_points, const rdp_geom_t *geom, int32_t coord_cols,
+                  void *workspace, size_t workspace_bytes,
+                  int32_t *coords, int32_t *inverse, int32_t *counts, int32_t *counters, void *stream);
+
+/*
+ * scatter_mean -> decorated features -> Linear + BatchNorm1d + ReLU -> scatter_max.
+ * Replaces dynamic_pillar_vfe.py:214-240 with PFNLayerV2.forward :35-46 (last layer).
+ * Must follow rdp_index_fwd on the same points / workspace / stream.
+ *   features    (cap n_points, c_out) fp32      rows [0,P)
+ *   argmax      (cap n_points, c_out) int32     KEPT-point index of the winning row (lowest index on
+ *                                               ties); NULL if not wanted
+ *   pillar_mean (cap n_points, 3) fp32          per-pillar xyz mean; NULL if not wanted
+ *   coords      the (P, coord_cols) tensor rdp_index_fwd wrote (pillar centres are derived from it)
+ *   bn_state    (rdp_bn_state_doubles(layout)) fp64: batch mean/var, folded scale/shift and the feature
+ *               moments the backward needs; required when train_bn, else may be NULL
+ */
+RDP_API int rdp_pfn_fwd(const float *points, int64_t n_points, const rdp_geom_t *geom, const rdp_layout_t *layout,
+                const rdp_pfn_params_t *params, void *workspace, size_t workspace_bytes,
+                const int32_t *counters, const int32_t *coords, float *features, int32_t *argmax,
+                float *pillar_mean, double *bn_state, void *stream);
+
+RDP_API int64_t rdp_bn_state_doubles(const rdp_layout_t *layout);
+
+/*
+ * Parameter gradients of the PFN (autograd of :35-46): argmax routing, ReLU', BatchNorm backward
+ * (batch statistics when params->train_bn, running statistics otherwise), dW = g_x^T f.
+ * Points are a non-differentiable leaf in the reference, so no point gradient is produced.
+ *   grad_features (P, c_out) fp32 ; features / argmax / pillar_mean / bn_state as written by rdp_pfn_fwd
+ *   d_weight (c_out, c_in), d_gamma (c_out) [NULL without norm], d_beta (c_out) [bias grad without norm]
+ *   n_pillars_hint: P if the caller knows it (sizes the grid), else -1
+ */
+RDP_API int rdp_pfn_bwd(const float *points, int64_t n_points, const rdp_geom_t *geom, const rdp_layout_t *layout,
+                const rdp_pfn_params_t *params, void *workspace, size_t workspace_bytes,
+                const int32_t *counters, const int32_t *coords, const float *grad_features, const float *features,
+                const int32_t *argmax, const float *pillar_mean, const double *bn_state,
+                float *d_weight, float *d_gamma, float *d_beta, int64_t n_pillars_hint, void *stream);
+
+/*
+ * Host-buffer convenience (what a non-torch caller binds): uploads `points` (host), runs
+ * rdp_index_fwd + rdp_pfn_fwd in eval mode, downloads the results and synchronises.
+ * Host output buffers must hold n_points rows; *n_kept / *n_pillars receive N and P.
+ * Parameters in `params` are HOST pointers here.
+ */
+RDP_API int rdp_encode_host(const float *points, int64_t n_points, const rdp_geom_t *geom, const rdp_layout_t *layout,
+                    const rdp_pfn_params_t *params, float *features, int32_t *coords, int32_t *inverse,
+                    int32_t *counts, int64_t *n_kept, int64_t *n_pillars);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RDP_H_ */

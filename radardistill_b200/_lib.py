@@ -1,0 +1,83 @@
+"""ctypes binding of librdp.so (include/rdp.h).  There is no fallback: if the CUDA library is
+missing or does not load, importing the encoder fails loudly."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "librdp.so")
+
+RDP_ABI_VERSION = 1
+RDP_NUM_COUNTERS = 16
+CNT_N, CNT_P, CNT_ERRFLAGS = 0, 1, 2
+LAYOUT_SIMPLE2D, LAYOUT_DYNPILLAR = 0, 1
+
+EXPORTS = ["rdp_abi_version", "rdp_status_string", "rdp_last_cuda_error", "rdp_workspace_bytes", "rdp_index_fwd",
+           "rdp_pfn_fwd", "rdp_bn_state_doubles", "rdp_pfn_bwd", "rdp_encode_host"]
+
+
+class Geom(C.Structure):
+    _fields_ = [("lo", C.c_float * 3), ("vsz", C.c_float * 3), ("off", C.c_float * 3),
+                ("nx", C.c_int32), ("ny", C.c_int32), ("batch_size", C.c_int32), ("cols", C.c_int32)]
+
+
+class Layout(C.Structure):
+    _fields_ = [("layout", C.c_int32), ("use_abs", C.c_int32), ("use_cluster", C.c_int32), ("use_relative", C.c_int32),
+                ("with_distance", C.c_int32), ("c_in", C.c_int32), ("c_out", C.c_int32), ("coord_cols", C.c_int32)]
+
+
+class PfnParams(C.Structure):
+    _fields_ = [("weight", C.c_void_p), ("bias", C.c_void_p), ("gamma", C.c_void_p), ("beta", C.c_void_p),
+                ("running_mean", C.c_void_p), ("running_var", C.c_void_p), ("eps", C.c_double), ("momentum", C.c_double),
+                ("train_bn", C.c_int32)]
+
+
+class RdpError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Loads librdp.so (built by ``python -m radardistill_b200.build`` / ``__graft_entry__.build()``)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RdpError(f"{LIB_PATH} is missing: build it with `python -m radardistill_b200.build` "
+                       "(nvcc, sm_100a).  There is no CPU or PyTorch fallback for the pillar encoder.")
+    lib = C.CDLL(LIB_PATH)
+    lib.rdp_abi_version.restype = C.c_int
+    if lib.rdp_abi_version() != RDP_ABI_VERSION:
+        raise RdpError("librdp.so ABI version mismatch -- rebuild")
+    lib.rdp_status_string.restype = C.c_char_p
+    lib.rdp_status_string.argtypes = [C.c_int]
+    lib.rdp_last_cuda_error.restype = C.c_char_p
+    lib.rdp_workspace_bytes.restype = C.c_int
+    lib.rdp_workspace_bytes.argtypes = [C.c_int64, C.POINTER(Geom), C.POINTER(Layout), C.POINTER(C.c_size_t)]
+    vp = C.c_void_p
+    lib.rdp_index_fwd.restype = C.c_int
+    lib.rdp_index_fwd.argtypes = [vp, C.c_int64, C.POINTER(Geom), C.c_int32, vp, C.c_size_t, vp, vp, vp, vp, vp]
+    lib.rdp_pfn_fwd.restype = C.c_int
+    lib.rdp_pfn_fwd.argtypes = [vp, C.c_int64, C.POINTER(Geom), C.POINTER(Layout), C.POINTER(PfnParams), vp, C.c_size_t,
+                                vp, vp, vp, vp, vp, vp, vp]
+    lib.rdp_bn_state_doubles.restype = C.c_int64
+    lib.rdp_bn_state_doubles.argtypes = [C.POINTER(Layout)]
+    lib.rdp_pfn_bwd.restype = C.c_int
+    lib.rdp_pfn_bwd.argtypes = [vp, C.c_int64, C.POINTER(Geom), C.POINTER(Layout), C.POINTER(PfnParams), vp, C.c_size_t,
+                                vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_int64, vp]
+    lib.rdp_encode_host.restype = C.c_int
+    lib.rdp_encode_host.argtypes = [vp, C.c_int64, C.POINTER(Geom), C.POINTER(Layout), C.POINTER(PfnParams), vp, vp, vp, vp,
+                                    C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    _lib = lib
+    return lib
+
+
+def check(status: int, what: str) -> None:
+    if status != 0:
+        lib = load()
+        msg = lib.rdp_status_string(status).decode()
+        cuda = lib.rdp_last_cuda_error().decode()
+        raise RdpError(f"{what} failed: {msg}" + (f" [{cuda}]" if status == -3 and cuda else ""))

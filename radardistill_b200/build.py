@@ -1,0 +1,86 @@
+"""Builds librdp.so (the C-ABI CUDA library) in-tree with nvcc for sm_100a.
+
+    python -m radardistill_b200.build [--force]
+
+One nvcc invocation per translation unit (the PFN configurations compile in parallel), then one link.
+The .so lands next to this file (git-ignored, shipped to the GPU box by gpurun).
+"""
+from __future__ import annotations
+
+import concurrent.futures as cf
+import hashlib
+import os
+import re
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+CSRC = os.path.join(HERE, "csrc")
+INCLUDE = os.path.join(ROOT, "include")
+OBJ = os.path.join(HERE, "_build")
+LIB = os.path.join(HERE, "librdp.so")
+
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
+         "--expt-relaxed-constexpr", "-I", INCLUDE, "-I", CSRC]
+
+
+def _config_ids():
+    txt = open(os.path.join(CSRC, "rdp_pfn_host.h")).read()
+    return [int(m) for m in re.findall(r"^\s*X\((\d+),", txt, flags=re.M)]
+
+
+def _units():
+    units = [("rdp_abi", "rdp_abi.cu", []), ("rdp_index", "rdp_index.cu", []), ("rdp_pfn", "rdp_pfn.cu", [])]
+    units += [(f"rdp_pfn_inst_{i}", "rdp_pfn_inst.cu", [f"-DRDP_CFG_ID={i}"]) for i in _config_ids()]
+    return units
+
+
+def _source_digest() -> str:
+    h = hashlib.sha256()
+    for d in (CSRC, INCLUDE):
+        for fn in sorted(os.listdir(d)):
+            with open(os.path.join(d, fn), "rb") as f:
+                h.update(fn.encode()); h.update(f.read())
+    h.update(" ".join(FLAGS + ARCH).encode())
+    return h.hexdigest()
+
+
+def _compile(unit, verbose):
+    name, src, defs = unit
+    out = os.path.join(OBJ, name + ".o")
+    cmd = [NVCC, *ARCH, *FLAGS, *defs, "-c", os.path.join(CSRC, src), "-o", out]
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"nvcc failed for {name}:\n{r.stdout}\n{r.stderr}")
+    return out, r.stderr
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    os.makedirs(OBJ, exist_ok=True)
+    stamp = os.path.join(OBJ, "digest.txt")
+    digest = _source_digest()
+    if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == digest:
+        return LIB
+    units = _units()
+    with cf.ThreadPoolExecutor(max_workers=min(len(units), os.cpu_count() or 4)) as ex:
+        results = list(ex.map(lambda u: _compile(u, verbose), units))
+    if verbose:
+        for (name, _, _), (_, log) in zip(units, results):
+            print(f"==== {name}\n{log}")
+    objs = [o for o, _ in results]
+    cmd = [NVCC, *ARCH, "-shared", "-Xcompiler", "-fPIC", "-o", LIB, *objs]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    with open(stamp, "w") as f:
+        f.write(digest)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

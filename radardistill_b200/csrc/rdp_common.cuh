@@ -1,0 +1,163 @@
+// rdp_common.cuh -- shared internals of librdp (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "rdp.h"
+
+namespace rdp {
+
+// ----------------------------------------------------------------------------- status plumbing
+void set_last_cuda_error(cudaError_t e, const char *where);
+
+#define RDP_CUDA_OK(expr)                                   \
+    do {                                                    \
+        cudaError_t _e = (expr);                            \
+        if (_e != cudaSuccess) {                            \
+            ::rdp::set_last_cuda_error(_e, #expr);          \
+            return RDP_ERR_CUDA;                            \
+        }                                                   \
+    } while (0)
+
+// ----------------------------------------------------------------------------- tiling constants
+constexpr int kIndexThreads = 256;
+constexpr int kIndexTileRows = 1024;  // points per CTA in the quantise / rank / fill kernels
+constexpr int kScanThreads = 256;
+constexpr int kScanGrid = 296;        // 2 CTAs per SM: every CTA of a chunked scan is co-resident
+constexpr int kPfnThreads = 256;
+constexpr int kPfnBatch = 256;        // points per CTA batch in the PFN kernels (== kPfnThreads)
+constexpr int kPfnTileRows = 1024;    // grouped points per PFN tile (pillar aligned)
+constexpr int kMaxCin = 24;
+constexpr int kMaxCout = 64;
+
+// extra counter slots (after the public ones of rdp.h)
+constexpr int kCntTicketA = 4;   // bitmap scan ticket
+constexpr int kCntTicketB = 5;   // count scan ticket
+constexpr int kCntPfnBlocks = 6; // blocks used by the last stats launch
+
+// ----------------------------------------------------------------------------- workspace layout
+struct Workspace {
+    // zeroed by one memset at the start of rdp_index_fwd: [zero_begin, zero_begin + zero_bytes)
+    uint64_t *scan_state_a;  // kScanGrid
+    uint64_t *scan_state_b;  // kScanGrid
+    uint32_t *bitmap;        // words
+    // not zeroed
+    uint32_t *word_prefix;   // words
+    int32_t *keys;           // n  (merged key, then overwritten by the pillar rank; -1 = dropped)
+    int32_t *tile_keep;      // index tiles
+    int32_t *ends;           // pcap  (exclusive starts -> after fill: inclusive ends)
+    int32_t *order;          // n     (grouped position -> original row)
+    int32_t *tile_start;     // pfn tiles + 2
+    double *partials;        // per-CTA partial sums of the train-mode statistics / backward
+    char *zero_begin;
+    size_t zero_bytes;
+    int32_t *orig2kept;      // n     (only written / read when the range mask dropped rows)
+    int32_t *kept2orig;      // n
+    int64_t words, n, pcap, index_tiles, pfn_tiles;
+    size_t index_bytes;      // bytes rdp_index_fwd needs (everything before `partials`)
+    size_t total_bytes;
+    int64_t partial_doubles_per_block;
+    int partial_blocks;
+};
+
+// Carves the workspace; `base` may be null to only compute total_bytes.
+int carve_workspace(void *base, int64_t n_points, const rdp_geom_t *geom, const rdp_layout_t *layout, Workspace *ws);
+
+// ----------------------------------------------------------------------------- device helpers
+#ifdef __CUDACC__
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+// --- mbarrier + 1-D bulk (TMA) copy: global -> shared, completion on an mbarrier
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// bytes must be a multiple of 16, src and dst 16-byte aligned.  SASS: UBLKCP.
+__device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// --- block-wide exclusive scan of one int per thread (blockDim.x == 256), returns exclusive prefix,
+//     *total receives the block sum.  `sm` needs 9 ints.
+__device__ __forceinline__ int block_excl_scan_256(int v, int *sm, int *total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += t;
+    }
+    if (lane == 31) sm[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        int w = lane < 8 ? sm[lane] : 0;
+        int winc = w;
+#pragma unroll
+        for (int d = 1; d < 8; d <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, winc, d);
+            if (lane >= d) winc += t;
+        }
+        if (lane < 8) sm[lane] = winc - w;
+        if (lane == 7) sm[8] = winc;
+    }
+    __syncthreads();
+    int res = sm[warp] + inc - v;
+    *total = sm[8];
+    __syncthreads();
+    return res;
+}
+
+// --- chunked-scan hand-off: CTA with ticket t publishes its aggregate and returns the sum of the
+//     aggregates of tickets < t.  Tickets are handed out in start order, so a CTA only ever waits
+//     for CTAs that are already running (no residency assumption, no deadlock).
+//     state[] must be zero before the launch.  Call from all threads; `sm` needs 1 uint32.
+__device__ __forceinline__ uint32_t chunk_exclusive_prefix(uint64_t *state, int ticket, uint32_t aggregate, uint32_t *sm) {
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicExch(reinterpret_cast<unsigned long long *>(state + ticket), (1ull << 63) | aggregate);
+    }
+    if (threadIdx.x < 32) {
+        uint32_t sum = 0;
+        for (int j = threadIdx.x; j < ticket; j += 32) {
+            unsigned long long v;
+            do {
+                v = *reinterpret_cast<volatile unsigned long long *>(state + j);
+                if (!(v >> 63)) __nanosleep(40);
+            } while (!(v >> 63));
+            sum += static_cast<uint32_t>(v);
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
+        if (threadIdx.x == 0) *sm = sum;
+    }
+    __syncthreads();
+    uint32_t r = *sm;
+    __syncthreads();
+    return r;
+}
+
+#endif  // __CUDACC__
+
+}  // namespace rdp

@@ -1,0 +1,334 @@
+// rdp_index.cu -- points -> pillars: quantise, range mask, merged key, sorted unique, inverse, counts,
+// coords, and the pillar-grouped point order the PFN kernels consume.
+//
+// Replaces /root/reference/pcdet/models/backbones_3d/vfe/dynamic_pillar_vfe.py:201-212,243-248
+// (identical code at :93-103,:132-138, :262-273, :322-333).
+//
+// The merged key  b*nx*ny + cx*ny + cy  (:208-210) is a small dense integer, so the "hash" is a
+// direct-addressed occupancy bitmap (collision-free open addressing with the identity hash) and
+// torch.unique's ascending order falls out of a popcount prefix scan over the bitmap -- a counting
+// sort with one-bit counters; no comparison sort, no ordering of floats, fully deterministic.
+//
+//   K1 quantize_mark   points (TMA bulk tile -> smem) -> key[i], bitmap |= bit(key)          [HBM: read rows]
+//   K2 bitmap_rank     popcount scan of the bitmap -> word_prefix, coords[rank], P
+//   K3 rank_count      key[i] -> rank = word_prefix + popc(below) ; inverse[j] ; counts[rank]++
+//   K4 count_scan      exclusive scan of counts -> starts, PFN tile boundaries
+//   K5 fill_order      order[start[rank]++] = i   (counting-sort fill; order inside a pillar is arbitrary,
+//                      every consumer is order independent)
+#include "rdp_common.cuh"
+
+namespace rdp {
+
+struct GeomDev {
+    float lo_x, lo_y, vx, vy;
+    int nx, ny, batch, cols;
+};
+
+// ----------------------------------------------------------------------------- K1
+__global__ void __launch_bounds__(kIndexThreads)
+quantize_mark_kernel(const float *__restrict__ pts, long long n0, GeomDev g, uint32_t *__restrict__ bitmap,
+                     int32_t *__restrict__ keys, int32_t *__restrict__ tile_keep, int32_t *__restrict__ counters) {
+    extern __shared__ __align__(128) float tile[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ int s_keep;
+
+    const int tid = threadIdx.x;
+    const long long row0 = (long long)blockIdx.x * kIndexTileRows;
+    const int rows = (int)min((long long)kIndexTileRows, n0 - row0);
+    const int floats = rows * g.cols;
+    const uint32_t bulk_bytes = (uint32_t)(floats * 4) & ~15u;
+    const float *src = pts + row0 * g.cols;
+
+    if (tid == 0) {
+        s_keep = 0;
+        mbar_init(&bar, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    if (tid == 0 && bulk_bytes) {
+        mbar_expect_tx(&bar, bulk_bytes);
+        tma_bulk_g2s(tile, src, bulk_bytes, &bar);  // one 1-D TMA copy of the whole row tile
+    }
+    for (int f = (int)(bulk_bytes >> 2) + tid; f < floats; f += kIndexThreads) tile[f] = src[f];  // <16 B tail
+    if (bulk_bytes) mbar_wait(&bar, 0);
+    __syncthreads();
+
+    const int sxy = g.nx * g.ny;
+    int kept = 0;
+    bool bad_batch = false;
+#pragma unroll
+    for (int k = 0; k < kIndexTileRows / kIndexThreads; ++k) {
+        const int r = k * kIndexThreads + tid;
+        if (r < rows) {
+            const float *p = tile + r * g.cols;
+            // IEEE fp32 subtract + divide + floor, as torch.floor((xy - lo) / vsz)  (:201-202)
+            const float qx = floorf(__fdiv_rn(__fsub_rn(p[1], g.lo_x), g.vx));
+            const float qy = floorf(__fdiv_rn(__fsub_rn(p[2], g.lo_y), g.vy));
+            bool ok = (qx >= 0.0f) && (qx < (float)g.nx) && (qy >= 0.0f) && (qy < (float)g.ny);  // NaN/inf fail
+            const int b = __float2int_rz(p[0]);  // .int() truncates
+            if (ok && (b < 0 || b >= g.batch)) { ok = false; bad_batch = true; }
+            int key = -1;
+            if (ok) {
+                key = b * sxy + (int)qx * g.ny + (int)qy;  // (:208-210)
+                atomicOr(bitmap + (key >> 5), 1u << (key & 31));
+                ++kept;
+            }
+            keys[row0 + r] = key;
+        }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) kept += __shfl_xor_sync(0xffffffffu, kept, d);
+    if ((tid & 31) == 0 && kept) atomicAdd(&s_keep, kept);
+    if (bad_batch) atomicOr(counters + RDP_CNT_ERRFLAGS, 1);
+    __syncthreads();
+    if (tid == 0) {
+        tile_keep[blockIdx.x] = s_keep;
+        if (s_keep) atomicAdd(counters + RDP_CNT_N, s_keep);
+    }
+}
+
+// ----------------------------------------------------------------------------- K2
+// Chunked two-sweep scan over the bitmap words: sweep 1 = popcount of my chunk, hand-off, sweep 2 =
+// ranks.  Emits coords in key order (:243-248) and zeroes counts[rank] for K3.
+__global__ void __launch_bounds__(kScanThreads)
+bitmap_rank_kernel(const uint32_t *__restrict__ bitmap, long long words, GeomDev g, int coord_cols,
+                   uint64_t *__restrict__ state, uint32_t *__restrict__ word_prefix, int32_t *__restrict__ coords,
+                   int32_t *__restrict__ counts, int32_t *__restrict__ counters) {
+    __shared__ int s_scan[9];
+    __shared__ uint32_t s_u32;
+    __shared__ int s_ticket;
+    const int tid = threadIdx.x;
+    if (tid == 0) s_ticket = atomicAdd(counters + kCntTicketA, 1);
+    __syncthreads();
+    const int ticket = s_ticket;
+    const long long per = (((words + gridDim.x - 1) / gridDim.x) + 1023) / 1024 * 1024;
+    const long long w0 = min(words, per * ticket), w1 = min(words, w0 + per);
+
+    // sweep 1
+    uint32_t local = 0;
+    for (long long w = w0 + tid * 4; w < w1; w += kScanThreads * 4) {
+        const uint4 v = *reinterpret_cast<const uint4 *>(bitmap + w);  // words padded to a multiple of 4
+        local += __popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w);
+    }
+    int tot;
+    block_excl_scan_256((int)local, s_scan, &tot);
+    uint32_t base = chunk_exclusive_prefix(state, ticket, (uint32_t)tot, &s_u32);
+    if (ticket == (int)gridDim.x - 1 && tid == 0) counters[RDP_CNT_P] = (int)(base + (uint32_t)tot);
+
+    // sweep 2
+    const int sxy = g.nx * g.ny;
+    for (long long wt = w0; wt < w1; wt += kScanThreads * 4) {
+        const long long w = wt + tid * 4;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (w < w1) v = *reinterpret_cast<const uint4 *>(bitmap + w);
+        const uint32_t wd[4] = {v.x, v.y, v.z, v.w};
+        const int c = __popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w);
+        int tile_total;
+        uint32_t rank = base + (uint32_t)block_excl_scan_256(c, s_scan, &tile_total);
+        base += (uint32_t)tile_total;
+        if (w < w1) {
+            uint4 pre;
+            pre.x = rank;
+            pre.y = pre.x + __popc(v.x);
+            pre.z = pre.y + __popc(v.y);
+            pre.w = pre.z + __popc(v.z);
+            *reinterpret_cast<uint4 *>(word_prefix + w) = pre;
+            if (c) {
+                // decode the first key of this thread once; later bits only carry
+                const long long key0 = w * 32;
+                const int b0 = (int)(key0 / sxy);
+                const int rem = (int)(key0 - (long long)b0 * sxy);
+                const int cx0 = rem / g.ny, cy0 = rem - cx0 * g.ny;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    uint32_t bits = wd[q];
+                    while (bits) {
+                        const int bit = __ffs(bits) - 1;
+                        bits &= bits - 1;
+                        int cy = cy0 + q * 32 + bit, cx = cx0, b = b0;
+                        while (cy >= g.ny) { cy -= g.ny; ++cx; }
+                        while (cx >= g.nx) { cx -= g.nx; ++b; }
+                        if (coord_cols == 3) {
+                            int32_t *o = coords + (size_t)rank * 3;
+                            o[0] = b; o[1] = cy; o[2] = cx;  // [b, y, x]  (:248)
+                        } else {
+                            *reinterpret_cast<int4 *>(coords + (size_t)rank * 4) = make_int4(b, 0, cy, cx);  // (:138)
+                        }
+                        counts[rank] = 0;
+                        ++rank;
+                    }
+                }
+            }
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------- K3
+__global__ void __launch_bounds__(kIndexThreads)
+rank_count_kernel(int32_t *__restrict__ keys, long long n0, const uint32_t *__restrict__ bitmap,
+                  const uint32_t *__restrict__ word_prefix, const int32_t *__restrict__ tile_keep,
+                  int32_t *__restrict__ inverse, int32_t *__restrict__ counts, const int32_t *__restrict__ counters,
+                  int32_t *__restrict__ orig2kept, int32_t *__restrict__ kept2orig) {
+    __shared__ int s_scan[9];
+    __shared__ long long s_base;
+    const int tid = threadIdx.x;
+    const long long row0 = (long long)blockIdx.x * kIndexTileRows;
+    const long long i0 = row0 + tid * 4;
+
+    int k[4] = {-1, -1, -1, -1};
+    if (i0 + 3 < n0) {
+        const int4 v = *reinterpret_cast<const int4 *>(keys + i0);
+        k[0] = v.x; k[1] = v.y; k[2] = v.z; k[3] = v.w;
+    } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) if (i0 + q < n0) k[q] = keys[i0 + q];
+    }
+    int r[4];
+    int c = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        r[q] = -1;
+        if (k[q] >= 0) {
+            const uint32_t w = bitmap[k[q] >> 5];
+            r[q] = (int)(word_prefix[k[q] >> 5] + __popc(w & ((1u << (k[q] & 31)) - 1u)));
+            ++c;
+        }
+    }
+    // position among the KEPT points (stable compaction of :204-206)
+    const bool none_dropped = (long long)counters[RDP_CNT_N] == n0;
+    if (!none_dropped) {
+        long long part = 0;
+        for (int t = tid; t < (int)blockIdx.x; t += kIndexThreads) part += tile_keep[t];
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
+        if (tid == 0) s_base = 0;
+        __syncthreads();
+        if ((tid & 31) == 0 && part) atomicAdd(reinterpret_cast<unsigned long long *>(&s_base), (unsigned long long)part);
+        __syncthreads();
+    }
+    int tot;
+    const int excl = block_excl_scan_256(c, s_scan, &tot);
+    long long j = none_dropped ? i0 : s_base + excl;
+    if (none_dropped && i0 + 3 < n0) {
+        *reinterpret_cast<int4 *>(inverse + i0) = make_int4(r[0], r[1], r[2], r[3]);
+    } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (r[q] >= 0) {
+                if (!none_dropped) { orig2kept[i0 + q] = (int)j; kept2orig[j] = (int)(i0 + q); }
+                inverse[j++] = r[q];
+            }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+        if (r[q] >= 0) atomicAdd(counts + r[q], 1);
+    if (i0 + 3 < n0) {
+        *reinterpret_cast<int4 *>(keys + i0) = make_int4(r[0], r[1], r[2], r[3]);  // key -> rank, in place
+    } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) if (i0 + q < n0) keys[i0 + q] = r[q];
+    }
+}
+
+// ----------------------------------------------------------------------------- K4
+__global__ void __launch_bounds__(kScanThreads)
+count_scan_kernel(const int32_t *__restrict__ counts, uint64_t *__restrict__ state, int32_t *__restrict__ ends,
+                  int32_t *__restrict__ tile_start, int32_t *__restrict__ counters, int pfn_tile_rows) {
+    __shared__ int s_scan[9];
+    __shared__ uint32_t s_u32;
+    __shared__ int s_ticket;
+    const int tid = threadIdx.x;
+    if (tid == 0) s_ticket = atomicAdd(counters + kCntTicketB, 1);
+    __syncthreads();
+    const int ticket = s_ticket;
+    const long long P = counters[RDP_CNT_P];
+    const long long per = (((P + gridDim.x - 1) / gridDim.x) + 1023) / 1024 * 1024;
+    const long long p0 = min(P, per * ticket), p1 = min(P, p0 + per);
+
+    int local = 0;
+    for (long long p = p0 + tid; p < p1; p += kScanThreads) local += counts[p];
+    int tot;
+    block_excl_scan_256(local, s_scan, &tot);
+    uint32_t base = chunk_exclusive_prefix(state, ticket, (uint32_t)tot, &s_u32);
+
+    if (ticket == 0 && tid == 0) tile_start[0] = 0;
+    for (long long pt = p0; pt < p1; pt += kScanThreads * 4) {
+        const long long p = pt + tid * 4;
+        int c[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) c[q] = (p + q < p1) ? counts[p + q] : 0;
+        int tile_total;
+        uint32_t s = base + (uint32_t)block_excl_scan_256(c[0] + c[1] + c[2] + c[3], s_scan, &tile_total);
+        base += (uint32_t)tile_total;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            if (p + q < p1) {
+                ends[p + q] = (int)s;  // exclusive start; K5 advances it to the inclusive end
+                const uint32_t e = s + (uint32_t)c[q];
+                // pillar p+q+1 is the first pillar starting at or after every tile boundary in (s, e]
+                for (uint32_t t = s / pfn_tile_rows + 1; t * (uint32_t)pfn_tile_rows <= e; ++t) tile_start[t] = (int)(p + q + 1);
+                if (p + q == P - 1 && e % pfn_tile_rows != 0) tile_start[e / pfn_tile_rows + 1] = (int)P;
+                s = e;
+            }
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------- K5
+__global__ void __launch_bounds__(kIndexThreads)
+fill_order_kernel(const int32_t *__restrict__ ranks, long long n0, int32_t *__restrict__ ends, int32_t *__restrict__ order) {
+    const long long i0 = ((long long)blockIdx.x * kIndexThreads + threadIdx.x) * 4;
+    if (i0 >= n0) return;
+    int r[4] = {-1, -1, -1, -1};
+    if (i0 + 3 < n0) {
+        const int4 v = *reinterpret_cast<const int4 *>(ranks + i0);
+        r[0] = v.x; r[1] = v.y; r[2] = v.z; r[3] = v.w;
+    } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) if (i0 + q < n0) r[q] = ranks[i0 + q];
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+        if (r[q] >= 0) order[atomicAdd(ends + r[q], 1)] = (int)(i0 + q);
+}
+
+static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+}  // namespace rdp
+
+using namespace rdp;
+
+extern "C" int rdp_index_fwd(const float *points, int64_t n_points, const rdp_geom_t *geom, int32_t coord_cols,
+                             void *workspace, size_t workspace_bytes, int32_t *coords, int32_t *inverse,
+                             int32_t *counts, int32_t *counters, void *stream_v) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+    if (!geom || !counters || n_points < 0 || (coord_cols != 3 && coord_cols != 4)) return RDP_ERR_INVALID_ARG;
+    if (n_points > 0 && (!points || !workspace || !coords || !inverse || !counts)) return RDP_ERR_INVALID_ARG;
+    if (!aligned16(points) || !aligned16(coords) || !aligned16(inverse) || !aligned16(workspace)) return RDP_ERR_INVALID_ARG;
+    if (n_points >= (1ll << 31) - 8) return RDP_ERR_UNSUPPORTED;
+    Workspace ws;
+    int rc = carve_workspace(workspace, n_points, geom, nullptr, &ws);
+    if (rc != RDP_OK) return rc;
+    if (n_points > 0 && ws.index_bytes > workspace_bytes) return RDP_ERR_WORKSPACE;
+
+    RDP_CUDA_OK(cudaMemsetAsync(counters, 0, sizeof(int32_t) * RDP_NUM_COUNTERS, stream));
+    if (n_points == 0) return RDP_OK;
+    RDP_CUDA_OK(cudaMemsetAsync(ws.zero_begin, 0, ws.zero_bytes, stream));
+
+    GeomDev g{geom->lo[0], geom->lo[1], geom->vsz[0], geom->vsz[1], geom->nx, geom->ny, geom->batch_size, geom->cols};
+    const size_t smem = (size_t)kIndexTileRows * geom->cols * sizeof(float);
+    if (smem > 200 * 1024) return RDP_ERR_UNSUPPORTED;
+    if (smem > 48 * 1024)
+        RDP_CUDA_OK(cudaFuncSetAttribute(quantize_mark_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int tiles = (int)ws.index_tiles;
+    quantize_mark_kernel<<<tiles, kIndexThreads, smem, stream>>>(points, n_points, g, ws.bitmap, ws.keys, ws.tile_keep, counters);
+    bitmap_rank_kernel<<<kScanGrid, kScanThreads, 0, stream>>>(ws.bitmap, ws.words, g, coord_cols, ws.scan_state_a,
+                                                             ws.word_prefix, coords, counts, counters);
+    rank_count_kernel<<<tiles, kIndexThreads, 0, stream>>>(ws.keys, n_points, ws.bitmap, ws.word_prefix, ws.tile_keep,
+                                                         inverse, counts, counters, ws.orig2kept, ws.kept2orig);
+    count_scan_kernel<<<kScanGrid, kScanThreads, 0, stream>>>(counts, ws.scan_state_b, ws.ends, ws.tile_start, counters,
+                                                            kPfnTileRows);
+    fill_order_kernel<<<tiles, kIndexThreads, 0, stream>>>(ws.keys, n_points, ws.ends, ws.order);
+    RDP_CUDA_OK(cudaGetLastError());
+    return RDP_OK;
+}

@@ -1,0 +1,37 @@
+// rdp_pfn_host.h -- host-side table of the compiled PFN configurations.
+#pragma once
+#include "rdp_pfn.cuh"
+
+namespace rdp {
+
+struct PfnLaunch {
+    int cols, layout, dist, cout, cs;
+    size_t fwd_smem, bwd_smem, bwdfin_smem;
+    int stats_partial_doubles, bwd_partial_doubles;
+    cudaError_t (*fwd)(const PfnArgs &a, int mode, int grid, cudaStream_t st);
+    cudaError_t (*bn_finalize)(const PfnArgs &a, int nblocks, double *bn_state, float *rm, float *rv, double momentum, cudaStream_t st);
+    cudaError_t (*bwd)(const PfnArgs &a, int grid, const float *grad, const float *feat, const int32_t *arg, const float *pmean,
+                       cudaStream_t st);
+    cudaError_t (*bwd_finalize)(const PfnArgs &a, int nblocks, const double *bn_state, int train_bn, float *dW, float *dg, float *db,
+                                cudaStream_t st);
+};
+
+// (id, cols, layout, with_distance, c_out) -- one translation unit each (rdp_pfn_inst.cu, -DRDP_CFG_ID=id)
+#define RDP_PFN_CONFIGS(X)                         \
+    X(0, 6, RDP_LAYOUT_SIMPLE2D, false, 32)        \
+    X(1, 7, RDP_LAYOUT_SIMPLE2D, false, 32)        \
+    X(2, 5, RDP_LAYOUT_DYNPILLAR, false, 64)       \
+    X(3, 5, RDP_LAYOUT_DYNPILLAR, true, 32)        \
+    X(4, 6, RDP_LAYOUT_SIMPLE2D, true, 32)         \
+    X(5, 5, RDP_LAYOUT_SIMPLE2D, false, 32)        \
+    X(6, 5, RDP_LAYOUT_DYNPILLAR, false, 32)       \
+    X(7, 6, RDP_LAYOUT_SIMPLE2D, false, 64)        \
+    X(8, 7, RDP_LAYOUT_SIMPLE2D, false, 64)        \
+    X(9, 6, RDP_LAYOUT_DYNPILLAR, false, 64)       \
+    X(10, 6, RDP_LAYOUT_DYNPILLAR, false, 32)
+
+#define RDP_DECLARE_CFG(id, cols, layout, dist, cout) const PfnLaunch *rdp_pfn_cfg_##id();
+RDP_PFN_CONFIGS(RDP_DECLARE_CFG)
+#undef RDP_DECLARE_CFG
+
+}  // namespace rdp

@@ -1,0 +1,256 @@
+"""PyTorch-facing operators over the C ABI (``include/rdp.h``): device memory, streams and autograd
+plumbing only -- every computation runs in librdp.so's sm_100a kernels.
+
+    encode(points, spec, params, training) -> EncodeResult
+
+replaces the body of the reference ``forward`` between reading ``points`` and writing the
+``batch_dict`` keys (``dynamic_pillar_vfe.py:200-249``).  There is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import Geom, Layout, PfnParams
+
+
+@dataclass(frozen=True)
+class EncoderSpec:
+    """Static description of one encoder (constructor arguments of the reference classes)."""
+    cols: int                     # 1 + num_point_features
+    layout: int                   # _lib.LAYOUT_*
+    use_abs: bool
+    use_cluster: bool
+    use_relative: bool
+    with_distance: bool
+    c_in: int
+    c_out: int
+    coord_cols: int               # 3: [b,y,x]   4: [b,0,y,x]
+    lo: tuple                     # point_cloud_range[0:3] (fp32 values)
+    vsz: tuple                    # voxel size (fp32 values)
+    off: tuple                    # voxel/2 + lo (double, rounded once to fp32)
+    nx: int
+    ny: int
+    eps: float = 1e-3
+    momentum: float = 0.01
+
+    def geom(self, batch_size: int) -> Geom:
+        g = Geom()
+        for k in range(3):
+            g.lo[k], g.vsz[k], g.off[k] = self.lo[k], self.vsz[k], self.off[k]
+        g.nx, g.ny, g.batch_size, g.cols = self.nx, self.ny, int(batch_size), self.cols
+        return g
+
+    def layout_struct(self) -> Layout:
+        return Layout(self.layout, int(self.use_abs), int(self.use_cluster), int(self.use_relative),
+                      int(self.with_distance), self.c_in, self.c_out, self.coord_cols)
+
+
+def make_spec(num_point_features: int, voxel_size, grid_size, point_cloud_range, layout: int, use_abs: bool,
+              use_cluster: bool, use_relative: bool, with_distance: bool, c_out: int) -> EncoderSpec:
+    c = int(num_point_features)
+    if layout == _lib.LAYOUT_SIMPLE2D:
+        c_in = 3 + (c if use_abs else c - 3) + (3 if use_cluster else 0) + (3 if use_relative else 0)
+        coord_cols = 3
+    else:
+        c_in = (c if use_abs else c - 3) + 6
+        use_cluster, use_relative, coord_cols = True, False, 4
+    c_in += 1 if with_distance else 0
+    pcr = np.asarray(point_cloud_range, dtype=np.float32)
+    vs = np.asarray([float(v) for v in voxel_size], dtype=np.float64)
+    lo = tuple(float(pcr[k]) for k in range(3))
+    vsz = tuple(float(np.float32(vs[k])) for k in range(3))
+    off = tuple(float(np.float32(vs[k] / 2.0 + float(pcr[k]))) for k in range(3))   # (:180-182)
+    return EncoderSpec(cols=c + 1, layout=layout, use_abs=bool(use_abs), use_cluster=bool(use_cluster),
+                       use_relative=bool(use_relative), with_distance=bool(with_distance), c_in=c_in, c_out=int(c_out),
+                       coord_cols=coord_cols, lo=lo, vsz=vsz, off=off, nx=int(grid_size[0]), ny=int(grid_size[1]))
+
+
+@dataclass
+class EncodeResult:
+    features: torch.Tensor            # (P, c_out) fp32
+    coords: torch.Tensor              # (P, coord_cols) int32
+    inverse: torch.Tensor             # (N,) int32   pillar of each KEPT point (torch.unique's inverse)
+    counts: torch.Tensor              # (P,) int32
+    argmax: Optional[torch.Tensor]    # (P, c_out) int32 kept-point index, training only
+    n_kept: int
+    n_pillars: int
+    # state for the backward
+    pillar_mean: Optional[torch.Tensor] = None
+    bn_state: Optional[torch.Tensor] = None
+    workspace: Optional[torch.Tensor] = None
+    counters: Optional[torch.Tensor] = None
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream_ptr():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+_pinned = {}
+
+
+def _pinned_counters(device) -> torch.Tensor:
+    key = (device.index, torch.cuda.current_stream().cuda_stream)
+    t = _pinned.get(key)
+    if t is None:
+        t = torch.empty(_lib.RDP_NUM_COUNTERS, dtype=torch.int32).pin_memory()
+        _pinned[key] = t
+    return t
+
+
+def _params_struct(spec: EncoderSpec, weight, bias, gamma, beta, running_mean, running_var, train_bn: bool) -> PfnParams:
+    p = PfnParams()
+    p.weight, p.bias = weight.data_ptr(), (bias.data_ptr() if bias is not None else None)
+    p.gamma = gamma.data_ptr() if gamma is not None else None
+    p.beta = beta.data_ptr() if beta is not None else None
+    p.running_mean = running_mean.data_ptr() if running_mean is not None else None
+    p.running_var = running_var.data_ptr() if running_var is not None else None
+    p.eps, p.momentum, p.train_bn = spec.eps, spec.momentum, int(train_bn)
+    return p
+
+
+def _check_param(t: Optional[torch.Tensor], shape, name: str):
+    if t is None:
+        return None
+    if not t.is_cuda or t.dtype != torch.float32 or tuple(t.shape) != tuple(shape):
+        raise ValueError(f"{name}: expected a CUDA float32 tensor of shape {tuple(shape)}, got {t.dtype} {tuple(t.shape)} on {t.device}")
+    return t.detach().contiguous() if not t.is_contiguous() else t.detach()
+
+
+def encode_forward(points: torch.Tensor, spec: EncoderSpec, batch_size: int, weight, bias, gamma, beta, running_mean,
+                   running_var, train_bn: bool, want_argmax: bool) -> EncodeResult:
+    """index + PFN forward on the current stream; one 64-byte read-back to learn N and P."""
+    lib = _lib.load()
+    if not points.is_cuda:
+        raise _lib.RdpError("the pillar encoder has no CPU path: `points` must be a CUDA tensor")
+    if points.dim() != 2 or points.shape[1] != spec.cols:
+        raise ValueError(f"points must be (N, {spec.cols}), got {tuple(points.shape)}")
+    pts = points.detach()
+    if pts.dtype != torch.float32:
+        pts = pts.float()
+    if not pts.is_contiguous() or pts.data_ptr() % 16:
+        pts = pts.contiguous().clone() if pts.data_ptr() % 16 else pts.contiguous()
+    dev = pts.device
+    n0 = pts.shape[0]
+    use_norm = gamma is not None
+    weight = _check_param(weight, (spec.c_out, spec.c_in), "linear.weight")
+    bias = _check_param(bias, (spec.c_out,), "linear.bias")
+    gamma = _check_param(gamma, (spec.c_out,), "norm.weight")
+    beta = _check_param(beta, (spec.c_out,), "norm.bias")
+    running_mean = _check_param(running_mean, (spec.c_out,), "norm.running_mean")
+    running_var = _check_param(running_var, (spec.c_out,), "norm.running_var")
+    train_bn = bool(train_bn and use_norm)
+
+    with torch.cuda.device(dev):
+        geom, layout = spec.geom(batch_size), spec.layout_struct()
+        nbytes = C.c_size_t(0)
+        _lib.check(lib.rdp_workspace_bytes(n0, C.byref(geom), C.byref(layout), C.byref(nbytes)), "rdp_workspace_bytes")
+        cap = max(n0, 1)
+        ws = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
+        coords = torch.empty((cap, spec.coord_cols), dtype=torch.int32, device=dev)
+        inverse = torch.empty(cap + 4, dtype=torch.int32, device=dev)
+        counts = torch.empty(cap + 4, dtype=torch.int32, device=dev)
+        counters = torch.empty(_lib.RDP_NUM_COUNTERS, dtype=torch.int32, device=dev)
+        features = torch.empty((cap, spec.c_out), dtype=torch.float32, device=dev)
+        argmax = torch.empty((cap, spec.c_out), dtype=torch.int32, device=dev) if want_argmax else None
+        pmean = torch.empty((cap, 3), dtype=torch.float32, device=dev) if want_argmax else None
+        bn_state = None
+        if train_bn:
+            bn_state = torch.zeros(int(lib.rdp_bn_state_doubles(C.byref(layout))), dtype=torch.float64, device=dev)
+        st = _stream_ptr()
+        _lib.check(lib.rdp_index_fwd(_ptr(pts), n0, C.byref(geom), spec.coord_cols, _ptr(ws), nbytes.value, _ptr(coords),
+                                     _ptr(inverse), _ptr(counts), _ptr(counters), st), "rdp_index_fwd")
+        prm = _params_struct(spec, weight, bias, gamma, beta, running_mean, running_var, train_bn)
+        _lib.check(lib.rdp_pfn_fwd(_ptr(pts), n0, C.byref(geom), C.byref(layout), C.byref(prm), _ptr(ws), nbytes.value,
+                                   _ptr(counters), _ptr(coords), _ptr(features), _ptr(argmax), _ptr(pmean), _ptr(bn_state), st),
+                   "rdp_pfn_fwd")
+        host = _pinned_counters(dev)
+        host.copy_(counters, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        n_kept, n_pillars, err = int(host[_lib.CNT_N]), int(host[_lib.CNT_P]), int(host[_lib.CNT_ERRFLAGS])
+    if err & 1:
+        raise ValueError(f"points[:, 0] holds a batch index outside [0, {batch_size})")
+    return EncodeResult(features=features[:n_pillars], coords=coords[:n_pillars], inverse=inverse[:n_kept],
+                        counts=counts[:n_pillars], argmax=None if argmax is None else argmax[:n_pillars],
+                        n_kept=n_kept, n_pillars=n_pillars, pillar_mean=pmean, bn_state=bn_state, workspace=ws,
+                        counters=counters)
+
+
+def encode_backward(points: torch.Tensor, spec: EncoderSpec, batch_size: int, res: EncodeResult, grad_features, weight,
+                    bias, gamma, beta, running_mean, running_var, train_bn: bool):
+    """Parameter gradients (d_weight, d_gamma | None, d_beta_or_bias)."""
+    lib = _lib.load()
+    dev = points.device
+    use_norm = gamma is not None
+    with torch.cuda.device(dev):
+        geom, layout = spec.geom(batch_size), spec.layout_struct()
+        d_w = torch.empty((spec.c_out, spec.c_in), dtype=torch.float32, device=dev)
+        d_g = torch.empty(spec.c_out, dtype=torch.float32, device=dev) if use_norm else None
+        d_b = torch.empty(spec.c_out, dtype=torch.float32, device=dev)
+        g = grad_features.contiguous().float()
+        prm = _params_struct(spec, weight.detach(), None if bias is None else bias.detach(),
+                             None if gamma is None else gamma.detach(), None if beta is None else beta.detach(),
+                             running_mean, running_var, bool(train_bn and use_norm))
+        feats = res.features if res.features.is_contiguous() else res.features.contiguous()
+        _lib.check(lib.rdp_pfn_bwd(_ptr(points), points.shape[0], C.byref(geom), C.byref(layout), C.byref(prm),
+                                   _ptr(res.workspace), res.workspace.numel(), _ptr(res.counters), _ptr(res.coords), _ptr(g),
+                                   _ptr(feats), _ptr(res.argmax), _ptr(res.pillar_mean), _ptr(res.bn_state), _ptr(d_w),
+                                   _ptr(d_g), _ptr(d_b), res.n_pillars, _stream_ptr()), "rdp_pfn_bwd")
+    return d_w, d_g, d_b
+
+
+class _PillarEncodeFn(torch.autograd.Function):
+    """Autograd node: saves (points, argmax, pillar means, BN state) -- never the (N, C) activations."""
+
+    @staticmethod
+    def forward(ctx, points, weight, bias, gamma, beta, running_mean, running_var, spec, batch_size, train_bn, holder):
+        needs_grad = any(t is not None and t.requires_grad for t in (weight, bias, gamma, beta))
+        res = encode_forward(points, spec, batch_size, weight, bias, gamma, beta, running_mean, running_var, train_bn,
+                             want_argmax=needs_grad)
+        holder.append(res)
+        ctx.res, ctx.spec, ctx.batch_size, ctx.train_bn = res, spec, batch_size, train_bn
+        pts = points.detach()
+        if pts.dtype != torch.float32 or not pts.is_contiguous() or pts.data_ptr() % 16:
+            pts = pts.float().contiguous()
+        ctx.points = pts
+        ctx.save_for_backward(weight, bias, gamma, beta)
+        ctx.rm, ctx.rv = running_mean, running_var
+        ctx.mark_non_differentiable(res.coords)
+        return res.features, res.coords
+
+    @staticmethod
+    def backward(ctx, grad_features, _grad_coords):
+        weight, bias, gamma, beta = ctx.saved_tensors
+        res = ctx.res
+        if res.argmax is None:
+            raise RuntimeError("backward through a forward that ran without requires_grad parameters")
+        d_w, d_g, d_b = encode_backward(ctx.points, ctx.spec, ctx.batch_size, res, grad_features, weight, bias, gamma, beta,
+                                        ctx.rm, ctx.rv, ctx.train_bn)
+        use_norm = gamma is not None
+        return (None, d_w, (None if use_norm else d_b), d_g, (d_b if use_norm else None), None, None, None, None, None, None)
+
+
+def encode(points, spec: EncoderSpec, batch_size: int, weight, bias=None, gamma=None, beta=None, running_mean=None,
+           running_var=None, train_bn: bool = False) -> EncodeResult:
+    """Differentiable (w.r.t. the PFN parameters) pillar encoding.  Returns the full EncodeResult."""
+    if points.requires_grad:
+        raise NotImplementedError("gradients w.r.t. points are not produced (points are a leaf in the reference)")
+    holder = []
+    if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in (weight, bias, gamma, beta)):
+        feats, coords = _PillarEncodeFn.apply(points, weight, bias, gamma, beta, running_mean, running_var, spec, batch_size,
+                                              train_bn, holder)
+        res = holder[0]
+        return EncodeResult(features=feats, coords=coords, inverse=res.inverse, counts=res.counts, argmax=res.argmax,
+                            n_kept=res.n_kept, n_pillars=res.n_pillars, pillar_mean=res.pillar_mean, bn_state=res.bn_state,
+                            workspace=res.workspace, counters=res.counters)
+    return encode_forward(points, spec, batch_size, weight, bias, gamma, beta, running_mean, running_var, train_bn,
+                          want_argmax=False)

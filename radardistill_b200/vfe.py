@@ -1,0 +1,175 @@
+"""Drop-in replacements for the reference's dynamic pillar encoders.
+
+Same class names, constructor signature, ``forward(batch_dict) -> batch_dict`` contract,
+``batch_dict`` keys and ``state_dict`` names as
+``/root/reference/pcdet/models/backbones_3d/vfe/dynamic_pillar_vfe.py``:
+
+* ``DynamicPillarVFE``                      (:49-142)   reads ``points``        -> ``pillar_features`` / ``voxel_features``, ``voxel_coords`` (P,4)
+* ``DynamicPillarVFESimple2D``              (:146-252)  reads ``points``        -> ``pillar_features``, ``pillar_coords`` (P,3)
+* ``Radar_DynamicPillarVFESimple2D``        (:255-313)  reads ``radar_points``  -> ``radar_pillar_features``, ``radar_pillar_coords``
+* ``Radar_DynamicPillarVFESimple2D_Test``   (:315-373)  reads ``points``        -> ``radar_pillar_*``
+
+``register(vfe_all)`` overwrites the four entries of the reference registry
+(``pcdet/models/backbones_3d/vfe/__init__.py:9-21``).  The forward runs entirely in the sm_100a
+kernels of librdp.so; there is no PyTorch/CPU fallback.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from . import _lib, ops
+
+
+class VFETemplate(nn.Module):
+    """Mirror of ``vfe_template.py:4-22``."""
+
+    def __init__(self, model_cfg, **kwargs):
+        super().__init__()
+        self.model_cfg = model_cfg
+
+    def get_output_feature_dim(self):
+        raise NotImplementedError
+
+    def forward(self, **kwargs):
+        raise NotImplementedError
+
+
+def _cfg_get(cfg, key, default=None):
+    if hasattr(cfg, "get"):
+        return cfg.get(key, default)
+    return getattr(cfg, key, default)
+
+
+def _cfg(cfg, key):
+    try:
+        return cfg[key] if isinstance(cfg, dict) else getattr(cfg, key)
+    except (KeyError, AttributeError):
+        raise AttributeError(f"model_cfg.{key} is required") from None
+
+
+class PFNLayerV2(nn.Module):
+    """Parameter holder with the reference's names (``dynamic_pillar_vfe.py:14-33``): ``linear`` and ``norm``.
+    The computation of its ``forward`` (:35-46) is fused into the encoder kernels."""
+
+    def __init__(self, in_channels, out_channels, use_norm=True, last_layer=False):
+        super().__init__()
+        self.last_vfe = last_layer
+        self.use_norm = use_norm
+        if not self.last_vfe:
+            out_channels = out_channels // 2
+        if self.use_norm:
+            self.linear = nn.Linear(in_channels, out_channels, bias=False)
+            self.norm = nn.BatchNorm1d(out_channels, eps=1e-3, momentum=0.01)
+        else:
+            self.linear = nn.Linear(in_channels, out_channels, bias=True)
+        self.relu = nn.ReLU()
+
+    def forward(self, inputs, unq_inv):  # pragma: no cover
+        raise _lib.RdpError("PFNLayerV2 is fused into the pillar-encoder kernels; call the VFE module instead")
+
+
+class _FusedDynamicPillarVFE(VFETemplate):
+    _layout = _lib.LAYOUT_SIMPLE2D
+    _points_key = "points"
+    _feature_keys = ("pillar_features",)
+    _coords_key = "pillar_coords"
+
+    def __init__(self, model_cfg, num_point_features, voxel_size, grid_size, point_cloud_range, **kwargs):
+        super().__init__(model_cfg=model_cfg)
+        self.use_norm = _cfg(model_cfg, "USE_NORM")
+        self.with_distance = _cfg(model_cfg, "WITH_DISTANCE")
+        self.use_absolute_xyz = _cfg(model_cfg, "USE_ABSLOTE_XYZ")
+        if self._layout == _lib.LAYOUT_SIMPLE2D:
+            self.use_cluster_xyz = _cfg_get(model_cfg, "USE_CLUSTER_XYZ", True)
+            self.use_relative_xyz = _cfg_get(model_cfg, "USE_RELATIVE_XYZ", True)
+            self.double_flip = _cfg_get(model_cfg, "DOUBLE_FLIP", False)
+        else:
+            self.use_cluster_xyz, self.use_relative_xyz, self.double_flip = True, False, False
+        self.num_filters = list(_cfg(model_cfg, "NUM_FILTERS"))
+        assert len(self.num_filters) > 0
+        if len(self.num_filters) != 1:
+            raise NotImplementedError("fused encoder covers the single-PFN-layer configurations the reference ships "
+                                      "(NUM_FILTERS of length 1); multi-layer PFN stacks are listed as 'next' in DESIGN.md")
+        self.spec = ops.make_spec(num_point_features, voxel_size, grid_size, point_cloud_range, self._layout,
+                                  bool(self.use_absolute_xyz), bool(self.use_cluster_xyz), bool(self.use_relative_xyz),
+                                  bool(self.with_distance), self.num_filters[-1])
+        self.num_point_features = self.spec.c_in
+        self.pfn_layers = nn.ModuleList([PFNLayerV2(self.spec.c_in, self.num_filters[0], self.use_norm, last_layer=True)])
+        self.voxel_x, self.voxel_y, self.voxel_z = voxel_size[0], voxel_size[1], voxel_size[2]
+        self.x_offset, self.y_offset, self.z_offset = self.spec.off
+        self.scale_xy = int(grid_size[0]) * int(grid_size[1])
+        self.scale_y = int(grid_size[1])
+        self.last_result = None  # EncodeResult of the latest forward (inverse / counts / argmax for inspection)
+
+    def get_output_feature_dim(self):
+        return self.num_filters[-1]
+
+    def _batch_size(self, batch_dict, points):
+        bs = batch_dict.get("batch_size", None)
+        if bs is not None:
+            return int(bs)
+        return int(points[:, 0].max().item()) + 1 if points.shape[0] else 1  # host sync; pass batch_size to avoid it
+
+    def forward(self, batch_dict, **kwargs):
+        if self.double_flip:
+            # the reference path uses `np` without importing it (dynamic_pillar_vfe.py:196-199) and cannot run
+            raise NotImplementedError("DOUBLE_FLIP is dead code in the reference (NameError) and is not provided")
+        points = batch_dict[self._points_key]
+        pfn = self.pfn_layers[0]
+        norm = pfn.norm if self.use_norm else None
+        train_bn = bool(self.use_norm and norm.training)
+        res = ops.encode(points, self.spec, self._batch_size(batch_dict, points), pfn.linear.weight,
+                         bias=None if self.use_norm else pfn.linear.bias,
+                         gamma=norm.weight if norm is not None else None, beta=norm.bias if norm is not None else None,
+                         running_mean=norm.running_mean if norm is not None else None,
+                         running_var=norm.running_var if norm is not None else None, train_bn=train_bn)
+        if train_bn:
+            if res.n_kept == 1:
+                raise ValueError(f"Expected more than 1 value per channel when training, got input size "
+                                 f"torch.Size([1, {self.spec.c_out}])")
+            norm.num_batches_tracked.add_(1)
+        self.last_result = res
+        for k in self._feature_keys:
+            batch_dict[k] = res.features
+        batch_dict[self._coords_key] = res.coords
+        return batch_dict
+
+
+class DynamicPillarVFE(_FusedDynamicPillarVFE):
+    _layout = _lib.LAYOUT_DYNPILLAR
+    _feature_keys = ("voxel_features", "pillar_features")
+    _coords_key = "voxel_coords"
+
+
+class DynamicPillarVFESimple2D(_FusedDynamicPillarVFE):
+    pass
+
+
+class Radar_DynamicPillarVFESimple2D(DynamicPillarVFESimple2D):
+    _points_key = "radar_points"
+    _feature_keys = ("radar_pillar_features",)
+    _coords_key = "radar_pillar_coords"
+
+
+class Radar_DynamicPillarVFESimple2D_Test(DynamicPillarVFESimple2D):
+    _points_key = "points"
+    _feature_keys = ("radar_pillar_features",)
+    _coords_key = "radar_pillar_coords"
+
+
+REGISTRY = {
+    "VFETemplate": VFETemplate,
+    "DynPillarVFE": DynamicPillarVFE,
+    "DynamicPillarVFESimple2D": DynamicPillarVFESimple2D,
+    "Radar_DynamicPillarVFESimple2D": Radar_DynamicPillarVFESimple2D,
+    "Radar_DynamicPillarVFESimple2D_Test": Radar_DynamicPillarVFESimple2D_Test,
+}
+
+
+def register(vfe_all: dict) -> dict:
+    """Overwrites the dynamic-pillar entries of ``pcdet.models.backbones_3d.vfe.__all__`` in place."""
+    for name in ("DynPillarVFE", "DynamicPillarVFESimple2D", "Radar_DynamicPillarVFESimple2D",
+                 "Radar_DynamicPillarVFESimple2D_Test"):
+        vfe_all[name] = REGISTRY[name]
+    return vfe_all

@@ -68,3 +68,24 @@ def argmax_mismatch_is_near_tie(arg_a, arg_b, x_post, inverse, tol):
         if abs(float(x_post[ia, c]) - float(x_post[ib, c])) > tol:
             return False
     return True
+
+
+# ------------------------------------------------------------------ CUDA-side helpers (gpu tests, smoke)
+def module_from_golden(g, device="cuda"):
+    """The drop-in module (radardistill_b200.vfe) configured like the golden's reference module."""
+    import torch
+    from oracle.ref_loader import Cfg
+    from radardistill_b200 import synth
+    from radardistill_b200.vfe import REGISTRY
+    name = "DynPillarVFE" if g["class_name"] in ("DynPillarVFE", "DynamicPillarVFE") else g["class_name"]
+    m = REGISTRY[name](model_cfg=Cfg(g["model_cfg"]), num_point_features=int(g["num_point_features"]),
+                       voxel_size=[float(v) for v in g["voxel_size"]], grid_size=grid_of(g),
+                       point_cloud_range=synth.PC_RANGE, depth_downsample_factor=None)
+    sd = {k[len("param."):]: torch.from_numpy(v) for k, v in g.items() if k.startswith("param.")}
+    missing, unexpected = m.load_state_dict(sd, strict=True)
+    assert not missing and not unexpected
+    return m.to(device)
+
+
+def points_key_of(g):
+    return "radar_points" if g["class_name"] == "Radar_DynamicPillarVFESimple2D" else "points"

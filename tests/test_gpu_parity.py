@@ -1,0 +1,170 @@
+"""GPU: the CUDA encoder (through the drop-in modules -> C ABI) against the oracle and the goldens.
+
+Bars (tests/helpers.py):  coords / inverse / counts / argmax bit-exact vs the oracle; forward features
+bit-exact vs the oracle's canonical arithmetic and within RTOL_FEATURES (norm-relative 1e-5) of the
+reference's own output; parameter gradients within RTOL_GRADS of oracle and reference.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as orc
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+FILES = H.golden_files()
+
+
+def run_module(m, g, pts_np, key, batch_size=None):
+    pts = torch.from_numpy(pts_np).cuda()
+    bd = {key: pts}
+    if batch_size is not None:
+        bd["batch_size"] = batch_size
+    out = m(bd)
+    fkey = [k for k in out if k.endswith("pillar_features")][0]
+    ckey = [k for k in out if k.endswith("_coords")][0]
+    return out, out[fkey], out[ckey], m.last_result
+
+
+@pytest.mark.parametrize("path", FILES, ids=lambda p: p.split("/")[-1][:-4])
+def test_cuda_matches_oracle_and_reference(path):
+    g = H.load_golden(path)
+    o = H.oracle_from_golden(g, orc.MEAN_F64)
+    m = H.module_from_golden(g)
+    m.train(g["training"])
+    r = o.forward(g["points"], training=g["training"])
+    out, feats, coords, res = run_module(m, g, g["points"], H.points_key_of(g))
+    assert str(g["feature_key"]) in out and str(g["coords_key"]) in out
+    # ---- integer outputs: bit-exact vs oracle AND vs the reference's golden
+    assert res.n_kept == r["n"] and res.n_pillars == r["p"]
+    assert coords.dtype == torch.int32 and feats.dtype == torch.float32
+    assert tuple(coords.shape) == tuple(g["coords"].shape) and tuple(feats.shape) == tuple(g["features"].shape)
+    np.testing.assert_array_equal(coords.cpu().numpy(), r["coords"])
+    np.testing.assert_array_equal(coords.cpu().numpy(), g["coords"])
+    np.testing.assert_array_equal(res.inverse.cpu().numpy(), g["inverse"])
+    np.testing.assert_array_equal(res.counts.cpu().numpy(), g["counts"])
+    if r["p"] == 0:
+        return
+    # ---- features: bit-exact vs the oracle's canonical arithmetic, tolerance vs the reference
+    f = feats.detach().cpu().numpy()
+    if not g["training"]:
+        np.testing.assert_array_equal(f, r["features"])
+    else:  # batch statistics are fp64 sums in a different order: allow the last-ulp effect of that
+        assert H.norm_rel_err(f, r["features"]) <= 1e-6
+    assert H.norm_rel_err(f, g["features"]) <= H.RTOL_FEATURES
+    # ---- backward: argmax bit-exact, gradients in tolerance
+    if "grad_features" in g:
+        np.testing.assert_array_equal(res.argmax.cpu().numpy(), r["argmax"])
+        gout = torch.from_numpy(g["grad_features"]).cuda()
+        feats.backward(gout)
+        b = o.backward(r, g["grad_features"])
+        pfn = m.pfn_layers[0]
+        dW = pfn.linear.weight.grad.cpu().numpy()
+        assert H.norm_rel_err(dW, b["d_weight"]) <= H.RTOL_GRADS
+        assert H.norm_rel_err(dW, g["grad.linear.weight"]) <= H.RTOL_GRADS
+        if o.cfg.use_norm:
+            assert H.norm_rel_err(pfn.norm.weight.grad.cpu().numpy(), b["d_gamma"]) <= H.RTOL_GRADS
+            assert H.norm_rel_err(pfn.norm.bias.grad.cpu().numpy(), b["d_beta"]) <= H.RTOL_GRADS
+            assert H.norm_rel_err(pfn.norm.weight.grad.cpu().numpy(), g["grad.norm.weight"]) <= H.RTOL_GRADS
+            assert H.norm_rel_err(pfn.norm.bias.grad.cpu().numpy(), g["grad.norm.bias"]) <= H.RTOL_GRADS
+        else:
+            assert H.norm_rel_err(pfn.linear.bias.grad.cpu().numpy(), g["grad.linear.bias"]) <= H.RTOL_GRADS
+    if "new.running_mean" in g:
+        pfn = m.pfn_layers[0]
+        assert H.norm_rel_err(pfn.norm.running_mean.cpu().numpy(), g["new.running_mean"]) <= H.RTOL_FEATURES
+        assert H.norm_rel_err(pfn.norm.running_var.cpu().numpy(), g["new.running_var"]) <= H.RTOL_FEATURES
+        assert int(pfn.norm.num_batches_tracked) == int(g["new.num_batches_tracked"])
+
+
+def _shipped_module(kind, train):
+    from oracle.ref_loader import Cfg
+    from radardistill_b200 import synth, vfe
+    cfg = Cfg(USE_NORM=True, WITH_DISTANCE=False, USE_ABSLOTE_XYZ=True, USE_CLUSTER_XYZ=True, NUM_FILTERS=[32])
+    cls, c = (vfe.DynamicPillarVFESimple2D, 5) if kind == "lidar" else (vfe.Radar_DynamicPillarVFESimple2D, 6)
+    torch.manual_seed(7)
+    m = cls(model_cfg=cfg, num_point_features=c, voxel_size=synth.VOXEL_SIZE, grid_size=synth.grid_size_of(),
+            point_cloud_range=synth.PC_RANGE).cuda()
+    n = m.pfn_layers[0].norm
+    with torch.no_grad():
+        n.weight.uniform_(0.5, 1.5); n.bias.normal_(0, 0.2); n.running_mean.normal_(0, 1); n.running_var.uniform_(0.5, 4)
+    m.train(train)
+    return m
+
+
+def _oracle_of(m, c):
+    from radardistill_b200 import synth
+    pfn = m.pfn_layers[0]
+    cfg = orc.OracleConfig(num_point_features=c, voxel_size=tuple(synth.VOXEL_SIZE), grid_size=tuple(synth.grid_size_of()),
+                           point_cloud_range=tuple(synth.PC_RANGE))
+    cp = lambda t: t.detach().cpu().numpy().copy()
+    return orc.PillarOracle(cfg, cp(pfn.linear.weight), cp(pfn.norm.weight), cp(pfn.norm.bias), cp(pfn.norm.running_mean),
+                            cp(pfn.norm.running_var))
+
+
+def test_lidar_two_frames_bit_exact_vs_oracle():
+    """Config-2-sized case (2 x ~340 k points): every output bit-exact against the oracle."""
+    from radardistill_b200 import synth
+    pts = synth.lidar_batch(2)
+    m = _shipped_module("lidar", train=False)
+    o = _oracle_of(m, 5)
+    orc.set_threads(8)
+    r = o.forward(pts, training=False, keep_intermediates=False)
+    with torch.no_grad():
+        out = m({"points": torch.from_numpy(pts).cuda(), "batch_size": 2})
+    res = m.last_result
+    assert res.n_pillars == r["p"] and res.n_kept == r["n"]
+    np.testing.assert_array_equal(out["pillar_coords"].cpu().numpy(), r["coords"])
+    np.testing.assert_array_equal(res.inverse.cpu().numpy(), r["inverse"])
+    np.testing.assert_array_equal(res.counts.cpu().numpy(), r["counts"])
+    np.testing.assert_array_equal(out["pillar_features"].cpu().numpy(), r["features"])
+
+
+def test_radar_train_step_vs_oracle():
+    """Config-1 radar branch: train-mode BN forward + backward on a batch of 4 frames."""
+    from radardistill_b200 import synth
+    pts = synth.radar_batch(4)
+    m = _shipped_module("radar", train=True)
+    o = _oracle_of(m, 6)
+    r = o.forward(pts, training=True)
+    out = m({"radar_points": torch.from_numpy(pts).cuda(), "batch_size": 4})
+    res = m.last_result
+    np.testing.assert_array_equal(out["radar_pillar_coords"].cpu().numpy(), r["coords"])
+    np.testing.assert_array_equal(res.argmax.cpu().numpy(), r["argmax"])
+    f = out["radar_pillar_features"]
+    assert H.norm_rel_err(f.detach().cpu().numpy(), r["features"]) <= 1e-6
+    gout = torch.randn(f.shape, generator=torch.Generator().manual_seed(3)).cuda()
+    f.backward(gout)
+    b = o.backward(r, gout.cpu().numpy())
+    pfn = m.pfn_layers[0]
+    assert H.norm_rel_err(pfn.linear.weight.grad.cpu().numpy(), b["d_weight"]) <= H.RTOL_GRADS
+    assert H.norm_rel_err(pfn.norm.weight.grad.cpu().numpy(), b["d_gamma"]) <= H.RTOL_GRADS
+    assert H.norm_rel_err(pfn.norm.bias.grad.cpu().numpy(), b["d_beta"]) <= H.RTOL_GRADS
+    assert H.norm_rel_err(pfn.norm.running_mean.cpu().numpy(), r["new_running_mean"]) <= 1e-6
+
+
+def test_deterministic_and_idempotent():
+    """Two runs on the same input give bit-identical outputs (atomics only touch integers)."""
+    from radardistill_b200 import synth
+    pts = torch.from_numpy(synth.lidar_batch(1)).cuda()
+    m = _shipped_module("lidar", train=False)
+    with torch.no_grad():
+        a = m({"points": pts, "batch_size": 1})
+        fa, ca = a["pillar_features"].clone(), a["pillar_coords"].clone()
+        b = m({"points": pts, "batch_size": 1})
+    assert torch.equal(fa, b["pillar_features"]) and torch.equal(ca, b["pillar_coords"])
+
+
+def test_single_point_train_raises_and_missing_batch_size():
+    g = H.load_golden([f for f in FILES if "single__eval" in f][0])
+    m = H.module_from_golden(g).train()
+    with pytest.raises(ValueError):
+        m({"points": torch.from_numpy(g["points"]).cuda()})
+    with pytest.raises(Exception):
+        m.eval()({"points": torch.from_numpy(g["points"])})  # CPU tensor: no fallback
+
+
+def test_bad_batch_index_is_reported():
+    g = H.load_golden([f for f in FILES if "lidar_s2d__sweep2__eval" in f][0])
+    m = H.module_from_golden(g).eval()
+    with pytest.raises(ValueError):
+        m({"points": torch.from_numpy(g["points"]).cuda(), "batch_size": 1})
