@@ -1,0 +1,407 @@
+#!/usr/bin/env python
+"""bench.py -- pillar-encoder throughput on B200 (BASELINE.json metric), one JSON line on stdout.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--mode B|A]
+
+Workload (BASELINE.json configs[2]/[3]): paired radar + LiDAR pillar encoding, forward + backward,
+8 frames per GPU with the radar_distill_train.yaml grid; synthetic nuScenes-shaped clouds
+(radardistill_b200/synth.py), random-init weights.  A "step" is one pass of both encoders over the batch.
+  mode B (default, the headline "fwd+bwd"): both encoders train-mode BN, forward + parameter backward
+          (teacher pre-training, tools/cfgs/nuscenes_models/pillarnet.yaml);
+  mode A (reference-faithful distillation step, radar_distill_train.yaml:68): LiDAR encoder frozen
+          (eval BN, forward only), radar encoder train-mode forward + backward.  Reported under "mode_a".
+value  = points/s over all ranks with inputs resident in HBM (CUDA events per step, L2 flushed between steps)
+e2e    = the same through the module API from pinned HOST buffers: H2D of the points, D2H of the features/coords
+--impl reference: the CPU oracle port (oracle/pillar_oracle.c, all host threads) on the same workload.
+Multi-GPU: frames shard over ranks (weak scaling, 8 frames per GPU); the only collective is DDP's gradient
+all-reduce of the PFN parameters.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FRAMES_PER_GPU = 8
+S2D_CFG = dict(USE_NORM=True, WITH_DISTANCE=False, USE_ABSLOTE_XYZ=True, USE_CLUSTER_XYZ=True, NUM_FILTERS=[32])
+
+
+class Cfg(dict):
+    __getattr__ = dict.__getitem__
+
+
+def make_clouds(rank: int, frames: int):
+    from radardistill_b200 import synth
+    lidar = synth.collate([synth.lidar_frame(rank * frames + b) for b in range(frames)])
+    radar = synth.collate([synth.radar_frame(rank * frames + b) for b in range(frames)])
+    return lidar, radar
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def oracle_pair(seed=0):
+    from oracle import oracle as orc
+    from radardistill_b200 import synth
+    rng = np.random.default_rng(seed)
+    out = {}
+    for kind, c in (("lidar", 5), ("radar", 6)):
+        cfg = orc.OracleConfig(num_point_features=c, voxel_size=tuple(synth.VOXEL_SIZE), grid_size=tuple(synth.grid_size_of()),
+                               point_cloud_range=tuple(synth.PC_RANGE))
+        w = (rng.standard_normal((32, cfg.c_in)) * 0.2).astype(np.float32)
+        out[kind] = orc.PillarOracle(cfg, w, rng.uniform(0.5, 1.5, 32), rng.normal(0, 0.2, 32), rng.normal(0, 1, 32),
+                                     rng.uniform(0.5, 4, 32))
+    return out
+
+
+def cpu_step(oracles, lidar, radar, mode):
+    """One step of the workload on the CPU oracle (same work as the GPU arm)."""
+    for kind, pts in (("lidar", lidar), ("radar", radar)):
+        o = oracles[kind]
+        train = (mode == "B") or kind == "radar"
+        r = o.forward(pts, training=train, keep_intermediates=train)
+        if train:
+            g = np.ones_like(r["features"])
+            o.backward(r, g)
+
+
+def time_cpu(lidar, radar, mode, steps, warmup, threads):
+    from oracle import oracle as orc
+    orc.set_threads(threads)
+    oracles = oracle_pair()
+    for _ in range(warmup):
+        cpu_step(oracles, lidar, radar, mode)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cpu_step(oracles, lidar, radar, mode)
+    dt = (time.perf_counter() - t0) / steps
+    return (len(lidar) + len(radar)) / dt, dt
+
+
+def run_reference(args):
+    """--impl reference: the CPU port of the reference path on the host cores (rank 0 only)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    frames = 2  # bounded sample: 2 of the 8 paired frames per step (same generators, same per-frame shapes)
+    lidar, radar = make_clouds(0, frames)
+    value, dt = time_cpu(lidar, radar, args.mode, max(args.steps, 1), min(args.warmup, 1), cores)
+    line = {"impl": "reference", "metric": "pillar-encoder points/s (fwd+bwd)", "value": value, "unit": "points/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args.mode, frames, len(lidar), len(radar)),
+            "cpu_baseline": {"value": value, "unit": "points/s", "cores": cores, "kind": "port",
+                             "sample": f"{frames} paired frames/step ({len(lidar)} LiDAR + {len(radar)} radar rows), C oracle, "
+                                       f"{cores} threads in the per-point loops"},
+            "e2e": {"value": value, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(mode, frames, n_lidar, n_radar):
+    return {"workload": "paired radar+LiDAR pillar encoding fwd+bwd (BASELINE.json configs[2]; radar_distill_train.yaml grid 1440x1440, "
+                        "0.075 m pillars)", "mode": "B: both encoders train-BN fwd+bwd" if mode == "B" else
+            "A: LiDAR frozen eval fwd, radar train fwd+bwd", "frames_per_gpu": frames, "lidar_rows_per_gpu": int(n_lidar),
+            "radar_rows_per_gpu": int(n_radar), "encoders": "DynamicPillarVFESimple2D 14->32 + Radar_DynamicPillarVFESimple2D 15->32",
+            "l2": "256 MiB scratch written between timed steps (L2 flushed)"}
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def build_modules(device, mode, ddp):
+    import torch
+    from radardistill_b200 import synth, vfe
+    torch.manual_seed(1234)
+    lid = vfe.DynamicPillarVFESimple2D(model_cfg=Cfg(S2D_CFG), num_point_features=5, voxel_size=synth.VOXEL_SIZE,
+                                       grid_size=synth.grid_size_of(), point_cloud_range=synth.PC_RANGE).to(device)
+    rad = vfe.Radar_DynamicPillarVFESimple2D(model_cfg=Cfg(S2D_CFG), num_point_features=6, voxel_size=synth.VOXEL_SIZE,
+                                             grid_size=synth.grid_size_of(), point_cloud_range=synth.PC_RANGE).to(device)
+    for m in (lid, rad):
+        n = m.pfn_layers[0].norm
+        with torch.no_grad():
+            n.weight.uniform_(0.5, 1.5); n.bias.normal_(0, 0.2); n.running_mean.normal_(0, 1); n.running_var.uniform_(0.5, 4)
+    if mode == "A":
+        lid.eval()
+        for p in lid.parameters():
+            p.requires_grad_(False)
+    else:
+        lid.train()
+    rad.train()
+    lid_call, rad_call = lid, rad
+    if ddp:
+        from torch.nn.parallel import DistributedDataParallel as DDP
+        rad_call = DDP(rad, device_ids=[device.index])
+        if mode == "B":
+            lid_call = DDP(lid, device_ids=[device.index])
+    return lid, rad, lid_call, rad_call
+
+
+def gpu_step(lid_call, rad_call, lidar_dev, radar_dev, mode, frames):
+    """One step: both encoders over the batch (+ backward of a sum loss), as PillarNet.forward does (pillarnet.py:28-33)."""
+    import torch
+    bd = {"points": lidar_dev, "radar_points": radar_dev, "batch_size": frames}
+    if mode == "A":
+        with torch.no_grad():
+            bd = lid_call(bd)
+    else:
+        bd = lid_call(bd)
+    bd = rad_call(bd)
+    loss = bd["radar_pillar_features"].sum()
+    if mode == "B":
+        loss = loss + bd["pillar_features"].sum()
+    loss.backward()
+    return bd
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from radardistill_b200 import _lib, ops
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    ddp = world > 1
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if ddp:
+        dist.init_process_group("nccl", device_id=device)
+    _lib.load()
+    mode, frames = args.mode, FRAMES_PER_GPU
+    lidar, radar = make_clouds(rank, frames)
+    n_rows = len(lidar) + len(radar)
+    lid, rad, lid_call, rad_call = build_modules(device, mode, ddp)
+    lidar_dev, radar_dev = torch.from_numpy(lidar).to(device), torch.from_numpy(radar).to(device)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
+
+    def barrier():
+        if ddp:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed_steps(m, k):
+        evs = []
+        for _ in range(k):
+            flush.fill_(1)
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            gpu_step(lid_call, rad_call, lidar_dev, radar_dev, m, frames)
+            e.record()
+            evs.append((s, e))
+        torch.cuda.synchronize()
+        return [s.elapsed_time(e) for s, e in evs]
+
+    for _ in range(max(args.warmup, 3)):
+        gpu_step(lid_call, rad_call, lidar_dev, radar_dev, mode, frames)
+    barrier()
+    with ClockSampler(local) as clk:
+        t_wall0 = time.perf_counter()
+        ms = timed_steps(mode, args.steps)
+        barrier()
+        wall = time.perf_counter() - t_wall0
+    step_ms = sum(ms) / len(ms)
+    if ddp:
+        t = torch.tensor([step_ms], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        step_ms = float(t.item())
+        tot = torch.tensor([float(n_rows)], device=device, dtype=torch.float64)
+        dist.all_reduce(tot)
+        total_rows = float(tot.item())
+    else:
+        total_rows = float(n_rows)
+    value = total_rows / (step_ms * 1e-3)
+
+    # ---- mode A beside it (reference-faithful step) when the headline is mode B, N == 1 only
+    extra = {}
+    if mode == "B" and not ddp:
+        lidA, radA, lcA, rcA = build_modules(device, "A", False)
+        for _ in range(3):
+            gpu_step(lcA, rcA, lidar_dev, radar_dev, "A", frames)
+        evs = []
+        for _ in range(args.steps):
+            flush.fill_(1)
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record(); gpu_step(lcA, rcA, lidar_dev, radar_dev, "A", frames); e.record()
+            evs.append((s, e))
+        torch.cuda.synchronize()
+        msA = sum(s.elapsed_time(e) for s, e in evs) / len(evs)
+        extra["mode_a"] = {"value": n_rows / (msA * 1e-3), "unit": "points/s", "ms_per_step": msA,
+                           "what": "LiDAR frozen eval-BN forward + radar train-BN forward+backward (radar_distill_train.yaml)"}
+
+    # ---- e2e: pinned host buffers in, host buffers out, through the module API
+    lidar_pin, radar_pin = torch.from_numpy(lidar).pin_memory(), torch.from_numpy(radar).pin_memory()
+    out_pin = {}
+
+    def e2e_step():
+        ld = lidar_pin.to(device, non_blocking=True)
+        rd = radar_pin.to(device, non_blocking=True)
+        bd = gpu_step(lid_call, rad_call, ld, rd, mode, frames)
+        nbytes = 0
+        for k in ("pillar_features", "pillar_coords", "radar_pillar_features", "radar_pillar_coords"):
+            t = bd[k].detach()
+            buf = out_pin.get(k)
+            if buf is None or buf.shape[0] < t.shape[0]:
+                buf = torch.empty((int(t.shape[0] * 1.1) + 16,) + tuple(t.shape[1:]), dtype=t.dtype).pin_memory()
+                out_pin[k] = buf
+            buf[:t.shape[0]].copy_(t, non_blocking=True)
+            nbytes += t.numel() * t.element_size()
+        torch.cuda.current_stream().synchronize()
+        return nbytes
+
+    for _ in range(2):
+        d2h = e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        d2h = e2e_step()
+    barrier()
+    e2e_dt = (time.perf_counter() - t0) / args.steps
+    if ddp:
+        t = torch.tensor([e2e_dt], device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_dt = float(t.item())
+    e2e = {"value": total_rows / e2e_dt, "unit": "points/s", "h2d_bytes_per_step": int(lidar.nbytes + radar.nbytes),
+           "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_dt * 1e3}
+
+    # ---- roofline of the dominant kernel: pfn_fwd_kernel<APPLY> on the LiDAR batch (one launch per rdp_pfn_fwd in
+    #      eval mode), timed live with CUDA events on the launching stream, L2 flushed before every launch.
+    roof = None
+    if rank == 0:
+        import ctypes as C
+        spec = lid.spec
+        norm = lid.pfn_layers[0].norm
+        lib = _lib.load()
+        geom, layout = spec.geom(frames), spec.layout_struct()
+        res = ops.encode_forward(lidar_dev, spec, frames, lid.pfn_layers[0].linear.weight, None, norm.weight, norm.bias,
+                                 norm.running_mean, norm.running_var, False, False)
+        prm = ops._params_struct(spec, lid.pfn_layers[0].linear.weight.detach(), None, norm.weight.detach(), norm.bias.detach(),
+                                 norm.running_mean, norm.running_var, False)
+        feats = torch.empty((len(lidar), spec.c_out), dtype=torch.float32, device=device)
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        durs, idx_durs = [], []
+        reps = max(args.steps, 10)
+        for i in range(reps + 3):
+            flush.fill_(1)
+            s0, s1, s2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            s0.record()
+            # index pass (5 kernels) re-run so the PFN launch sees a cold L2 state comparable to the real step
+            _lib.check(lib.rdp_index_fwd(ops._ptr(lidar_dev), len(lidar), C.byref(geom), spec.coord_cols, ops._ptr(res.workspace),
+                                         res.workspace.numel(), ops._ptr(res.coords), ops._ptr(res.inverse), ops._ptr(res.counts),
+                                         ops._ptr(res.counters), st), "rdp_index_fwd")
+            s1.record()
+            _lib.check(lib.rdp_pfn_fwd(ops._ptr(lidar_dev), len(lidar), C.byref(geom), C.byref(layout), C.byref(prm),
+                                       ops._ptr(res.workspace), res.workspace.numel(), ops._ptr(res.counters), ops._ptr(res.coords),
+                                       ops._ptr(feats), None, None, None, st), "rdp_pfn_fwd")
+            s2.record()
+            torch.cuda.synchronize()
+            if i >= 3:
+                idx_durs.append(s0.elapsed_time(s1)); durs.append(s1.elapsed_time(s2))
+        n_kept, n_pil = res.n_kept, res.n_pillars
+        row_bytes = 4 * spec.cols
+        alg = row_bytes * n_kept + 4 * spec.c_out * n_pil           # rows read once + feature rows written once
+        alg_fwd = row_bytes * len(lidar) + 4 * n_kept + n_pil * (4 * spec.c_out + 4 * spec.coord_cols + 4)  # SURVEY 8(d) B_fwd
+        peak, peak_src = peaks()
+        dur = sum(durs) / len(durs)
+        idx = sum(idx_durs) / len(idx_durs)
+        roof = {"bound": "hbm", "kernel": "pfn_fwd_kernel<Simple2D 6 cols, 32 ch, APPLY> (LiDAR batch, eval BN)",
+                "achieved": alg / (dur * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": alg / (dur * 1e-3) / 1e9 / peak,
+                "traffic": None, "peak_source": peak_src, "kernel_ms": dur, "algorithmic_bytes": int(alg),
+                "frac_of_8000_nominal": alg / (dur * 1e-3) / 1e9 / 8000.0,
+                "whole_forward": {"algorithmic_bytes": int(alg_fwd), "ms": idx + dur, "index_ms": idx,
+                                  "achieved": alg_fwd / ((idx + dur) * 1e-3) / 1e9,
+                                  "frac": alg_fwd / ((idx + dur) * 1e-3) / 1e9 / peak}}
+
+    if rank == 0:
+        cpu = None
+        if not ddp:
+            cores = os.cpu_count() or 1
+            fr = 2
+            l2, r2 = make_clouds(0, fr)
+            v, dt = time_cpu(l2, r2, mode, 3, 1, cores)
+            cpu = {"value": v, "unit": "points/s", "cores": cores, "kind": "port",
+                   "sample": f"{fr} of the {frames} paired frames ({len(l2)} LiDAR + {len(r2)} radar rows) x 3 steps, C oracle "
+                             f"(oracle/pillar_oracle.c), {cores} threads in the per-point loops, {dt:.2f} s/step"}
+        launches_lidar = 5 + (3 if mode == "B" else 1) + (2 if mode == "B" else 0)
+        launches = (launches_lidar + 10) * args.steps
+        line = {"metric": "pillar-encoder points/s (fwd+bwd)", "value": value, "unit": "points/s", "n_gpus": world,
+                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": step_ms, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": workload_config(mode, frames, len(lidar), len(radar)), "e2e": e2e, "gpu_launches": launches,
+                "clocks": clk.summary(), "roofline": roof, "cpu_baseline": cpu, "wall_s_timed_region": wall}
+        line.update(extra)
+        print(json.dumps(line), flush=True)
+    if ddp:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mode", default="B", choices=["A", "B"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

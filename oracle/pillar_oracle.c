@@ -270,18 +270,20 @@ void orc_linear(const float *f, int64_t n, int cin, const float *W, int cout, fl
 
 /* Train-mode batch statistics over the n kept points: mean and BIASED variance, in fp64. */
 void orc_bn_batch_stats(const float *x, int64_t n, int cout, double *mean, double *var) {
-    for (int c = 0; c < cout; ++c) {
-        double s = 0.0, s2 = 0.0;
-        for (int64_t j = 0; j < n; ++j) {
+    double *s = (double *)calloc((size_t)(2 * cout), sizeof(double)), *s2 = s + cout;
+    for (int64_t j = 0; j < n; ++j)          /* per channel: rows in ascending order */
+        for (int c = 0; c < cout; ++c) {
             double v = (double)x[j * cout + c];
-            s += v;
-            s2 += v * v;
+            s[c] += v;
+            s2[c] += v * v;
         }
-        double m = n > 0 ? s / (double)n : 0.0;
-        double vv = n > 0 ? s2 / (double)n - m * m : 0.0;
+    for (int c = 0; c < cout; ++c) {
+        double m = n > 0 ? s[c] / (double)n : 0.0;
+        double vv = n > 0 ? s2[c] / (double)n - m * m : 0.0;
         mean[c] = m;
         var[c] = vv > 0.0 ? vv : 0.0;
     }
+    free(s);
 }
 
 /* y = x*scale + shift with scale = gamma/sqrt(var+eps), shift = beta - mean*scale (fp64, one rounding). */
@@ -315,39 +317,96 @@ void orc_act_max(const float *x, int64_t n, int cout, const float *scale, const 
  * running stats => g_x = scale * g_y), dW = g_x^T f.  All reductions in fp64.
  * use_norm == 0: linear has a bias, y = x + b: dbias -> dbeta slot, dgamma = 0.
  */
+typedef struct {
+    const float *gy, *f, *x;
+    const double *mu, *inv_std, *a, *db, *dg;
+    int cin, cout, pass, dense;
+    int64_t n;
+    double *acc; /* per job: pass 0 -> [db(cout) | dg(cout)], pass 1 -> dW (cout*cin) */
+    int64_t lo, hi;
+} bwd_job;
+
+static void bwd_range(bwd_job *J) {
+    const int cin = J->cin, cout = J->cout;
+    for (int64_t j = J->lo; j < J->hi; ++j) {
+        const float *gyj = J->gy + j * cout, *xj = J->x + j * cout, *fj = J->f + j * cin;
+        if (J->pass == 0) {
+            for (int c = 0; c < cout; ++c) {
+                if (gyj[c] == 0.0f) continue;
+                double xh = ((double)xj[c] - J->mu[c]) * J->inv_std[c];
+                J->acc[c] += (double)gyj[c];
+                J->acc[cout + c] += (double)gyj[c] * xh;
+            }
+        } else {
+            for (int c = 0; c < cout; ++c) {
+                double gx = (double)gyj[c];
+                if (J->dense) {
+                    double xh = ((double)xj[c] - J->mu[c]) * J->inv_std[c];
+                    gx = gx - J->db[c] / (double)J->n - xh * J->dg[c] / (double)J->n;
+                } else if (gx == 0.0) continue;
+                gx *= J->a[c];
+                double *w = J->acc + c * cin;
+                for (int k = 0; k < cin; ++k) w[k] += gx * (double)fj[k];
+            }
+        }
+    }
+}
+static void *bwd_tramp(void *p) { bwd_range((bwd_job *)p); return NULL; }
+
+static void bwd_pass(bwd_job *proto, int64_t n, int width, double *out) {
+    int t = g_threads;
+    if (n < 4096) t = 1;
+    bwd_job jobs[256];
+    pthread_t th[256];
+    int64_t chunk = (n + t - 1) / t;
+    int used = 0;
+    for (int i = 0; i < t; ++i) {
+        int64_t lo = i * chunk, hi = lo + chunk > n ? n : lo + chunk;
+        if (lo >= hi) break;
+        jobs[i] = *proto;
+        jobs[i].lo = lo; jobs[i].hi = hi;
+        jobs[i].acc = (double *)calloc((size_t)width, sizeof(double));
+        used = i + 1;
+    }
+    for (int i = 0; i < used; ++i)
+        if (used == 1 || pthread_create(&th[i], NULL, bwd_tramp, &jobs[i]) != 0) { bwd_range(&jobs[i]); th[i] = 0; jobs[i].pass |= 256; }
+    for (int i = 0; i < used; ++i) if (!(jobs[i].pass & 256)) pthread_join(th[i], NULL);
+    for (int q = 0; q < width; ++q) out[q] = 0.0;
+    for (int i = 0; i < used; ++i) {        /* fixed combination order */
+        for (int q = 0; q < width; ++q) out[q] += jobs[i].acc[q];
+        free(jobs[i].acc);
+    }
+}
+
 void orc_backward(const float *g, const float *f, const float *x, const float *out, const int32_t *arg,
                   int64_t n, int64_t P, int cin, int cout, const float *gamma, const double *mean,
                   const double *var, double eps, int train_bn, int use_norm,
                   float *dW, float *dgamma, float *dbeta) {
-    double *gy = (double *)calloc((size_t)(n * cout + 1), sizeof(double));
+    /* g_z routed to the argmax row, times ReLU' (out > 0).  One (pillar, channel) -> one row. */
+    float *gy = (float *)calloc((size_t)(n * cout + 1), sizeof(float));
     for (int64_t q = 0; q < P; ++q)
         for (int c = 0; c < cout; ++c)
             if (out[q * cout + c] > 0.0f && arg[q * cout + c] < n)
-                gy[(int64_t)arg[q * cout + c] * cout + c] += (double)g[q * cout + c];
+                gy[(int64_t)arg[q * cout + c] * cout + c] = g[q * cout + c];
+    double *mu = (double *)calloc((size_t)(6 * cout), sizeof(double));
+    double *inv_std = mu + cout, *a = mu + 2 * cout, *dbdg = mu + 3 * cout; /* db | dg */
     for (int c = 0; c < cout; ++c) {
-        double inv_std = use_norm ? 1.0 / sqrt(var[c] + eps) : 1.0;
-        double mu = use_norm ? mean[c] : 0.0;
-        double db = 0.0, dg = 0.0;
-        for (int64_t j = 0; j < n; ++j) {
-            double xh = ((double)x[j * cout + c] - mu) * inv_std;
-            db += gy[j * cout + c];
-            dg += gy[j * cout + c] * xh;
-        }
-        dbeta[c] = (float)db;
-        dgamma[c] = use_norm ? (float)dg : 0.0f;
-        double a = use_norm ? (double)gamma[c] * inv_std : 1.0;
-        for (int k = 0; k < cin; ++k) {
-            double acc = 0.0;
-            for (int64_t j = 0; j < n; ++j) {
-                double gx = gy[j * cout + c];
-                if (use_norm && train_bn) {
-                    double xh = ((double)x[j * cout + c] - mu) * inv_std;
-                    gx = gx - db / (double)n - xh * dg / (double)n;
-                }
-                acc += a * gx * (double)f[j * cin + k];
-            }
-            dW[c * cin + k] = (float)acc;
-        }
+        inv_std[c] = use_norm ? 1.0 / sqrt(var[c] + eps) : 1.0;
+        mu[c] = use_norm ? mean[c] : 0.0;
+        a[c] = use_norm ? (double)gamma[c] * inv_std[c] : 1.0;
     }
+    bwd_job J = {gy, f, x, mu, inv_std, a, dbdg, dbdg + cout, cin, cout, 0, 0, n, NULL, 0, 0};
+    bwd_pass(&J, n, 2 * cout, dbdg);
+    for (int c = 0; c < cout; ++c) {
+        dbeta[c] = (float)dbdg[c];
+        dgamma[c] = use_norm ? (float)dbdg[cout + c] : 0.0f;
+    }
+    double *dw = (double *)calloc((size_t)(cout * cin), sizeof(double));
+    J.pass = 1;
+    J.dense = (use_norm && train_bn) ? 1 : 0;
+    bwd_pass(&J, n, cout * cin, dw);
+    for (int q = 0; q < cout * cin; ++q) dW[q] = (float)dw[q];
+    free(dw);
+    free(mu);
     free(gy);
 }

@@ -293,13 +293,15 @@ __global__ void __launch_bounds__(kPfnThreads, 2) pfn_fwd_kernel(const __grid_co
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
             if (pa[u] >= 0 && (u == 0 || NPAIR > kPfnThreads)) {
-                float acc = 0.0f;
+                // fp64 throughout: tight clusters make var << mean^2 and the backward's (S2 w - mu S1) cancels
+                double acc = 0.0;
                 if (pb[u] >= 0) {
-                    for (int j = 0; j < np; ++j) acc = fmaf(S.f[j * Cfg::FSTRIDE + pa[u]], S.f[j * Cfg::FSTRIDE + pb[u]], acc);
+                    for (int j = 0; j < np; ++j)
+                        acc = fma((double)S.f[j * Cfg::FSTRIDE + pa[u]], (double)S.f[j * Cfg::FSTRIDE + pb[u]], acc);
                 } else {
-                    for (int j = 0; j < np; ++j) acc += S.f[j * Cfg::FSTRIDE + pa[u]];
+                    for (int j = 0; j < np; ++j) acc += (double)S.f[j * Cfg::FSTRIDE + pa[u]];
                 }
-                st_m[u] += (double)acc;
+                st_m[u] += acc;
             }
         }
         __syncthreads();
