@@ -344,7 +344,7 @@ def run_ours(args):
                                          ops._ptr(res.counters), st), "rdp_index_fwd")
             s1.record()
             _lib.check(lib.rdp_pfn_fwd(ops._ptr(lidar_dev), len(lidar), C.byref(geom), C.byref(layout), C.byref(prm),
-                                       ops._ptr(res.workspace), res.workspace.numel(), ops._ptr(res.counters), ops._ptr(res.coords),
+                                       ops._ptr(res.workspace), res.workspace.numel(), ops._ptr(res.counters),
                                        ops._ptr(feats), None, None, None, st), "rdp_pfn_fwd")
             s2.record()
             torch.cuda.synchronize()
@@ -375,7 +375,7 @@ def run_ours(args):
             cpu = {"value": v, "unit": "points/s", "cores": cores, "kind": "port",
                    "sample": f"{fr} of the {frames} paired frames ({len(l2)} LiDAR + {len(r2)} radar rows) x 3 steps, C oracle "
                              f"(oracle/pillar_oracle.c), {cores} threads in the per-point loops, {dt:.2f} s/step"}
-        launches_lidar = 5 + (3 if mode == "B" else 1) + (2 if mode == "B" else 0)
+        launches_lidar = 5 + (3 if mode == "B" else 1) + (2 if mode == "B" else 0)  # index 5, pfn stats+finalize+apply | apply, bwd 2
         launches = (launches_lidar + 10) * args.steps
         line = {"metric": "pillar-encoder points/s (fwd+bwd)", "value": value, "unit": "points/s", "n_gpus": world,
                 "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": step_ms, "higher_is_better": True,

@@ -114,17 +114,17 @@ RDP_API int rdp_index_fwd(const float *points, int64_t n_points, const rdp_geom_
  * Replaces dynamic_pillar_vfe.py:214-240 with PFNLayerV2.forward :35-46 (last layer).
  * Must follow rdp_index_fwd on the same points / workspace / stream.
  *   features    (cap n_points, c_out) fp32      rows [0,P)
- *   argmax      (cap n_points, c_out) int32     KEPT-point index of the winning row (lowest index on
- *                                               ties); NULL if not wanted
- *   pillar_mean (cap n_points, 3) fp32          per-pillar xyz mean; NULL if not wanted
- *   coords      the (P, coord_cols) tensor rdp_index_fwd wrote (pillar centres are derived from it)
+ *   argpos      (cap n_points, c_out) int32     winning row of every (pillar, channel) as a position in the
+ *                                               workspace's pillar-grouped order (lowest kept index on ties);
+ *                                               input of rdp_pfn_bwd / rdp_argmax_kept.  NULL if not wanted.
+ *   pillar_mean (cap n_points, 3) fp32          per-pillar xyz mean (scatter_mean, :226); NULL if not wanted
  *   bn_state    (rdp_bn_state_doubles(layout)) fp64: batch mean/var, folded scale/shift and the feature
  *               moments the backward needs; required when train_bn, else may be NULL
  */
 RDP_API int rdp_pfn_fwd(const float *points, int64_t n_points, const rdp_geom_t *geom, const rdp_layout_t *layout,
-                const rdp_pfn_params_t *params, void *workspace, size_t workspace_bytes,
-                const int32_t *counters, const int32_t *coords, float *features, int32_t *argmax,
-                float *pillar_mean, double *bn_state, void *stream);
+                        const rdp_pfn_params_t *params, void *workspace, size_t workspace_bytes,
+                        const int32_t *counters, float *features, int32_t *argpos, float *pillar_mean,
+                        double *bn_state, void *stream);
 
 RDP_API int64_t rdp_bn_state_doubles(const rdp_layout_t *layout);
 
@@ -132,15 +132,22 @@ RDP_API int64_t rdp_bn_state_doubles(const rdp_layout_t *layout);
  * Parameter gradients of the PFN (autograd of :35-46): argmax routing, ReLU', BatchNorm backward
  * (batch statistics when params->train_bn, running statistics otherwise), dW = g_x^T f.
  * Points are a non-differentiable leaf in the reference, so no point gradient is produced.
- *   grad_features (P, c_out) fp32 ; features / argmax / pillar_mean / bn_state as written by rdp_pfn_fwd
+ *   grad_features (P, c_out) fp32 ; features / argpos / bn_state as written by rdp_pfn_fwd; same workspace
  *   d_weight (c_out, c_in), d_gamma (c_out) [NULL without norm], d_beta (c_out) [bias grad without norm]
- *   n_pillars_hint: P if the caller knows it (sizes the grid), else -1
  */
 RDP_API int rdp_pfn_bwd(const float *points, int64_t n_points, const rdp_geom_t *geom, const rdp_layout_t *layout,
-                const rdp_pfn_params_t *params, void *workspace, size_t workspace_bytes,
-                const int32_t *counters, const int32_t *coords, const float *grad_features, const float *features,
-                const int32_t *argmax, const float *pillar_mean, const double *bn_state,
-                float *d_weight, float *d_gamma, float *d_beta, int64_t n_pillars_hint, void *stream);
+                        const rdp_pfn_params_t *params, void *workspace, size_t workspace_bytes,
+                        const int32_t *counters, const float *grad_features, const float *features,
+                        const int32_t *argpos, const double *bn_state,
+                        float *d_weight, float *d_gamma, float *d_beta, void *stream);
+
+/*
+ * scatter_max's argmax in the reference's numbering (:40): argmax_kept[p][c] = index, among the points kept by the
+ * range mask (:204-206), of the row that attains features[p][c]; ties -> lowest index (torch_scatter CPU rule).
+ */
+RDP_API int rdp_argmax_kept(int64_t n_points, const rdp_geom_t *geom, const rdp_layout_t *layout, void *workspace,
+                            size_t workspace_bytes, const int32_t *counters, const int32_t *argpos,
+                            int32_t *argmax_kept, void *stream);
 
 /*
  * Host-buffer convenience (what a non-torch caller binds): uploads `points` (host), runs

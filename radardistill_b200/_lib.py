@@ -14,7 +14,7 @@ CNT_N, CNT_P, CNT_ERRFLAGS = 0, 1, 2
 LAYOUT_SIMPLE2D, LAYOUT_DYNPILLAR = 0, 1
 
 EXPORTS = ["rdp_abi_version", "rdp_status_string", "rdp_last_cuda_error", "rdp_workspace_bytes", "rdp_index_fwd",
-           "rdp_pfn_fwd", "rdp_bn_state_doubles", "rdp_pfn_bwd", "rdp_encode_host"]
+           "rdp_pfn_fwd", "rdp_bn_state_doubles", "rdp_pfn_bwd", "rdp_argmax_kept", "rdp_encode_host"]
 
 
 class Geom(C.Structure):
@@ -62,12 +62,14 @@ def load() -> C.CDLL:
     lib.rdp_index_fwd.argtypes = [vp, C.c_int64, C.POINTER(Geom), C.c_int32, vp, C.c_size_t, vp, vp, vp, vp, vp]
     lib.rdp_pfn_fwd.restype = C.c_int
     lib.rdp_pfn_fwd.argtypes = [vp, C.c_int64, C.POINTER(Geom), C.POINTER(Layout), C.POINTER(PfnParams), vp, C.c_size_t,
-                                vp, vp, vp, vp, vp, vp, vp]
+                                vp, vp, vp, vp, vp, vp]
     lib.rdp_bn_state_doubles.restype = C.c_int64
     lib.rdp_bn_state_doubles.argtypes = [C.POINTER(Layout)]
     lib.rdp_pfn_bwd.restype = C.c_int
     lib.rdp_pfn_bwd.argtypes = [vp, C.c_int64, C.POINTER(Geom), C.POINTER(Layout), C.POINTER(PfnParams), vp, C.c_size_t,
-                                vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_int64, vp]
+                                vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.rdp_argmax_kept.restype = C.c_int
+    lib.rdp_argmax_kept.argtypes = [C.c_int64, C.POINTER(Geom), C.POINTER(Layout), vp, C.c_size_t, vp, vp, vp, vp]
     lib.rdp_encode_host.restype = C.c_int
     lib.rdp_encode_host.argtypes = [vp, C.c_int64, C.POINTER(Geom), C.POINTER(Layout), C.POINTER(PfnParams), vp, vp, vp, vp,
                                     C.POINTER(C.c_int64), C.POINTER(C.c_int64)]

@@ -25,12 +25,12 @@ int carve_workspace(void *base, int64_t n_points, const rdp_geom_t *geom, const 
     ws->words = (cells + 31) / 32;
     ws->pcap = n < cells ? n : cells;
     ws->index_tiles = (n + kIndexTileRows - 1) / kIndexTileRows;
-    ws->pfn_tiles = (n + kPfnTileRows - 1) / kPfnTileRows;
-    ws->partial_blocks = 148 * 4;
+    ws->partial_blocks = kPfnGridCap;
     int cin = kMaxCin, cout = kMaxCout;
     if (layout) { cin = layout->c_in; cout = layout->c_out; }
     const int64_t cs = cin + 9;  // super-feature count upper bound (unused layout options carry zero weights)
-    const int64_t stats_d = 2 * cout + cs * (cs + 3) / 2;
+    const int64_t t4 = (cs + 1 + 3) / 4;       // 4x4 blocks of the (features + ones column) Gram matrix
+    const int64_t stats_d = 2 * cout + 16 * t4 * (t4 + 1) / 2;
     const int64_t bwd_d = (int64_t)cout * (cs + 2);
     ws->partial_doubles_per_block = stats_d > bwd_d ? stats_d : bwd_d;
 
@@ -51,8 +51,10 @@ int carve_workspace(void *base, int64_t n_points, const rdp_geom_t *geom, const 
     ws->keys = reinterpret_cast<int32_t *>(take(sizeof(int32_t) * (size_t)(n + 4)));
     ws->tile_keep = reinterpret_cast<int32_t *>(take(sizeof(int32_t) * (size_t)ws->index_tiles));
     ws->ends = reinterpret_cast<int32_t *>(take(sizeof(int32_t) * (size_t)(ws->pcap + 4)));
-    ws->order = reinterpret_cast<int32_t *>(take(sizeof(int32_t) * (size_t)(n + 4)));
-    ws->tile_start = reinterpret_cast<int32_t *>(take(sizeof(int32_t) * (size_t)(ws->pfn_tiles + 2)));
+    const size_t pad = kPfnCap + 8;
+    ws->grows = reinterpret_cast<float *>(take(sizeof(float) * (size_t)(n + pad) * geom->cols));
+    ws->gpid = reinterpret_cast<int32_t *>(take(sizeof(int32_t) * (size_t)(n + pad + 4)));
+    ws->gorder = reinterpret_cast<int32_t *>(take(sizeof(int32_t) * (size_t)(n + pad)));
     ws->orig2kept = reinterpret_cast<int32_t *>(take(sizeof(int32_t) * (size_t)(n + 4)));
     ws->kept2orig = reinterpret_cast<int32_t *>(take(sizeof(int32_t) * (size_t)(n + 4)));
     ws->index_bytes = off;
@@ -147,7 +149,7 @@ extern "C" int rdp_encode_host(const float *points, int64_t n_points, const rdp_
     dp.train_bn = 0;
     rc = rdp_index_fwd(d_pts, n_points, geom, kc, d_ws, ws_bytes, d_coords, d_inv, d_cnt, d_counters, st);
     if (rc == RDP_OK)
-        rc = rdp_pfn_fwd(d_pts, n_points, geom, layout, &dp, d_ws, ws_bytes, d_counters, d_coords, d_feat, nullptr, nullptr, nullptr, st);
+        rc = rdp_pfn_fwd(d_pts, n_points, geom, layout, &dp, d_ws, ws_bytes, d_counters, d_feat, nullptr, nullptr, nullptr, st);
     if (rc != RDP_OK) { cleanup(); return rc; }
     RDP_TRY(cudaMemcpyAsync(h_counters, d_counters, sizeof(h_counters), cudaMemcpyDeviceToHost, st));
     RDP_TRY(cudaStreamSynchronize(st));

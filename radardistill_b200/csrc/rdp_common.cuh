@@ -25,9 +25,10 @@ constexpr int kIndexThreads = 256;
 constexpr int kIndexTileRows = 1024;  // points per CTA in the quantise / rank / fill kernels
 constexpr int kScanThreads = 256;
 constexpr int kScanGrid = 296;        // 2 CTAs per SM: every CTA of a chunked scan is co-resident
-constexpr int kPfnThreads = 256;
-constexpr int kPfnBatch = 256;        // points per CTA batch in the PFN kernels (== kPfnThreads)
-constexpr int kPfnTileRows = 1024;    // grouped points per PFN tile (pillar aligned)
+constexpr int kPfnThreads = 128;
+constexpr int kPfnWin = 128;          // grouped rows per PFN tile window (a tile owns the pillars that START in it)
+constexpr int kPfnCap = 192;          // rows staged per tile: the window + 64 rows of overhang for the last pillar
+constexpr int kPfnGridCap = 148 * 4;  // persistent PFN CTAs (also the number of partial-sum slots)
 constexpr int kMaxCin = 24;
 constexpr int kMaxCout = 64;
 
@@ -47,14 +48,15 @@ struct Workspace {
     int32_t *keys;           // n  (merged key, then overwritten by the pillar rank; -1 = dropped)
     int32_t *tile_keep;      // index tiles
     int32_t *ends;           // pcap  (exclusive starts -> after fill: inclusive ends)
-    int32_t *order;          // n     (grouped position -> original row)
-    int32_t *tile_start;     // pfn tiles + 2
+    float *grows;            // (n + pad) * cols : rows physically grouped by pillar (pillar order == key order)
+    int32_t *gpid;           // 4 + n + pad       : gpid[4 + pos] = pillar of grouped position pos, gpid[0..3] = -1
+    int32_t *gorder;         // n + pad           : grouped position -> original row
     double *partials;        // per-CTA partial sums of the train-mode statistics / backward
     char *zero_begin;
     size_t zero_bytes;
     int32_t *orig2kept;      // n     (only written / read when the range mask dropped rows)
     int32_t *kept2orig;      // n
-    int64_t words, n, pcap, index_tiles, pfn_tiles;
+    int64_t words, n, pcap, index_tiles;
     size_t index_bytes;      // bytes rdp_index_fwd needs (everything before `partials`)
     size_t total_bytes;
     int64_t partial_doubles_per_block;

@@ -12,9 +12,10 @@
 //   K1 quantize_mark   points (TMA bulk tile -> smem) -> key[i], bitmap |= bit(key)          [HBM: read rows]
 //   K2 bitmap_rank     popcount scan of the bitmap -> word_prefix, coords[rank], P
 //   K3 rank_count      key[i] -> rank = word_prefix + popc(below) ; inverse[j] ; counts[rank]++
-//   K4 count_scan      exclusive scan of counts -> starts, PFN tile boundaries
-//   K5 fill_order      order[start[rank]++] = i   (counting-sort fill; order inside a pillar is arbitrary,
-//                      every consumer is order independent)
+//   K4 count_scan      exclusive scan of counts -> pillar start offsets
+//   K5 group_rows      pos = start[rank]++ ; grouped_rows[pos] = row i, gpid[pos] = rank, gorder[pos] = i
+//                      (counting-sort fill; the order inside a pillar is arbitrary, every consumer is order
+//                      independent).  The PFN kernels then stream contiguous, pillar-aligned row tiles with TMA.
 #include "rdp_common.cuh"
 
 namespace rdp {
@@ -233,7 +234,7 @@ rank_count_kernel(int32_t *__restrict__ keys, long long n0, const uint32_t *__re
 // ----------------------------------------------------------------------------- K4
 __global__ void __launch_bounds__(kScanThreads)
 count_scan_kernel(const int32_t *__restrict__ counts, uint64_t *__restrict__ state, int32_t *__restrict__ ends,
-                  int32_t *__restrict__ tile_start, int32_t *__restrict__ counters, int pfn_tile_rows) {
+                  int32_t *__restrict__ counters) {
     __shared__ int s_scan[9];
     __shared__ uint32_t s_u32;
     __shared__ int s_ticket;
@@ -251,7 +252,6 @@ count_scan_kernel(const int32_t *__restrict__ counts, uint64_t *__restrict__ sta
     block_excl_scan_256(local, s_scan, &tot);
     uint32_t base = chunk_exclusive_prefix(state, ticket, (uint32_t)tot, &s_u32);
 
-    if (ticket == 0 && tid == 0) tile_start[0] = 0;
     for (long long pt = p0; pt < p1; pt += kScanThreads * 4) {
         const long long p = pt + tid * 4;
         int c[4];
@@ -264,11 +264,7 @@ count_scan_kernel(const int32_t *__restrict__ counts, uint64_t *__restrict__ sta
         for (int q = 0; q < 4; ++q) {
             if (p + q < p1) {
                 ends[p + q] = (int)s;  // exclusive start; K5 advances it to the inclusive end
-                const uint32_t e = s + (uint32_t)c[q];
-                // pillar p+q+1 is the first pillar starting at or after every tile boundary in (s, e]
-                for (uint32_t t = s / pfn_tile_rows + 1; t * (uint32_t)pfn_tile_rows <= e; ++t) tile_start[t] = (int)(p + q + 1);
-                if (p + q == P - 1 && e % pfn_tile_rows != 0) tile_start[e / pfn_tile_rows + 1] = (int)P;
-                s = e;
+                s += (uint32_t)c[q];
             }
         }
     }
@@ -276,20 +272,52 @@ count_scan_kernel(const int32_t *__restrict__ counts, uint64_t *__restrict__ sta
 
 // ----------------------------------------------------------------------------- K5
 __global__ void __launch_bounds__(kIndexThreads)
-fill_order_kernel(const int32_t *__restrict__ ranks, long long n0, int32_t *__restrict__ ends, int32_t *__restrict__ order) {
-    const long long i0 = ((long long)blockIdx.x * kIndexThreads + threadIdx.x) * 4;
-    if (i0 >= n0) return;
-    int r[4] = {-1, -1, -1, -1};
-    if (i0 + 3 < n0) {
-        const int4 v = *reinterpret_cast<const int4 *>(ranks + i0);
-        r[0] = v.x; r[1] = v.y; r[2] = v.z; r[3] = v.w;
-    } else {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) if (i0 + q < n0) r[q] = ranks[i0 + q];
+group_rows_kernel(const float *__restrict__ pts, const int32_t *__restrict__ ranks, long long n0, int cols,
+                  int32_t *__restrict__ ends, float *__restrict__ grows, int32_t *__restrict__ gpid,
+                  int32_t *__restrict__ gorder) {
+    extern __shared__ __align__(128) float tile[];
+    __shared__ __align__(8) uint64_t bar;
+    const int tid = threadIdx.x;
+    const long long row0 = (long long)blockIdx.x * kIndexTileRows;
+    const int rows = (int)min((long long)kIndexTileRows, n0 - row0);
+    const int floats = rows * cols;
+    const uint32_t bulk_bytes = (uint32_t)(floats * 4) & ~15u;
+    const float *src = pts + row0 * cols;
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        fence_mbar_init();
     }
+    __syncthreads();
+    if (tid == 0 && bulk_bytes) {
+        mbar_expect_tx(&bar, bulk_bytes);
+        tma_bulk_g2s(tile, src, bulk_bytes, &bar);
+    }
+    for (int f = (int)(bulk_bytes >> 2) + tid; f < floats; f += kIndexThreads) tile[f] = src[f];
+    if (blockIdx.x == 0 && tid < 4) gpid[tid] = -1;  // "no pillar" in front of grouped position 0
+    // claim the grouped positions while the tile is in flight
+    int pos[kIndexTileRows / kIndexThreads], rk[kIndexTileRows / kIndexThreads];
 #pragma unroll
-    for (int q = 0; q < 4; ++q)
-        if (r[q] >= 0) order[atomicAdd(ends + r[q], 1)] = (int)(i0 + q);
+    for (int k = 0; k < kIndexTileRows / kIndexThreads; ++k) {
+        const int r = k * kIndexThreads + tid;
+        rk[k] = (r < rows) ? ranks[row0 + r] : -1;
+        pos[k] = (rk[k] >= 0) ? atomicAdd(ends + rk[k], 1) : -1;
+    }
+    if (bulk_bytes) mbar_wait(&bar, 0);
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < kIndexTileRows / kIndexThreads; ++k) {
+        if (pos[k] < 0) continue;
+        const int r = k * kIndexThreads + tid;
+        const float *p = tile + r * cols;
+        float *d = grows + (size_t)pos[k] * cols;
+        if ((cols & 1) == 0) {
+            for (int c = 0; c < cols; c += 2) *reinterpret_cast<float2 *>(d + c) = make_float2(p[c], p[c + 1]);
+        } else {
+            for (int c = 0; c < cols; ++c) d[c] = p[c];
+        }
+        gpid[4 + pos[k]] = rk[k];
+        gorder[pos[k]] = (int)(row0 + r);
+    }
 }
 
 static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
@@ -318,17 +346,19 @@ extern "C" int rdp_index_fwd(const float *points, int64_t n_points, const rdp_ge
     GeomDev g{geom->lo[0], geom->lo[1], geom->vsz[0], geom->vsz[1], geom->nx, geom->ny, geom->batch_size, geom->cols};
     const size_t smem = (size_t)kIndexTileRows * geom->cols * sizeof(float);
     if (smem > 200 * 1024) return RDP_ERR_UNSUPPORTED;
-    if (smem > 48 * 1024)
+    if (smem > 48 * 1024) {
         RDP_CUDA_OK(cudaFuncSetAttribute(quantize_mark_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        RDP_CUDA_OK(cudaFuncSetAttribute(group_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
     const int tiles = (int)ws.index_tiles;
     quantize_mark_kernel<<<tiles, kIndexThreads, smem, stream>>>(points, n_points, g, ws.bitmap, ws.keys, ws.tile_keep, counters);
     bitmap_rank_kernel<<<kScanGrid, kScanThreads, 0, stream>>>(ws.bitmap, ws.words, g, coord_cols, ws.scan_state_a,
                                                              ws.word_prefix, coords, counts, counters);
     rank_count_kernel<<<tiles, kIndexThreads, 0, stream>>>(ws.keys, n_points, ws.bitmap, ws.word_prefix, ws.tile_keep,
                                                          inverse, counts, counters, ws.orig2kept, ws.kept2orig);
-    count_scan_kernel<<<kScanGrid, kScanThreads, 0, stream>>>(counts, ws.scan_state_b, ws.ends, ws.tile_start, counters,
-                                                            kPfnTileRows);
-    fill_order_kernel<<<tiles, kIndexThreads, 0, stream>>>(ws.keys, n_points, ws.ends, ws.order);
+    count_scan_kernel<<<kScanGrid, kScanThreads, 0, stream>>>(counts, ws.scan_state_b, ws.ends, counters);
+    group_rows_kernel<<<tiles, kIndexThreads, smem, stream>>>(points, ws.keys, n_points, geom->cols, ws.ends, ws.grows,
+                                                            ws.gpid, ws.gorder);
     RDP_CUDA_OK(cudaGetLastError());
     return RDP_OK;
 }

@@ -36,13 +36,11 @@ static int build_kmap(const rdp_geom_t *g, const rdp_layout_t *l, int8_t *kmap, 
     return RDP_OK;
 }
 
-static int fill_args(PfnArgs *a, const PfnLaunch *L, const float *points, int64_t n_points, const rdp_geom_t *geom,
-                     const rdp_layout_t *layout, const rdp_pfn_params_t *prm, const Workspace &ws, const int32_t *counters,
-                     const int32_t *coords) {
+static int fill_args(PfnArgs *a, const PfnLaunch *L, int64_t n_points, const rdp_geom_t *geom, const rdp_layout_t *layout,
+                     const rdp_pfn_params_t *prm, const Workspace &ws, const int32_t *counters) {
     memset(a, 0, sizeof(*a));
-    a->pts = points;
-    a->order = ws.order; a->ends = ws.ends; a->tile_start = ws.tile_start; a->counters = counters; a->coords = coords;
-    a->orig2kept = ws.orig2kept; a->kept2orig = ws.kept2orig;
+    a->grows = ws.grows; a->gpid = ws.gpid; a->gorder = ws.gorder; a->ends = ws.ends; a->counters = counters;
+    a->orig2kept = ws.orig2kept;
     a->weight = prm->weight; a->bias = prm->bias; a->gamma = prm->gamma; a->beta = prm->beta;
     a->rmean = prm->running_mean; a->rvar = prm->running_var;
     a->partials = ws.partials;
@@ -50,9 +48,25 @@ static int fill_args(PfnArgs *a, const PfnLaunch *L, const float *points, int64_
     a->eps = prm->eps;
     for (int i = 0; i < 3; ++i) { a->lo[i] = geom->lo[i]; a->vsz[i] = geom->vsz[i]; a->off[i] = geom->off[i]; }
     a->c_in = layout->c_in;
-    a->coord_cols = layout->coord_cols;
     a->use_norm = prm->gamma != nullptr;
     return build_kmap(geom, layout, a->kmap, L->cs);
+}
+
+// argmax in the reference's numbering: index of the winning row among the KEPT points (dynamic_pillar_vfe.py:204-206).
+__global__ void argpos_to_kept_kernel(const int32_t *__restrict__ argpos, const int32_t *__restrict__ gorder,
+                                      const int32_t *__restrict__ orig2kept, const int32_t *__restrict__ counters, long long n0,
+                                      int cout, int32_t *__restrict__ out) {
+    const long long total = (long long)counters[RDP_CNT_P] * cout;
+    const bool none_dropped = ((long long)counters[RDP_CNT_N] == n0);
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const int row = gorder[argpos[e]];
+        out[e] = none_dropped ? row : orig2kept[row];
+    }
+}
+
+static int pfn_grid(int64_t n_points) {
+    const int64_t tiles = (n_points + kPfnWin - 1) / kPfnWin;
+    return (int)(tiles < kPfnGridCap ? (tiles < 1 ? 1 : tiles) : kPfnGridCap);
 }
 
 }  // namespace rdp
@@ -60,19 +74,17 @@ static int fill_args(PfnArgs *a, const PfnLaunch *L, const float *points, int64_
 using namespace rdp;
 
 extern "C" int rdp_pfn_fwd(const float *points, int64_t n_points, const rdp_geom_t *geom, const rdp_layout_t *layout,
-                              const rdp_pfn_params_t *prm, void *workspace, size_t workspace_bytes, const int32_t *counters,
-                              const int32_t *coords, float *features, int32_t *argmax, float *pillar_mean, double *bn_state,
-                              void *stream_v) {
+                           const rdp_pfn_params_t *prm, void *workspace, size_t workspace_bytes, const int32_t *counters,
+                           float *features, int32_t *argpos, float *pillar_mean, double *bn_state, void *stream_v) {
     cudaStream_t st = static_cast<cudaStream_t>(stream_v);
     if (!geom || !layout || !prm || !counters || n_points < 0) return RDP_ERR_INVALID_ARG;
     if (n_points == 0) return RDP_OK;
-    if (!points || !workspace || !coords || !features || !prm->weight) return RDP_ERR_INVALID_ARG;
-    if ((reinterpret_cast<uintptr_t>(features) & 15u) || (argmax && (reinterpret_cast<uintptr_t>(argmax) & 15u))) return RDP_ERR_INVALID_ARG;
+    if (!points || !workspace || !features || !prm->weight) return RDP_ERR_INVALID_ARG;
+    if ((reinterpret_cast<uintptr_t>(features) & 15u) || (argpos && (reinterpret_cast<uintptr_t>(argpos) & 15u))) return RDP_ERR_INVALID_ARG;
     const bool use_norm = prm->gamma != nullptr;
     if (use_norm && (!prm->beta || !prm->running_mean || !prm->running_var)) return RDP_ERR_INVALID_ARG;
     const bool train = use_norm && prm->train_bn;
     if (train && !bn_state) return RDP_ERR_INVALID_ARG;
-    if (layout->coord_cols != 3 && layout->coord_cols != 4) return RDP_ERR_INVALID_ARG;
     const PfnLaunch *L = lookup(geom, layout);
     if (!L) return RDP_ERR_UNSUPPORTED;
     Workspace ws;
@@ -80,39 +92,38 @@ extern "C" int rdp_pfn_fwd(const float *points, int64_t n_points, const rdp_geom
     if (rc != RDP_OK) return rc;
     if (ws.total_bytes > workspace_bytes) return RDP_ERR_WORKSPACE;
     PfnArgs a;
-    rc = fill_args(&a, L, points, n_points, geom, layout, prm, ws, counters, coords);
+    rc = fill_args(&a, L, n_points, geom, layout, prm, ws, counters);
     if (rc != RDP_OK) return rc;
     a.features = features;
-    a.argmax = argmax;
+    a.argpos = argpos;
     a.pillar_mean = pillar_mean;
-    const int tiles = (int)ws.pfn_tiles;
+    const int grid = pfn_grid(n_points);
     if (train) {
         if (L->stats_partial_doubles > ws.partial_doubles_per_block) return RDP_ERR_WORKSPACE;
-        const int gs = tiles < ws.partial_blocks ? tiles : ws.partial_blocks;
-        RDP_CUDA_OK(L->fwd(a, PFN_MODE_STATS, gs, st));
-        RDP_CUDA_OK(L->bn_finalize(a, gs, bn_state, prm->running_mean, prm->running_var, prm->momentum, st));
+        RDP_CUDA_OK(L->tile(a, PFN_MODE_STATS, grid, st));
+        RDP_CUDA_OK(L->bn_finalize(a, grid, bn_state, prm->running_mean, prm->running_var, prm->momentum, st));
         a.bn_state = bn_state;
         a.fold_from_state = 1;
     }
-    const int cap = 148 * 8;
-    RDP_CUDA_OK(L->fwd(a, PFN_MODE_APPLY, tiles < cap ? tiles : cap, st));
+    RDP_CUDA_OK(L->tile(a, PFN_MODE_APPLY, grid, st));
     return RDP_OK;
 }
 
 extern "C" int rdp_pfn_bwd(const float *points, int64_t n_points, const rdp_geom_t *geom, const rdp_layout_t *layout,
-                              const rdp_pfn_params_t *prm, void *workspace, size_t workspace_bytes, const int32_t *counters,
-                              const int32_t *coords, const float *grad_features, const float *features, const int32_t *argmax,
-                              const float *pillar_mean, const double *bn_state, float *d_weight, float *d_gamma, float *d_beta,
-                              int64_t n_pillars_hint, void *stream_v) {
+                           const rdp_pfn_params_t *prm, void *workspace, size_t workspace_bytes, const int32_t *counters,
+                           const float *grad_features, const float *features, const int32_t *argpos, const double *bn_state,
+                           float *d_weight, float *d_gamma, float *d_beta, void *stream_v) {
     cudaStream_t st = static_cast<cudaStream_t>(stream_v);
     if (!geom || !layout || !prm || !counters || !d_weight || !d_beta || n_points < 0) return RDP_ERR_INVALID_ARG;
     const bool use_norm = prm->gamma != nullptr;
     const bool train = use_norm && prm->train_bn;
-    RDP_CUDA_OK(cudaMemsetAsync(d_weight, 0, sizeof(float) * layout->c_out * layout->c_in, st));
-    RDP_CUDA_OK(cudaMemsetAsync(d_beta, 0, sizeof(float) * layout->c_out, st));
-    if (d_gamma) RDP_CUDA_OK(cudaMemsetAsync(d_gamma, 0, sizeof(float) * layout->c_out, st));
-    if (n_points == 0 || n_pillars_hint == 0) return RDP_OK;
-    if (!points || !workspace || !coords || !grad_features || !features || !argmax || !pillar_mean) return RDP_ERR_INVALID_ARG;
+    if (n_points == 0) {
+        RDP_CUDA_OK(cudaMemsetAsync(d_weight, 0, sizeof(float) * layout->c_out * layout->c_in, st));
+        RDP_CUDA_OK(cudaMemsetAsync(d_beta, 0, sizeof(float) * layout->c_out, st));
+        if (d_gamma) RDP_CUDA_OK(cudaMemsetAsync(d_gamma, 0, sizeof(float) * layout->c_out, st));
+        return RDP_OK;
+    }
+    if (!points || !workspace || !grad_features || !features || !argpos) return RDP_ERR_INVALID_ARG;
     if (train && !bn_state) return RDP_ERR_INVALID_ARG;
     const PfnLaunch *L = lookup(geom, layout);
     if (!L) return RDP_ERR_UNSUPPORTED;
@@ -122,11 +133,29 @@ extern "C" int rdp_pfn_bwd(const float *points, int64_t n_points, const rdp_geom
     if (ws.total_bytes > workspace_bytes) return RDP_ERR_WORKSPACE;
     if (L->bwd_partial_doubles > ws.partial_doubles_per_block) return RDP_ERR_WORKSPACE;
     PfnArgs a;
-    rc = fill_args(&a, L, points, n_points, geom, layout, prm, ws, counters, coords);
+    rc = fill_args(&a, L, n_points, geom, layout, prm, ws, counters);
     if (rc != RDP_OK) return rc;
-    int64_t want = n_pillars_hint > 0 ? (n_pillars_hint + 7) / 8 : ws.partial_blocks;
-    const int grid = (int)(want < ws.partial_blocks ? (want < 1 ? 1 : want) : ws.partial_blocks);
-    RDP_CUDA_OK(L->bwd(a, grid, grad_features, features, argmax, pillar_mean, st));
+    a.grad = grad_features;
+    a.feat_out = features;
+    a.argpos = const_cast<int32_t *>(argpos);
+    const int grid = pfn_grid(n_points);
+    RDP_CUDA_OK(L->tile(a, PFN_MODE_BWD, grid, st));
     RDP_CUDA_OK(L->bwd_finalize(a, grid, bn_state, train ? 1 : 0, d_weight, d_gamma, d_beta, st));
+    return RDP_OK;
+}
+
+extern "C" int rdp_argmax_kept(int64_t n_points, const rdp_geom_t *geom, const rdp_layout_t *layout, void *workspace,
+                               size_t workspace_bytes, const int32_t *counters, const int32_t *argpos, int32_t *argmax_kept,
+                               void *stream_v) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream_v);
+    if (!geom || !layout || !counters || n_points < 0) return RDP_ERR_INVALID_ARG;
+    if (n_points == 0) return RDP_OK;
+    if (!workspace || !argpos || !argmax_kept) return RDP_ERR_INVALID_ARG;
+    Workspace ws;
+    int rc = carve_workspace(workspace, n_points, geom, layout, &ws);
+    if (rc != RDP_OK) return rc;
+    if (ws.index_bytes > workspace_bytes) return RDP_ERR_WORKSPACE;
+    argpos_to_kept_kernel<<<148 * 8, 256, 0, st>>>(argpos, ws.gorder, ws.orig2kept, counters, n_points, layout->c_out, argmax_kept);
+    RDP_CUDA_OK(cudaGetLastError());
     return RDP_OK;
 }

@@ -4,17 +4,23 @@
 // PFNLayerV2.forward :35-46: scatter_mean, f_center / f_cluster / f_relative, concat,
 // Linear(no bias)+BatchNorm1d+ReLU, scatter_max (+argmax), and the autograd of that chain.
 //
-// Work decomposition (one CTA = 256 threads, persistent over pillar-aligned tiles of the grouped order):
-//   batch    = up to 256 grouped points that form WHOLE pillars (a pillar with more points than
-//              that takes the "giant" path: block-wide mean, then chunks with a running max)
-//   phase A  thread = point : gather the row, find its pillar in the batch, stash xyz
-//   phase B  thread = pillar: fp64 sum of xyz -> mean (one rounding), pillar centre
-//   phase C1 thread = point : decorated features -> smem  (same op order/roundings as the reference)
-//   phase C2 thread = 4 channels x PT points register tile: x = W f as a k-ascending fmaf chain with the
-//            weight rows held in registers, then y = fma(x, scale, shift)       -> smem
-//   phase D  thread = (pillar, 4 channels): max over the pillar's rows (+ lowest-index argmax), coalesced store
-// Arithmetic is the canonical form of oracle/pillar_oracle.c (ORC_MEAN_F64), so every output is
-// bit-identical to the oracle.
+// Input is the pillar-grouped row array written by group_rows_kernel (rdp_index.cu): rows of one pillar are
+// contiguous and pillars are in key order.  One persistent CTA (128 threads) walks a contiguous range of
+// tiles; tile t owns the pillars that START in grouped rows [128 t, 128 t + 128) and reads rows
+// [128 t, 128 t + 192) -- a fixed-size, 16-byte aligned window that is prefetched one tile ahead with 1-D TMA
+// bulk copies (rows + pillar ids + original-row ids) onto an mbarrier, double buffered.  A pillar that runs
+// past the staged window (> 64 rows of overhang) takes the "big pillar" path straight from global memory.
+//
+//   P0  head flags from the pillar ids -> first/last pillar of the tile                (thread = row)
+//   P1  row -> pillar slot, pillar start table                                         (thread = row)
+//   P2  per-pillar fp64 xyz sum -> mean (one rounding), pillar centre                  (thread = pillar)
+//   C1  decorated features (same op order / roundings as the reference) -> smem        (thread = row)
+//   C2  x = W f as a k-ascending fmaf chain, weight rows in registers, 4 channels x 12 rows per thread;
+//       y = fma(x, scale, shift)                                                       (register tile)
+//   D   APPLY: max over each pillar's rows (+ lowest-index argmax) -> coalesced 16 B stores
+//       STATS: fp64 sum x, sum x^2 and the Gram matrix of the features (4x4 register blocks)
+//       BWD  : per (pillar, channel) route the gradient to the winning row and accumulate dbeta, G, A
+// Arithmetic is the canonical form of oracle/pillar_oracle.c (ORC_MEAN_F64): outputs are bit-identical to it.
 #pragma once
 
 #include "rdp_common.cuh"
@@ -24,23 +30,25 @@ namespace rdp {
 constexpr int kMaxSuper = 24;
 
 struct PfnArgs {
-    const float *pts;
-    const int32_t *order, *ends, *tile_start, *counters, *coords, *orig2kept, *kept2orig;
+    const float *grows;
+    const int32_t *gpid, *gorder, *ends, *counters, *orig2kept;
     const float *weight, *bias, *gamma, *beta, *rmean, *rvar;
     const double *bn_state;  // train apply: folded scale / shift live here
     float *features;
-    int32_t *argmax;
+    int32_t *argpos;         // winning GROUPED position per (pillar, channel); see argpos_to_kept_kernel
     float *pillar_mean;
     double *partials;
+    const float *grad, *feat_out;  // backward inputs
     long long n0;
     double eps;
     float lo[3], vsz[3], off[3];
     int c_in;
-    int coord_cols;
     int use_norm;
-    int fold_from_state;  // 1: scale/shift from bn_state (train), 0: fold running stats in-kernel (eval)
+    int fold_from_state;     // 1: scale/shift from bn_state (train), 0: fold running stats in-kernel (eval)
     int8_t kmap[kMaxSuper];  // super-feature -> layout column of W, or -1 (zero weight)
 };
+
+enum { PFN_MODE_APPLY = 0, PFN_MODE_STATS = 1, PFN_MODE_BWD = 2 };
 
 // Compile-time shape of one encoder family.  "Super features" are every decoration the layout could
 // use, in the layout's concat order; options switched off in model_cfg get a zero weight column
@@ -50,45 +58,59 @@ struct PfnCfg {
     static constexpr int COLS = COLS_, LAYOUT = LAYOUT_, COUT = COUT_, C = COLS_ - 1;
     static constexpr bool DIST = DIST_;
     static constexpr int CS = (LAYOUT_ == RDP_LAYOUT_SIMPLE2D) ? (3 + C + 3 + (DIST_ ? 1 : 0) + 3) : (C + 6 + (DIST_ ? 1 : 0));
-    static constexpr int CSP4 = (CS + 3) / 4 * 4;
-    static constexpr int FSTRIDE = (CSP4 % 16 == 0) ? CSP4 + 4 : CSP4;  // smem row stride of features (conflict free)
-    static constexpr int QUADS = COUT / 4;                               // channel quads
-    static constexpr int GROUPS = kPfnThreads / QUADS;                   // point groups in the register tiling
-    static constexpr int BATCH = (COUT <= 32) ? 256 : 128;               // points per batch
-    static constexpr int PT = BATCH / GROUPS;                            // points per thread in phase C2
+    static constexpr int T4 = (CS + 1 + 3) / 4;   // 4-wide column blocks of [features | 1]
+    static constexpr int FW = 4 * T4;
+    static constexpr int FSTRIDE = (FW % 16 == 0) ? FW + 4 : FW;  // smem row stride of features (bank-conflict free)
+    static constexpr int QUADS = COUT / 4;                         // channel quads
+    static constexpr int GROUPS = kPfnThreads / QUADS;             // row groups in the register tiling
+    static constexpr int RPT = (kPfnCap + GROUPS - 1) / GROUPS;    // rows per thread in C2
     static constexpr int ZSTRIDE = COUT + 4;
+    static constexpr int NBLK = T4 * (T4 + 1) / 2;                 // upper-triangle 4x4 blocks of the Gram matrix
+    static constexpr int RG = kPfnThreads / NBLK;                  // row groups in the Gram phase
+    static constexpr int STATS_DOUBLES = 2 * COUT + 16 * NBLK;
+    static constexpr int BWD_PER = CS + 2;
+    static constexpr int BWD_DOUBLES = COUT * BWD_PER;
+    static constexpr uint32_t ROW_BYTES = kPfnCap * COLS * 4, GP_BYTES = (kPfnCap + 4) * 4, ORD_BYTES = kPfnCap * 4;
     static_assert(CS <= kMaxSuper, "too many features");
-    static_assert(BATCH % GROUPS == 0 && BATCH <= kPfnThreads, "tiling");
+    static_assert(ROW_BYTES % 16 == 0 && GP_BYTES % 16 == 0 && ORD_BYTES % 16 == 0, "TMA sizes");
+    static_assert(NBLK <= kPfnThreads && COUT % 32 == 0, "tiling");
 };
 
 template <class Cfg>
-struct PfnSmem {
-    float z[Cfg::BATCH * Cfg::ZSTRIDE];   // activations of the batch
-    float f[Cfg::BATCH * Cfg::FSTRIDE];   // decorated features of the batch
-    float xyz[Cfg::BATCH * 3];
-    float mean[Cfg::BATCH * 3];
-    float cen[Cfg::BATCH * 2];
-    int ends[Cfg::BATCH + 1];
-    int row[Cfg::BATCH];                  // original row of each point
-    int kept[Cfg::BATCH];                 // kept-order index of each point (argmax numbering)
-    int lp[Cfg::BATCH];                   // pillar (within batch) of each point
-    float scale[Cfg::COUT], shift[Cfg::COUT];
-    float part_v[(kPfnThreads / Cfg::QUADS) * Cfg::COUT];  // giant path partials
-    int part_i[(kPfnThreads / Cfg::QUADS) * Cfg::COUT];
-    float carry_v[Cfg::COUT];
-    int carry_i[Cfg::COUT];
-    double red[kPfnThreads * 3];
-    int misc[4];
+struct PfnStage {
+    alignas(16) float rows[kPfnCap * Cfg::COLS];
+    alignas(16) int gp[kPfnCap + 4];   // gp[4 + j] = pillar of row j of the window, gp[0..3] = the 4 rows before it
+    alignas(16) int ord[kPfnCap];
 };
 
-enum { PFN_MODE_APPLY = 0, PFN_MODE_STATS = 1 };
+template <class Cfg, int MODE>
+struct PfnSmem {
+    static constexpr size_t Z_BYTES = (MODE == PFN_MODE_APPLY) ? sizeof(float) * kPfnCap * Cfg::ZSTRIDE : 0;
+    static constexpr size_t S_BYTES = (MODE == PFN_MODE_STATS) ? sizeof(double) * kPfnThreads * 16 : 0;
+    static constexpr size_t B_BYTES = (MODE == PFN_MODE_BWD) ? sizeof(double) * (kPfnThreads / 32) * Cfg::BWD_DOUBLES : 0;
+    static constexpr size_t SCR = Z_BYTES > S_BYTES ? (Z_BYTES > B_BYTES ? Z_BYTES : B_BYTES) : (S_BYTES > B_BYTES ? S_BYTES : B_BYTES);
+    PfnStage<Cfg> st[2];
+    alignas(8) uint64_t full[2];
+    alignas(16) float f[kPfnCap * Cfg::FSTRIDE];   // decorated features; big-pillar partials alias it after C2
+    alignas(16) unsigned char scr[SCR];            // APPLY: activations z; STATS / BWD: fp64 reduction scratch
+    int start[kPfnCap + 1];
+    int lp[kPfnCap];
+    int kept[kPfnCap];
+    float mean[kPfnCap * 3];
+    float cen[kPfnCap * 2];
+    float scale[Cfg::COUT], shift[Cfg::COUT];
+    float carry_v[Cfg::COUT];
+    int carry_k[Cfg::COUT], carry_p[Cfg::COUT];
+    int wred[3][kPfnThreads / 32];
+    double dred[kPfnThreads * 3];
+};
 
 // ------------------------------------------------------------------------------------------- features
 template <class Cfg>
 __device__ __forceinline__ void decorate(const float *r, float cenx, float ceny, const float *mean, const PfnArgs &a, float *f) {
     const float x = r[1], y = r[2], z = r[3];
     float cen[3], clu[3];
-    cen[0] = __fsub_rn(x, cenx);               // x - (cx*vx + x_off); the bracket is per pillar (phase B)
+    cen[0] = __fsub_rn(x, cenx);               // x - (cx*vx + x_off); the bracket is per pillar (P2)
     cen[1] = __fsub_rn(y, ceny);
     cen[2] = __fsub_rn(z, a.off[2]);           // (:217) z - z_offset
     clu[0] = __fsub_rn(x, mean[0]);            // (:227) xyz - mean[inv]
@@ -111,21 +133,6 @@ __device__ __forceinline__ void decorate(const float *r, float cenx, float ceny,
     }
 }
 
-template <class Cfg>
-__device__ __forceinline__ void load_row(const float *pts, long long row, float *r) {
-    const float *p = pts + row * Cfg::COLS;
-    if (Cfg::COLS % 2 == 0) {
-#pragma unroll
-        for (int c = 0; c < Cfg::COLS; c += 2) {
-            const float2 v = __ldg(reinterpret_cast<const float2 *>(p + c));
-            r[c] = v.x; r[c + 1] = v.y;
-        }
-    } else {
-#pragma unroll
-        for (int c = 0; c < Cfg::COLS; ++c) r[c] = __ldg(p + c);
-    }
-}
-
 // BatchNorm folded to y = fma(x, scale, shift) in fp64 with one rounding (oracle: orc_bn_fold).
 __device__ __forceinline__ void fold_bn(double gamma, double beta, double mean, double var, double eps, float *scale, float *shift) {
     const double inv_std = __ddiv_rn(1.0, __dsqrt_rn(__dadd_rn(var, eps)));
@@ -134,130 +141,128 @@ __device__ __forceinline__ void fold_bn(double gamma, double beta, double mean, 
     *shift = (float)__dsub_rn(beta, __dmul_rn(mean, s));
 }
 
-// ------------------------------------------------------------------------------------------- forward
-template <class Cfg, int MODE>
-__global__ void __launch_bounds__(kPfnThreads, 2) pfn_fwd_kernel(const __grid_constant__ PfnArgs a) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    PfnSmem<Cfg> &S = *reinterpret_cast<PfnSmem<Cfg> *>(smem_raw);
-    constexpr int COUT = Cfg::COUT, CS = Cfg::CS, QUADS = Cfg::QUADS, GROUPS = Cfg::GROUPS, PT = Cfg::PT, BATCH = Cfg::BATCH;
-    const int tid = threadIdx.x;
-    const long long N = a.counters[RDP_CNT_N];
-    const int P = a.counters[RDP_CNT_P];
-    const bool none_dropped = (N == a.n0);
-    const int ntiles = (int)((N + kPfnTileRows - 1) / kPfnTileRows);
-    const bool want_arg = (MODE == PFN_MODE_APPLY) && a.argmax != nullptr;
+// pillar centre of the cell that holds (x, y): cx*vx + x_off with separate mul / add roundings (:215-216);
+// the quantisation repeats quantize_mark_kernel's IEEE ops, so cx / cy equal the emitted coords.
+__device__ __forceinline__ void pillar_centre(float x, float y, const PfnArgs &a, float *cenx, float *ceny) {
+    const float qx = floorf(__fdiv_rn(__fsub_rn(x, a.lo[0]), a.vsz[0]));
+    const float qy = floorf(__fdiv_rn(__fsub_rn(y, a.lo[1]), a.vsz[1]));
+    *cenx = __fadd_rn(__fmul_rn((float)(int)qx, a.vsz[0]), a.off[0]);
+    *ceny = __fadd_rn(__fmul_rn((float)(int)qy, a.vsz[1]), a.off[1]);
+}
 
-    // ---- per-CTA constants: BN fold, weight rows of my channel quad in registers
-    if (tid < COUT) {
+__device__ __forceinline__ int warp_min(int v) { return __reduce_min_sync(0xffffffffu, v); }
+__device__ __forceinline__ int warp_max(int v) { return __reduce_max_sync(0xffffffffu, v); }
+
+// ------------------------------------------------------------------------------------------- the tile kernel
+template <class Cfg, int MODE>
+__global__ void __launch_bounds__(kPfnThreads, 3) pfn_tile_kernel(const __grid_constant__ PfnArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    using Smem = PfnSmem<Cfg, MODE>;
+    Smem &S = *reinterpret_cast<Smem *>(smem_raw);
+    constexpr int COUT = Cfg::COUT, CS = Cfg::CS, COLS = Cfg::COLS, QUADS = Cfg::QUADS, GROUPS = Cfg::GROUPS;
+    constexpr int WIN = kPfnWin, CAP = kPfnCap, NT = kPfnThreads, INF = 0x7fffffff;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long N = a.counters[RDP_CNT_N];
+    const bool none_dropped = (N == a.n0);
+    const int ntiles = (int)((N + WIN - 1) / WIN);
+    const int per = (ntiles + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int t_begin = min(ntiles, (int)blockIdx.x * per), t_end = min(ntiles, t_begin + per);
+    const bool want_arg = (MODE == PFN_MODE_APPLY) && a.argpos != nullptr;
+    float *sz = reinterpret_cast<float *>(S.scr);
+    double *dscr = reinterpret_cast<double *>(S.scr);
+
+    // ---- per-CTA constants
+    if (tid == 0) {
+        mbar_init(&S.full[0], 1);
+        mbar_init(&S.full[1], 1);
+        fence_mbar_init();
+    }
+    if (MODE != PFN_MODE_BWD && tid < COUT) {
         float sc = 1.0f, sh = a.bias ? a.bias[tid] : 0.0f;
         if (a.use_norm) {
-            if (a.fold_from_state) {
-                sc = (float)a.bn_state[2 * COUT + tid];
-                sh = (float)a.bn_state[3 * COUT + tid];
-            } else {
-                fold_bn((double)a.gamma[tid], (double)a.beta[tid], (double)a.rmean[tid], (double)a.rvar[tid], a.eps, &sc, &sh);
-            }
+            if (a.fold_from_state) { sc = (float)a.bn_state[2 * COUT + tid]; sh = (float)a.bn_state[3 * COUT + tid]; }
+            else fold_bn((double)a.gamma[tid], (double)a.beta[tid], (double)a.rmean[tid], (double)a.rvar[tid], a.eps, &sc, &sh);
         }
         S.scale[tid] = sc;
         S.shift[tid] = sh;
     }
+    // weight rows in registers: FWD: my channel quad (4 x CS);  BWD: my channel(s) (COUT/32 x CS)
+    constexpr int WR = (MODE == PFN_MODE_BWD) ? COUT / 32 : 4;
     const int quad = tid % QUADS, grp = tid / QUADS;
-    float W[4][CS];
+    float W[WR][CS];
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
+    for (int j = 0; j < WR; ++j)
 #pragma unroll
         for (int s = 0; s < CS; ++s) {
             const int k = a.kmap[s];
-            W[j][s] = (k >= 0) ? __ldg(a.weight + (quad * 4 + j) * a.c_in + k) : 0.0f;
+            const int ch = (MODE == PFN_MODE_BWD) ? (lane + 32 * j) : (quad * 4 + j);
+            W[j][s] = (k >= 0) ? __ldg(a.weight + ch * a.c_in + k) : 0.0f;
         }
     __syncthreads();
     float sc4[4], sh4[4];
+    if (MODE != PFN_MODE_BWD) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) { sc4[j] = S.scale[quad * 4 + j]; sh4[j] = S.shift[quad * 4 + j]; }
+        for (int j = 0; j < 4; ++j) { sc4[j] = S.scale[quad * 4 + j]; sh4[j] = S.shift[quad * 4 + j]; }
+    }
 
-    // ---- STATS accumulators (fp64, live across the whole CTA lifetime)
-    double st_x = 0.0, st_x2 = 0.0, st_m[2] = {0.0, 0.0};
-    constexpr int NPAIR = CS * (CS + 1) / 2 + CS;  // S2 upper triangle, then S1
-    int pa[2] = {0, 0}, pb[2] = {0, 0};
+    // ---- accumulators that live for the whole CTA
+    double st_x[4] = {0, 0, 0, 0}, st_x2[4] = {0, 0, 0, 0}, st_m[16];
+    int gba = 0, gbb = 0;
+    const int grg = tid % Cfg::RG, gblk = tid / Cfg::RG;
     if (MODE == PFN_MODE_STATS) {
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            int item = tid + u * kPfnThreads;
-            if (item < CS * (CS + 1) / 2) {
-                int aa = 0, rem = item;
-                while (rem >= CS - aa) { rem -= CS - aa; ++aa; }
-                pa[u] = aa; pb[u] = aa + rem;
-            } else if (item < NPAIR) {
-                pa[u] = item - CS * (CS + 1) / 2; pb[u] = -1;
-            } else {
-                pa[u] = -1;
-            }
+        for (int e = 0; e < 16; ++e) st_m[e] = 0.0;
+        int rem = gblk;
+        while (gba < Cfg::T4 && rem >= Cfg::T4 - gba) { rem -= Cfg::T4 - gba; ++gba; }
+        gbb = gba + rem;  // block (gba, gbb), gba <= gbb, valid when gblk < NBLK
+    }
+    constexpr int CPL = COUT / 32;
+    double dB[CPL], dG[CPL], dA[CPL][CS];
+    if (MODE == PFN_MODE_BWD) {
+#pragma unroll
+        for (int cc = 0; cc < CPL; ++cc) {
+            dB[cc] = dG[cc] = 0.0;
+#pragma unroll
+            for (int k = 0; k < CS; ++k) dA[cc][k] = 0.0;
         }
     }
 
-    // One batch: np points starting at grouped position s; nb pillars starting at p (nb == 0: chunk of giant pillar p).
-    auto run_points = [&](int s, int np, int p, int nb) {
-        // phase A
-        if (tid < np) {
-            const int gpos = s + tid;
-            const int row = a.order[gpos];
-            S.row[tid] = row;
-            int lp = 0;
-            if (nb > 0) {
-                int lo = 0, hi = nb;  // first q with ends[q] > gpos
-                while (lo < hi) {
-                    const int mid = (lo + hi) >> 1;
-                    if (S.ends[mid] > gpos) hi = mid; else lo = mid + 1;
-                }
-                lp = lo;
-            }
-            S.lp[tid] = lp;
-            const float *r = a.pts + (long long)row * Cfg::COLS;
-            S.xyz[tid * 3 + 0] = __ldg(r + 1);
-            S.xyz[tid * 3 + 1] = __ldg(r + 2);
-            S.xyz[tid * 3 + 2] = __ldg(r + 3);
-            if (want_arg) S.kept[tid] = none_dropped ? row : a.orig2kept[row];
-        }
-        __syncthreads();
-        // phase B (whole pillars only; the giant path fills mean/cen slot 0 itself)
-        if (tid < nb) {
-            const int b0 = (tid == 0 ? s : S.ends[tid - 1]) - s, b1 = S.ends[tid] - s;
-            double sx = 0.0, sy = 0.0, sz = 0.0;
-            for (int j = b0; j < b1; ++j) { sx += (double)S.xyz[j * 3]; sy += (double)S.xyz[j * 3 + 1]; sz += (double)S.xyz[j * 3 + 2]; }
-            const double cnt = (double)(b1 - b0);
-            const float mx = (float)__ddiv_rn(sx, cnt), my = (float)__ddiv_rn(sy, cnt), mz = (float)__ddiv_rn(sz, cnt);
-            S.mean[tid * 3] = mx; S.mean[tid * 3 + 1] = my; S.mean[tid * 3 + 2] = mz;
-            const int32_t *co = a.coords + (size_t)(p + tid) * a.coord_cols + (a.coord_cols - 2);
-            const int cy = co[0], cx = co[1];
-            // (:215-216) cx.float()*voxel_x + x_offset : separate mul and add roundings
-            S.cen[tid * 2] = __fadd_rn(__fmul_rn((float)cx, a.vsz[0]), a.off[0]);
-            S.cen[tid * 2 + 1] = __fadd_rn(__fmul_rn((float)cy, a.vsz[1]), a.off[1]);
-            if (MODE == PFN_MODE_APPLY && a.pillar_mean) {
-                float *pm = a.pillar_mean + (size_t)(p + tid) * 3;
-                pm[0] = mx; pm[1] = my; pm[2] = mz;
-            }
-        }
-        __syncthreads();
-        // phase C1
-        if (tid < np) {
-            float r[Cfg::COLS], f[CS];
-            load_row<Cfg>(a.pts, S.row[tid], r);
-            const int lp = S.lp[tid];
+    auto issue = [&](int t, int s) {
+        PfnStage<Cfg> &T = S.st[s];
+        mbar_expect_tx(&S.full[s], Cfg::ROW_BYTES + Cfg::GP_BYTES + Cfg::ORD_BYTES);
+        tma_bulk_g2s(T.rows, a.grows + (size_t)t * WIN * COLS, Cfg::ROW_BYTES, &S.full[s]);
+        tma_bulk_g2s(T.gp, a.gpid + (size_t)t * WIN, Cfg::GP_BYTES, &S.full[s]);
+        tma_bulk_g2s(T.ord, a.gorder + (size_t)t * WIN, Cfg::ORD_BYTES, &S.full[s]);
+    };
+
+    // C1: decorated features of rows [rowbase, rowbase + np) of `rows` -> S.f[0..np)
+    auto c1 = [&](const float *rows, int rowbase, int np) {
+        for (int jj = tid; jj < np; jj += NT) {
+            float r[COLS], f[Cfg::FW];
+            const float *src = rows + (rowbase + jj) * COLS;
+#pragma unroll
+            for (int c = 0; c < COLS; ++c) r[c] = src[c];
+            const int lp = S.lp[jj];
             decorate<Cfg>(r, S.cen[lp * 2], S.cen[lp * 2 + 1], &S.mean[lp * 3], a, f);
-            float *dst = &S.f[tid * Cfg::FSTRIDE];
+            f[CS] = 1.0f;  // ones column: the Gram matrix then carries sum f (S1) as well
 #pragma unroll
-            for (int k = 0; k < CS; ++k) dst[k] = f[k];
+            for (int k = CS + 1; k < Cfg::FW; ++k) f[k] = 0.0f;
+            float4 *dst = reinterpret_cast<float4 *>(&S.f[jj * Cfg::FSTRIDE]);
+#pragma unroll
+            for (int k4 = 0; k4 < Cfg::T4; ++k4) dst[k4] = make_float4(f[k4 * 4], f[k4 * 4 + 1], f[k4 * 4 + 2], f[k4 * 4 + 3]);
         }
-        __syncthreads();
-        // phase C2: rows grp + GROUPS*r, channels quad*4..+3
-#pragma unroll
-        for (int r = 0; r < PT; ++r) {
+    };
+
+    // C2: rows grp + GROUPS*r, channels quad*4..+3
+    auto c2 = [&](int np) {
+#pragma unroll 2
+        for (int r = 0; r < Cfg::RPT; ++r) {
             const int j = grp + GROUPS * r;
-            if (j < np) {  // warp-uniform up to the last partial group
-                float f[Cfg::CSP4];
+            if (j < np) {
+                float f[Cfg::FW];
                 const float4 *src = reinterpret_cast<const float4 *>(&S.f[j * Cfg::FSTRIDE]);
 #pragma unroll
-                for (int k4 = 0; k4 < Cfg::CSP4 / 4; ++k4) {
+                for (int k4 = 0; k4 < (CS + 3) / 4; ++k4) {
                     const float4 v = src[k4];
                     f[k4 * 4] = v.x; f[k4 * 4 + 1] = v.y; f[k4 * 4 + 2] = v.z; f[k4 * 4 + 3] = v.w;
                 }
@@ -267,198 +272,348 @@ __global__ void __launch_bounds__(kPfnThreads, 2) pfn_fwd_kernel(const __grid_co
                     float acc = 0.0f;
 #pragma unroll
                     for (int k = 0; k < CS; ++k) acc = fmaf(W[c][k], f[k], acc);
-                    if (MODE == PFN_MODE_STATS) o[c] = acc;
-                    else {
+                    if (MODE == PFN_MODE_STATS) {
+                        const double v = (double)acc;
+                        st_x[c] += v;
+                        st_x2[c] = fma(v, v, st_x2[c]);
+                    } else {
                         const float y = fmaf(acc, sc4[c], sh4[c]);
                         o[c] = want_arg ? fmaxf(y, 0.0f) : y;  // eval: ReLU folds into the max with 0
                     }
                 }
-                *reinterpret_cast<float4 *>(&S.z[j * Cfg::ZSTRIDE + quad * 4]) = make_float4(o[0], o[1], o[2], o[3]);
+                if (MODE == PFN_MODE_APPLY)
+                    *reinterpret_cast<float4 *>(&sz[j * Cfg::ZSTRIDE + quad * 4]) = make_float4(o[0], o[1], o[2], o[3]);
             }
         }
-        __syncthreads();
     };
 
-    // STATS: fold the batch in smem into the per-thread fp64 accumulators.
-    auto accumulate_stats = [&](int np) {
-        {
-            const int c = tid % COUT, part = tid / COUT;
-            constexpr int PARTS = kPfnThreads / COUT;
-            for (int j = part; j < np; j += PARTS) {
-                const double v = (double)S.z[j * Cfg::ZSTRIDE + c];
-                st_x += v;
-                st_x2 = fma(v, v, st_x2);
+    // STATS: Gram matrix of [features | 1] over the np rows in S.f, 4x4 register blocks
+    auto gram = [&](int np) {
+        if (gblk < Cfg::NBLK) {
+            for (int j = grg; j < np; j += Cfg::RG) {
+                const float4 A = *reinterpret_cast<const float4 *>(&S.f[j * Cfg::FSTRIDE + gba * 4]);
+                const float4 B = *reinterpret_cast<const float4 *>(&S.f[j * Cfg::FSTRIDE + gbb * 4]);
+                const double av[4] = {(double)A.x, (double)A.y, (double)A.z, (double)A.w};
+                const double bv[4] = {(double)B.x, (double)B.y, (double)B.z, (double)B.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j2 = 0; j2 < 4; ++j2) st_m[i * 4 + j2] = fma(av[i], bv[j2], st_m[i * 4 + j2]);
             }
         }
+    };
+
+    if (t_begin < t_end && tid == 0) issue(t_begin, 0);
+    uint32_t par0 = 0, par1 = 0;
+
+    for (int t = t_begin; t < t_end; ++t) {
+        const int s = (t - t_begin) & 1;
+        if (tid == 0 && t + 1 < t_end) issue(t + 1, s ^ 1);
+        if (s == 0) { mbar_wait(&S.full[0], par0); par0 ^= 1; } else { mbar_wait(&S.full[1], par1); par1 ^= 1; }
+        PfnStage<Cfg> &T = S.st[s];
+        const long long base = (long long)t * WIN;
+
+        // ---- P0: which pillars does this tile own?
+        int jmin = INF, jend = INF, jlast = -1;
+        for (int j = tid; j < CAP; j += NT) {
+            const bool valid = base + j < N;
+            const bool head = valid && (T.gp[j + 4] != T.gp[j + 3]);
+            if (j < WIN) {
+                if (head) { jmin = min(jmin, j); jlast = max(jlast, j); }
+                if (!valid) jend = min(jend, j);
+            } else if (head || !valid) {
+                jend = min(jend, j);
+            }
+        }
+        jmin = warp_min(jmin); jend = warp_min(jend); jlast = warp_max(jlast);
+        if (lane == 0) { S.wred[0][warp] = jmin; S.wred[1][warp] = jend; S.wred[2][warp] = jlast; }
+        __syncthreads();
+        jmin = INF; jend = INF; jlast = -1;
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            if (pa[u] >= 0 && (u == 0 || NPAIR > kPfnThreads)) {
-                // fp64 throughout: tight clusters make var << mean^2 and the backward's (S2 w - mu S1) cancels
-                double acc = 0.0;
-                if (pb[u] >= 0) {
-                    for (int j = 0; j < np; ++j)
-                        acc = fma((double)S.f[j * Cfg::FSTRIDE + pa[u]], (double)S.f[j * Cfg::FSTRIDE + pb[u]], acc);
-                } else {
-                    for (int j = 0; j < np; ++j) acc += (double)S.f[j * Cfg::FSTRIDE + pa[u]];
+        for (int w = 0; w < NT / 32; ++w) { jmin = min(jmin, S.wred[0][w]); jend = min(jend, S.wred[1][w]); jlast = max(jlast, S.wred[2][w]); }
+        if (jmin == INF) { __syncthreads(); continue; }  // a pillar from an earlier tile covers the whole window
+        const bool big = (jend == INF);                   // the last pillar runs past the staged rows
+        const int j0 = jmin, jstop = big ? jlast : jend, np = jstop - j0;
+        const int ps = T.gp[j0 + 4];
+        const int nb = np > 0 ? T.gp[jstop - 1 + 4] - ps + 1 : 0;
+
+        if (np > 0) {
+            // ---- P1
+            for (int jj = tid; jj < np; jj += NT) {
+                const int j = j0 + jj, gid = T.gp[j + 4];
+                S.lp[jj] = gid - ps;
+                if (gid != T.gp[j + 3]) S.start[gid - ps] = jj;
+                if (want_arg) { const int row = T.ord[j]; S.kept[jj] = none_dropped ? row : a.orig2kept[row]; }
+            }
+            if (tid == 0) S.start[nb] = np;
+            __syncthreads();
+            // ---- P2
+            for (int q = tid; q < nb; q += NT) {
+                const int b0 = S.start[q], b1 = S.start[q + 1];
+                double sx = 0.0, sy = 0.0, sz3 = 0.0;
+                for (int jj = b0; jj < b1; ++jj) {
+                    const float *r = T.rows + (j0 + jj) * COLS;
+                    sx += (double)r[1]; sy += (double)r[2]; sz3 += (double)r[3];
                 }
-                st_m[u] += acc;
+                const double cnt = (double)(b1 - b0);
+                const float mx = (float)__ddiv_rn(sx, cnt), my = (float)__ddiv_rn(sy, cnt), mz = (float)__ddiv_rn(sz3, cnt);
+                S.mean[q * 3] = mx; S.mean[q * 3 + 1] = my; S.mean[q * 3 + 2] = mz;
+                const float *r0 = T.rows + (j0 + b0) * COLS;
+                pillar_centre(r0[1], r0[2], a, &S.cen[q * 2], &S.cen[q * 2 + 1]);
+                if (MODE == PFN_MODE_APPLY && a.pillar_mean) {
+                    float *pm = a.pillar_mean + (size_t)(ps + q) * 3;
+                    pm[0] = mx; pm[1] = my; pm[2] = mz;
+                }
+            }
+            __syncthreads();
+            c1(T.rows, j0, np);
+            __syncthreads();
+            if (MODE == PFN_MODE_APPLY) {
+                c2(np);
+                __syncthreads();
+                // ---- D
+                for (int item = tid; item < nb * QUADS; item += NT) {
+                    const int q = item / QUADS, qd = item % QUADS;
+                    const int b0 = S.start[q], b1 = S.start[q + 1];
+                    if (!want_arg) {
+                        float4 m = make_float4(0.f, 0.f, 0.f, 0.f);
+                        for (int j = b0; j < b1; ++j) {
+                            const float4 v = *reinterpret_cast<const float4 *>(&sz[j * Cfg::ZSTRIDE + qd * 4]);
+                            m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+                        }
+                        *reinterpret_cast<float4 *>(a.features + (size_t)(ps + q) * COUT + qd * 4) = m;
+                    } else {
+                        float m[4] = {-1.f, -1.f, -1.f, -1.f};
+                        int mk[4] = {INF, INF, INF, INF}, mp[4] = {0, 0, 0, 0};
+                        for (int j = b0; j < b1; ++j) {
+                            const float4 v4 = *reinterpret_cast<const float4 *>(&sz[j * Cfg::ZSTRIDE + qd * 4]);
+                            const float v[4] = {v4.x, v4.y, v4.z, v4.w};
+                            const int kj = S.kept[j];
+#pragma unroll
+                            for (int c = 0; c < 4; ++c)
+                                if (v[c] > m[c] || (v[c] == m[c] && kj < mk[c])) { m[c] = v[c]; mk[c] = kj; mp[c] = j; }
+                        }
+                        const int gb = (int)base + j0;
+                        *reinterpret_cast<float4 *>(a.features + (size_t)(ps + q) * COUT + qd * 4) = make_float4(m[0], m[1], m[2], m[3]);
+                        *reinterpret_cast<int4 *>(a.argpos + (size_t)(ps + q) * COUT + qd * 4) =
+                            make_int4(gb + mp[0], gb + mp[1], gb + mp[2], gb + mp[3]);
+                    }
+                }
+            } else if (MODE == PFN_MODE_STATS) {
+                gram(np);
+                c2(np);
+            } else {
+                // ---- E (backward): warp = pillar, lane = channel
+                float tB[CPL], tG[CPL], tA[CPL][CS];
+#pragma unroll
+                for (int cc = 0; cc < CPL; ++cc) {
+                    tB[cc] = tG[cc] = 0.0f;
+#pragma unroll
+                    for (int k = 0; k < CS; ++k) tA[cc][k] = 0.0f;
+                }
+                const int gb = (int)base + j0;
+                for (int q = warp; q < nb; q += NT / 32) {
+#pragma unroll
+                    for (int cc = 0; cc < CPL; ++cc) {
+                        const size_t o = (size_t)(ps + q) * COUT + lane + 32 * cc;
+                        const float gy = a.feat_out[o] > 0.0f ? a.grad[o] : 0.0f;
+                        const int jj = a.argpos[o] - gb;
+                        float f[Cfg::FW];
+                        const float4 *src = reinterpret_cast<const float4 *>(&S.f[jj * Cfg::FSTRIDE]);
+#pragma unroll
+                        for (int k4 = 0; k4 < (CS + 3) / 4; ++k4) {
+                            const float4 v = src[k4];
+                            f[k4 * 4] = v.x; f[k4 * 4 + 1] = v.y; f[k4 * 4 + 2] = v.z; f[k4 * 4 + 3] = v.w;
+                        }
+                        float x = 0.0f;
+#pragma unroll
+                        for (int k = 0; k < CS; ++k) x = fmaf(W[cc][k], f[k], x);
+                        tB[cc] += gy;
+                        tG[cc] = fmaf(gy, x, tG[cc]);
+#pragma unroll
+                        for (int k = 0; k < CS; ++k) tA[cc][k] = fmaf(gy, f[k], tA[cc][k]);
+                    }
+                }
+#pragma unroll
+                for (int cc = 0; cc < CPL; ++cc) {
+                    dB[cc] += (double)tB[cc];
+                    dG[cc] += (double)tG[cc];
+#pragma unroll
+                    for (int k = 0; k < CS; ++k) dA[cc][k] += (double)tA[cc][k];
+                }
             }
         }
-        __syncthreads();
-    };
 
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int p_lo = a.tile_start[tile], p_hi = a.tile_start[tile + 1];
-        int p = p_lo;
-        while (p < p_hi) {
-            const int s = (p == 0) ? 0 : a.ends[p - 1];
-            const int e_mine = (tid < BATCH && p + tid < p_hi) ? a.ends[p + tid] : 0x7fffffff;
-            const int fits = (e_mine != 0x7fffffff) && (e_mine - s <= BATCH);
-            const int nb = __syncthreads_count(fits);
-            if (nb > 0) {
-                if (tid < nb) S.ends[tid] = e_mine;
-                __syncthreads();
-                const int np = S.ends[nb - 1] - s;
-                run_points(s, np, p, nb);
-                if (MODE == PFN_MODE_STATS) {
-                    accumulate_stats(np);
-                } else {
-                    // phase D
-                    for (int item = tid; item < nb * QUADS; item += kPfnThreads) {
-                        const int q = item / QUADS, qd = item % QUADS;
-                        const int b0 = (q == 0 ? s : S.ends[q - 1]) - s, b1 = S.ends[q] - s;
-                        if (!want_arg) {
-                            float4 m = make_float4(0.f, 0.f, 0.f, 0.f);
-                            for (int j = b0; j < b1; ++j) {
-                                const float4 v = *reinterpret_cast<const float4 *>(&S.z[j * Cfg::ZSTRIDE + qd * 4]);
-                                m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
-                            }
-                            *reinterpret_cast<float4 *>(a.features + (size_t)(p + q) * COUT + qd * 4) = m;
-                        } else {
-                            float m[4] = {-1.f, -1.f, -1.f, -1.f};
-                            int mi[4] = {0x7fffffff, 0x7fffffff, 0x7fffffff, 0x7fffffff};
-                            for (int j = b0; j < b1; ++j) {
-                                const float4 v4 = *reinterpret_cast<const float4 *>(&S.z[j * Cfg::ZSTRIDE + qd * 4]);
-                                const float v[4] = {v4.x, v4.y, v4.z, v4.w};
-                                const int kj = S.kept[j];
+        if (big) {
+            // ---- big pillar pb = rows [a0, e): straight from global memory
+            __syncthreads();
+            const int pb = T.gp[jlast + 4];
+            const long long a0 = base + jlast;
+            const long long e = a.ends[pb];
+            double sx = 0.0, sy = 0.0, sz3 = 0.0;
+            for (long long g = a0 + tid; g < e; g += NT) {
+                const float *r = a.grows + g * COLS;
+                sx += (double)r[1]; sy += (double)r[2]; sz3 += (double)r[3];
+            }
+            S.dred[tid * 3] = sx; S.dred[tid * 3 + 1] = sy; S.dred[tid * 3 + 2] = sz3;
+            __syncthreads();
+            if (tid < 3) {
+                double tsum = 0.0;  // fp64 adds of fp32 values in this range are exact: order is immaterial
+                for (int j = 0; j < NT; ++j) tsum += S.dred[j * 3 + tid];
+                const float m = (float)__ddiv_rn(tsum, (double)(e - a0));
+                S.mean[tid] = m;
+                if (MODE == PFN_MODE_APPLY && a.pillar_mean) a.pillar_mean[(size_t)pb * 3 + tid] = m;
+            }
+            if (tid == 32) {
+                const float *r0 = a.grows + a0 * COLS;
+                pillar_centre(r0[1], r0[2], a, &S.cen[0], &S.cen[1]);
+            }
+            if (tid < COUT) { S.carry_v[tid] = want_arg ? -1.0f : 0.0f; S.carry_k[tid] = INF; S.carry_p[tid] = 0; }
+            __syncthreads();
+            if (MODE == PFN_MODE_BWD) {
+                if (warp == 0) {
 #pragma unroll
-                                for (int c = 0; c < 4; ++c)
-                                    if (v[c] > m[c] || (v[c] == m[c] && kj < mi[c])) { m[c] = v[c]; mi[c] = kj; }
-                            }
-                            *reinterpret_cast<float4 *>(a.features + (size_t)(p + q) * COUT + qd * 4) = make_float4(m[0], m[1], m[2], m[3]);
-                            *reinterpret_cast<int4 *>(a.argmax + (size_t)(p + q) * COUT + qd * 4) = make_int4(mi[0], mi[1], mi[2], mi[3]);
-                        }
+                    for (int cc = 0; cc < CPL; ++cc) {
+                        const size_t o = (size_t)pb * COUT + lane + 32 * cc;
+                        const float gy = a.feat_out[o] > 0.0f ? a.grad[o] : 0.0f;
+                        const float *src = a.grows + (size_t)a.argpos[o] * COLS;
+                        float r[COLS], f[Cfg::FW];
+#pragma unroll
+                        for (int c = 0; c < COLS; ++c) r[c] = src[c];
+                        decorate<Cfg>(r, S.cen[0], S.cen[1], &S.mean[0], a, f);
+                        float x = 0.0f;
+#pragma unroll
+                        for (int k = 0; k < CS; ++k) x = fmaf(W[cc][k], f[k], x);
+                        dB[cc] += (double)gy;
+                        dG[cc] = fma((double)gy, (double)x, dG[cc]);
+#pragma unroll
+                        for (int k = 0; k < CS; ++k) dA[cc][k] = fma((double)gy, (double)f[k], dA[cc][k]);
+                    }
+                }
+            } else {
+                float *rows = T.rows;  // this stage's row buffer is free again (the next TMA targets the other stage)
+                for (long long cs = a0; cs < e; cs += CAP) {
+                    const int npc = (int)min((long long)CAP, e - cs);
+                    for (int i = tid; i < npc * COLS; i += NT) rows[i] = a.grows[cs * COLS + i];
+                    for (int jj = tid; jj < npc; jj += NT) {
+                        S.lp[jj] = 0;
+                        if (want_arg) { const int row = a.gorder[cs + jj]; S.kept[jj] = none_dropped ? row : a.orig2kept[row]; }
                     }
                     __syncthreads();
-                }
-                p += nb;
-            } else {
-                // ---- giant pillar: more than BATCH points in pillar p
-                const int e = a.ends[p];
-                double sx = 0.0, sy = 0.0, sz = 0.0;
-                for (int g = s + tid; g < e; g += kPfnThreads) {
-                    const float *r = a.pts + (long long)a.order[g] * Cfg::COLS;
-                    sx += (double)__ldg(r + 1); sy += (double)__ldg(r + 2); sz += (double)__ldg(r + 3);
-                }
-                S.red[tid * 3] = sx; S.red[tid * 3 + 1] = sy; S.red[tid * 3 + 2] = sz;
-                __syncthreads();
-                if (tid < 3) {
-                    // fp64 adds of fp32 values in this range are exact, so the order is immaterial
-                    double t = 0.0;
-                    for (int j = 0; j < kPfnThreads; ++j) t += S.red[j * 3 + tid];
-                    const float m = (float)__ddiv_rn(t, (double)(e - s));
-                    S.mean[tid] = m;
-                    if (MODE == PFN_MODE_APPLY && a.pillar_mean) a.pillar_mean[(size_t)p * 3 + tid] = m;
-                }
-                if (tid == 32) {
-                    const int32_t *co = a.coords + (size_t)p * a.coord_cols + (a.coord_cols - 2);
-                    S.cen[0] = __fadd_rn(__fmul_rn((float)co[1], a.vsz[0]), a.off[0]);
-                    S.cen[1] = __fadd_rn(__fmul_rn((float)co[0], a.vsz[1]), a.off[1]);
-                }
-                if (tid < COUT) { S.carry_v[tid] = want_arg ? -1.0f : 0.0f; S.carry_i[tid] = 0x7fffffff; }
-                __syncthreads();
-                for (int cs = s; cs < e; cs += BATCH) {
-                    const int np = min(BATCH, e - cs);
-                    run_points(cs, np, p, 0);
+                    c1(rows, 0, npc);
+                    __syncthreads();
                     if (MODE == PFN_MODE_STATS) {
-                        accumulate_stats(np);
+                        gram(npc);
+                        c2(npc);
+                        __syncthreads();
                     } else {
-                        // column reduce: thread = (row group g, quad qd)
-                        const int qd = tid % QUADS, g = tid / QUADS;
+                        c2(npc);
+                        __syncthreads();
+                        // column reduce: thread = (row group, quad); partials alias S.f (free after C2)
+                        float *pv = S.f;
+                        int *pk = reinterpret_cast<int *>(S.f) + GROUPS * COUT, *pp = pk + GROUPS * COUT;
                         float m[4];
-                        int mi[4];
+                        int mk[4], mp[4];
 #pragma unroll
-                        for (int c = 0; c < 4; ++c) { m[c] = want_arg ? -1.0f : 0.0f; mi[c] = 0x7fffffff; }
-                        for (int j = g; j < np; j += GROUPS) {
-                            const float4 v4 = *reinterpret_cast<const float4 *>(&S.z[j * Cfg::ZSTRIDE + qd * 4]);
+                        for (int c = 0; c < 4; ++c) { m[c] = want_arg ? -1.0f : 0.0f; mk[c] = INF; mp[c] = 0; }
+                        for (int j = grp; j < npc; j += GROUPS) {
+                            const float4 v4 = *reinterpret_cast<const float4 *>(&sz[j * Cfg::ZSTRIDE + quad * 4]);
                             const float v[4] = {v4.x, v4.y, v4.z, v4.w};
                             const int kj = want_arg ? S.kept[j] : 0;
 #pragma unroll
                             for (int c = 0; c < 4; ++c)
-                                if (v[c] > m[c] || (want_arg && v[c] == m[c] && kj < mi[c])) { m[c] = v[c]; mi[c] = kj; }
+                                if (v[c] > m[c] || (want_arg && v[c] == m[c] && kj < mk[c])) { m[c] = v[c]; mk[c] = kj; mp[c] = (int)(cs + j); }
                         }
 #pragma unroll
-                        for (int c = 0; c < 4; ++c) { S.part_v[g * COUT + qd * 4 + c] = m[c]; S.part_i[g * COUT + qd * 4 + c] = mi[c]; }
+                        for (int c = 0; c < 4; ++c) {
+                            pv[grp * COUT + quad * 4 + c] = m[c]; pk[grp * COUT + quad * 4 + c] = mk[c]; pp[grp * COUT + quad * 4 + c] = mp[c];
+                        }
                         __syncthreads();
                         if (tid < COUT) {
                             float bm = S.carry_v[tid];
-                            int bi = S.carry_i[tid];
+                            int bk = S.carry_k[tid], bp = S.carry_p[tid];
                             for (int gg = 0; gg < GROUPS; ++gg) {
-                                const float v = S.part_v[gg * COUT + tid];
-                                const int vi = S.part_i[gg * COUT + tid];
-                                if (v > bm || (want_arg && v == bm && vi < bi)) { bm = v; bi = vi; }
+                                const float v = pv[gg * COUT + tid];
+                                const int vk = pk[gg * COUT + tid];
+                                if (v > bm || (want_arg && v == bm && vk < bk)) { bm = v; bk = vk; bp = pp[gg * COUT + tid]; }
                             }
-                            S.carry_v[tid] = bm; S.carry_i[tid] = bi;
+                            S.carry_v[tid] = bm; S.carry_k[tid] = bk; S.carry_p[tid] = bp;
                         }
                         __syncthreads();
                     }
                 }
                 if (MODE == PFN_MODE_APPLY && tid < COUT) {
-                    a.features[(size_t)p * COUT + tid] = S.carry_v[tid];
-                    if (want_arg) a.argmax[(size_t)p * COUT + tid] = S.carry_i[tid];
+                    a.features[(size_t)pb * COUT + tid] = S.carry_v[tid];
+                    if (want_arg) a.argpos[(size_t)pb * COUT + tid] = S.carry_p[tid];
                 }
-                __syncthreads();
-                p += 1;
+                fence_proxy_async();  // generic-proxy writes to the stage buffer before a later TMA reuses it
             }
         }
+        __syncthreads();
     }
 
+    // ---- per-CTA partial sums
     if (MODE == PFN_MODE_STATS) {
-        // per-CTA partials: [sum x (COUT) | sum x^2 (COUT) | S2 upper + S1 (NPAIR)]
-        constexpr int PARTS = kPfnThreads / COUT;
-        double *red = S.red;  // kPfnThreads*3 doubles
-        red[tid] = st_x; red[kPfnThreads + tid] = st_x2;
+        // layout: [sum x (COUT) | sum x^2 (COUT) | NBLK blocks of 16]
+        double *out = a.partials + (size_t)blockIdx.x * Cfg::STATS_DOUBLES;
         __syncthreads();
-        double *out = a.partials + (size_t)blockIdx.x * (2 * COUT + NPAIR);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            dscr[(grp * COUT + quad * 4 + c) * 2] = st_x[c];
+            dscr[(grp * COUT + quad * 4 + c) * 2 + 1] = st_x2[c];
+        }
+        __syncthreads();
         if (tid < COUT) {
             double sx = 0.0, sx2 = 0.0;
-            for (int q = 0; q < PARTS; ++q) { sx += red[q * COUT + tid]; sx2 += red[kPfnThreads + q * COUT + tid]; }
+            for (int g = 0; g < GROUPS; ++g) { sx += dscr[(g * COUT + tid) * 2]; sx2 += dscr[(g * COUT + tid) * 2 + 1]; }
             out[tid] = sx; out[COUT + tid] = sx2;
         }
+        __syncthreads();
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            const int item = tid + u * kPfnThreads;
-            if (item < NPAIR) out[2 * COUT + item] = st_m[u];
+        for (int e = 0; e < 16; ++e) dscr[tid * 16 + e] = st_m[e];
+        __syncthreads();
+        for (int e = tid; e < Cfg::NBLK * 16; e += NT) {
+            const int blk = e / 16, el = e % 16;
+            double sacc = 0.0;
+            for (int g = 0; g < Cfg::RG; ++g) sacc += dscr[(blk * Cfg::RG + g) * 16 + el];
+            out[2 * COUT + e] = sacc;
+        }
+    }
+    if (MODE == PFN_MODE_BWD) {
+        // layout: per channel [dbeta | G | A(CS)]
+        constexpr int PER = Cfg::BWD_PER;
+        __syncthreads();
+#pragma unroll
+        for (int cc = 0; cc < CPL; ++cc) {
+            double *dst = dscr + ((size_t)warp * COUT + lane + 32 * cc) * PER;
+            dst[0] = dB[cc]; dst[1] = dG[cc];
+#pragma unroll
+            for (int k = 0; k < CS; ++k) dst[2 + k] = dA[cc][k];
+        }
+        __syncthreads();
+        double *out = a.partials + (size_t)blockIdx.x * Cfg::BWD_DOUBLES;
+        for (int e = tid; e < COUT * PER; e += NT) {
+            double sacc = 0.0;
+            for (int w = 0; w < NT / 32; ++w) sacc += dscr[(size_t)w * COUT * PER + e];
+            out[e] = sacc;
         }
     }
 }
 
 // ------------------------------------------------------------------------------------------- BN finalize (train)
-// One CTA.  Reduces the per-CTA partials in a fixed order (deterministic), folds the batch statistics into
-// scale/shift, updates the running statistics, and expands the feature moments for the backward.
+// Reduces the per-CTA partials in a fixed order (deterministic), folds the batch statistics into scale/shift,
+// updates the running statistics, and expands the feature moments for the backward.
 // bn_state = [mean(COUT) | var(COUT) | scale(COUT) | shift(COUT) | n | S1(CIN) | S2(CIN*CIN)]
 template <class Cfg>
-__global__ void __launch_bounds__(kPfnThreads) bn_finalize_kernel(const __grid_constant__ PfnArgs a, int nblocks, double *bn_state,
-                                                                 float *running_mean, float *running_var, double momentum) {
-    constexpr int COUT = Cfg::COUT, CS = Cfg::CS, NPAIR = CS * (CS + 1) / 2 + CS, TOT = 2 * COUT + NPAIR;
+__global__ void __launch_bounds__(256) bn_finalize_kernel(const __grid_constant__ PfnArgs a, int nblocks, double *bn_state,
+                                                         float *running_mean, float *running_var, double momentum) {
+    constexpr int COUT = Cfg::COUT, CS = Cfg::CS, TOT = Cfg::STATS_DOUBLES, T4 = Cfg::T4;
     __shared__ double tot[TOT];
     const int tid = threadIdx.x;
     const long long N = a.counters[RDP_CNT_N];
-    const int ntiles = (int)((N + kPfnTileRows - 1) / kPfnTileRows);
-    const int used = min(nblocks, ntiles);
-    for (int e = tid; e < TOT; e += kPfnThreads) {
+    for (int e = tid; e < TOT; e += blockDim.x) {
         double s = 0.0;
-        for (int b = 0; b < used; ++b) s += a.partials[(size_t)b * TOT + e];
+        for (int b = 0; b < nblocks; ++b) s += a.partials[(size_t)b * TOT + e];
         tot[e] = s;
     }
     __syncthreads();
@@ -478,113 +633,40 @@ __global__ void __launch_bounds__(kPfnThreads) bn_finalize_kernel(const __grid_c
         bn_state[2 * COUT + tid] = (double)sc;
         bn_state[3 * COUT + tid] = (double)sh;
         if (N > 1) {  // torch raises for N == 1 and leaves the buffers alone for N == 0
-            const double m = momentum;
-            running_mean[tid] = (float)((1.0 - m) * (double)running_mean[tid] + m * mean);
-            running_var[tid] = (float)((1.0 - m) * (double)running_var[tid] + m * var * (n / (n - 1.0)));
+            running_mean[tid] = (float)((1.0 - momentum) * (double)running_mean[tid] + momentum * mean);
+            running_var[tid] = (float)((1.0 - momentum) * (double)running_var[tid] + momentum * var * (n / (n - 1.0)));
         }
     }
     if (tid == 0) bn_state[4 * COUT] = (double)N;
     double *S1 = bn_state + 4 * COUT + 1, *S2 = S1 + cin;
-    for (int e = tid; e < NPAIR; e += kPfnThreads) {
-        if (e < CS * (CS + 1) / 2) {
-            int aa = 0, rem = e;
-            while (rem >= CS - aa) { rem -= CS - aa; ++aa; }
-            const int ka = a.kmap[aa], kb = a.kmap[aa + rem];
-            if (ka >= 0 && kb >= 0) { S2[ka * cin + kb] = tot[2 * COUT + e]; S2[kb * cin + ka] = tot[2 * COUT + e]; }
-        } else {
-            const int ka = a.kmap[e - CS * (CS + 1) / 2];
-            if (ka >= 0) S1[ka] = tot[2 * COUT + e];
-        }
+    // Gram entry of super features (fa <= fb): block (fa/4, fb/4), element (fa%4, fb%4)
+    auto gram_at = [&](int fa, int fb) {
+        const int ba = fa / 4, bb = fb / 4;
+        const int blk = ba * T4 - ba * (ba - 1) / 2 + (bb - ba);
+        return tot[2 * COUT + blk * 16 + (fa % 4) * 4 + (fb % 4)];
+    };
+    for (int e = tid; e < CS * CS; e += blockDim.x) {
+        const int fa = e / CS, fb = e % CS;
+        const int ka = a.kmap[fa], kb = a.kmap[fb];
+        if (ka >= 0 && kb >= 0) S2[ka * cin + kb] = fa <= fb ? gram_at(fa, fb) : gram_at(fb, fa);
     }
+    for (int fa = tid; fa < CS; fa += blockDim.x)
+        if (a.kmap[fa] >= 0) S1[a.kmap[fa]] = gram_at(fa, CS);
 }
 
-// ------------------------------------------------------------------------------------------- backward
-// warp = pillar, lane = channel (+32).  For every (pillar, channel): route g to the argmax row when the
-// output is positive (ReLU'), rebuild that row's features and pre-activation, and accumulate
-//   dbeta_c += gy,  G_c += gy * x_lin,  A_ck += gy * f_k.
-// per-CTA partials (fp64): [dbeta(COUT) | G(COUT) | A(COUT*CIN)]
-template <class Cfg>
-__global__ void __launch_bounds__(kPfnThreads) pfn_bwd_kernel(const __grid_constant__ PfnArgs a, const float *__restrict__ grad,
-                                                            const float *__restrict__ feat_out, const int32_t *__restrict__ arg,
-                                                            const float *__restrict__ pmean) {
-    constexpr int COUT = Cfg::COUT, CS = Cfg::CS, CPL = COUT / 32;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    double *red = reinterpret_cast<double *>(smem_raw);  // (kPfnThreads/32) * COUT * (CS+2)
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int P = a.counters[RDP_CNT_P];
-    const bool none_dropped = ((long long)a.counters[RDP_CNT_N] == a.n0);
-    float W[CPL][CS];
-#pragma unroll
-    for (int cc = 0; cc < CPL; ++cc)
-#pragma unroll
-        for (int s = 0; s < CS; ++s) {
-            const int k = a.kmap[s];
-            W[cc][s] = (k >= 0) ? __ldg(a.weight + (lane + 32 * cc) * a.c_in + k) : 0.0f;
-        }
-    double dA[CPL][CS], dB[CPL], dG[CPL];
-#pragma unroll
-    for (int cc = 0; cc < CPL; ++cc) {
-        dB[cc] = dG[cc] = 0.0;
-#pragma unroll
-        for (int s = 0; s < CS; ++s) dA[cc][s] = 0.0;
-    }
-    const int nwarps = gridDim.x * (kPfnThreads / 32);
-    for (int p = blockIdx.x * (kPfnThreads / 32) + warp; p < P; p += nwarps) {
-        const int32_t *co = a.coords + (size_t)p * a.coord_cols + (a.coord_cols - 2);
-        const float cenx = __fadd_rn(__fmul_rn((float)co[1], a.vsz[0]), a.off[0]);
-        const float ceny = __fadd_rn(__fmul_rn((float)co[0], a.vsz[1]), a.off[1]);
-        const float mean[3] = {pmean[(size_t)p * 3], pmean[(size_t)p * 3 + 1], pmean[(size_t)p * 3 + 2]};
-#pragma unroll
-        for (int cc = 0; cc < CPL; ++cc) {
-            const size_t o = (size_t)p * COUT + lane + 32 * cc;
-            const float out = feat_out[o];
-            const float gy = out > 0.0f ? grad[o] : 0.0f;
-            const int kj = arg[o];
-            const int row = none_dropped ? kj : a.kept2orig[kj];
-            float r[Cfg::COLS], f[CS];
-            load_row<Cfg>(a.pts, row, r);
-            decorate<Cfg>(r, cenx, ceny, mean, a, f);
-            float x = 0.0f;
-#pragma unroll
-            for (int k = 0; k < CS; ++k) x = fmaf(W[cc][k], f[k], x);
-            const double g = (double)gy;
-            dB[cc] += g;
-            dG[cc] = fma(g, (double)x, dG[cc]);
-#pragma unroll
-            for (int k = 0; k < CS; ++k) dA[cc][k] = fma(g, (double)f[k], dA[cc][k]);
-        }
-    }
-    // reduce the warps of this CTA
-    constexpr int PER = CS + 2;
-#pragma unroll
-    for (int cc = 0; cc < CPL; ++cc) {
-        double *dst = red + ((size_t)warp * COUT + lane + 32 * cc) * PER;
-        dst[0] = dB[cc]; dst[1] = dG[cc];
-#pragma unroll
-        for (int k = 0; k < CS; ++k) dst[2 + k] = dA[cc][k];
-    }
-    __syncthreads();
-    double *out = a.partials + (size_t)blockIdx.x * COUT * PER;
-    for (int e = tid; e < COUT * PER; e += kPfnThreads) {
-        double s = 0.0;
-        for (int w = 0; w < kPfnThreads / 32; ++w) s += red[(size_t)w * COUT * PER + e];
-        out[e] = s;
-    }
-}
-
-// One CTA: fixed-order reduction of the partials, then the closed-form BatchNorm backward:
+// One CTA: fixed-order reduction of the backward partials, then the closed-form BatchNorm backward:
 //   dgamma_c = (G_c - mu_c dbeta_c) / sigma_c
 //   dW_ck    = (gamma_c/sigma_c) [ A_ck - dbeta_c/N S1_k - dgamma_c/N ((S2 w_c)_k - mu_c S1_k)/sigma_c ]   (train)
 //   dW_ck    = (gamma_c/sigma_c) A_ck                                                                    (eval BN)
 template <class Cfg>
-__global__ void __launch_bounds__(kPfnThreads) bwd_finalize_kernel(const __grid_constant__ PfnArgs a, int nblocks, const double *bn_state,
-                                                                  int train_bn, float *d_weight, float *d_gamma, float *d_beta) {
-    constexpr int COUT = Cfg::COUT, CS = Cfg::CS, PER = CS + 2;
+__global__ void __launch_bounds__(256) bwd_finalize_kernel(const __grid_constant__ PfnArgs a, int nblocks, const double *bn_state,
+                                                          int train_bn, float *d_weight, float *d_gamma, float *d_beta) {
+    constexpr int COUT = Cfg::COUT, CS = Cfg::CS, PER = Cfg::BWD_PER;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *tot = reinterpret_cast<double *>(smem_raw);  // COUT*PER
     double *dgam = tot + COUT * PER;                       // COUT
     const int tid = threadIdx.x, cin = a.c_in;
-    for (int e = tid; e < COUT * PER; e += kPfnThreads) {
+    for (int e = tid; e < COUT * PER; e += blockDim.x) {
         double s = 0.0;
         for (int b = 0; b < nblocks; ++b) s += a.partials[(size_t)b * COUT * PER + e];
         tot[e] = s;
@@ -609,7 +691,7 @@ __global__ void __launch_bounds__(kPfnThreads) bwd_finalize_kernel(const __grid_
     }
     __syncthreads();
     const double *S1 = bn_state ? bn_state + 4 * COUT + 1 : nullptr, *S2 = S1 ? S1 + cin : nullptr;
-    for (int e = tid; e < COUT * CS; e += kPfnThreads) {
+    for (int e = tid; e < COUT * CS; e += blockDim.x) {
         const int c = e / CS, s = e % CS, k = a.kmap[s];
         if (k < 0) continue;
         double mu, is;

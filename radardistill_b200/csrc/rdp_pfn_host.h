@@ -6,12 +6,9 @@ namespace rdp {
 
 struct PfnLaunch {
     int cols, layout, dist, cout, cs;
-    size_t fwd_smem, bwd_smem, bwdfin_smem;
     int stats_partial_doubles, bwd_partial_doubles;
-    cudaError_t (*fwd)(const PfnArgs &a, int mode, int grid, cudaStream_t st);
+    cudaError_t (*tile)(const PfnArgs &a, int mode, int grid, cudaStream_t st);
     cudaError_t (*bn_finalize)(const PfnArgs &a, int nblocks, double *bn_state, float *rm, float *rv, double momentum, cudaStream_t st);
-    cudaError_t (*bwd)(const PfnArgs &a, int grid, const float *grad, const float *feat, const int32_t *arg, const float *pmean,
-                       cudaStream_t st);
     cudaError_t (*bwd_finalize)(const PfnArgs &a, int nblocks, const double *bn_state, int train_bn, float *dW, float *dg, float *db,
                                 cudaStream_t st);
 };

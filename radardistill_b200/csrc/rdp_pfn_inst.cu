@@ -7,47 +7,39 @@
 
 namespace rdp {
 
-#define RDP_PICK(id, cols, layout, dist, cout)                      \
-    template <> struct CfgOf<id> { using type = PfnCfg<cols, layout, dist, cout>; };
 template <int ID> struct CfgOf;
+#define RDP_PICK(id, cols, layout, dist, cout) \
+    template <> struct CfgOf<id> { using type = PfnCfg<cols, layout, dist, cout>; };
 RDP_PFN_CONFIGS(RDP_PICK)
 #undef RDP_PICK
 
 using Cfg = CfgOf<RDP_CFG_ID>::type;
 
-static cudaError_t fwd(const PfnArgs &a, int mode, int grid, cudaStream_t st) {
-    const size_t smem = sizeof(PfnSmem<Cfg>);
-    if (mode == PFN_MODE_STATS) {
-        cudaError_t e = cudaFuncSetAttribute(pfn_fwd_kernel<Cfg, PFN_MODE_STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        pfn_fwd_kernel<Cfg, PFN_MODE_STATS><<<grid, kPfnThreads, smem, st>>>(a);
-    } else {
-        cudaError_t e = cudaFuncSetAttribute(pfn_fwd_kernel<Cfg, PFN_MODE_APPLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        pfn_fwd_kernel<Cfg, PFN_MODE_APPLY><<<grid, kPfnThreads, smem, st>>>(a);
-    }
+template <int MODE>
+static cudaError_t launch_tile(const PfnArgs &a, int grid, cudaStream_t st) {
+    const size_t smem = sizeof(PfnSmem<Cfg, MODE>);
+    cudaError_t e = cudaFuncSetAttribute(pfn_tile_kernel<Cfg, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    pfn_tile_kernel<Cfg, MODE><<<grid, kPfnThreads, smem, st>>>(a);
     return cudaGetLastError();
+}
+
+static cudaError_t tile(const PfnArgs &a, int mode, int grid, cudaStream_t st) {
+    if (mode == PFN_MODE_STATS) return launch_tile<PFN_MODE_STATS>(a, grid, st);
+    if (mode == PFN_MODE_BWD) return launch_tile<PFN_MODE_BWD>(a, grid, st);
+    return launch_tile<PFN_MODE_APPLY>(a, grid, st);
 }
 
 static cudaError_t bn_finalize(const PfnArgs &a, int nblocks, double *bn_state, float *rm, float *rv, double momentum, cudaStream_t st) {
-    bn_finalize_kernel<Cfg><<<1, kPfnThreads, 0, st>>>(a, nblocks, bn_state, rm, rv, momentum);
+    bn_finalize_kernel<Cfg><<<1, 256, 0, st>>>(a, nblocks, bn_state, rm, rv, momentum);
     return cudaGetLastError();
 }
 
-constexpr size_t kBwdSmem = sizeof(double) * (kPfnThreads / 32) * Cfg::COUT * (Cfg::CS + 2);
-constexpr size_t kBwdFinSmem = sizeof(double) * (Cfg::COUT * (Cfg::CS + 2) + Cfg::COUT);
-
-static cudaError_t bwd(const PfnArgs &a, int grid, const float *grad, const float *feat, const int32_t *arg, const float *pmean,
-                       cudaStream_t st) {
-    cudaError_t e = cudaFuncSetAttribute(pfn_bwd_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmem);
-    if (e != cudaSuccess) return e;
-    pfn_bwd_kernel<Cfg><<<grid, kPfnThreads, kBwdSmem, st>>>(a, grad, feat, arg, pmean);
-    return cudaGetLastError();
-}
+constexpr size_t kBwdFinSmem = sizeof(double) * (Cfg::BWD_DOUBLES + Cfg::COUT);
 
 static cudaError_t bwd_finalize(const PfnArgs &a, int nblocks, const double *bn_state, int train_bn, float *dW, float *dg, float *db,
                                 cudaStream_t st) {
-    bwd_finalize_kernel<Cfg><<<1, kPfnThreads, kBwdFinSmem, st>>>(a, nblocks, bn_state, train_bn, dW, dg, db);
+    bwd_finalize_kernel<Cfg><<<1, 256, kBwdFinSmem, st>>>(a, nblocks, bn_state, train_bn, dW, dg, db);
     return cudaGetLastError();
 }
 
@@ -55,9 +47,7 @@ static cudaError_t bwd_finalize(const PfnArgs &a, int nblocks, const double *bn_
 #define RDP_CAT(a, b) RDP_CAT2(a, b)
 const PfnLaunch *RDP_CAT(rdp_pfn_cfg_, RDP_CFG_ID)() {
     static const PfnLaunch L = {Cfg::COLS, Cfg::LAYOUT, Cfg::DIST ? 1 : 0, Cfg::COUT, Cfg::CS,
-                                sizeof(PfnSmem<Cfg>), kBwdSmem, kBwdFinSmem,
-                                2 * Cfg::COUT + Cfg::CS * (Cfg::CS + 1) / 2 + Cfg::CS, Cfg::COUT * (Cfg::CS + 2),
-                                fwd, bn_finalize, bwd, bwd_finalize};
+                                Cfg::STATS_DOUBLES, Cfg::BWD_DOUBLES, tile, bn_finalize, bwd_finalize};
     return &L;
 }
 

@@ -77,14 +77,34 @@ class EncodeResult:
     coords: torch.Tensor              # (P, coord_cols) int32
     inverse: torch.Tensor             # (N,) int32   pillar of each KEPT point (torch.unique's inverse)
     counts: torch.Tensor              # (P,) int32
-    argmax: Optional[torch.Tensor]    # (P, c_out) int32 kept-point index, training only
+    argpos: Optional[torch.Tensor]    # (P, c_out) int32 winning row as a position in the grouped order (internal)
     n_kept: int
     n_pillars: int
-    # state for the backward
+    # state for the backward / inspection
     pillar_mean: Optional[torch.Tensor] = None
     bn_state: Optional[torch.Tensor] = None
     workspace: Optional[torch.Tensor] = None
     counters: Optional[torch.Tensor] = None
+    spec: Optional["EncoderSpec"] = None
+    batch_size: int = 1
+    n_points: int = 0
+    _argmax: Optional[torch.Tensor] = None
+
+    @property
+    def argmax(self) -> Optional[torch.Tensor]:
+        """scatter_max's argmax in the reference's numbering: (P, c_out) int32 index among the KEPT points."""
+        if self.argpos is None:
+            return None
+        if self._argmax is None:
+            lib = _lib.load()
+            out = torch.empty((max(self.n_pillars, 1), self.spec.c_out), dtype=torch.int32, device=self.argpos.device)
+            with torch.cuda.device(self.argpos.device):
+                geom, layout = self.spec.geom(self.batch_size), self.spec.layout_struct()
+                _lib.check(lib.rdp_argmax_kept(self.n_points, C.byref(geom), C.byref(layout), _ptr(self.workspace),
+                                               self.workspace.numel(), _ptr(self.counters), _ptr(self.argpos), _ptr(out),
+                                               _stream_ptr()), "rdp_argmax_kept")
+            self._argmax = out[:self.n_pillars]
+        return self._argmax
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -161,8 +181,8 @@ def encode_forward(points: torch.Tensor, spec: EncoderSpec, batch_size: int, wei
         counts = torch.empty(cap + 4, dtype=torch.int32, device=dev)
         counters = torch.empty(_lib.RDP_NUM_COUNTERS, dtype=torch.int32, device=dev)
         features = torch.empty((cap, spec.c_out), dtype=torch.float32, device=dev)
-        argmax = torch.empty((cap, spec.c_out), dtype=torch.int32, device=dev) if want_argmax else None
-        pmean = torch.empty((cap, 3), dtype=torch.float32, device=dev) if want_argmax else None
+        argpos = torch.empty((cap, spec.c_out), dtype=torch.int32, device=dev) if want_argmax else None
+        pmean = None
         bn_state = None
         if train_bn:
             bn_state = torch.zeros(int(lib.rdp_bn_state_doubles(C.byref(layout))), dtype=torch.float64, device=dev)
@@ -171,7 +191,7 @@ def encode_forward(points: torch.Tensor, spec: EncoderSpec, batch_size: int, wei
                                      _ptr(inverse), _ptr(counts), _ptr(counters), st), "rdp_index_fwd")
         prm = _params_struct(spec, weight, bias, gamma, beta, running_mean, running_var, train_bn)
         _lib.check(lib.rdp_pfn_fwd(_ptr(pts), n0, C.byref(geom), C.byref(layout), C.byref(prm), _ptr(ws), nbytes.value,
-                                   _ptr(counters), _ptr(coords), _ptr(features), _ptr(argmax), _ptr(pmean), _ptr(bn_state), st),
+                                   _ptr(counters), _ptr(features), _ptr(argpos), _ptr(pmean), _ptr(bn_state), st),
                    "rdp_pfn_fwd")
         host = _pinned_counters(dev)
         host.copy_(counters, non_blocking=True)
@@ -180,9 +200,9 @@ def encode_forward(points: torch.Tensor, spec: EncoderSpec, batch_size: int, wei
     if err & 1:
         raise ValueError(f"points[:, 0] holds a batch index outside [0, {batch_size})")
     return EncodeResult(features=features[:n_pillars], coords=coords[:n_pillars], inverse=inverse[:n_kept],
-                        counts=counts[:n_pillars], argmax=None if argmax is None else argmax[:n_pillars],
+                        counts=counts[:n_pillars], argpos=None if argpos is None else argpos[:n_pillars],
                         n_kept=n_kept, n_pillars=n_pillars, pillar_mean=pmean, bn_state=bn_state, workspace=ws,
-                        counters=counters)
+                        counters=counters, spec=spec, batch_size=int(batch_size), n_points=int(n0))
 
 
 def encode_backward(points: torch.Tensor, spec: EncoderSpec, batch_size: int, res: EncodeResult, grad_features, weight,
@@ -202,9 +222,9 @@ def encode_backward(points: torch.Tensor, spec: EncoderSpec, batch_size: int, re
                              running_mean, running_var, bool(train_bn and use_norm))
         feats = res.features if res.features.is_contiguous() else res.features.contiguous()
         _lib.check(lib.rdp_pfn_bwd(_ptr(points), points.shape[0], C.byref(geom), C.byref(layout), C.byref(prm),
-                                   _ptr(res.workspace), res.workspace.numel(), _ptr(res.counters), _ptr(res.coords), _ptr(g),
-                                   _ptr(feats), _ptr(res.argmax), _ptr(res.pillar_mean), _ptr(res.bn_state), _ptr(d_w),
-                                   _ptr(d_g), _ptr(d_b), res.n_pillars, _stream_ptr()), "rdp_pfn_bwd")
+                                   _ptr(res.workspace), res.workspace.numel(), _ptr(res.counters), _ptr(g),
+                                   _ptr(feats), _ptr(res.argpos), _ptr(res.bn_state), _ptr(d_w),
+                                   _ptr(d_g), _ptr(d_b), _stream_ptr()), "rdp_pfn_bwd")
     return d_w, d_g, d_b
 
 
@@ -231,7 +251,7 @@ class _PillarEncodeFn(torch.autograd.Function):
     def backward(ctx, grad_features, _grad_coords):
         weight, bias, gamma, beta = ctx.saved_tensors
         res = ctx.res
-        if res.argmax is None:
+        if res.argpos is None:
             raise RuntimeError("backward through a forward that ran without requires_grad parameters")
         d_w, d_g, d_b = encode_backward(ctx.points, ctx.spec, ctx.batch_size, res, grad_features, weight, bias, gamma, beta,
                                         ctx.rm, ctx.rv, ctx.train_bn)
@@ -249,8 +269,7 @@ def encode(points, spec: EncoderSpec, batch_size: int, weight, bias=None, gamma=
         feats, coords = _PillarEncodeFn.apply(points, weight, bias, gamma, beta, running_mean, running_var, spec, batch_size,
                                               train_bn, holder)
         res = holder[0]
-        return EncodeResult(features=feats, coords=coords, inverse=res.inverse, counts=res.counts, argmax=res.argmax,
-                            n_kept=res.n_kept, n_pillars=res.n_pillars, pillar_mean=res.pillar_mean, bn_state=res.bn_state,
-                            workspace=res.workspace, counters=res.counters)
+        import dataclasses
+        return dataclasses.replace(res, features=feats, coords=coords)
     return encode_forward(points, spec, batch_size, weight, bias, gamma, beta, running_mean, running_var, train_bn,
                           want_argmax=False)
