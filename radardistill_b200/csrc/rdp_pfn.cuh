@@ -15,10 +15,10 @@
 //   P1  row -> pillar slot, pillar start table                                         (thread = row)
 //   P2  per-pillar fp64 xyz sum -> mean (one rounding), pillar centre                  (thread = pillar)
 //   C1  decorated features (same op order / roundings as the reference) -> smem        (thread = row)
-//   C2  x = W f as a k-ascending fmaf chain, weight rows in registers, 4 channels x 12 rows per thread;
-//       y = fma(x, scale, shift)                                                       (register tile)
-//   D   APPLY: max over each pillar's rows (+ lowest-index argmax) -> coalesced 16 B stores
-//       STATS: fp64 sum x, sum x^2 and the Gram matrix of the features (4x4 register blocks)
+//   ST  lane = output channel, its weight row in registers; each warp streams a pillar-aligned quarter of the
+//       tile's rows: x = W f as a k-ascending fmaf chain (feature row broadcast from smem), y = fma(x, scale,
+//       shift), running max (+ lowest-index argmax), one coalesced 128 B store when a pillar's last row is in.
+//       STATS: fp64 sum x, sum x^2 per lane and the Gram matrix of the features (4x4 register blocks)
 //       BWD  : per (pillar, channel) route the gradient to the winning row and accumulate dbeta, G, A
 // Arithmetic is the canonical form of oracle/pillar_oracle.c (ORC_MEAN_F64): outputs are bit-identical to it.
 #pragma once
@@ -85,16 +85,16 @@ struct PfnStage {
 
 template <class Cfg, int MODE>
 struct PfnSmem {
-    static constexpr size_t Z_BYTES = (MODE == PFN_MODE_APPLY) ? sizeof(float) * kPfnCap * Cfg::ZSTRIDE : 0;
+    static constexpr size_t Z_BYTES = 16;
     static constexpr size_t S_BYTES = (MODE == PFN_MODE_STATS) ? sizeof(double) * kPfnThreads * 16 : 0;
     static constexpr size_t B_BYTES = (MODE == PFN_MODE_BWD) ? sizeof(double) * (kPfnThreads / 32) * Cfg::BWD_DOUBLES : 0;
     static constexpr size_t SCR = Z_BYTES > S_BYTES ? (Z_BYTES > B_BYTES ? Z_BYTES : B_BYTES) : (S_BYTES > B_BYTES ? S_BYTES : B_BYTES);
     PfnStage<Cfg> st[2];
     alignas(8) uint64_t full[2];
-    alignas(16) float f[kPfnCap * Cfg::FSTRIDE];   // decorated features; big-pillar partials alias it after C2
-    alignas(16) unsigned char scr[SCR];            // APPLY: activations z; STATS / BWD: fp64 reduction scratch
+    alignas(16) float f[kPfnCap * Cfg::FSTRIDE];   // decorated features of the tile's rows
+    alignas(16) unsigned char scr[SCR];            // STATS / BWD: fp64 reduction scratch at kernel end
     int start[kPfnCap + 1];
-    int lp[kPfnCap];
+    int lp[kPfnCap];                               // (pillar slot << 1) | last-row-of-pillar flag
     int kept[kPfnCap];
     float mean[kPfnCap * 3];
     float cen[kPfnCap * 2];
@@ -155,12 +155,12 @@ __device__ __forceinline__ int warp_max(int v) { return __reduce_max_sync(0xffff
 
 // ------------------------------------------------------------------------------------------- the tile kernel
 template <class Cfg, int MODE>
-__global__ void __launch_bounds__(kPfnThreads, 3) pfn_tile_kernel(const __grid_constant__ PfnArgs a) {
+__global__ void __launch_bounds__(kPfnThreads, 4) pfn_tile_kernel(const __grid_constant__ PfnArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     using Smem = PfnSmem<Cfg, MODE>;
     Smem &S = *reinterpret_cast<Smem *>(smem_raw);
-    constexpr int COUT = Cfg::COUT, CS = Cfg::CS, COLS = Cfg::COLS, QUADS = Cfg::QUADS, GROUPS = Cfg::GROUPS;
-    constexpr int WIN = kPfnWin, CAP = kPfnCap, NT = kPfnThreads, INF = 0x7fffffff;
+    constexpr int COUT = Cfg::COUT, CS = Cfg::CS, COLS = Cfg::COLS, CPL = COUT / 32;
+    constexpr int WIN = kPfnWin, CAP = kPfnCap, NT = kPfnThreads, NW = kPfnThreads / 32, INF = 0x7fffffff;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long long N = a.counters[RDP_CNT_N];
     const bool none_dropped = (N == a.n0);
@@ -168,7 +168,6 @@ __global__ void __launch_bounds__(kPfnThreads, 3) pfn_tile_kernel(const __grid_c
     const int per = (ntiles + (int)gridDim.x - 1) / (int)gridDim.x;
     const int t_begin = min(ntiles, (int)blockIdx.x * per), t_end = min(ntiles, t_begin + per);
     const bool want_arg = (MODE == PFN_MODE_APPLY) && a.argpos != nullptr;
-    float *sz = reinterpret_cast<float *>(S.scr);
     double *dscr = reinterpret_cast<double *>(S.scr);
 
     // ---- per-CTA constants
@@ -177,46 +176,41 @@ __global__ void __launch_bounds__(kPfnThreads, 3) pfn_tile_kernel(const __grid_c
         mbar_init(&S.full[1], 1);
         fence_mbar_init();
     }
-    if (MODE != PFN_MODE_BWD && tid < COUT) {
-        float sc = 1.0f, sh = a.bias ? a.bias[tid] : 0.0f;
-        if (a.use_norm) {
-            if (a.fold_from_state) { sc = (float)a.bn_state[2 * COUT + tid]; sh = (float)a.bn_state[3 * COUT + tid]; }
-            else fold_bn((double)a.gamma[tid], (double)a.beta[tid], (double)a.rmean[tid], (double)a.rvar[tid], a.eps, &sc, &sh);
-        }
-        S.scale[tid] = sc;
-        S.shift[tid] = sh;
-    }
-    // weight rows in registers: FWD: my channel quad (4 x CS);  BWD: my channel(s) (COUT/32 x CS)
-    constexpr int WR = (MODE == PFN_MODE_BWD) ? COUT / 32 : 4;
-    const int quad = tid % QUADS, grp = tid / QUADS;
-    float W[WR][CS];
+    // lane = output channel (+32): its weight row(s) live in registers for the whole kernel
+    float W[CPL][CS], sc[CPL], sh[CPL];
 #pragma unroll
-    for (int j = 0; j < WR; ++j)
+    for (int cc = 0; cc < CPL; ++cc) {
+        const int ch = lane + 32 * cc;
 #pragma unroll
         for (int s = 0; s < CS; ++s) {
             const int k = a.kmap[s];
-            const int ch = (MODE == PFN_MODE_BWD) ? (lane + 32 * j) : (quad * 4 + j);
-            W[j][s] = (k >= 0) ? __ldg(a.weight + ch * a.c_in + k) : 0.0f;
+            W[cc][s] = (k >= 0) ? __ldg(a.weight + ch * a.c_in + k) : 0.0f;
         }
-    __syncthreads();
-    float sc4[4], sh4[4];
-    if (MODE != PFN_MODE_BWD) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) { sc4[j] = S.scale[quad * 4 + j]; sh4[j] = S.shift[quad * 4 + j]; }
+        sc[cc] = 1.0f;
+        sh[cc] = 0.0f;
+        if (MODE == PFN_MODE_APPLY) {
+            if (a.bias) sh[cc] = a.bias[ch];
+            if (a.use_norm) {
+                if (a.fold_from_state) { sc[cc] = (float)a.bn_state[2 * COUT + ch]; sh[cc] = (float)a.bn_state[3 * COUT + ch]; }
+                else fold_bn((double)a.gamma[ch], (double)a.beta[ch], (double)a.rmean[ch], (double)a.rvar[ch], a.eps, &sc[cc], &sh[cc]);
+            }
+        }
     }
+    __syncthreads();
 
     // ---- accumulators that live for the whole CTA
-    double st_x[4] = {0, 0, 0, 0}, st_x2[4] = {0, 0, 0, 0}, st_m[16];
+    double st_x[CPL], st_x2[CPL], st_m[16];
     int gba = 0, gbb = 0;
     const int grg = tid % Cfg::RG, gblk = tid / Cfg::RG;
     if (MODE == PFN_MODE_STATS) {
+#pragma unroll
+        for (int cc = 0; cc < CPL; ++cc) st_x[cc] = st_x2[cc] = 0.0;
 #pragma unroll
         for (int e = 0; e < 16; ++e) st_m[e] = 0.0;
         int rem = gblk;
         while (gba < Cfg::T4 && rem >= Cfg::T4 - gba) { rem -= Cfg::T4 - gba; ++gba; }
         gbb = gba + rem;  // block (gba, gbb), gba <= gbb, valid when gblk < NBLK
     }
-    constexpr int CPL = COUT / 32;
     double dB[CPL], dG[CPL], dA[CPL][CS];
     if (MODE == PFN_MODE_BWD) {
 #pragma unroll
@@ -242,7 +236,7 @@ __global__ void __launch_bounds__(kPfnThreads, 3) pfn_tile_kernel(const __grid_c
             const float *src = rows + (rowbase + jj) * COLS;
 #pragma unroll
             for (int c = 0; c < COLS; ++c) r[c] = src[c];
-            const int lp = S.lp[jj];
+            const int lp = S.lp[jj] >> 1;
             decorate<Cfg>(r, S.cen[lp * 2], S.cen[lp * 2 + 1], &S.mean[lp * 3], a, f);
             f[CS] = 1.0f;  // ones column: the Gram matrix then carries sum f (S1) as well
 #pragma unroll
@@ -253,36 +247,95 @@ __global__ void __launch_bounds__(kPfnThreads, 3) pfn_tile_kernel(const __grid_c
         }
     };
 
-    // C2: rows grp + GROUPS*r, channels quad*4..+3
-    auto c2 = [&](int np) {
-#pragma unroll 2
-        for (int r = 0; r < Cfg::RPT; ++r) {
-            const int j = grp + GROUPS * r;
-            if (j < np) {
-                float f[Cfg::FW];
-                const float4 *src = reinterpret_cast<const float4 *>(&S.f[j * Cfg::FSTRIDE]);
+    // x[cc] = W[cc] . f(row j) as a k-ascending fmaf chain
+    auto dot_row = [&](int j, float *x) {
+        float f[Cfg::FW];
+        const float4 *src = reinterpret_cast<const float4 *>(&S.f[j * Cfg::FSTRIDE]);
 #pragma unroll
-                for (int k4 = 0; k4 < (CS + 3) / 4; ++k4) {
-                    const float4 v = src[k4];
-                    f[k4 * 4] = v.x; f[k4 * 4 + 1] = v.y; f[k4 * 4 + 2] = v.z; f[k4 * 4 + 3] = v.w;
+        for (int k4 = 0; k4 < (CS + 3) / 4; ++k4) {
+            const float4 v = src[k4];
+            f[k4 * 4] = v.x; f[k4 * 4 + 1] = v.y; f[k4 * 4 + 2] = v.z; f[k4 * 4 + 3] = v.w;
+        }
+#pragma unroll
+        for (int cc = 0; cc < CPL; ++cc) {
+            float acc = 0.0f;
+#pragma unroll
+            for (int k = 0; k < CS; ++k) acc = fmaf(W[cc][k], f[k], acc);
+            x[cc] = acc;
+        }
+    };
+
+    // running max state of the pillar a warp is streaming (lane = channel)
+    float m[CPL];
+    int mk[CPL], mp[CPL];
+    auto reset_max = [&]() {
+#pragma unroll
+        for (int cc = 0; cc < CPL; ++cc) { m[cc] = want_arg ? -1.0f : 0.0f; mk[cc] = INF; mp[cc] = 0; }
+    };
+    auto fold_max = [&](const float *x, int kj, int pos) {
+#pragma unroll
+        for (int cc = 0; cc < CPL; ++cc) {
+            const float y = fmaf(x[cc], sc[cc], sh[cc]);
+            if (!want_arg) {
+                m[cc] = fmaxf(m[cc], y);  // ReLU folds into the max with 0
+            } else {
+                const float z = fmaxf(y, 0.0f);
+                if (z > m[cc] || (z == m[cc] && kj < mk[cc])) { m[cc] = z; mk[cc] = kj; mp[cc] = pos; }
+            }
+        }
+    };
+
+    // STREAM: warp w walks rows [ra, rb) of S.f; APPLY keeps the running max and stores a pillar when its last row
+    // has been folded in (S.lp[j] = (pillar slot << 1) | last-row flag); STATS accumulates sum x / sum x^2.
+    auto stream = [&](int ra, int rb, int ps, int gb) {
+        if (MODE == PFN_MODE_APPLY) reset_max();
+        int j = ra;
+        for (; j + 1 < rb; j += 2) {  // two rows in flight: two independent fmaf chains per channel
+            float x0[CPL], x1[CPL];
+            dot_row(j, x0);
+            dot_row(j + 1, x1);
+            if (MODE == PFN_MODE_STATS) {
+#pragma unroll
+                for (int cc = 0; cc < CPL; ++cc) {
+                    const double v0 = (double)x0[cc], v1 = (double)x1[cc];
+                    st_x[cc] += v0; st_x2[cc] = fma(v0, v0, st_x2[cc]);
+                    st_x[cc] += v1; st_x2[cc] = fma(v1, v1, st_x2[cc]);
                 }
-                float o[4];
+            } else {
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    float acc = 0.0f;
+                for (int h = 0; h < 2; ++h) {
+                    const int jj = j + h, meta = S.lp[jj];
+                    fold_max(h ? x1 : x0, want_arg ? S.kept[jj] : 0, gb + jj);
+                    if (meta & 1) {
 #pragma unroll
-                    for (int k = 0; k < CS; ++k) acc = fmaf(W[c][k], f[k], acc);
-                    if (MODE == PFN_MODE_STATS) {
-                        const double v = (double)acc;
-                        st_x[c] += v;
-                        st_x2[c] = fma(v, v, st_x2[c]);
-                    } else {
-                        const float y = fmaf(acc, sc4[c], sh4[c]);
-                        o[c] = want_arg ? fmaxf(y, 0.0f) : y;  // eval: ReLU folds into the max with 0
+                        for (int cc = 0; cc < CPL; ++cc) {
+                            const size_t o = (size_t)(ps + (meta >> 1)) * COUT + lane + 32 * cc;
+                            a.features[o] = m[cc];
+                            if (want_arg) a.argpos[o] = mp[cc];
+                        }
+                        reset_max();
                     }
                 }
-                if (MODE == PFN_MODE_APPLY)
-                    *reinterpret_cast<float4 *>(&sz[j * Cfg::ZSTRIDE + quad * 4]) = make_float4(o[0], o[1], o[2], o[3]);
+            }
+        }
+        if (j < rb) {
+            float x0[CPL];
+            dot_row(j, x0);
+            if (MODE == PFN_MODE_STATS) {
+#pragma unroll
+                for (int cc = 0; cc < CPL; ++cc) { const double v0 = (double)x0[cc]; st_x[cc] += v0; st_x2[cc] = fma(v0, v0, st_x2[cc]); }
+            } else {
+                const int meta = S.lp[j];
+                fold_max(x0, want_arg ? S.kept[j] : 0, gb + j);
+                if (meta & 1) {
+#pragma unroll
+                    for (int cc = 0; cc < CPL; ++cc) {
+                        const size_t o = (size_t)(ps + (meta >> 1)) * COUT + lane + 32 * cc;
+                        a.features[o] = m[cc];
+                        if (want_arg) a.argpos[o] = mp[cc];
+                    }
+                    reset_max();
+                }
             }
         }
     };
@@ -330,24 +383,26 @@ __global__ void __launch_bounds__(kPfnThreads, 3) pfn_tile_kernel(const __grid_c
         __syncthreads();
         jmin = INF; jend = INF; jlast = -1;
 #pragma unroll
-        for (int w = 0; w < NT / 32; ++w) { jmin = min(jmin, S.wred[0][w]); jend = min(jend, S.wred[1][w]); jlast = max(jlast, S.wred[2][w]); }
+        for (int w = 0; w < NW; ++w) { jmin = min(jmin, S.wred[0][w]); jend = min(jend, S.wred[1][w]); jlast = max(jlast, S.wred[2][w]); }
         if (jmin == INF) { __syncthreads(); continue; }  // a pillar from an earlier tile covers the whole window
         const bool big = (jend == INF);                   // the last pillar runs past the staged rows
         const int j0 = jmin, jstop = big ? jlast : jend, np = jstop - j0;
         const int ps = T.gp[j0 + 4];
         const int nb = np > 0 ? T.gp[jstop - 1 + 4] - ps + 1 : 0;
+        const int gb = (int)base + j0;
 
         if (np > 0) {
-            // ---- P1
+            // ---- P1: row -> (pillar slot, last-row flag); pillar start table
             for (int jj = tid; jj < np; jj += NT) {
                 const int j = j0 + jj, gid = T.gp[j + 4];
-                S.lp[jj] = gid - ps;
+                const int last = (jj == np - 1) || (T.gp[j + 5] != gid);
+                S.lp[jj] = ((gid - ps) << 1) | last;
                 if (gid != T.gp[j + 3]) S.start[gid - ps] = jj;
                 if (want_arg) { const int row = T.ord[j]; S.kept[jj] = none_dropped ? row : a.orig2kept[row]; }
             }
             if (tid == 0) S.start[nb] = np;
             __syncthreads();
-            // ---- P2
+            // ---- P2: per-pillar mean and centre
             for (int q = tid; q < nb; q += NT) {
                 const int b0 = S.start[q], b1 = S.start[q + 1];
                 double sx = 0.0, sy = 0.0, sz3 = 0.0;
@@ -368,40 +423,13 @@ __global__ void __launch_bounds__(kPfnThreads, 3) pfn_tile_kernel(const __grid_c
             __syncthreads();
             c1(T.rows, j0, np);
             __syncthreads();
-            if (MODE == PFN_MODE_APPLY) {
-                c2(np);
-                __syncthreads();
-                // ---- D
-                for (int item = tid; item < nb * QUADS; item += NT) {
-                    const int q = item / QUADS, qd = item % QUADS;
-                    const int b0 = S.start[q], b1 = S.start[q + 1];
-                    if (!want_arg) {
-                        float4 m = make_float4(0.f, 0.f, 0.f, 0.f);
-                        for (int j = b0; j < b1; ++j) {
-                            const float4 v = *reinterpret_cast<const float4 *>(&sz[j * Cfg::ZSTRIDE + qd * 4]);
-                            m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
-                        }
-                        *reinterpret_cast<float4 *>(a.features + (size_t)(ps + q) * COUT + qd * 4) = m;
-                    } else {
-                        float m[4] = {-1.f, -1.f, -1.f, -1.f};
-                        int mk[4] = {INF, INF, INF, INF}, mp[4] = {0, 0, 0, 0};
-                        for (int j = b0; j < b1; ++j) {
-                            const float4 v4 = *reinterpret_cast<const float4 *>(&sz[j * Cfg::ZSTRIDE + qd * 4]);
-                            const float v[4] = {v4.x, v4.y, v4.z, v4.w};
-                            const int kj = S.kept[j];
-#pragma unroll
-                            for (int c = 0; c < 4; ++c)
-                                if (v[c] > m[c] || (v[c] == m[c] && kj < mk[c])) { m[c] = v[c]; mk[c] = kj; mp[c] = j; }
-                        }
-                        const int gb = (int)base + j0;
-                        *reinterpret_cast<float4 *>(a.features + (size_t)(ps + q) * COUT + qd * 4) = make_float4(m[0], m[1], m[2], m[3]);
-                        *reinterpret_cast<int4 *>(a.argpos + (size_t)(ps + q) * COUT + qd * 4) =
-                            make_int4(gb + mp[0], gb + mp[1], gb + mp[2], gb + mp[3]);
-                    }
-                }
-            } else if (MODE == PFN_MODE_STATS) {
-                gram(np);
-                c2(np);
+            if (MODE != PFN_MODE_BWD) {
+                // warp w streams a pillar-aligned quarter of the rows
+                const int r_lo = (warp * np) / NW, r_hi = ((warp + 1) * np) / NW;
+                const int ra = (warp == 0) ? 0 : S.start[S.lp[r_lo] >> 1];
+                const int rb = (warp == NW - 1) ? np : S.start[S.lp[r_hi] >> 1];
+                if (MODE == PFN_MODE_STATS) gram(np);
+                stream(ra, rb, ps, gb);
             } else {
                 // ---- E (backward): warp = pillar, lane = channel
                 float tB[CPL], tG[CPL], tA[CPL][CS];
@@ -411,8 +439,7 @@ __global__ void __launch_bounds__(kPfnThreads, 3) pfn_tile_kernel(const __grid_c
 #pragma unroll
                     for (int k = 0; k < CS; ++k) tA[cc][k] = 0.0f;
                 }
-                const int gb = (int)base + j0;
-                for (int q = warp; q < nb; q += NT / 32) {
+                for (int q = warp; q < nb; q += NW) {
 #pragma unroll
                     for (int cc = 0; cc < CPL; ++cc) {
                         const size_t o = (size_t)(ps + q) * COUT + lane + 32 * cc;
@@ -460,9 +487,9 @@ __global__ void __launch_bounds__(kPfnThreads, 3) pfn_tile_kernel(const __grid_c
             if (tid < 3) {
                 double tsum = 0.0;  // fp64 adds of fp32 values in this range are exact: order is immaterial
                 for (int j = 0; j < NT; ++j) tsum += S.dred[j * 3 + tid];
-                const float m = (float)__ddiv_rn(tsum, (double)(e - a0));
-                S.mean[tid] = m;
-                if (MODE == PFN_MODE_APPLY && a.pillar_mean) a.pillar_mean[(size_t)pb * 3 + tid] = m;
+                const float mv = (float)__ddiv_rn(tsum, (double)(e - a0));
+                S.mean[tid] = mv;
+                if (MODE == PFN_MODE_APPLY && a.pillar_mean) a.pillar_mean[(size_t)pb * 3 + tid] = mv;
             }
             if (tid == 32) {
                 const float *r0 = a.grows + a0 * COLS;
@@ -496,49 +523,31 @@ __global__ void __launch_bounds__(kPfnThreads, 3) pfn_tile_kernel(const __grid_c
                     const int npc = (int)min((long long)CAP, e - cs);
                     for (int i = tid; i < npc * COLS; i += NT) rows[i] = a.grows[cs * COLS + i];
                     for (int jj = tid; jj < npc; jj += NT) {
-                        S.lp[jj] = 0;
+                        S.lp[jj] = 0;  // slot 0, never "last": the carry below closes the pillar
                         if (want_arg) { const int row = a.gorder[cs + jj]; S.kept[jj] = none_dropped ? row : a.orig2kept[row]; }
                     }
                     __syncthreads();
                     c1(rows, 0, npc);
                     __syncthreads();
-                    if (MODE == PFN_MODE_STATS) {
-                        gram(npc);
-                        c2(npc);
-                        __syncthreads();
-                    } else {
-                        c2(npc);
-                        __syncthreads();
-                        // column reduce: thread = (row group, quad); partials alias S.f (free after C2)
-                        float *pv = S.f;
-                        int *pk = reinterpret_cast<int *>(S.f) + GROUPS * COUT, *pp = pk + GROUPS * COUT;
-                        float m[4];
-                        int mk[4], mp[4];
+                    if (MODE == PFN_MODE_STATS) gram(npc);
+                    stream((warp * npc) / NW, ((warp + 1) * npc) / NW, pb, (int)cs);
+                    if (MODE == PFN_MODE_APPLY) {
+                        // merge the warps' running maxima into the carry, in warp order (deterministic)
+                        for (int w = 0; w < NW; ++w) {
+                            if (warp == w) {
 #pragma unroll
-                        for (int c = 0; c < 4; ++c) { m[c] = want_arg ? -1.0f : 0.0f; mk[c] = INF; mp[c] = 0; }
-                        for (int j = grp; j < npc; j += GROUPS) {
-                            const float4 v4 = *reinterpret_cast<const float4 *>(&sz[j * Cfg::ZSTRIDE + quad * 4]);
-                            const float v[4] = {v4.x, v4.y, v4.z, v4.w};
-                            const int kj = want_arg ? S.kept[j] : 0;
-#pragma unroll
-                            for (int c = 0; c < 4; ++c)
-                                if (v[c] > m[c] || (want_arg && v[c] == m[c] && kj < mk[c])) { m[c] = v[c]; mk[c] = kj; mp[c] = (int)(cs + j); }
-                        }
-#pragma unroll
-                        for (int c = 0; c < 4; ++c) {
-                            pv[grp * COUT + quad * 4 + c] = m[c]; pk[grp * COUT + quad * 4 + c] = mk[c]; pp[grp * COUT + quad * 4 + c] = mp[c];
-                        }
-                        __syncthreads();
-                        if (tid < COUT) {
-                            float bm = S.carry_v[tid];
-                            int bk = S.carry_k[tid], bp = S.carry_p[tid];
-                            for (int gg = 0; gg < GROUPS; ++gg) {
-                                const float v = pv[gg * COUT + tid];
-                                const int vk = pk[gg * COUT + tid];
-                                if (v > bm || (want_arg && v == bm && vk < bk)) { bm = v; bk = vk; bp = pp[gg * COUT + tid]; }
+                                for (int cc = 0; cc < CPL; ++cc) {
+                                    const int ch = lane + 32 * cc;
+                                    const float bm = S.carry_v[ch];
+                                    const int bk = S.carry_k[ch];
+                                    if (m[cc] > bm || (want_arg && m[cc] == bm && mk[cc] < bk)) {
+                                        S.carry_v[ch] = m[cc]; S.carry_k[ch] = mk[cc]; S.carry_p[ch] = mp[cc];
+                                    }
+                                }
                             }
-                            S.carry_v[tid] = bm; S.carry_k[tid] = bk; S.carry_p[tid] = bp;
+                            __syncthreads();
                         }
+                    } else {
                         __syncthreads();
                     }
                 }
@@ -558,14 +567,14 @@ __global__ void __launch_bounds__(kPfnThreads, 3) pfn_tile_kernel(const __grid_c
         double *out = a.partials + (size_t)blockIdx.x * Cfg::STATS_DOUBLES;
         __syncthreads();
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            dscr[(grp * COUT + quad * 4 + c) * 2] = st_x[c];
-            dscr[(grp * COUT + quad * 4 + c) * 2 + 1] = st_x2[c];
+        for (int cc = 0; cc < CPL; ++cc) {
+            dscr[(warp * COUT + lane + 32 * cc) * 2] = st_x[cc];
+            dscr[(warp * COUT + lane + 32 * cc) * 2 + 1] = st_x2[cc];
         }
         __syncthreads();
         if (tid < COUT) {
             double sx = 0.0, sx2 = 0.0;
-            for (int g = 0; g < GROUPS; ++g) { sx += dscr[(g * COUT + tid) * 2]; sx2 += dscr[(g * COUT + tid) * 2 + 1]; }
+            for (int w = 0; w < NW; ++w) { sx += dscr[(w * COUT + tid) * 2]; sx2 += dscr[(w * COUT + tid) * 2 + 1]; }
             out[tid] = sx; out[COUT + tid] = sx2;
         }
         __syncthreads();
@@ -594,7 +603,7 @@ __global__ void __launch_bounds__(kPfnThreads, 3) pfn_tile_kernel(const __grid_c
         double *out = a.partials + (size_t)blockIdx.x * Cfg::BWD_DOUBLES;
         for (int e = tid; e < COUT * PER; e += NT) {
             double sacc = 0.0;
-            for (int w = 0; w < NT / 32; ++w) sacc += dscr[(size_t)w * COUT * PER + e];
+            for (int w = 0; w < NW; ++w) sacc += dscr[(size_t)w * COUT * PER + e];
             out[e] = sacc;
         }
     }

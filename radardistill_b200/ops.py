@@ -9,6 +9,7 @@ replaces the body of the reference ``forward`` between reading ``points`` and wr
 from __future__ import annotations
 
 import ctypes as C
+import dataclasses
 from dataclasses import dataclass
 from typing import Optional
 
@@ -205,8 +206,8 @@ def encode_forward(points: torch.Tensor, spec: EncoderSpec, batch_size: int, wei
                         counters=counters, spec=spec, batch_size=int(batch_size), n_points=int(n0))
 
 
-def encode_backward(points: torch.Tensor, spec: EncoderSpec, batch_size: int, res: EncodeResult, grad_features, weight,
-                    bias, gamma, beta, running_mean, running_var, train_bn: bool):
+def encode_backward(points: torch.Tensor, spec: EncoderSpec, batch_size: int, res: EncodeResult, features, grad_features,
+                    weight, bias, gamma, beta, running_mean, running_var, train_bn: bool):
     """Parameter gradients (d_weight, d_gamma | None, d_beta_or_bias)."""
     lib = _lib.load()
     dev = points.device
@@ -220,7 +221,7 @@ def encode_backward(points: torch.Tensor, spec: EncoderSpec, batch_size: int, re
         prm = _params_struct(spec, weight.detach(), None if bias is None else bias.detach(),
                              None if gamma is None else gamma.detach(), None if beta is None else beta.detach(),
                              running_mean, running_var, bool(train_bn and use_norm))
-        feats = res.features if res.features.is_contiguous() else res.features.contiguous()
+        feats = features if features.is_contiguous() else features.contiguous()
         _lib.check(lib.rdp_pfn_bwd(_ptr(points), points.shape[0], C.byref(geom), C.byref(layout), C.byref(prm),
                                    _ptr(res.workspace), res.workspace.numel(), _ptr(res.counters), _ptr(g),
                                    _ptr(feats), _ptr(res.argpos), _ptr(res.bn_state), _ptr(d_w),
@@ -237,24 +238,26 @@ class _PillarEncodeFn(torch.autograd.Function):
         res = encode_forward(points, spec, batch_size, weight, bias, gamma, beta, running_mean, running_var, train_bn,
                              want_argmax=needs_grad)
         holder.append(res)
-        ctx.res, ctx.spec, ctx.batch_size, ctx.train_bn = res, spec, batch_size, train_bn
+        # the node must not reference its own outputs (reference cycle => the ~1 GB of state would wait for the GC)
+        ctx.res = dataclasses.replace(res, features=None, coords=None)
+        ctx.spec, ctx.batch_size, ctx.train_bn = spec, batch_size, train_bn
         pts = points.detach()
         if pts.dtype != torch.float32 or not pts.is_contiguous() or pts.data_ptr() % 16:
             pts = pts.float().contiguous()
         ctx.points = pts
-        ctx.save_for_backward(weight, bias, gamma, beta)
+        ctx.save_for_backward(weight, bias, gamma, beta, res.features)
         ctx.rm, ctx.rv = running_mean, running_var
         ctx.mark_non_differentiable(res.coords)
         return res.features, res.coords
 
     @staticmethod
     def backward(ctx, grad_features, _grad_coords):
-        weight, bias, gamma, beta = ctx.saved_tensors
+        weight, bias, gamma, beta, features = ctx.saved_tensors
         res = ctx.res
         if res.argpos is None:
             raise RuntimeError("backward through a forward that ran without requires_grad parameters")
-        d_w, d_g, d_b = encode_backward(ctx.points, ctx.spec, ctx.batch_size, res, grad_features, weight, bias, gamma, beta,
-                                        ctx.rm, ctx.rv, ctx.train_bn)
+        d_w, d_g, d_b = encode_backward(ctx.points, ctx.spec, ctx.batch_size, res, features, grad_features, weight, bias,
+                                        gamma, beta, ctx.rm, ctx.rv, ctx.train_bn)
         use_norm = gamma is not None
         return (None, d_w, (None if use_norm else d_b), d_g, (d_b if use_norm else None), None, None, None, None, None, None)
 
@@ -268,8 +271,6 @@ def encode(points, spec: EncoderSpec, batch_size: int, weight, bias=None, gamma=
     if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in (weight, bias, gamma, beta)):
         feats, coords = _PillarEncodeFn.apply(points, weight, bias, gamma, beta, running_mean, running_var, spec, batch_size,
                                               train_bn, holder)
-        res = holder[0]
-        import dataclasses
-        return dataclasses.replace(res, features=feats, coords=coords)
+        return dataclasses.replace(holder[0], features=feats, coords=coords)
     return encode_forward(points, spec, batch_size, weight, bias, gamma, beta, running_mean, running_var, train_bn,
                           want_argmax=False)
