@@ -52,13 +52,12 @@ int carve_workspace(void *base, int64_t n_points, const rdp_geom_t *geom, const 
     ws->tile_keep = reinterpret_cast<int32_t *>(take(sizeof(int32_t) * (size_t)ws->index_tiles));
     ws->ends = reinterpret_cast<int32_t *>(take(sizeof(int32_t) * (size_t)(ws->pcap + 4)));
     const size_t pad = kPfnCap + 8;
-    ws->grows = reinterpret_cast<float *>(take(sizeof(float) * (size_t)(n + pad) * geom->cols));
-    ws->gpid = reinterpret_cast<int32_t *>(take(sizeof(int32_t) * (size_t)(n + pad + 4)));
-    ws->gorder = reinterpret_cast<int32_t *>(take(sizeof(int32_t) * (size_t)(n + pad)));
+    ws->grows = reinterpret_cast<float *>(take(sizeof(float) * (size_t)(n + pad + 1) * grouped_row_floats(geom->cols)));
     ws->orig2kept = reinterpret_cast<int32_t *>(take(sizeof(int32_t) * (size_t)(n + 4)));
     ws->kept2orig = reinterpret_cast<int32_t *>(take(sizeof(int32_t) * (size_t)(n + 4)));
     ws->index_bytes = off;
     ws->partials = reinterpret_cast<double *>(take(sizeof(double) * (size_t)ws->partial_blocks * ws->partial_doubles_per_block));
+    ws->totals = reinterpret_cast<double *>(take(sizeof(double) * (size_t)ws->partial_doubles_per_block));
     ws->total_bytes = off;
     return RDP_OK;
 }

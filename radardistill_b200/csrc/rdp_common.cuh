@@ -29,6 +29,7 @@ constexpr int kPfnThreads = 128;
 constexpr int kPfnWin = 128;          // grouped rows per PFN tile window (a tile owns the pillars that START in it)
 constexpr int kPfnCap = 192;          // rows staged per tile: the window + 64 rows of overhang for the last pillar
 constexpr int kPfnGridCap = 148 * 4;  // persistent PFN CTAs (also the number of partial-sum slots)
+__host__ __device__ constexpr int grouped_row_floats(int cols) { return (cols + 2 + 3) / 4 * 4; }
 constexpr int kMaxCin = 24;
 constexpr int kMaxCout = 64;
 
@@ -48,10 +49,11 @@ struct Workspace {
     int32_t *keys;           // n  (merged key, then overwritten by the pillar rank; -1 = dropped)
     int32_t *tile_keep;      // index tiles
     int32_t *ends;           // pcap  (exclusive starts -> after fill: inclusive ends)
-    float *grows;            // (n + pad) * cols : rows physically grouped by pillar (pillar order == key order)
-    int32_t *gpid;           // 4 + n + pad       : gpid[4 + pos] = pillar of grouped position pos, gpid[0..3] = -1
-    int32_t *gorder;         // n + pad           : grouped position -> original row
+    float *grows;            // (1 + n + pad) * RS : rows physically grouped by pillar (pillar order == key order);
+                             // RS floats per row = [row | pad | original row id | pillar id]; row 0 is a sentinel
+                             // (pillar id -1) in front of grouped position 0
     double *partials;        // per-CTA partial sums of the train-mode statistics / backward
+    double *totals;          // their fixed-order sum (reduce_partials_kernel)
     char *zero_begin;
     size_t zero_bytes;
     int32_t *orig2kept;      // n     (only written / read when the range mask dropped rows)

@@ -10,7 +10,8 @@
 // sort with one-bit counters; no comparison sort, no ordering of floats, fully deterministic.
 //
 //   K1 quantize_mark   points (TMA bulk tile -> smem) -> key[i], bitmap |= bit(key)          [HBM: read rows]
-//   K2 bitmap_rank     popcount scan of the bitmap -> word_prefix, coords[rank], P
+//   K2 bitmap_rank     popcount scan of the bitmap -> word_prefix, P
+//   K2b emit_coords    one thread per bitmap word -> coords[rank] in key order
 //   K3 rank_count      key[i] -> rank = word_prefix + popc(below) ; inverse[j] ; counts[rank]++
 //   K4 count_scan      exclusive scan of counts -> pillar start offsets
 //   K5 group_rows      pos = start[rank]++ ; grouped_rows[pos] = row i, gpid[pos] = rank, gorder[pos] = i
@@ -90,11 +91,10 @@ quantize_mark_kernel(const float *__restrict__ pts, long long n0, GeomDev g, uin
 
 // ----------------------------------------------------------------------------- K2
 // Chunked two-sweep scan over the bitmap words: sweep 1 = popcount of my chunk, hand-off, sweep 2 =
-// ranks.  Emits coords in key order (:243-248) and zeroes counts[rank] for K3.
+// the exclusive rank of every word.
 __global__ void __launch_bounds__(kScanThreads)
-bitmap_rank_kernel(const uint32_t *__restrict__ bitmap, long long words, GeomDev g, int coord_cols,
-                   uint64_t *__restrict__ state, uint32_t *__restrict__ word_prefix, int32_t *__restrict__ coords,
-                   int32_t *__restrict__ counts, int32_t *__restrict__ counters) {
+bitmap_rank_kernel(const uint32_t *__restrict__ bitmap, long long words,
+                   uint64_t *__restrict__ state, uint32_t *__restrict__ word_prefix, int32_t *__restrict__ counters) {
     __shared__ int s_scan[9];
     __shared__ uint32_t s_u32;
     __shared__ int s_ticket;
@@ -117,12 +117,10 @@ bitmap_rank_kernel(const uint32_t *__restrict__ bitmap, long long words, GeomDev
     if (ticket == (int)gridDim.x - 1 && tid == 0) counters[RDP_CNT_P] = (int)(base + (uint32_t)tot);
 
     // sweep 2
-    const int sxy = g.nx * g.ny;
     for (long long wt = w0; wt < w1; wt += kScanThreads * 4) {
         const long long w = wt + tid * 4;
         uint4 v = make_uint4(0, 0, 0, 0);
         if (w < w1) v = *reinterpret_cast<const uint4 *>(bitmap + w);
-        const uint32_t wd[4] = {v.x, v.y, v.z, v.w};
         const int c = __popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w);
         int tile_total;
         uint32_t rank = base + (uint32_t)block_excl_scan_256(c, s_scan, &tile_total);
@@ -134,33 +132,39 @@ bitmap_rank_kernel(const uint32_t *__restrict__ bitmap, long long words, GeomDev
             pre.z = pre.y + __popc(v.y);
             pre.w = pre.z + __popc(v.z);
             *reinterpret_cast<uint4 *>(word_prefix + w) = pre;
-            if (c) {
-                // decode the first key of this thread once; later bits only carry
-                const long long key0 = w * 32;
-                const int b0 = (int)(key0 / sxy);
-                const int rem = (int)(key0 - (long long)b0 * sxy);
-                const int cx0 = rem / g.ny, cy0 = rem - cx0 * g.ny;
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    uint32_t bits = wd[q];
-                    while (bits) {
-                        const int bit = __ffs(bits) - 1;
-                        bits &= bits - 1;
-                        int cy = cy0 + q * 32 + bit, cx = cx0, b = b0;
-                        while (cy >= g.ny) { cy -= g.ny; ++cx; }
-                        while (cx >= g.nx) { cx -= g.nx; ++b; }
-                        if (coord_cols == 3) {
-                            int32_t *o = coords + (size_t)rank * 3;
-                            o[0] = b; o[1] = cy; o[2] = cx;  // [b, y, x]  (:248)
-                        } else {
-                            *reinterpret_cast<int4 *>(coords + (size_t)rank * 4) = make_int4(b, 0, cy, cx);  // (:138)
-                        }
-                        counts[rank] = 0;
-                        ++rank;
-                    }
-                }
-            }
         }
+    }
+}
+
+// ----------------------------------------------------------------------------- K2b
+// One thread per bitmap word: coords of its set bits in key order (:243-248); zeroes counts[rank] for K3.
+__global__ void __launch_bounds__(kScanThreads)
+emit_coords_kernel(const uint32_t *__restrict__ bitmap, const uint32_t *__restrict__ word_prefix, long long words, GeomDev g,
+                   int coord_cols, int32_t *__restrict__ coords, int32_t *__restrict__ counts) {
+    const long long w = (long long)blockIdx.x * kScanThreads + threadIdx.x;
+    if (w >= words) return;
+    uint32_t bits = bitmap[w];
+    if (!bits) return;
+    uint32_t rank = word_prefix[w];
+    const int sxy = g.nx * g.ny;
+    const long long key0 = w * 32;  // decode the word's first key once; later bits only carry
+    const int b0 = (int)(key0 / sxy);
+    const int rem = (int)(key0 - (long long)b0 * sxy);
+    const int cx0 = rem / g.ny, cy0 = rem - cx0 * g.ny;
+    while (bits) {
+        const int bit = __ffs(bits) - 1;
+        bits &= bits - 1;
+        int cy = cy0 + bit, cx = cx0, b = b0;
+        while (cy >= g.ny) { cy -= g.ny; ++cx; }
+        while (cx >= g.nx) { cx -= g.nx; ++b; }
+        if (coord_cols == 3) {
+            int32_t *o = coords + (size_t)rank * 3;
+            o[0] = b; o[1] = cy; o[2] = cx;  // [b, y, x]  (:248)
+        } else {
+            *reinterpret_cast<int4 *>(coords + (size_t)rank * 4) = make_int4(b, 0, cy, cx);  // (:138)
+        }
+        counts[rank] = 0;
+        ++rank;
     }
 }
 
@@ -271,13 +275,15 @@ count_scan_kernel(const int32_t *__restrict__ counts, uint64_t *__restrict__ sta
 }
 
 // ----------------------------------------------------------------------------- K5
+// Grouped row layout: RS = grouped_row_floats(cols) floats = [row | pad | original row id | pillar id], written with
+// 16-byte stores only (the scatter is bound by store requests, not bytes).
 __global__ void __launch_bounds__(kIndexThreads)
 group_rows_kernel(const float *__restrict__ pts, const int32_t *__restrict__ ranks, long long n0, int cols,
-                  int32_t *__restrict__ ends, float *__restrict__ grows, int32_t *__restrict__ gpid,
-                  int32_t *__restrict__ gorder) {
+                  int32_t *__restrict__ ends, float *__restrict__ grows) {
     extern __shared__ __align__(128) float tile[];
     __shared__ __align__(8) uint64_t bar;
     const int tid = threadIdx.x;
+    const int rs = grouped_row_floats(cols);
     const long long row0 = (long long)blockIdx.x * kIndexTileRows;
     const int rows = (int)min((long long)kIndexTileRows, n0 - row0);
     const int floats = rows * cols;
@@ -293,7 +299,7 @@ group_rows_kernel(const float *__restrict__ pts, const int32_t *__restrict__ ran
         tma_bulk_g2s(tile, src, bulk_bytes, &bar);
     }
     for (int f = (int)(bulk_bytes >> 2) + tid; f < floats; f += kIndexThreads) tile[f] = src[f];
-    if (blockIdx.x == 0 && tid < 4) gpid[tid] = -1;  // "no pillar" in front of grouped position 0
+    if (blockIdx.x == 0 && tid == 0) grows[rs - 1] = __int_as_float(-1);  // sentinel row: "no pillar" before position 0
     // claim the grouped positions while the tile is in flight
     int pos[kIndexTileRows / kIndexThreads], rk[kIndexTileRows / kIndexThreads];
 #pragma unroll
@@ -309,14 +315,16 @@ group_rows_kernel(const float *__restrict__ pts, const int32_t *__restrict__ ran
         if (pos[k] < 0) continue;
         const int r = k * kIndexThreads + tid;
         const float *p = tile + r * cols;
-        float *d = grows + (size_t)pos[k] * cols;
-        if ((cols & 1) == 0) {
-            for (int c = 0; c < cols; c += 2) *reinterpret_cast<float2 *>(d + c) = make_float2(p[c], p[c + 1]);
-        } else {
-            for (int c = 0; c < cols; ++c) d[c] = p[c];
+        float4 *d = reinterpret_cast<float4 *>(grows + ((size_t)pos[k] + 1) * rs);
+        for (int c4 = 0; c4 < rs; c4 += 4) {
+            float v[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int c = c4 + i;
+                v[i] = c < cols ? p[c] : (c == rs - 2 ? __int_as_float((int)(row0 + r)) : (c == rs - 1 ? __int_as_float(rk[k]) : 0.0f));
+            }
+            d[c4 >> 2] = make_float4(v[0], v[1], v[2], v[3]);
         }
-        gpid[4 + pos[k]] = rk[k];
-        gorder[pos[k]] = (int)(row0 + r);
     }
 }
 
@@ -352,13 +360,13 @@ extern "C" int rdp_index_fwd(const float *points, int64_t n_points, const rdp_ge
     }
     const int tiles = (int)ws.index_tiles;
     quantize_mark_kernel<<<tiles, kIndexThreads, smem, stream>>>(points, n_points, g, ws.bitmap, ws.keys, ws.tile_keep, counters);
-    bitmap_rank_kernel<<<kScanGrid, kScanThreads, 0, stream>>>(ws.bitmap, ws.words, g, coord_cols, ws.scan_state_a,
-                                                             ws.word_prefix, coords, counts, counters);
+    bitmap_rank_kernel<<<kScanGrid, kScanThreads, 0, stream>>>(ws.bitmap, ws.words, ws.scan_state_a, ws.word_prefix, counters);
+    emit_coords_kernel<<<(unsigned)((ws.words + kScanThreads - 1) / kScanThreads), kScanThreads, 0, stream>>>(
+        ws.bitmap, ws.word_prefix, ws.words, g, coord_cols, coords, counts);
     rank_count_kernel<<<tiles, kIndexThreads, 0, stream>>>(ws.keys, n_points, ws.bitmap, ws.word_prefix, ws.tile_keep,
                                                          inverse, counts, counters, ws.orig2kept, ws.kept2orig);
     count_scan_kernel<<<kScanGrid, kScanThreads, 0, stream>>>(counts, ws.scan_state_b, ws.ends, counters);
-    group_rows_kernel<<<tiles, kIndexThreads, smem, stream>>>(points, ws.keys, n_points, geom->cols, ws.ends, ws.grows,
-                                                            ws.gpid, ws.gorder);
+    group_rows_kernel<<<tiles, kIndexThreads, smem, stream>>>(points, ws.keys, n_points, geom->cols, ws.ends, ws.grows);
     RDP_CUDA_OK(cudaGetLastError());
     return RDP_OK;
 }

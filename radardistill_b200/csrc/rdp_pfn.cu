@@ -39,7 +39,7 @@ static int build_kmap(const rdp_geom_t *g, const rdp_layout_t *l, int8_t *kmap, 
 static int fill_args(PfnArgs *a, const PfnLaunch *L, int64_t n_points, const rdp_geom_t *geom, const rdp_layout_t *layout,
                      const rdp_pfn_params_t *prm, const Workspace &ws, const int32_t *counters) {
     memset(a, 0, sizeof(*a));
-    a->grows = ws.grows; a->gpid = ws.gpid; a->gorder = ws.gorder; a->ends = ws.ends; a->counters = counters;
+    a->grows = ws.grows; a->ends = ws.ends; a->counters = counters;
     a->orig2kept = ws.orig2kept;
     a->weight = prm->weight; a->bias = prm->bias; a->gamma = prm->gamma; a->beta = prm->beta;
     a->rmean = prm->running_mean; a->rvar = prm->running_var;
@@ -53,14 +53,32 @@ static int fill_args(PfnArgs *a, const PfnLaunch *L, int64_t n_points, const rdp
 }
 
 // argmax in the reference's numbering: index of the winning row among the KEPT points (dynamic_pillar_vfe.py:204-206).
-__global__ void argpos_to_kept_kernel(const int32_t *__restrict__ argpos, const int32_t *__restrict__ gorder,
+__global__ void argpos_to_kept_kernel(const int32_t *__restrict__ argpos, const float *__restrict__ grows, int rs,
                                       const int32_t *__restrict__ orig2kept, const int32_t *__restrict__ counters, long long n0,
                                       int cout, int32_t *__restrict__ out) {
     const long long total = (long long)counters[RDP_CNT_P] * cout;
     const bool none_dropped = ((long long)counters[RDP_CNT_N] == n0);
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-        const int row = gorder[argpos[e]];
+        const int row = __float_as_int(grows[((size_t)argpos[e] + 1) * rs + rs - 2]);
         out[e] = none_dropped ? row : orig2kept[row];
+    }
+}
+
+// Sums the per-CTA partial vectors partials[b][e] over b in a fixed order (deterministic): lane = element,
+// warp w adds CTAs w, w+8, ..., then the 8 warp sums are combined in warp order.
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const double *__restrict__ partials, int nblocks, int el,
+                                                             double *__restrict__ totals) {
+    __shared__ double sm[8][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, e = blockIdx.x * 32 + lane;
+    double acc = 0.0;
+    if (e < el)
+        for (int b = warp; b < nblocks; b += 8) acc += partials[(size_t)b * el + e];
+    sm[warp][lane] = acc;
+    __syncthreads();
+    if (warp == 0 && e < el) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += sm[w][lane];
+        totals[e] = t;
     }
 }
 
@@ -101,7 +119,8 @@ extern "C" int rdp_pfn_fwd(const float *points, int64_t n_points, const rdp_geom
     if (train) {
         if (L->stats_partial_doubles > ws.partial_doubles_per_block) return RDP_ERR_WORKSPACE;
         RDP_CUDA_OK(L->tile(a, PFN_MODE_STATS, grid, st));
-        RDP_CUDA_OK(L->bn_finalize(a, grid, bn_state, prm->running_mean, prm->running_var, prm->momentum, st));
+        reduce_partials_kernel<<<(L->stats_partial_doubles + 31) / 32, 256, 0, st>>>(ws.partials, grid, L->stats_partial_doubles, ws.totals);
+        RDP_CUDA_OK(L->bn_finalize(a, ws.totals, bn_state, prm->running_mean, prm->running_var, prm->momentum, st));
         a.bn_state = bn_state;
         a.fold_from_state = 1;
     }
@@ -140,7 +159,8 @@ extern "C" int rdp_pfn_bwd(const float *points, int64_t n_points, const rdp_geom
     a.argpos = const_cast<int32_t *>(argpos);
     const int grid = pfn_grid(n_points);
     RDP_CUDA_OK(L->tile(a, PFN_MODE_BWD, grid, st));
-    RDP_CUDA_OK(L->bwd_finalize(a, grid, bn_state, train ? 1 : 0, d_weight, d_gamma, d_beta, st));
+    reduce_partials_kernel<<<(L->bwd_partial_doubles + 31) / 32, 256, 0, st>>>(ws.partials, grid, L->bwd_partial_doubles, ws.totals);
+    RDP_CUDA_OK(L->bwd_finalize(a, ws.totals, bn_state, train ? 1 : 0, d_weight, d_gamma, d_beta, st));
     return RDP_OK;
 }
 
@@ -155,7 +175,8 @@ extern "C" int rdp_argmax_kept(int64_t n_points, const rdp_geom_t *geom, const r
     int rc = carve_workspace(workspace, n_points, geom, layout, &ws);
     if (rc != RDP_OK) return rc;
     if (ws.index_bytes > workspace_bytes) return RDP_ERR_WORKSPACE;
-    argpos_to_kept_kernel<<<148 * 8, 256, 0, st>>>(argpos, ws.gorder, ws.orig2kept, counters, n_points, layout->c_out, argmax_kept);
+    argpos_to_kept_kernel<<<148 * 8, 256, 0, st>>>(argpos, ws.grows, grouped_row_floats(geom->cols), ws.orig2kept, counters, n_points,
+                                                    layout->c_out, argmax_kept);
     RDP_CUDA_OK(cudaGetLastError());
     return RDP_OK;
 }

@@ -31,7 +31,7 @@ constexpr int kMaxSuper = 24;
 
 struct PfnArgs {
     const float *grows;
-    const int32_t *gpid, *gorder, *ends, *counters, *orig2kept;
+    const int32_t *ends, *counters, *orig2kept;
     const float *weight, *bias, *gamma, *beta, *rmean, *rvar;
     const double *bn_state;  // train apply: folded scale / shift live here
     float *features;
@@ -70,17 +70,21 @@ struct PfnCfg {
     static constexpr int STATS_DOUBLES = 2 * COUT + 16 * NBLK;
     static constexpr int BWD_PER = CS + 2;
     static constexpr int BWD_DOUBLES = COUT * BWD_PER;
-    static constexpr uint32_t ROW_BYTES = kPfnCap * COLS * 4, GP_BYTES = (kPfnCap + 4) * 4, ORD_BYTES = kPfnCap * 4;
+    static constexpr int RS = (COLS + 2 + 3) / 4 * 4;  // floats per grouped row: the row, padding, original row id, pillar id
+    static constexpr uint32_t ROW_BYTES = (kPfnCap + 1) * RS * 4;  // the window plus the row in front of it
     static_assert(CS <= kMaxSuper, "too many features");
-    static_assert(ROW_BYTES % 16 == 0 && GP_BYTES % 16 == 0 && ORD_BYTES % 16 == 0, "TMA sizes");
+    static_assert(ROW_BYTES % 16 == 0, "TMA sizes");
     static_assert(NBLK <= kPfnThreads && COUT % 32 == 0, "tiling");
 };
 
+// One staged tile: grouped rows [128 t - 1, 128 t + 192); row j of the window is rows[(j + 1) * RS ...].
+// Slot RS-2 of a row holds its original row index, slot RS-1 its pillar id (int bit patterns).
 template <class Cfg>
 struct PfnStage {
-    alignas(16) float rows[kPfnCap * Cfg::COLS];
-    alignas(16) int gp[kPfnCap + 4];   // gp[4 + j] = pillar of row j of the window, gp[0..3] = the 4 rows before it
-    alignas(16) int ord[kPfnCap];
+    alignas(16) float rows[(kPfnCap + 1) * Cfg::RS];
+    __device__ __forceinline__ int gid(int j) const { return __float_as_int(rows[(j + 1) * Cfg::RS + Cfg::RS - 1]); }
+    __device__ __forceinline__ int ord(int j) const { return __float_as_int(rows[(j + 1) * Cfg::RS + Cfg::RS - 2]); }
+    __device__ __forceinline__ const float *row(int j) const { return rows + (j + 1) * Cfg::RS; }
 };
 
 template <class Cfg, int MODE>
@@ -89,8 +93,13 @@ struct PfnSmem {
     static constexpr size_t S_BYTES = (MODE == PFN_MODE_STATS) ? sizeof(double) * kPfnThreads * 16 : 0;
     static constexpr size_t B_BYTES = (MODE == PFN_MODE_BWD) ? sizeof(double) * (kPfnThreads / 32) * Cfg::BWD_DOUBLES : 0;
     static constexpr size_t SCR = Z_BYTES > S_BYTES ? (Z_BYTES > B_BYTES ? Z_BYTES : B_BYTES) : (S_BYTES > B_BYTES ? S_BYTES : B_BYTES);
+    static constexpr int PCH = (MODE == PFN_MODE_BWD) ? 96 : 1;  // pillars per backward prefetch chunk
     PfnStage<Cfg> st[2];
     alignas(8) uint64_t full[2];
+    alignas(8) uint64_t pre;                       // BWD: arrival of the tile's (grad, features, argpos) rows
+    alignas(16) float pre_grad[(MODE == PFN_MODE_BWD) ? PCH * Cfg::COUT : 4];
+    alignas(16) float pre_out[(MODE == PFN_MODE_BWD) ? PCH * Cfg::COUT : 4];
+    alignas(16) int pre_arg[(MODE == PFN_MODE_BWD) ? PCH * Cfg::COUT : 4];
     alignas(16) float f[kPfnCap * Cfg::FSTRIDE];   // decorated features of the tile's rows
     alignas(16) unsigned char scr[SCR];            // STATS / BWD: fp64 reduction scratch at kernel end
     int start[kPfnCap + 1];
@@ -159,7 +168,7 @@ __global__ void __launch_bounds__(kPfnThreads, 4) pfn_tile_kernel(const __grid_c
     extern __shared__ __align__(16) unsigned char smem_raw[];
     using Smem = PfnSmem<Cfg, MODE>;
     Smem &S = *reinterpret_cast<Smem *>(smem_raw);
-    constexpr int COUT = Cfg::COUT, CS = Cfg::CS, COLS = Cfg::COLS, CPL = COUT / 32;
+    constexpr int COUT = Cfg::COUT, CS = Cfg::CS, COLS = Cfg::COLS, RS = Cfg::RS, CPL = COUT / 32;
     constexpr int WIN = kPfnWin, CAP = kPfnCap, NT = kPfnThreads, NW = kPfnThreads / 32, INF = 0x7fffffff;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long long N = a.counters[RDP_CNT_N];
@@ -174,6 +183,7 @@ __global__ void __launch_bounds__(kPfnThreads, 4) pfn_tile_kernel(const __grid_c
     if (tid == 0) {
         mbar_init(&S.full[0], 1);
         mbar_init(&S.full[1], 1);
+        mbar_init(&S.pre, 1);
         fence_mbar_init();
     }
     // lane = output channel (+32): its weight row(s) live in registers for the whole kernel
@@ -223,17 +233,15 @@ __global__ void __launch_bounds__(kPfnThreads, 4) pfn_tile_kernel(const __grid_c
 
     auto issue = [&](int t, int s) {
         PfnStage<Cfg> &T = S.st[s];
-        mbar_expect_tx(&S.full[s], Cfg::ROW_BYTES + Cfg::GP_BYTES + Cfg::ORD_BYTES);
-        tma_bulk_g2s(T.rows, a.grows + (size_t)t * WIN * COLS, Cfg::ROW_BYTES, &S.full[s]);
-        tma_bulk_g2s(T.gp, a.gpid + (size_t)t * WIN, Cfg::GP_BYTES, &S.full[s]);
-        tma_bulk_g2s(T.ord, a.gorder + (size_t)t * WIN, Cfg::ORD_BYTES, &S.full[s]);
+        mbar_expect_tx(&S.full[s], Cfg::ROW_BYTES);
+        tma_bulk_g2s(T.rows, a.grows + (size_t)t * WIN * RS, Cfg::ROW_BYTES, &S.full[s]);  // grows row 0 = the row before position 0
     };
 
     // C1: decorated features of rows [rowbase, rowbase + np) of `rows` -> S.f[0..np)
     auto c1 = [&](const float *rows, int rowbase, int np) {
         for (int jj = tid; jj < np; jj += NT) {
             float r[COLS], f[Cfg::FW];
-            const float *src = rows + (rowbase + jj) * COLS;
+            const float *src = rows + (rowbase + jj) * RS;
 #pragma unroll
             for (int c = 0; c < COLS; ++c) r[c] = src[c];
             const int lp = S.lp[jj] >> 1;
@@ -356,8 +364,17 @@ __global__ void __launch_bounds__(kPfnThreads, 4) pfn_tile_kernel(const __grid_c
         }
     };
 
+    // BWD: the upstream gradient, forward output and argmax rows of pillars [p0, p0 + n) -> smem, asynchronously
+    auto prefetch_bwd = [&](int p0, int n) {
+        const uint32_t bytes = (uint32_t)n * COUT * 4;
+        mbar_expect_tx(&S.pre, 3 * bytes);
+        tma_bulk_g2s(S.pre_grad, a.grad + (size_t)p0 * COUT, bytes, &S.pre);
+        tma_bulk_g2s(S.pre_out, a.feat_out + (size_t)p0 * COUT, bytes, &S.pre);
+        tma_bulk_g2s(S.pre_arg, a.argpos + (size_t)p0 * COUT, bytes, &S.pre);
+    };
+
     if (t_begin < t_end && tid == 0) issue(t_begin, 0);
-    uint32_t par0 = 0, par1 = 0;
+    uint32_t par0 = 0, par1 = 0, ppar = 0;
 
     for (int t = t_begin; t < t_end; ++t) {
         const int s = (t - t_begin) & 1;
@@ -370,7 +387,7 @@ __global__ void __launch_bounds__(kPfnThreads, 4) pfn_tile_kernel(const __grid_c
         int jmin = INF, jend = INF, jlast = -1;
         for (int j = tid; j < CAP; j += NT) {
             const bool valid = base + j < N;
-            const bool head = valid && (T.gp[j + 4] != T.gp[j + 3]);
+            const bool head = valid && (T.gid(j) != T.gid(j - 1));
             if (j < WIN) {
                 if (head) { jmin = min(jmin, j); jlast = max(jlast, j); }
                 if (!valid) jend = min(jend, j);
@@ -387,18 +404,19 @@ __global__ void __launch_bounds__(kPfnThreads, 4) pfn_tile_kernel(const __grid_c
         if (jmin == INF) { __syncthreads(); continue; }  // a pillar from an earlier tile covers the whole window
         const bool big = (jend == INF);                   // the last pillar runs past the staged rows
         const int j0 = jmin, jstop = big ? jlast : jend, np = jstop - j0;
-        const int ps = T.gp[j0 + 4];
-        const int nb = np > 0 ? T.gp[jstop - 1 + 4] - ps + 1 : 0;
+        const int ps = T.gid(j0);
+        const int nb = np > 0 ? T.gid(jstop - 1) - ps + 1 : 0;
         const int gb = (int)base + j0;
+        if (MODE == PFN_MODE_BWD && np > 0 && tid == 0) prefetch_bwd(ps, min(Smem::PCH, nb));  // lands while P1..C1 run
 
         if (np > 0) {
             // ---- P1: row -> (pillar slot, last-row flag); pillar start table
             for (int jj = tid; jj < np; jj += NT) {
-                const int j = j0 + jj, gid = T.gp[j + 4];
-                const int last = (jj == np - 1) || (T.gp[j + 5] != gid);
+                const int j = j0 + jj, gid = T.gid(j);
+                const int last = (jj == np - 1) || (T.gid(j + 1) != gid);
                 S.lp[jj] = ((gid - ps) << 1) | last;
-                if (gid != T.gp[j + 3]) S.start[gid - ps] = jj;
-                if (want_arg) { const int row = T.ord[j]; S.kept[jj] = none_dropped ? row : a.orig2kept[row]; }
+                if (gid != T.gid(j - 1)) S.start[gid - ps] = jj;
+                if (want_arg) { const int row = T.ord(j); S.kept[jj] = none_dropped ? row : a.orig2kept[row]; }
             }
             if (tid == 0) S.start[nb] = np;
             __syncthreads();
@@ -407,13 +425,13 @@ __global__ void __launch_bounds__(kPfnThreads, 4) pfn_tile_kernel(const __grid_c
                 const int b0 = S.start[q], b1 = S.start[q + 1];
                 double sx = 0.0, sy = 0.0, sz3 = 0.0;
                 for (int jj = b0; jj < b1; ++jj) {
-                    const float *r = T.rows + (j0 + jj) * COLS;
+                    const float *r = T.row(j0 + jj);
                     sx += (double)r[1]; sy += (double)r[2]; sz3 += (double)r[3];
                 }
                 const double cnt = (double)(b1 - b0);
                 const float mx = (float)__ddiv_rn(sx, cnt), my = (float)__ddiv_rn(sy, cnt), mz = (float)__ddiv_rn(sz3, cnt);
                 S.mean[q * 3] = mx; S.mean[q * 3 + 1] = my; S.mean[q * 3 + 2] = mz;
-                const float *r0 = T.rows + (j0 + b0) * COLS;
+                const float *r0 = T.row(j0 + b0);
                 pillar_centre(r0[1], r0[2], a, &S.cen[q * 2], &S.cen[q * 2 + 1]);
                 if (MODE == PFN_MODE_APPLY && a.pillar_mean) {
                     float *pm = a.pillar_mean + (size_t)(ps + q) * 3;
@@ -421,7 +439,7 @@ __global__ void __launch_bounds__(kPfnThreads, 4) pfn_tile_kernel(const __grid_c
                 }
             }
             __syncthreads();
-            c1(T.rows, j0, np);
+            c1(T.rows, j0 + 1, np);
             __syncthreads();
             if (MODE != PFN_MODE_BWD) {
                 // warp w streams a pillar-aligned quarter of the rows
@@ -439,12 +457,20 @@ __global__ void __launch_bounds__(kPfnThreads, 4) pfn_tile_kernel(const __grid_c
 #pragma unroll
                     for (int k = 0; k < CS; ++k) tA[cc][k] = 0.0f;
                 }
-                for (int q = warp; q < nb; q += NW) {
+                for (int q0 = 0; q0 < nb; q0 += Smem::PCH) {
+                  const int nq = min(Smem::PCH, nb - q0);
+                  if (q0 > 0) {  // rare: more pillars in the tile than one prefetch chunk holds
+                      __syncthreads();
+                      if (tid == 0) prefetch_bwd(ps + q0, nq);
+                  }
+                  mbar_wait(&S.pre, ppar);
+                  ppar ^= 1;
+                  for (int q = warp; q < nq; q += NW) {
 #pragma unroll
                     for (int cc = 0; cc < CPL; ++cc) {
-                        const size_t o = (size_t)(ps + q) * COUT + lane + 32 * cc;
-                        const float gy = a.feat_out[o] > 0.0f ? a.grad[o] : 0.0f;
-                        const int jj = a.argpos[o] - gb;
+                        const int o = q * COUT + lane + 32 * cc;
+                        const float gy = S.pre_out[o] > 0.0f ? S.pre_grad[o] : 0.0f;
+                        const int jj = S.pre_arg[o] - gb;
                         float f[Cfg::FW];
                         const float4 *src = reinterpret_cast<const float4 *>(&S.f[jj * Cfg::FSTRIDE]);
 #pragma unroll
@@ -460,6 +486,7 @@ __global__ void __launch_bounds__(kPfnThreads, 4) pfn_tile_kernel(const __grid_c
 #pragma unroll
                         for (int k = 0; k < CS; ++k) tA[cc][k] = fmaf(gy, f[k], tA[cc][k]);
                     }
+                  }
                 }
 #pragma unroll
                 for (int cc = 0; cc < CPL; ++cc) {
@@ -474,12 +501,12 @@ __global__ void __launch_bounds__(kPfnThreads, 4) pfn_tile_kernel(const __grid_c
         if (big) {
             // ---- big pillar pb = rows [a0, e): straight from global memory
             __syncthreads();
-            const int pb = T.gp[jlast + 4];
+            const int pb = T.gid(jlast);
             const long long a0 = base + jlast;
             const long long e = a.ends[pb];
             double sx = 0.0, sy = 0.0, sz3 = 0.0;
             for (long long g = a0 + tid; g < e; g += NT) {
-                const float *r = a.grows + g * COLS;
+                const float *r = a.grows + (g + 1) * RS;
                 sx += (double)r[1]; sy += (double)r[2]; sz3 += (double)r[3];
             }
             S.dred[tid * 3] = sx; S.dred[tid * 3 + 1] = sy; S.dred[tid * 3 + 2] = sz3;
@@ -492,7 +519,7 @@ __global__ void __launch_bounds__(kPfnThreads, 4) pfn_tile_kernel(const __grid_c
                 if (MODE == PFN_MODE_APPLY && a.pillar_mean) a.pillar_mean[(size_t)pb * 3 + tid] = mv;
             }
             if (tid == 32) {
-                const float *r0 = a.grows + a0 * COLS;
+                const float *r0 = a.grows + (a0 + 1) * RS;
                 pillar_centre(r0[1], r0[2], a, &S.cen[0], &S.cen[1]);
             }
             if (tid < COUT) { S.carry_v[tid] = want_arg ? -1.0f : 0.0f; S.carry_k[tid] = INF; S.carry_p[tid] = 0; }
@@ -503,7 +530,7 @@ __global__ void __launch_bounds__(kPfnThreads, 4) pfn_tile_kernel(const __grid_c
                     for (int cc = 0; cc < CPL; ++cc) {
                         const size_t o = (size_t)pb * COUT + lane + 32 * cc;
                         const float gy = a.feat_out[o] > 0.0f ? a.grad[o] : 0.0f;
-                        const float *src = a.grows + (size_t)a.argpos[o] * COLS;
+                        const float *src = a.grows + ((size_t)a.argpos[o] + 1) * RS;
                         float r[COLS], f[Cfg::FW];
 #pragma unroll
                         for (int c = 0; c < COLS; ++c) r[c] = src[c];
@@ -521,10 +548,10 @@ __global__ void __launch_bounds__(kPfnThreads, 4) pfn_tile_kernel(const __grid_c
                 float *rows = T.rows;  // this stage's row buffer is free again (the next TMA targets the other stage)
                 for (long long cs = a0; cs < e; cs += CAP) {
                     const int npc = (int)min((long long)CAP, e - cs);
-                    for (int i = tid; i < npc * COLS; i += NT) rows[i] = a.grows[cs * COLS + i];
+                    for (int i = tid; i < npc * RS; i += NT) rows[i] = a.grows[(cs + 1) * RS + i];
                     for (int jj = tid; jj < npc; jj += NT) {
                         S.lp[jj] = 0;  // slot 0, never "last": the carry below closes the pillar
-                        if (want_arg) { const int row = a.gorder[cs + jj]; S.kept[jj] = none_dropped ? row : a.orig2kept[row]; }
+                        if (want_arg) { const int row = __float_as_int(a.grows[(cs + jj + 1) * RS + RS - 2]); S.kept[jj] = none_dropped ? row : a.orig2kept[row]; }
                     }
                     __syncthreads();
                     c1(rows, 0, npc);
@@ -614,17 +641,13 @@ __global__ void __launch_bounds__(kPfnThreads, 4) pfn_tile_kernel(const __grid_c
 // updates the running statistics, and expands the feature moments for the backward.
 // bn_state = [mean(COUT) | var(COUT) | scale(COUT) | shift(COUT) | n | S1(CIN) | S2(CIN*CIN)]
 template <class Cfg>
-__global__ void __launch_bounds__(256) bn_finalize_kernel(const __grid_constant__ PfnArgs a, int nblocks, double *bn_state,
+__global__ void __launch_bounds__(256) bn_finalize_kernel(const __grid_constant__ PfnArgs a, const double *totals, double *bn_state,
                                                          float *running_mean, float *running_var, double momentum) {
     constexpr int COUT = Cfg::COUT, CS = Cfg::CS, TOT = Cfg::STATS_DOUBLES, T4 = Cfg::T4;
     __shared__ double tot[TOT];
     const int tid = threadIdx.x;
     const long long N = a.counters[RDP_CNT_N];
-    for (int e = tid; e < TOT; e += blockDim.x) {
-        double s = 0.0;
-        for (int b = 0; b < nblocks; ++b) s += a.partials[(size_t)b * TOT + e];
-        tot[e] = s;
-    }
+    for (int e = tid; e < TOT; e += blockDim.x) tot[e] = totals[e];  // reduce_partials_kernel's fixed-order sums
     __syncthreads();
     const int cin = a.c_in;
     if (tid < COUT) {
@@ -668,18 +691,14 @@ __global__ void __launch_bounds__(256) bn_finalize_kernel(const __grid_constant_
 //   dW_ck    = (gamma_c/sigma_c) [ A_ck - dbeta_c/N S1_k - dgamma_c/N ((S2 w_c)_k - mu_c S1_k)/sigma_c ]   (train)
 //   dW_ck    = (gamma_c/sigma_c) A_ck                                                                    (eval BN)
 template <class Cfg>
-__global__ void __launch_bounds__(256) bwd_finalize_kernel(const __grid_constant__ PfnArgs a, int nblocks, const double *bn_state,
+__global__ void __launch_bounds__(256) bwd_finalize_kernel(const __grid_constant__ PfnArgs a, const double *totals, const double *bn_state,
                                                           int train_bn, float *d_weight, float *d_gamma, float *d_beta) {
     constexpr int COUT = Cfg::COUT, CS = Cfg::CS, PER = Cfg::BWD_PER;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *tot = reinterpret_cast<double *>(smem_raw);  // COUT*PER
     double *dgam = tot + COUT * PER;                       // COUT
     const int tid = threadIdx.x, cin = a.c_in;
-    for (int e = tid; e < COUT * PER; e += blockDim.x) {
-        double s = 0.0;
-        for (int b = 0; b < nblocks; ++b) s += a.partials[(size_t)b * COUT * PER + e];
-        tot[e] = s;
-    }
+    for (int e = tid; e < COUT * PER; e += blockDim.x) tot[e] = totals[e];
     __syncthreads();
     const double n = (double)a.counters[RDP_CNT_N];
     auto stat = [&](int c, double *mu, double *inv_std) {

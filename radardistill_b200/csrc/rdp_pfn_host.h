@@ -8,8 +8,8 @@ struct PfnLaunch {
     int cols, layout, dist, cout, cs;
     int stats_partial_doubles, bwd_partial_doubles;
     cudaError_t (*tile)(const PfnArgs &a, int mode, int grid, cudaStream_t st);
-    cudaError_t (*bn_finalize)(const PfnArgs &a, int nblocks, double *bn_state, float *rm, float *rv, double momentum, cudaStream_t st);
-    cudaError_t (*bwd_finalize)(const PfnArgs &a, int nblocks, const double *bn_state, int train_bn, float *dW, float *dg, float *db,
+    cudaError_t (*bn_finalize)(const PfnArgs &a, const double *totals, double *bn_state, float *rm, float *rv, double momentum, cudaStream_t st);
+    cudaError_t (*bwd_finalize)(const PfnArgs &a, const double *totals, const double *bn_state, int train_bn, float *dW, float *dg, float *db,
                                 cudaStream_t st);
 };
 

@@ -30,16 +30,17 @@ static cudaError_t tile(const PfnArgs &a, int mode, int grid, cudaStream_t st) {
     return launch_tile<PFN_MODE_APPLY>(a, grid, st);
 }
 
-static cudaError_t bn_finalize(const PfnArgs &a, int nblocks, double *bn_state, float *rm, float *rv, double momentum, cudaStream_t st) {
-    bn_finalize_kernel<Cfg><<<1, 256, 0, st>>>(a, nblocks, bn_state, rm, rv, momentum);
+static cudaError_t bn_finalize(const PfnArgs &a, const double *totals, double *bn_state, float *rm, float *rv, double momentum,
+                               cudaStream_t st) {
+    bn_finalize_kernel<Cfg><<<1, 256, 0, st>>>(a, totals, bn_state, rm, rv, momentum);
     return cudaGetLastError();
 }
 
 constexpr size_t kBwdFinSmem = sizeof(double) * (Cfg::BWD_DOUBLES + Cfg::COUT);
 
-static cudaError_t bwd_finalize(const PfnArgs &a, int nblocks, const double *bn_state, int train_bn, float *dW, float *dg, float *db,
-                                cudaStream_t st) {
-    bwd_finalize_kernel<Cfg><<<1, 256, kBwdFinSmem, st>>>(a, nblocks, bn_state, train_bn, dW, dg, db);
+static cudaError_t bwd_finalize(const PfnArgs &a, const double *totals, const double *bn_state, int train_bn, float *dW, float *dg,
+                                float *db, cudaStream_t st) {
+    bwd_finalize_kernel<Cfg><<<1, 256, kBwdFinSmem, st>>>(a, totals, bn_state, train_bn, dW, dg, db);
     return cudaGetLastError();
 }
 
