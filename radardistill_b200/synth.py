@@ -79,7 +79,7 @@ def lidar_frame(seed: int = 0, sweeps: int = 10, beams: int = 32, azimuths: int 
 
 
 def stress_frame(seed: int = 0, n_points: int = 1_000_000, pc_range=PC_RANGE) -> np.ndarray:
-    """Stress frame (config 5): 50 % uniform, 30 % in 64 tight blobs, 20 % exact duplicates."""
+    """Stress frame (config 5): 50 % uniform, 30 % in 64 Gaussian blobs (8 of them 2 cm wide), 20 % exact duplicates."""
     rng = np.random.default_rng(3000 + seed)
     n_u = n_points // 2
     n_b = (n_points * 3) // 10
@@ -88,7 +88,8 @@ def stress_frame(seed: int = 0, n_points: int = 1_000_000, pc_range=PC_RANGE) ->
     uni = rng.uniform(lo, hi, (n_u, 3))
     centres = rng.uniform(lo[:2] * 0.9, hi[:2] * 0.9, (64, 2))
     which = rng.integers(0, 64, n_b)
-    blob_xy = centres[which] + 0.3 * rng.standard_normal((n_b, 2))
+    sigma = np.where(which < 8, 0.02, 0.3)[:, None]  # 8 very tight blobs: >= 1000 points in the hottest pillars
+    blob_xy = centres[which] + sigma * rng.standard_normal((n_b, 2))
     blob = np.concatenate([blob_xy, rng.normal(0.0, 0.5, (n_b, 1))], 1)
     xyz = np.concatenate([uni, blob], 0)
     feats = np.stack([rng.uniform(0, 255, len(xyz)), rng.uniform(0, 0.5, len(xyz))], 1)

@@ -1,0 +1,107 @@
+"""CPU: the C-ABI library loads and exports every symbol include/rdp.h declares (no compute calls), and the
+drop-in modules keep the reference's constructor / state_dict / registry contract."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from radardistill_b200 import _lib, ops, synth, vfe
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    txt = open(os.path.join(ROOT, "include", "rdp.h")).read()
+    return sorted(set(re.findall(r"RDP_API\s+[\w\s\*]+?\b(rdp_\w+)\s*\(", txt)))
+
+
+def test_header_symbols_are_exported():
+    lib = _lib.load()
+    syms = declared_symbols()
+    assert len(syms) >= 9 and set(syms) == set(_lib.EXPORTS)
+    for s in syms:
+        assert getattr(lib, s) is not None
+    assert lib.rdp_abi_version() == _lib.RDP_ABI_VERSION
+    assert lib.rdp_status_string(0) == b"ok"
+    assert b"workspace" in lib.rdp_status_string(-2)
+
+
+def test_workspace_bytes_and_argument_checks_need_no_gpu():
+    lib = _lib.load()
+    spec = ops.make_spec(5, synth.VOXEL_SIZE, synth.grid_size_of(), synth.PC_RANGE, _lib.LAYOUT_SIMPLE2D, True, True, True, False, 32)
+    assert (spec.c_in, spec.coord_cols, spec.nx, spec.ny) == (14, 3, 1440, 1440)
+    assert spec.off == (float(np.float32(-53.9625)), float(np.float32(-53.9625)), float(np.float32(-4.9)))
+    geom, layout = spec.geom(8), spec.layout_struct()
+    n = C.c_size_t(0)
+    assert lib.rdp_workspace_bytes(2_700_000, C.byref(geom), C.byref(layout), C.byref(n)) == 0
+    assert 100e6 < n.value < 400e6
+    small = C.c_size_t(0)
+    assert lib.rdp_workspace_bytes(10, C.byref(geom), C.byref(layout), C.byref(small)) == 0 and small.value < n.value
+    geom_big = spec.geom(2000)  # 2000 * 1440^2 > 2^31 keys
+    assert lib.rdp_workspace_bytes(10, C.byref(geom_big), C.byref(layout), C.byref(small)) == -5
+    assert lib.rdp_workspace_bytes(10, C.byref(geom), C.byref(layout), None) == -1
+    assert lib.rdp_index_fwd(None, 10, C.byref(geom), 3, None, 0, None, None, None, None, None) == -1
+    assert lib.rdp_bn_state_doubles(C.byref(layout)) == 4 * 32 + 1 + 14 + 14 * 14
+
+
+class Cfg(dict):
+    __getattr__ = dict.__getitem__
+
+
+S2D = dict(USE_NORM=True, WITH_DISTANCE=False, USE_ABSLOTE_XYZ=True, USE_CLUSTER_XYZ=True, NUM_FILTERS=[32])
+
+
+def test_modules_keep_reference_contract():
+    grid = synth.grid_size_of()
+    lid = vfe.DynamicPillarVFESimple2D(model_cfg=Cfg(S2D), num_point_features=5, voxel_size=synth.VOXEL_SIZE, grid_size=grid,
+                                       point_cloud_range=synth.PC_RANGE, depth_downsample_factor=None)
+    rad = vfe.Radar_DynamicPillarVFESimple2D(model_cfg=Cfg(S2D), num_point_features=6, voxel_size=synth.VOXEL_SIZE,
+                                             grid_size=grid, point_cloud_range=synth.PC_RANGE)
+    dyn = vfe.DynamicPillarVFE(model_cfg=Cfg(USE_NORM=True, WITH_DISTANCE=False, USE_ABSLOTE_XYZ=True, NUM_FILTERS=[64]),
+                               num_point_features=4, voxel_size=synth.VOXEL_SIZE, grid_size=grid, point_cloud_range=synth.PC_RANGE)
+    keys = ["pfn_layers.0.linear.weight", "pfn_layers.0.norm.weight", "pfn_layers.0.norm.bias", "pfn_layers.0.norm.running_mean",
+            "pfn_layers.0.norm.running_var", "pfn_layers.0.norm.num_batches_tracked"]
+    assert list(lid.state_dict().keys()) == keys
+    assert tuple(lid.state_dict()[keys[0]].shape) == (32, 14)      # LiDAR 14 -> 32
+    assert tuple(rad.state_dict()[keys[0]].shape) == (32, 15)      # radar 15 -> 32
+    assert tuple(dyn.state_dict()[keys[0]].shape) == (64, 10)      # DynamicPillarVFE 10 -> 64
+    assert (lid.get_output_feature_dim(), dyn.get_output_feature_dim()) == (32, 64)
+    # PillarNet freezes by class __name__ (pillarnet.py:19-23)
+    assert [type(m).__name__ for m in (lid, rad, dyn)] == ["DynamicPillarVFESimple2D", "Radar_DynamicPillarVFESimple2D",
+                                                            "DynamicPillarVFE"]
+    assert isinstance(rad, vfe.DynamicPillarVFESimple2D) and isinstance(lid, vfe.VFETemplate)
+    nonorm = vfe.DynamicPillarVFESimple2D(model_cfg=Cfg(S2D, USE_NORM=False), num_point_features=5, voxel_size=synth.VOXEL_SIZE,
+                                          grid_size=grid, point_cloud_range=synth.PC_RANGE)
+    assert list(nonorm.state_dict().keys()) == ["pfn_layers.0.linear.weight", "pfn_layers.0.linear.bias"]
+    reg = vfe.register({"MeanVFE": object})
+    assert reg["DynPillarVFE"] is vfe.DynamicPillarVFE and reg["Radar_DynamicPillarVFESimple2D_Test"] is vfe.Radar_DynamicPillarVFESimple2D_Test
+    assert reg["MeanVFE"] is object
+    with pytest.raises(NotImplementedError):
+        vfe.DynamicPillarVFESimple2D(model_cfg=Cfg(S2D, NUM_FILTERS=[32, 64]), num_point_features=5, voxel_size=synth.VOXEL_SIZE,
+                                     grid_size=grid, point_cloud_range=synth.PC_RANGE)
+    flip = vfe.DynamicPillarVFESimple2D(model_cfg=Cfg(S2D, DOUBLE_FLIP=True), num_point_features=5, voxel_size=synth.VOXEL_SIZE,
+                                        grid_size=grid, point_cloud_range=synth.PC_RANGE)
+    with pytest.raises(NotImplementedError):
+        flip({"points": torch.zeros((0, 6))})
+
+
+def test_no_cpu_fallback():
+    lid = vfe.DynamicPillarVFESimple2D(model_cfg=Cfg(S2D), num_point_features=5, voxel_size=synth.VOXEL_SIZE,
+                                       grid_size=synth.grid_size_of(), point_cloud_range=synth.PC_RANGE).eval()
+    with pytest.raises(_lib.RdpError):
+        lid({"points": torch.zeros((4, 6)), "batch_size": 1})
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="reference tree only exists in the build container")
+def test_state_dict_matches_the_reference_class():
+    from oracle import ref_loader as rl
+    ref = rl.build_reference("Radar_DynamicPillarVFESimple2D", S2D, 6, synth.VOXEL_SIZE, synth.grid_size_of(), synth.PC_RANGE)
+    ours = vfe.Radar_DynamicPillarVFESimple2D(model_cfg=Cfg(S2D), num_point_features=6, voxel_size=synth.VOXEL_SIZE,
+                                              grid_size=synth.grid_size_of(), point_cloud_range=synth.PC_RANGE)
+    a, b = ref.state_dict(), ours.state_dict()
+    assert list(a.keys()) == list(b.keys())
+    assert all(tuple(a[k].shape) == tuple(b[k].shape) and a[k].dtype == b[k].dtype for k in a)
+    ours.load_state_dict(a, strict=True)

@@ -168,3 +168,81 @@ def test_bad_batch_index_is_reported():
     m = H.module_from_golden(g).eval()
     with pytest.raises(ValueError):
         m({"points": torch.from_numpy(g["points"]).cuda(), "batch_size": 1})
+
+
+def test_stress_frame_bit_exact_vs_oracle():
+    """Config-5 stress cloud (1 M points, 0.05 m pillars, 2160 x 2160 grid, hot pillars with > 1000 points, 20 % exact
+    duplicates): eval forward bit-exact, and a train step whose argmax (lowest index on the many exact ties) is bit-exact."""
+    from oracle.ref_loader import Cfg
+    from radardistill_b200 import synth, vfe
+    grid = synth.grid_size_of(synth.PC_RANGE, synth.STRESS_VOXEL_SIZE)
+    pts = synth.stress_batch(2, n_points=500_000)
+    cfg = Cfg(USE_NORM=True, WITH_DISTANCE=False, USE_ABSLOTE_XYZ=True, USE_CLUSTER_XYZ=True, NUM_FILTERS=[32])
+    torch.manual_seed(11)
+    m = vfe.DynamicPillarVFESimple2D(model_cfg=cfg, num_point_features=5, voxel_size=synth.STRESS_VOXEL_SIZE, grid_size=grid,
+                                     point_cloud_range=synth.PC_RANGE).cuda()
+    n = m.pfn_layers[0].norm
+    with torch.no_grad():
+        n.weight.uniform_(0.5, 1.5); n.bias.normal_(0, 0.2); n.running_mean.normal_(0, 1); n.running_var.uniform_(0.5, 4)
+    pfn = m.pfn_layers[0]
+    ocfg = orc.OracleConfig(num_point_features=5, voxel_size=tuple(synth.STRESS_VOXEL_SIZE), grid_size=tuple(grid),
+                            point_cloud_range=tuple(synth.PC_RANGE))
+    cp = lambda t: t.detach().cpu().numpy().copy()
+    o = orc.PillarOracle(ocfg, cp(pfn.linear.weight), cp(n.weight), cp(n.bias), cp(n.running_mean), cp(n.running_var))
+    orc.set_threads(8)
+    dev = torch.from_numpy(pts).cuda()
+    # eval
+    m.eval()
+    r = o.forward(pts, training=False, keep_intermediates=False)
+    assert r["counts"].max() > 1000
+    with torch.no_grad():
+        out = m({"points": dev, "batch_size": 2})
+    np.testing.assert_array_equal(out["pillar_coords"].cpu().numpy(), r["coords"])
+    np.testing.assert_array_equal(m.last_result.counts.cpu().numpy(), r["counts"])
+    np.testing.assert_array_equal(m.last_result.inverse.cpu().numpy(), r["inverse"])
+    np.testing.assert_array_equal(out["pillar_features"].cpu().numpy(), r["features"])
+    # train: argmax with ties, gradients
+    m.train()
+    r = o.forward(pts, training=True)
+    out = m({"points": dev, "batch_size": 2})
+    np.testing.assert_array_equal(m.last_result.argmax.cpu().numpy(), r["argmax"])
+    f = out["pillar_features"]
+    assert H.norm_rel_err(f.detach().cpu().numpy(), r["features"]) <= 1e-6
+    gout = torch.randn(f.shape, generator=torch.Generator().manual_seed(5)).cuda()
+    f.backward(gout)
+    b = o.backward(r, gout.cpu().numpy())
+    assert H.norm_rel_err(pfn.linear.weight.grad.cpu().numpy(), b["d_weight"]) <= H.RTOL_GRADS
+    assert H.norm_rel_err(n.weight.grad.cpu().numpy(), b["d_gamma"]) <= H.RTOL_GRADS
+    assert H.norm_rel_err(n.bias.grad.cpu().numpy(), b["d_beta"]) <= H.RTOL_GRADS
+
+
+def test_host_buffer_c_abi_entry_point():
+    """rdp_encode_host: host pointers in, host pointers out (what a non-torch caller binds)."""
+    import ctypes as C
+    from radardistill_b200 import _lib, ops, synth
+    lib = _lib.load()
+    pts = synth.lidar_batch(1, sweeps=2)
+    spec = ops.make_spec(5, synth.VOXEL_SIZE, synth.grid_size_of(), synth.PC_RANGE, _lib.LAYOUT_SIMPLE2D, True, True, True, False, 32)
+    rng = np.random.default_rng(3)
+    w = (rng.standard_normal((32, 14)) * 0.2).astype(np.float32)
+    gamma, beta = rng.uniform(0.5, 1.5, 32).astype(np.float32), rng.normal(0, 0.2, 32).astype(np.float32)
+    rm, rv = rng.normal(0, 1, 32).astype(np.float32), rng.uniform(0.5, 4, 32).astype(np.float32)
+    n = len(pts)
+    feats = np.empty((n, 32), np.float32); coords = np.empty((n, 3), np.int32)
+    inv = np.empty(n + 4, np.int32); cnt = np.empty(n + 4, np.int32)
+    prm = _lib.PfnParams()
+    vp = lambda a: a.ctypes.data_as(C.c_void_p).value
+    prm.weight, prm.gamma, prm.beta, prm.running_mean, prm.running_var = vp(w), vp(gamma), vp(beta), vp(rm), vp(rv)
+    prm.eps, prm.momentum, prm.train_bn = 1e-3, 0.01, 0
+    geom, layout = spec.geom(1), spec.layout_struct()
+    nk, npil = C.c_int64(0), C.c_int64(0)
+    rc = lib.rdp_encode_host(vp(pts), n, C.byref(geom), C.byref(layout), C.byref(prm), vp(feats), vp(coords), vp(inv), vp(cnt),
+                             C.byref(nk), C.byref(npil))
+    assert rc == 0, lib.rdp_status_string(rc)
+    cfg = orc.OracleConfig(num_point_features=5, voxel_size=tuple(synth.VOXEL_SIZE), grid_size=tuple(synth.grid_size_of()),
+                           point_cloud_range=tuple(synth.PC_RANGE))
+    r = orc.PillarOracle(cfg, w, gamma, beta, rm, rv).forward(pts)
+    assert (nk.value, npil.value) == (r["n"], r["p"])
+    np.testing.assert_array_equal(coords[:r["p"]], r["coords"])
+    np.testing.assert_array_equal(inv[:r["n"]], r["inverse"])
+    np.testing.assert_array_equal(feats[:r["p"]], r["features"])
