@@ -124,7 +124,7 @@ extern "C" int rdp_pfn_fwd(const float *points, int64_t n_points, const rdp_geom
         a.bn_state = bn_state;
         a.fold_from_state = 1;
     }
-    RDP_CUDA_OK(L->tile(a, PFN_MODE_APPLY, grid, st));
+    RDP_CUDA_OK(L->tile(a, argpos ? PFN_MODE_APPLY_ARG : PFN_MODE_APPLY, grid, st));
     return RDP_OK;
 }
 

@@ -48,7 +48,7 @@ struct PfnArgs {
     int8_t kmap[kMaxSuper];  // super-feature -> layout column of W, or -1 (zero weight)
 };
 
-enum { PFN_MODE_APPLY = 0, PFN_MODE_STATS = 1, PFN_MODE_BWD = 2 };
+enum { PFN_MODE_APPLY = 0, PFN_MODE_STATS = 1, PFN_MODE_BWD = 2, PFN_MODE_APPLY_ARG = 3 };  // APPLY_ARG also records the argmax
 
 // Compile-time shape of one encoder family.  "Super features" are every decoration the layout could
 // use, in the layout's concat order; options switched off in model_cfg get a zero weight column
@@ -60,7 +60,7 @@ struct PfnCfg {
     static constexpr int CS = (LAYOUT_ == RDP_LAYOUT_SIMPLE2D) ? (3 + C + 3 + (DIST_ ? 1 : 0) + 3) : (C + 6 + (DIST_ ? 1 : 0));
     static constexpr int T4 = (CS + 1 + 3) / 4;   // 4-wide column blocks of [features | 1]
     static constexpr int FW = 4 * T4;
-    static constexpr int FS2 = 2 * FW + 4;  // smem row stride: every feature stored twice ({f, f}) + 16 B of padding (conflict free)
+    static constexpr int FSTRIDE = (FW % 16 == 0) ? FW + 4 : FW;  // smem row stride of features (bank-conflict free)
     static constexpr int QUADS = COUT / 4;                         // channel quads
     static constexpr int GROUPS = kPfnThreads / QUADS;             // row groups in the register tiling
     static constexpr int RPT = (kPfnCap + GROUPS - 1) / GROUPS;    // rows per thread in C2
@@ -100,7 +100,7 @@ struct PfnSmem {
     alignas(16) float pre_grad[(MODE == PFN_MODE_BWD) ? PCH * Cfg::COUT : 4];
     alignas(16) float pre_out[(MODE == PFN_MODE_BWD) ? PCH * Cfg::COUT : 4];
     alignas(16) int pre_arg[(MODE == PFN_MODE_BWD) ? PCH * Cfg::COUT : 4];
-    alignas(16) float f[kPfnCap * Cfg::FS2];       // decorated features of the tile's rows, each value twice
+    alignas(16) float f[kPfnCap * Cfg::FSTRIDE];   // decorated features of the tile's rows
     alignas(16) unsigned char scr[SCR];            // STATS / BWD: fp64 reduction scratch at kernel end
     int start[kPfnCap + 1];
     int lp[kPfnCap];                               // (pillar slot << 1) | last-row-of-pillar flag
@@ -159,17 +159,6 @@ __device__ __forceinline__ void pillar_centre(float x, float y, const PfnArgs &a
     *ceny = __fadd_rn(__fmul_rn((float)(int)qy, a.vsz[1]), a.off[1]);
 }
 
-// two fp32 lanes in one 64-bit register; FFMA2 (fma.rn.f32x2) advances two fmaf chains per issue slot
-__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
-    return (uint64_t)__float_as_uint(lo) | ((uint64_t)__float_as_uint(hi) << 32);
-}
-__device__ __forceinline__ float unpack(uint64_t v, int h) { return __uint_as_float((uint32_t)(h ? (v >> 32) : v)); }
-__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
-    uint64_t d;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-    return d;
-}
-
 __device__ __forceinline__ int warp_min(int v) { return __reduce_min_sync(0xffffffffu, v); }
 __device__ __forceinline__ int warp_max(int v) { return __reduce_max_sync(0xffffffffu, v); }
 
@@ -187,7 +176,8 @@ __global__ void __launch_bounds__(kPfnThreads, (MODE == PFN_MODE_APPLY) ? 5 : 4)
     const int ntiles = (int)((N + WIN - 1) / WIN);
     const int per = (ntiles + (int)gridDim.x - 1) / (int)gridDim.x;
     const int t_begin = min(ntiles, (int)blockIdx.x * per), t_end = min(ntiles, t_begin + per);
-    const bool want_arg = (MODE == PFN_MODE_APPLY) && a.argpos != nullptr;
+    constexpr bool want_arg = (MODE == PFN_MODE_APPLY_ARG);   // compile-time: the eval kernel carries no argmax state
+    constexpr bool is_apply = (MODE == PFN_MODE_APPLY) || (MODE == PFN_MODE_APPLY_ARG);
     double *dscr = reinterpret_cast<double *>(S.scr);
 
     // ---- per-CTA constants
@@ -197,49 +187,35 @@ __global__ void __launch_bounds__(kPfnThreads, (MODE == PFN_MODE_APPLY) ? 5 : 4)
         mbar_init(&S.pre, 1);
         fence_mbar_init();
     }
-    // Forward modes: a half-warp streams rows; lane hl of the half owns the channel pair (2 hl, 2 hl + 1) (+32 p).  The
-    // pair's weight columns sit in 64-bit registers so one FFMA2 (fma.rn.f32x2) advances both channels' fmaf chains.
-    // Backward: lane = channel (+32 cc), weights as plain floats.
-    const int half = lane >> 4, hl = lane & 15;
-    uint64_t W2[CPL][CS], SC2[CPL], SH2[CPL];
-    float W[CPL][CS];
+    // lane = output channel (+32): its weight row(s) live in registers for the whole kernel
+    float W[CPL][CS], sc[CPL], sh[CPL];
 #pragma unroll
-    for (int p = 0; p < CPL; ++p) {
-        float sc[2] = {1.0f, 1.0f}, sh[2] = {0.0f, 0.0f};
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int ch = 2 * hl + h + 32 * p;
-            if (MODE == PFN_MODE_APPLY) {
-                if (a.bias) sh[h] = a.bias[ch];
-                if (a.use_norm) {
-                    if (a.fold_from_state) { sc[h] = (float)a.bn_state[2 * COUT + ch]; sh[h] = (float)a.bn_state[3 * COUT + ch]; }
-                    else fold_bn((double)a.gamma[ch], (double)a.beta[ch], (double)a.rmean[ch], (double)a.rvar[ch], a.eps, &sc[h], &sh[h]);
-                }
-            }
-        }
-        SC2[p] = pack2(sc[0], sc[1]);
-        SH2[p] = pack2(sh[0], sh[1]);
+    for (int cc = 0; cc < CPL; ++cc) {
+        const int ch = lane + 32 * cc;
 #pragma unroll
         for (int s = 0; s < CS; ++s) {
             const int k = a.kmap[s];
-            if (MODE == PFN_MODE_BWD) {
-                W[p][s] = (k >= 0) ? __ldg(a.weight + (lane + 32 * p) * a.c_in + k) : 0.0f;
-            } else {
-                const float w0 = (k >= 0) ? __ldg(a.weight + (2 * hl + 32 * p) * a.c_in + k) : 0.0f;
-                const float w1 = (k >= 0) ? __ldg(a.weight + (2 * hl + 1 + 32 * p) * a.c_in + k) : 0.0f;
-                W2[p][s] = pack2(w0, w1);
+            W[cc][s] = (k >= 0) ? __ldg(a.weight + ch * a.c_in + k) : 0.0f;
+        }
+        sc[cc] = 1.0f;
+        sh[cc] = 0.0f;
+        if (is_apply) {
+            if (a.bias) sh[cc] = a.bias[ch];
+            if (a.use_norm) {
+                if (a.fold_from_state) { sc[cc] = (float)a.bn_state[2 * COUT + ch]; sh[cc] = (float)a.bn_state[3 * COUT + ch]; }
+                else fold_bn((double)a.gamma[ch], (double)a.beta[ch], (double)a.rmean[ch], (double)a.rvar[ch], a.eps, &sc[cc], &sh[cc]);
             }
         }
     }
     __syncthreads();
 
     // ---- accumulators that live for the whole CTA
-    double st_x[CPL][2], st_x2[CPL][2], st_m[16];
+    double st_x[CPL], st_x2[CPL], st_m[16];
     int gba = 0, gbb = 0;
     const int grg = tid % Cfg::RG, gblk = tid / Cfg::RG;
     if (MODE == PFN_MODE_STATS) {
 #pragma unroll
-        for (int cc = 0; cc < CPL; ++cc) st_x[cc][0] = st_x[cc][1] = st_x2[cc][0] = st_x2[cc][1] = 0.0;
+        for (int cc = 0; cc < CPL; ++cc) st_x[cc] = st_x2[cc] = 0.0;
 #pragma unroll
         for (int e = 0; e < 16; ++e) st_m[e] = 0.0;
         int rem = gblk;
@@ -274,94 +250,107 @@ __global__ void __launch_bounds__(kPfnThreads, (MODE == PFN_MODE_APPLY) ? 5 : 4)
             f[CS] = 1.0f;  // ones column: the Gram matrix then carries sum f (S1) as well
 #pragma unroll
             for (int k = CS + 1; k < Cfg::FW; ++k) f[k] = 0.0f;
-            // every value is stored twice, {f, f}: an LDS.128 then yields the f32x2 operands of two chain steps
-            float4 *dst = reinterpret_cast<float4 *>(&S.f[jj * Cfg::FS2]);
+            float4 *dst = reinterpret_cast<float4 *>(&S.f[jj * Cfg::FSTRIDE]);
 #pragma unroll
-            for (int k2 = 0; k2 < Cfg::FW / 2; ++k2) dst[k2] = make_float4(f[k2 * 2], f[k2 * 2], f[k2 * 2 + 1], f[k2 * 2 + 1]);
+            for (int k4 = 0; k4 < Cfg::T4; ++k4) dst[k4] = make_float4(f[k4 * 4], f[k4 * 4 + 1], f[k4 * 4 + 2], f[k4 * 4 + 3]);
         }
     };
 
-    // acc[p] = the channel pair's two pre-activations of row j: k-ascending fmaf chains, two per FFMA2
-    auto dot_row = [&](int j, uint64_t *acc) {
-        const ulonglong2 *src = reinterpret_cast<const ulonglong2 *>(&S.f[j * Cfg::FS2]);
+    // x[cc] = W[cc] . f(row j) as a k-ascending fmaf chain
+    auto dot_row = [&](int j, float *x) {
+        float f[Cfg::FW];
+        const float4 *src = reinterpret_cast<const float4 *>(&S.f[j * Cfg::FSTRIDE]);
 #pragma unroll
-        for (int p = 0; p < CPL; ++p) acc[p] = 0ull;
+        for (int k4 = 0; k4 < (CS + 3) / 4; ++k4) {
+            const float4 v = src[k4];
+            f[k4 * 4] = v.x; f[k4 * 4 + 1] = v.y; f[k4 * 4 + 2] = v.z; f[k4 * 4 + 3] = v.w;
+        }
 #pragma unroll
-        for (int k2 = 0; k2 < (CS + 1) / 2; ++k2) {
-            const ulonglong2 v = src[k2];  // {f[2k2], f[2k2]}, {f[2k2+1], f[2k2+1]}
+        for (int cc = 0; cc < CPL; ++cc) {
+            float acc = 0.0f;
 #pragma unroll
-            for (int p = 0; p < CPL; ++p) {
-                acc[p] = ffma2(W2[p][2 * k2], v.x, acc[p]);
-                if (2 * k2 + 1 < CS) acc[p] = ffma2(W2[p][2 * k2 + 1], v.y, acc[p]);
+            for (int k = 0; k < CS; ++k) acc = fmaf(W[cc][k], f[k], acc);
+            x[cc] = acc;
+        }
+    };
+
+    // running max state of the pillar a warp is streaming (lane = channel)
+    float m[CPL];
+    int mk[CPL], mp[CPL];
+    auto reset_max = [&]() {
+#pragma unroll
+        for (int cc = 0; cc < CPL; ++cc) { m[cc] = want_arg ? -1.0f : 0.0f; mk[cc] = INF; mp[cc] = 0; }
+    };
+    auto fold_max = [&](const float *x, int kj, int pos) {
+#pragma unroll
+        for (int cc = 0; cc < CPL; ++cc) {
+            const float y = fmaf(x[cc], sc[cc], sh[cc]);
+            if (!want_arg) {
+                m[cc] = fmaxf(m[cc], y);  // ReLU folds into the max with 0
+            } else {
+                const float z = fmaxf(y, 0.0f);
+                if (z > m[cc] || (z == m[cc] && kj < mk[cc])) { m[cc] = z; mk[cc] = kj; mp[cc] = pos; }
             }
         }
     };
 
-    // running max state of the pillar a half-warp is streaming (lane = channel pair)
-    float m[CPL][2];
-    int mk[CPL][2], mp[CPL][2];
-    auto reset_max = [&]() {
-#pragma unroll
-        for (int p = 0; p < CPL; ++p)
-#pragma unroll
-            for (int h = 0; h < 2; ++h) { m[p][h] = want_arg ? -1.0f : 0.0f; mk[p][h] = INF; mp[p][h] = 0; }
-    };
-    // one row: BN (+ReLU) on the pair, then either the running max or the fp64 statistics
-    auto fold_row = [&](const uint64_t *acc, int kj, int pos) {
-#pragma unroll
-        for (int p = 0; p < CPL; ++p) {
+    // STREAM: warp w walks rows [ra, rb) of S.f; APPLY keeps the running max and stores a pillar when its last row
+    // has been folded in (S.lp[j] = (pillar slot << 1) | last-row flag); STATS accumulates sum x / sum x^2.
+    auto stream = [&](int ra, int rb, int ps, int gb) {
+        if (is_apply) reset_max();
+        // first pillar this warp closes = the pillar of its first row (ranges are pillar aligned)
+        const int slot0 = (ra < rb) ? (S.lp[ra] >> 1) : 0;
+        float *fout = a.features + (size_t)(ps + slot0) * COUT + lane;
+        int32_t *aout = want_arg ? a.argpos + (size_t)(ps + slot0) * COUT + lane : nullptr;
+        int j = ra;
+        for (; j + 1 < rb; j += 2) {  // two rows in flight: two independent fmaf chains per channel
+            float x0[CPL], x1[CPL];
+            dot_row(j, x0);
+            dot_row(j + 1, x1);
             if (MODE == PFN_MODE_STATS) {
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const double v = (double)unpack(acc[p], h);
-                    st_x[p][h] += v;
-                    st_x2[p][h] = fma(v, v, st_x2[p][h]);
+                for (int cc = 0; cc < CPL; ++cc) {
+                    const double v0 = (double)x0[cc], v1 = (double)x1[cc];
+                    st_x[cc] += v0; st_x2[cc] = fma(v0, v0, st_x2[cc]);
+                    st_x[cc] += v1; st_x2[cc] = fma(v1, v1, st_x2[cc]);
                 }
             } else {
-                const uint64_t y2 = ffma2(acc[p], SC2[p], SH2[p]);
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
-                    const float y = unpack(y2, h);
-                    if (!want_arg) {
-                        m[p][h] = fmaxf(m[p][h], y);  // ReLU folds into the max with 0
-                    } else {
-                        const float z = fmaxf(y, 0.0f);
-                        if (z > m[p][h] || (z == m[p][h] && kj < mk[p][h])) { m[p][h] = z; mk[p][h] = kj; mp[p][h] = pos; }
+                    const int jj = j + h, meta = S.lp[jj];
+                    fold_max(h ? x1 : x0, want_arg ? S.kept[jj] : 0, gb + jj);
+                    if (meta & 1) {  // pillars close in order: the output row pointer just advances
+#pragma unroll
+                        for (int cc = 0; cc < CPL; ++cc) {
+                            fout[32 * cc] = m[cc];
+                            if (want_arg) aout[32 * cc] = mp[cc];
+                        }
+                        fout += COUT;
+                        if (want_arg) aout += COUT;
+                        reset_max();
                     }
                 }
             }
         }
-    };
-    auto flush = [&](int pillar) {
+        if (j < rb) {
+            float x0[CPL];
+            dot_row(j, x0);
+            if (MODE == PFN_MODE_STATS) {
 #pragma unroll
-        for (int p = 0; p < CPL; ++p) {
-            const size_t o = (size_t)pillar * COUT + 2 * hl + 32 * p;
-            *reinterpret_cast<float2 *>(a.features + o) = make_float2(m[p][0], m[p][1]);
-            if (want_arg) *reinterpret_cast<int2 *>(a.argpos + o) = make_int2(mp[p][0], mp[p][1]);
-        }
-        reset_max();
-    };
-
-    // STREAM: each half-warp walks its own rows [ra, rb) of S.f, two rows in flight.  APPLY stores a pillar when its
-    // last row has been folded in (S.lp[j] = (pillar slot << 1) | last-row flag).
-    auto stream = [&](int ra, int rb, int ps, int gb) {
-        if (MODE == PFN_MODE_APPLY) reset_max();
-        const int span = max(__shfl_sync(0xffffffffu, rb - ra, 0), __shfl_sync(0xffffffffu, rb - ra, 16));
-        for (int i = 0; i < span; i += 2) {
-            const int j0r = ra + i, j1r = ra + i + 1;
-            const bool on0 = j0r < rb, on1 = j1r < rb;
-            uint64_t x0[CPL], x1[CPL];
-            dot_row(on0 ? j0r : 0, x0);  // idle half / odd tail: row 0 is always valid smem, result unused
-            dot_row(on1 ? j1r : 0, x1);
-            if (on0) {
-                const int meta = S.lp[j0r];
-                fold_row(x0, want_arg ? S.kept[j0r] : 0, gb + j0r);
-                if (MODE == PFN_MODE_APPLY && (meta & 1)) flush(ps + (meta >> 1));
-            }
-            if (on1) {
-                const int meta = S.lp[j1r];
-                fold_row(x1, want_arg ? S.kept[j1r] : 0, gb + j1r);
-                if (MODE == PFN_MODE_APPLY && (meta & 1)) flush(ps + (meta >> 1));
+                for (int cc = 0; cc < CPL; ++cc) { const double v0 = (double)x0[cc]; st_x[cc] += v0; st_x2[cc] = fma(v0, v0, st_x2[cc]); }
+            } else {
+                const int meta = S.lp[j];
+                fold_max(x0, want_arg ? S.kept[j] : 0, gb + j);
+                if (meta & 1) {
+#pragma unroll
+                    for (int cc = 0; cc < CPL; ++cc) {
+                        fout[32 * cc] = m[cc];
+                        if (want_arg) aout[32 * cc] = mp[cc];
+                    }
+                    fout += COUT;
+                    if (want_arg) aout += COUT;
+                    reset_max();
+                }
             }
         }
     };
@@ -370,12 +359,10 @@ __global__ void __launch_bounds__(kPfnThreads, (MODE == PFN_MODE_APPLY) ? 5 : 4)
     auto gram = [&](int np) {
         if (gblk < Cfg::NBLK) {
             for (int j = grg; j < np; j += Cfg::RG) {
-                const float4 A0 = *reinterpret_cast<const float4 *>(&S.f[j * Cfg::FS2 + gba * 8]);
-                const float4 A1 = *reinterpret_cast<const float4 *>(&S.f[j * Cfg::FS2 + gba * 8 + 4]);
-                const float4 B0 = *reinterpret_cast<const float4 *>(&S.f[j * Cfg::FS2 + gbb * 8]);
-                const float4 B1 = *reinterpret_cast<const float4 *>(&S.f[j * Cfg::FS2 + gbb * 8 + 4]);
-                const double av[4] = {(double)A0.x, (double)A0.z, (double)A1.x, (double)A1.z};
-                const double bv[4] = {(double)B0.x, (double)B0.z, (double)B1.x, (double)B1.z};
+                const float4 A = *reinterpret_cast<const float4 *>(&S.f[j * Cfg::FSTRIDE + gba * 4]);
+                const float4 B = *reinterpret_cast<const float4 *>(&S.f[j * Cfg::FSTRIDE + gbb * 4]);
+                const double av[4] = {(double)A.x, (double)A.y, (double)A.z, (double)A.w};
+                const double bv[4] = {(double)B.x, (double)B.y, (double)B.z, (double)B.w};
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -453,7 +440,7 @@ __global__ void __launch_bounds__(kPfnThreads, (MODE == PFN_MODE_APPLY) ? 5 : 4)
                 S.mean[q * 3] = mx; S.mean[q * 3 + 1] = my; S.mean[q * 3 + 2] = mz;
                 const float *r0 = T.row(j0 + b0);
                 pillar_centre(r0[1], r0[2], a, &S.cen[q * 2], &S.cen[q * 2 + 1]);
-                if (MODE == PFN_MODE_APPLY && a.pillar_mean) {
+                if (is_apply && a.pillar_mean) {
                     float *pm = a.pillar_mean + (size_t)(ps + q) * 3;
                     pm[0] = mx; pm[1] = my; pm[2] = mz;
                 }
@@ -462,10 +449,10 @@ __global__ void __launch_bounds__(kPfnThreads, (MODE == PFN_MODE_APPLY) ? 5 : 4)
             c1(T.rows, j0 + 1, np);
             __syncthreads();
             if (MODE != PFN_MODE_BWD) {
-                // half-warp hw streams a pillar-aligned eighth of the rows
-                const int hw = warp * 2 + half, r_lo = (hw * np) / (2 * NW), r_hi = ((hw + 1) * np) / (2 * NW);
-                const int ra = (hw == 0) ? 0 : S.start[S.lp[r_lo] >> 1];
-                const int rb = (hw == 2 * NW - 1) ? np : S.start[S.lp[r_hi] >> 1];
+                // warp w streams a pillar-aligned quarter of the rows
+                const int r_lo = (warp * np) / NW, r_hi = ((warp + 1) * np) / NW;
+                const int ra = (warp == 0) ? 0 : S.start[S.lp[r_lo] >> 1];
+                const int rb = (warp == NW - 1) ? np : S.start[S.lp[r_hi] >> 1];
                 if (MODE == PFN_MODE_STATS) gram(np);
                 stream(ra, rb, ps, gb);
             } else {
@@ -492,11 +479,11 @@ __global__ void __launch_bounds__(kPfnThreads, (MODE == PFN_MODE_APPLY) ? 5 : 4)
                         const float gy = S.pre_out[o] > 0.0f ? S.pre_grad[o] : 0.0f;
                         const int jj = S.pre_arg[o] - gb;
                         float f[Cfg::FW];
-                        const float4 *src = reinterpret_cast<const float4 *>(&S.f[jj * Cfg::FS2]);
+                        const float4 *src = reinterpret_cast<const float4 *>(&S.f[jj * Cfg::FSTRIDE]);
 #pragma unroll
-                        for (int k2 = 0; k2 < (CS + 1) / 2; ++k2) {
-                            const float4 v = src[k2];
-                            f[k2 * 2] = v.x; f[k2 * 2 + 1] = v.z;
+                        for (int k4 = 0; k4 < (CS + 3) / 4; ++k4) {
+                            const float4 v = src[k4];
+                            f[k4 * 4] = v.x; f[k4 * 4 + 1] = v.y; f[k4 * 4 + 2] = v.z; f[k4 * 4 + 3] = v.w;
                         }
                         float x = 0.0f;
 #pragma unroll
@@ -536,7 +523,7 @@ __global__ void __launch_bounds__(kPfnThreads, (MODE == PFN_MODE_APPLY) ? 5 : 4)
                 for (int j = 0; j < NT; ++j) tsum += S.dred[j * 3 + tid];
                 const float mv = (float)__ddiv_rn(tsum, (double)(e - a0));
                 S.mean[tid] = mv;
-                if (MODE == PFN_MODE_APPLY && a.pillar_mean) a.pillar_mean[(size_t)pb * 3 + tid] = mv;
+                if (is_apply && a.pillar_mean) a.pillar_mean[(size_t)pb * 3 + tid] = mv;
             }
             if (tid == 32) {
                 const float *r0 = a.grows + (a0 + 1) * RS;
@@ -577,23 +564,20 @@ __global__ void __launch_bounds__(kPfnThreads, (MODE == PFN_MODE_APPLY) ? 5 : 4)
                     c1(rows, 0, npc);
                     __syncthreads();
                     if (MODE == PFN_MODE_STATS) gram(npc);
-                    const int hw = warp * 2 + half;
-                    stream((hw * npc) / (2 * NW), ((hw + 1) * npc) / (2 * NW), pb, (int)cs);
-                    if (MODE == PFN_MODE_APPLY) {
-                        // merge the half-warps' running maxima into the carry, in half-warp order (deterministic)
-                        for (int w = 0; w < 2 * NW; ++w) {
-                            if (hw == w) {
+                    stream((warp * npc) / NW, ((warp + 1) * npc) / NW, pb, (int)cs);
+                    if (is_apply) {
+                        // merge the warps' running maxima into the carry, in warp order (deterministic)
+                        for (int w = 0; w < NW; ++w) {
+                            if (warp == w) {
 #pragma unroll
-                                for (int p = 0; p < CPL; ++p)
-#pragma unroll
-                                    for (int h = 0; h < 2; ++h) {
-                                        const int ch = 2 * hl + h + 32 * p;
-                                        const float bm = S.carry_v[ch];
-                                        const int bk = S.carry_k[ch];
-                                        if (m[p][h] > bm || (want_arg && m[p][h] == bm && mk[p][h] < bk)) {
-                                            S.carry_v[ch] = m[p][h]; S.carry_k[ch] = mk[p][h]; S.carry_p[ch] = mp[p][h];
-                                        }
+                                for (int cc = 0; cc < CPL; ++cc) {
+                                    const int ch = lane + 32 * cc;
+                                    const float bm = S.carry_v[ch];
+                                    const int bk = S.carry_k[ch];
+                                    if (m[cc] > bm || (want_arg && m[cc] == bm && mk[cc] < bk)) {
+                                        S.carry_v[ch] = m[cc]; S.carry_k[ch] = mk[cc]; S.carry_p[ch] = mp[cc];
                                     }
+                                }
                             }
                             __syncthreads();
                         }
@@ -601,7 +585,7 @@ __global__ void __launch_bounds__(kPfnThreads, (MODE == PFN_MODE_APPLY) ? 5 : 4)
                         __syncthreads();
                     }
                 }
-                if (MODE == PFN_MODE_APPLY && tid < COUT) {
+                if (is_apply && tid < COUT) {
                     a.features[(size_t)pb * COUT + tid] = S.carry_v[tid];
                     if (want_arg) a.argpos[(size_t)pb * COUT + tid] = S.carry_p[tid];
                 }
@@ -617,17 +601,14 @@ __global__ void __launch_bounds__(kPfnThreads, (MODE == PFN_MODE_APPLY) ? 5 : 4)
         double *out = a.partials + (size_t)blockIdx.x * Cfg::STATS_DOUBLES;
         __syncthreads();
 #pragma unroll
-        for (int p = 0; p < CPL; ++p)
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int ch = 2 * hl + h + 32 * p, hw = warp * 2 + half;
-                dscr[(hw * COUT + ch) * 2] = st_x[p][h];
-                dscr[(hw * COUT + ch) * 2 + 1] = st_x2[p][h];
-            }
+        for (int cc = 0; cc < CPL; ++cc) {
+            dscr[(warp * COUT + lane + 32 * cc) * 2] = st_x[cc];
+            dscr[(warp * COUT + lane + 32 * cc) * 2 + 1] = st_x2[cc];
+        }
         __syncthreads();
         if (tid < COUT) {
             double sx = 0.0, sx2 = 0.0;
-            for (int w = 0; w < 2 * NW; ++w) { sx += dscr[(w * COUT + tid) * 2]; sx2 += dscr[(w * COUT + tid) * 2 + 1]; }
+            for (int w = 0; w < NW; ++w) { sx += dscr[(w * COUT + tid) * 2]; sx2 += dscr[(w * COUT + tid) * 2 + 1]; }
             out[tid] = sx; out[COUT + tid] = sx2;
         }
         __syncthreads();

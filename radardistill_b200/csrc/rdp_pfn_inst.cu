@@ -27,6 +27,7 @@ static cudaError_t launch_tile(const PfnArgs &a, int grid, cudaStream_t st) {
 static cudaError_t tile(const PfnArgs &a, int mode, int grid, cudaStream_t st) {
     if (mode == PFN_MODE_STATS) return launch_tile<PFN_MODE_STATS>(a, grid, st);
     if (mode == PFN_MODE_BWD) return launch_tile<PFN_MODE_BWD>(a, grid, st);
+    if (mode == PFN_MODE_APPLY_ARG) return launch_tile<PFN_MODE_APPLY_ARG>(a, grid, st);
     return launch_tile<PFN_MODE_APPLY>(a, grid, st);
 }
 
