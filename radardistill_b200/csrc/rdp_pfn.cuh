@@ -91,9 +91,9 @@ template <class Cfg, int MODE>
 struct PfnSmem {
     static constexpr size_t Z_BYTES = 16;
     static constexpr size_t S_BYTES = (MODE == PFN_MODE_STATS) ? sizeof(double) * kPfnThreads * 16 : 0;
-    static constexpr size_t B_BYTES = (MODE == PFN_MODE_BWD) ? sizeof(double) * (kPfnThreads / 32) * Cfg::BWD_DOUBLES : 0;
+    static constexpr size_t B_BYTES = 0;  // BWD: the end-of-kernel scratch aliases f + the prefetch buffers (see bwd_scratch())
     static constexpr size_t SCR = Z_BYTES > S_BYTES ? (Z_BYTES > B_BYTES ? Z_BYTES : B_BYTES) : (S_BYTES > B_BYTES ? S_BYTES : B_BYTES);
-    static constexpr int PCH = (MODE == PFN_MODE_BWD) ? 96 : 1;  // pillars per backward prefetch chunk
+    static constexpr int PCH = (MODE == PFN_MODE_BWD) ? 64 : 1;  // pillars per backward prefetch chunk
     PfnStage<Cfg> st[2];
     alignas(8) uint64_t full[2];
     alignas(8) uint64_t pre;                       // BWD: arrival of the tile's (grad, features, argpos) rows
@@ -178,7 +178,11 @@ __global__ void __launch_bounds__(kPfnThreads, (MODE == PFN_MODE_APPLY) ? 5 : 4)
     const int t_begin = min(ntiles, (int)blockIdx.x * per), t_end = min(ntiles, t_begin + per);
     constexpr bool want_arg = (MODE == PFN_MODE_APPLY_ARG);   // compile-time: the eval kernel carries no argmax state
     constexpr bool is_apply = (MODE == PFN_MODE_APPLY) || (MODE == PFN_MODE_APPLY_ARG);
-    double *dscr = reinterpret_cast<double *>(S.scr);
+    // fp64 reduction scratch used once at the end of the kernel; in BWD it aliases the (then idle) prefetch + feature buffers
+    double *dscr = (MODE == PFN_MODE_BWD) ? reinterpret_cast<double *>(S.pre_grad) : reinterpret_cast<double *>(S.scr);
+    static_assert(MODE != PFN_MODE_BWD ||
+                  sizeof(double) * (kPfnThreads / 32) * Cfg::BWD_DOUBLES <= 3 * sizeof(float) * Smem::PCH * Cfg::COUT + sizeof(S.f),
+                  "backward scratch must fit in pre_grad | pre_out | pre_arg | f");
 
     // ---- per-CTA constants
     if (tid == 0) {

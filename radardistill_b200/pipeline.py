@@ -1,0 +1,74 @@
+"""Host-buffer pipeline around the encoder modules: pinned host points in, pinned host features / coords out.
+
+The encoders themselves take CUDA tensors (like the reference's, after ``load_data_to_gpu``,
+``pcdet/models/__init__.py:23-36``).  When inputs and outputs live on the host, the PCIe copies dominate a step
+(66 MB up, 191 MB down for a batch of 8 LiDAR + radar frames), so this helper overlaps them with the kernels:
+uploads of step i+1 run on an input stream and downloads of step i on an output stream while step i+1 computes on
+the main stream.  Every copy uses pinned buffers; results are valid after ``finish()`` / ``wait(step)``.
+"""
+from __future__ import annotations
+
+import torch
+
+
+class HostPipeline:
+    def __init__(self, step_fn, device, out_keys, depth: int = 2):
+        """``step_fn(device_inputs: dict) -> batch_dict`` runs one step on the current stream."""
+        self.step_fn, self.device, self.out_keys, self.depth = step_fn, device, tuple(out_keys), depth
+        self.in_stream, self.out_stream = torch.cuda.Stream(device), torch.cuda.Stream(device)
+        self.slots = [dict(inputs=None, up=None, host={}, done=None, shapes={}) for _ in range(depth)]
+        self.counter = 0
+
+    def _upload(self, slot, host_inputs):
+        main = torch.cuda.current_stream(self.device)
+        with torch.cuda.stream(self.in_stream):
+            self.in_stream.wait_stream(main)  # the slot's previous device inputs are no longer in use
+            slot["inputs"] = {k: (v.to(self.device, non_blocking=True) if isinstance(v, torch.Tensor) else v)
+                              for k, v in host_inputs.items()}
+            slot["up"] = torch.cuda.Event()
+            slot["up"].record(self.in_stream)
+
+    def submit(self, host_inputs: dict, next_host_inputs: dict = None):
+        """Runs one step; if ``next_host_inputs`` is given its upload overlaps this step's kernels."""
+        slot = self.slots[self.counter % self.depth]
+        if slot["done"] is not None:
+            slot["done"].synchronize()  # host buffers of this slot are about to be overwritten
+        if slot["up"] is None or slot.get("for") != self.counter:
+            self._upload(slot, host_inputs)
+        main = torch.cuda.current_stream(self.device)
+        main.wait_event(slot["up"])
+        if next_host_inputs is not None:
+            nxt = self.slots[(self.counter + 1) % self.depth]
+            if nxt["done"] is not None:
+                nxt["done"].synchronize()
+            self._upload(nxt, next_host_inputs)
+            nxt["for"] = self.counter + 1
+        bd = self.step_fn(slot["inputs"])
+        ready = torch.cuda.Event()
+        ready.record(main)
+        nbytes = 0
+        with torch.cuda.stream(self.out_stream):
+            self.out_stream.wait_event(ready)
+            for k in self.out_keys:
+                t = bd[k].detach()
+                t.record_stream(self.out_stream)
+                buf = slot["host"].get(k)
+                if buf is None or buf.shape[0] < t.shape[0] or buf.shape[1:] != t.shape[1:]:
+                    buf = torch.empty((int(t.shape[0] * 1.1) + 16,) + tuple(t.shape[1:]), dtype=t.dtype).pin_memory()
+                    slot["host"][k] = buf
+                buf[:t.shape[0]].copy_(t, non_blocking=True)
+                slot["shapes"][k] = t.shape[0]
+                nbytes += t.numel() * t.element_size()
+            slot["done"] = torch.cuda.Event()
+            slot["done"].record(self.out_stream)
+        self.counter += 1
+        return nbytes
+
+    def finish(self):
+        self.out_stream.synchronize()
+        torch.cuda.current_stream(self.device).synchronize()
+
+    def result(self, step: int) -> dict:
+        slot = self.slots[step % self.depth]
+        slot["done"].synchronize()
+        return {k: slot["host"][k][:slot["shapes"][k]] for k in self.out_keys}
