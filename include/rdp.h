@@ -150,6 +150,13 @@ RDP_API int rdp_argmax_kept(int64_t n_points, const rdp_geom_t *geom, const rdp_
                             int32_t *argmax_kept, void *stream);
 
 /*
+ * Copies counters[] to `host_mapped` (pinned, device-visible host memory: cudaHostAlloc / torch pin_memory under UVA)
+ * from a one-warp kernel instead of a DMA transfer, so the 64-byte read-back never queues behind bulk copies on the
+ * copy engines.  The values are visible on the host once `stream` has been synchronised.
+ */
+RDP_API int rdp_publish_counters(const int32_t *counters, int32_t *host_mapped, void *stream);
+
+/*
  * Host-buffer convenience (what a non-torch caller binds): uploads `points` (host), runs
  * rdp_index_fwd + rdp_pfn_fwd in eval mode, downloads the results and synchronises.
  * Host output buffers must hold n_points rows; *n_kept / *n_pillars receive N and P.

@@ -14,7 +14,8 @@ CNT_N, CNT_P, CNT_ERRFLAGS = 0, 1, 2
 LAYOUT_SIMPLE2D, LAYOUT_DYNPILLAR = 0, 1
 
 EXPORTS = ["rdp_abi_version", "rdp_status_string", "rdp_last_cuda_error", "rdp_workspace_bytes", "rdp_index_fwd",
-           "rdp_pfn_fwd", "rdp_bn_state_doubles", "rdp_pfn_bwd", "rdp_argmax_kept", "rdp_encode_host"]
+           "rdp_pfn_fwd", "rdp_bn_state_doubles", "rdp_pfn_bwd", "rdp_argmax_kept", "rdp_publish_counters",
+           "rdp_encode_host"]
 
 
 class Geom(C.Structure):
@@ -70,6 +71,8 @@ def load() -> C.CDLL:
                                 vp, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.rdp_argmax_kept.restype = C.c_int
     lib.rdp_argmax_kept.argtypes = [C.c_int64, C.POINTER(Geom), C.POINTER(Layout), vp, C.c_size_t, vp, vp, vp, vp]
+    lib.rdp_publish_counters.restype = C.c_int
+    lib.rdp_publish_counters.argtypes = [vp, vp, vp]
     lib.rdp_encode_host.restype = C.c_int
     lib.rdp_encode_host.argtypes = [vp, C.c_int64, C.POINTER(Geom), C.POINTER(Layout), C.POINTER(PfnParams), vp, vp, vp, vp,
                                     C.POINTER(C.c_int64), C.POINTER(C.c_int64)]

@@ -328,6 +328,11 @@ group_rows_kernel(const float *__restrict__ pts, const int32_t *__restrict__ ran
     }
 }
 
+__global__ void publish_counters_kernel(const int32_t *__restrict__ counters, volatile int32_t *host_mapped) {
+    if (threadIdx.x < RDP_NUM_COUNTERS) host_mapped[threadIdx.x] = counters[threadIdx.x];
+    __threadfence_system();
+}
+
 static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 }  // namespace rdp
@@ -367,6 +372,13 @@ extern "C" int rdp_index_fwd(const float *points, int64_t n_points, const rdp_ge
                                                          inverse, counts, counters, ws.orig2kept, ws.kept2orig);
     count_scan_kernel<<<kScanGrid, kScanThreads, 0, stream>>>(counts, ws.scan_state_b, ws.ends, counters);
     group_rows_kernel<<<tiles, kIndexThreads, smem, stream>>>(points, ws.keys, n_points, geom->cols, ws.ends, ws.grows);
+    RDP_CUDA_OK(cudaGetLastError());
+    return RDP_OK;
+}
+
+extern "C" int rdp_publish_counters(const int32_t *counters, int32_t *host_mapped, void *stream_v) {
+    if (!counters || !host_mapped) return RDP_ERR_INVALID_ARG;
+    publish_counters_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream_v)>>>(counters, host_mapped);
     RDP_CUDA_OK(cudaGetLastError());
     return RDP_OK;
 }

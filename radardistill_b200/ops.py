@@ -194,8 +194,8 @@ def encode_forward(points: torch.Tensor, spec: EncoderSpec, batch_size: int, wei
         _lib.check(lib.rdp_pfn_fwd(_ptr(pts), n0, C.byref(geom), C.byref(layout), C.byref(prm), _ptr(ws), nbytes.value,
                                    _ptr(counters), _ptr(features), _ptr(argpos), _ptr(pmean), _ptr(bn_state), st),
                    "rdp_pfn_fwd")
-        host = _pinned_counters(dev)
-        host.copy_(counters, non_blocking=True)
+        host = _pinned_counters(dev)  # written by a kernel (zero-copy): never queues behind bulk DMA on the copy engines
+        _lib.check(lib.rdp_publish_counters(_ptr(counters), C.c_void_p(host.data_ptr()), st), "rdp_publish_counters")
         torch.cuda.current_stream().synchronize()
         n_kept, n_pillars, err = int(host[_lib.CNT_N]), int(host[_lib.CNT_P]), int(host[_lib.CNT_ERRFLAGS])
     if err & 1:

@@ -12,7 +12,7 @@ import torch
 
 
 class HostPipeline:
-    def __init__(self, step_fn, device, out_keys, depth: int = 2):
+    def __init__(self, step_fn, device, out_keys, depth: int = 3):
         """``step_fn(device_inputs: dict) -> batch_dict`` runs one step on the current stream."""
         self.step_fn, self.device, self.out_keys, self.depth = step_fn, device, tuple(out_keys), depth
         self.in_stream, self.out_stream = torch.cuda.Stream(device), torch.cuda.Stream(device)
@@ -39,9 +39,7 @@ class HostPipeline:
         main.wait_event(slot["up"])
         if next_host_inputs is not None:
             nxt = self.slots[(self.counter + 1) % self.depth]
-            if nxt["done"] is not None:
-                nxt["done"].synchronize()
-            self._upload(nxt, next_host_inputs)
+            self._upload(nxt, next_host_inputs)  # its device inputs are free: the step that used them has completed
             nxt["for"] = self.counter + 1
         bd = self.step_fn(slot["inputs"])
         ready = torch.cuda.Event()

@@ -1,0 +1,17 @@
+import sys, os, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch, bench
+from radardistill_b200.pipeline import HostPipeline
+lidar, radar = bench.make_clouds(0, 8)
+dev = torch.device("cuda", 0)
+mode = "B"
+lid, rad, call = bench.build_modules(dev, mode, False)
+host_in = {"points": torch.from_numpy(lidar).pin_memory(), "radar_points": torch.from_numpy(radar).pin_memory()}
+pipe = HostPipeline(lambda d: bench.gpu_step(call, d["points"], d["radar_points"], mode, 8), dev,
+                    ("pillar_features", "pillar_coords", "radar_pillar_features", "radar_pillar_coords"))
+for i in range(16):
+    t0 = time.perf_counter()
+    pipe.submit(host_in, host_in)
+    t1 = time.perf_counter()
+    print(i, f"submit {1e3*(t1-t0):7.3f} ms  reserved {torch.cuda.memory_reserved()/1e9:.2f} GB", flush=True)
+t0 = time.perf_counter(); pipe.finish(); print("finish", 1e3*(time.perf_counter()-t0))
