@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librdp.so")
+LIB_PATH = os.environ.get("RDP_LIB_PATH", os.path.join(_HERE, "librdp.so"))  # override: kernel-variant experiments
 
 RDP_ABI_VERSION = 1
 RDP_NUM_COUNTERS = 16

@@ -19,11 +19,12 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(ROOT, "include")
 OBJ = os.path.join(HERE, "_build")
-LIB = os.path.join(HERE, "librdp.so")
+LIB = os.environ.get("RDP_LIB_OUT", os.path.join(HERE, "librdp.so"))
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
+EXTRA = os.environ.get("RDP_EXTRA_FLAGS", "").split()
+FLAGS = [*EXTRA, "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
          "--expt-relaxed-constexpr", "-I", INCLUDE, "-I", CSRC]
 
 

@@ -27,8 +27,14 @@ constexpr int kScanThreads = 256;
 constexpr int kScanGrid = 296;        // 2 CTAs per SM: every CTA of a chunked scan is co-resident
 constexpr int kPfnThreads = 128;
 constexpr int kPfnWin = 128;          // grouped rows per PFN tile window (a tile owns the pillars that START in it)
-constexpr int kPfnCap = 192;          // rows staged per tile: the window + 64 rows of overhang for the last pillar
-constexpr int kPfnGridCap = 148 * 4;  // persistent PFN CTAs (also the number of partial-sum slots)
+#ifndef RDP_PFN_CAP
+#define RDP_PFN_CAP 192
+#endif
+constexpr int kPfnCap = RDP_PFN_CAP;          // rows staged per tile: the window + 64 rows of overhang for the last pillar
+#ifndef RDP_PFN_GRID_PER_SM
+#define RDP_PFN_GRID_PER_SM 4
+#endif
+constexpr int kPfnGridCap = 148 * RDP_PFN_GRID_PER_SM;  // persistent PFN CTAs (also the number of partial-sum slots)
 __host__ __device__ constexpr int grouped_row_floats(int cols) { return (cols + 2 + 3) / 4 * 4; }
 constexpr int kMaxCin = 24;
 constexpr int kMaxCout = 64;
