@@ -166,6 +166,17 @@ __device__ __forceinline__ void pillar_centre(float x, float y, const PfnArgs &a
     *ceny = __fadd_rn(__fmul_rn((float)(int)qy, a.vsz[1]), a.off[1]);
 }
 
+// (sx, sy, sz) / cnt, each correctly rounded in fp64 and then rounded once to fp32 -- bit-identical to the three IEEE
+// divisions of the oracle, but with one reciprocal: y = RN(1/b), q = RN(a y), r = a - b q (exact, FMA), RN(q + r y) is the
+// correctly rounded quotient (Markstein); b is a small exact integer here.
+__device__ __forceinline__ void mean3(double sx, double sy, double sz, int cnt, float *mx, float *my, float *mz) {
+    const double b = (double)cnt, y = __drcp_rn(b);
+    const double qx = __dmul_rn(sx, y), qy = __dmul_rn(sy, y), qz = __dmul_rn(sz, y);
+    *mx = (float)__fma_rn(__fma_rn(-qx, b, sx), y, qx);
+    *my = (float)__fma_rn(__fma_rn(-qy, b, sy), y, qy);
+    *mz = (float)__fma_rn(__fma_rn(-qz, b, sz), y, qz);
+}
+
 __device__ __forceinline__ int warp_min(int v) { return __reduce_min_sync(0xffffffffu, v); }
 __device__ __forceinline__ int warp_max(int v) { return __reduce_max_sync(0xffffffffu, v); }
 
@@ -255,15 +266,25 @@ __global__ void __launch_bounds__(kPfnThreads, (MODE == PFN_MODE_APPLY) ? RDP_AP
     };
 
     // C1: decorated features of rows [rowbase, rowbase + np) of `rows` -> S.f[0..np)
-    auto c1 = [&](const float *rows, int rowbase, int np) {
+    // C1: decorated features of rows [rowbase, rowbase + np) of `rows` -> S.f[0..np).  `g0 >= 0`: rows of a staged tile,
+    // the pillar slot is gid - g0 and the "last row of its pillar" flag comes from the next row; g0 < 0: big-pillar chunk
+    // (slot 0, never last).  In the APPLY modes slot CS of the feature row carries (slot << 1 | last) for the stream.
+    auto c1 = [&](const float *rows, int rowbase, int np, int g0) {
         for (int jj = tid; jj < np; jj += NT) {
             float r[COLS], f[Cfg::FW];
             const float *src = rows + (rowbase + jj) * RS;
 #pragma unroll
             for (int c = 0; c < COLS; ++c) r[c] = src[c];
-            const int lp = S.lp[jj] >> 1;
-            decorate<Cfg>(r, S.cen[lp * 2], S.cen[lp * 2 + 1], &S.mean[lp * 3], a, f);
-            f[CS] = 1.0f;  // ones column: the Gram matrix then carries sum f (S1) as well
+            int slot = 0, last = 0;
+            if (g0 >= 0) {
+                const int gid = __float_as_int(src[RS - 1]);
+                slot = gid - g0;
+                last = (jj == np - 1) || (__float_as_int(src[RS + RS - 1]) != gid);
+            }
+            if (want_arg) { const int row = __float_as_int(src[RS - 2]); S.kept[jj] = none_dropped ? row : a.orig2kept[row]; }
+            decorate<Cfg>(r, S.cen[slot * 2], S.cen[slot * 2 + 1], &S.mean[slot * 3], a, f);
+            // STATS: ones column (the Gram matrix then carries sum f as well); APPLY: the row's pillar slot and last flag
+            f[CS] = (MODE == PFN_MODE_STATS || MODE == PFN_MODE_BWD) ? 1.0f : __int_as_float((slot << 1) | last);
 #pragma unroll
             for (int k = CS + 1; k < Cfg::FW; ++k) f[k] = 0.0f;
             float4 *dst = reinterpret_cast<float4 *>(&S.f[jj * Cfg::FSTRIDE]);
@@ -300,13 +321,14 @@ __global__ void __launch_bounds__(kPfnThreads, (MODE == PFN_MODE_APPLY) ? RDP_AP
 
     // STREAM: the 8 (16) threads of a row group walk the same pillar-aligned rows [ra, rb) of S.f, each for its own
     // channel quad.  APPLY keeps the running max and stores 16 bytes per thread -- a coalesced feature row per group --
-    // when a pillar's last row has been folded in (S.lp[j] = (pillar slot << 1) | last-row flag); STATS accumulates
+    // when a pillar's last row has been folded in (slot CS of the feature row = (pillar slot << 1) | last flag); STATS accumulates
     // sum x / sum x^2.
-    auto stream = [&](int ra, int rb, int ps, int gb) {
+    auto stream = [&](int ra, int rb, int pillar0, int gb) {  // pillar0 = global id of pillar slot 0
         if (is_apply) reset_max();
-        const int slot0 = (ra < rb) ? (S.lp[ra] >> 1) : 0;  // pillars close in order: the output pointers just advance
-        float *fout = a.features + (size_t)(ps + slot0) * COUT + quad * 4;
-        int32_t *aout = want_arg ? a.argpos + (size_t)(ps + slot0) * COUT + quad * 4 : nullptr;
+        // pillars close in order, so the output pointers just advance from the first row's pillar
+        const int slot0 = (is_apply && ra < rb) ? (__float_as_int(S.f[ra * Cfg::FSTRIDE + CS]) >> 1) : 0;
+        float *fout = a.features + (size_t)(pillar0 + slot0) * COUT + quad * 4;
+        int32_t *aout = want_arg ? a.argpos + (size_t)(pillar0 + slot0) * COUT + quad * 4 : nullptr;
         for (int j = ra; j < rb; ++j) {
             float x[4];
             dot_row(j, x);
@@ -314,7 +336,7 @@ __global__ void __launch_bounds__(kPfnThreads, (MODE == PFN_MODE_APPLY) ? RDP_AP
 #pragma unroll
                 for (int c = 0; c < 4; ++c) { const double v = (double)x[c]; st_x[c] += v; st_x2[c] = fma(v, v, st_x2[c]); }
             } else {
-                const int meta = S.lp[j];
+                const int meta = __float_as_int(S.f[j * Cfg::FSTRIDE + CS]);
                 if (!want_arg) {
 #pragma unroll
                     for (int c = 0; c < 4; ++c) m[c] = fmaxf(m[c], fmaf(x[c], sc[c], sh[c]));  // ReLU folds into the max with 0
@@ -374,17 +396,42 @@ __global__ void __launch_bounds__(kPfnThreads, (MODE == PFN_MODE_APPLY) ? RDP_AP
         PfnStage<Cfg> &T = S.st[s];
         const long long base = (long long)t * WIN;
 
-        // ---- P0: which pillars does this tile own?
+        // ---- A: head flags -> tile bounds (block reduction) and, in the same pass, every pillar that starts in the
+        //         window is reduced by the thread of its head row: fp64 xyz sum -> mean, pillar centre.
+        const int g0 = T.gid(0);  // pillar of window row 0: pillar slots of this tile are gid - g0 (< CAP)
         int jmin = INF, jend = INF, jlast = -1;
         for (int j = tid; j < CAP; j += NT) {
             const bool valid = base + j < N;
-            const bool head = valid && (T.gid(j) != T.gid(j - 1));
+            const int gid = T.gid(j);
+            const bool head = valid && (gid != T.gid(j - 1));
             if (j < WIN) {
                 if (head) { jmin = min(jmin, j); jlast = max(jlast, j); }
                 if (!valid) jend = min(jend, j);
             } else if (head || !valid) {
                 jend = min(jend, j);
             }
+#if !defined(RDP_ABLATE) || RDP_ABLATE < 3
+            if (head && j < WIN) {
+                double sx = 0.0, sy = 0.0, sz3 = 0.0;
+                int e = j;
+                for (; e < CAP && base + e < N && T.gid(e) == gid; ++e) {
+                    const float *r = T.row(e);
+                    sx += (double)r[1]; sy += (double)r[2]; sz3 += (double)r[3];
+                }
+                if (e < CAP || base + e >= N) {  // else: runs past the staged rows -> big-pillar path below
+                    const int slot = gid - g0;
+                    float mx, my, mz;
+                    mean3(sx, sy, sz3, e - j, &mx, &my, &mz);
+                    S.mean[slot * 3] = mx; S.mean[slot * 3 + 1] = my; S.mean[slot * 3 + 2] = mz;
+                    const float *r0 = T.row(j);
+                    pillar_centre(r0[1], r0[2], a, &S.cen[slot * 2], &S.cen[slot * 2 + 1]);
+                    if (is_apply && a.pillar_mean) {
+                        float *pm = a.pillar_mean + (size_t)gid * 3;
+                        pm[0] = mx; pm[1] = my; pm[2] = mz;
+                    }
+                }
+            }
+#endif
         }
         jmin = warp_min(jmin); jend = warp_min(jend); jlast = warp_max(jlast);
         if (lane == 0) { S.wred[0][warp] = jmin; S.wred[1][warp] = jend; S.wred[2][warp] = jlast; }
@@ -398,47 +445,23 @@ __global__ void __launch_bounds__(kPfnThreads, (MODE == PFN_MODE_APPLY) ? RDP_AP
         const int ps = T.gid(j0);
         const int nb = np > 0 ? T.gid(jstop - 1) - ps + 1 : 0;
         const int gb = (int)base + j0;
-        if (MODE == PFN_MODE_BWD && np > 0 && tid == 0) prefetch_bwd(ps, min(Smem::PCH, nb));  // lands while P1..C1 run
+        if (MODE == PFN_MODE_BWD && np > 0 && tid == 0) prefetch_bwd(ps, min(Smem::PCH, nb));  // lands while C1 runs
 
         if (np > 0) {
-            // ---- P1: row -> (pillar slot, last-row flag); pillar start table
-            for (int jj = tid; jj < np; jj += NT) {
-                const int j = j0 + jj, gid = T.gid(j);
-                const int last = (jj == np - 1) || (T.gid(j + 1) != gid);
-                S.lp[jj] = ((gid - ps) << 1) | last;
-                if (gid != T.gid(j - 1)) S.start[gid - ps] = jj;
-                if (want_arg) { const int row = T.ord(j); S.kept[jj] = none_dropped ? row : a.orig2kept[row]; }
-            }
-            if (tid == 0) S.start[nb] = np;
-            __syncthreads();
-            // ---- P2: per-pillar mean and centre
-            for (int q = tid; q < nb; q += NT) {
-                const int b0 = S.start[q], b1 = S.start[q + 1];
-                double sx = 0.0, sy = 0.0, sz3 = 0.0;
-                for (int jj = b0; jj < b1; ++jj) {
-                    const float *r = T.row(j0 + jj);
-                    sx += (double)r[1]; sy += (double)r[2]; sz3 += (double)r[3];
-                }
-                const double cnt = (double)(b1 - b0);
-                const float mx = (float)__ddiv_rn(sx, cnt), my = (float)__ddiv_rn(sy, cnt), mz = (float)__ddiv_rn(sz3, cnt);
-                S.mean[q * 3] = mx; S.mean[q * 3 + 1] = my; S.mean[q * 3 + 2] = mz;
-                const float *r0 = T.row(j0 + b0);
-                pillar_centre(r0[1], r0[2], a, &S.cen[q * 2], &S.cen[q * 2 + 1]);
-                if (is_apply && a.pillar_mean) {
-                    float *pm = a.pillar_mean + (size_t)(ps + q) * 3;
-                    pm[0] = mx; pm[1] = my; pm[2] = mz;
-                }
-            }
-            __syncthreads();
-            c1(T.rows, j0 + 1, np);
+#if !defined(RDP_ABLATE) || RDP_ABLATE < 2
+            c1(T.rows, j0 + 1, np, g0);
+#endif
             __syncthreads();
             if (MODE != PFN_MODE_BWD) {
                 // row group g streams a pillar-aligned 1/GROUPS of the rows
                 const int r_lo = (grp * np) / GROUPS, r_hi = ((grp + 1) * np) / GROUPS;
-                const int ra = (grp == 0) ? 0 : S.start[S.lp[r_lo] >> 1];
-                const int rb = (grp == GROUPS - 1) ? np : S.start[S.lp[r_hi] >> 1];
+                int ra = r_lo, rb = r_hi;  // advance both to the next pillar start
+                while (ra > 0 && ra < np && T.gid(j0 + ra) == T.gid(j0 + ra - 1)) ++ra;
+                while (rb < np && T.gid(j0 + rb) == T.gid(j0 + rb - 1)) ++rb;
+#if !defined(RDP_ABLATE) || RDP_ABLATE < 1
                 if (MODE == PFN_MODE_STATS) gram(np);
-                stream(ra, rb, ps, gb);
+                stream(ra, rb, g0, gb);
+#endif
             } else {
                 // ---- E (backward): warp = pillar, lane = channel
                 float tB[CPL], tG[CPL], tA[CPL][CS];
@@ -540,12 +563,8 @@ __global__ void __launch_bounds__(kPfnThreads, (MODE == PFN_MODE_APPLY) ? RDP_AP
                 for (long long cs = a0; cs < e; cs += CAP) {
                     const int npc = (int)min((long long)CAP, e - cs);
                     for (int i = tid; i < npc * RS; i += NT) rows[i] = a.grows[(cs + 1) * RS + i];
-                    for (int jj = tid; jj < npc; jj += NT) {
-                        S.lp[jj] = 0;  // slot 0, never "last": the carry below closes the pillar
-                        if (want_arg) { const int row = __float_as_int(a.grows[(cs + jj + 1) * RS + RS - 2]); S.kept[jj] = none_dropped ? row : a.orig2kept[row]; }
-                    }
                     __syncthreads();
-                    c1(rows, 0, npc);
+                    c1(rows, 0, npc, -1);
                     __syncthreads();
                     if (MODE == PFN_MODE_STATS) gram(npc);
                     stream((grp * npc) / GROUPS, ((grp + 1) * npc) / GROUPS, pb, (int)cs);

@@ -13,7 +13,8 @@ def main(frames=8, reps=15):
     pts = torch.from_numpy(lidar).to(dev)
     spec, norm, w = lid.spec, lid.pfn_layers[0].norm, lid.pfn_layers[0].linear.weight.detach()
     geom, layout = spec.geom(frames), spec.layout_struct()
-    res = ops.encode_forward(pts, spec, frames, w, None, norm.weight, norm.bias, norm.running_mean, norm.running_var, True, True)
+    only_eval = bool(os.environ.get('RDP_BENCH_ONLY_EVAL'))
+    res = ops.encode_forward(pts, spec, frames, w, None, norm.weight, norm.bias, norm.running_mean, norm.running_var, not only_eval, not only_eval)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
     feats = torch.empty((len(lidar), spec.c_out), dtype=torch.float32, device=dev)
@@ -46,8 +47,9 @@ def main(frames=8, reps=15):
                                    P(dw), P(dg), P(db), st), "bwd")
     timeit("index_us", index)
     timeit("pfn_eval_us", lambda: pfn(False, False))
-    timeit("pfn_train_us(stats+apply_arg)", lambda: pfn(True, True))
-    timeit("pfn_bwd_us", bwd)
+    if not only_eval:
+        timeit("pfn_train_us(stats+apply_arg)", lambda: pfn(True, True))
+        timeit("pfn_bwd_us", bwd)
     out["lib"] = os.path.basename(_lib.LIB_PATH); out["N"] = res.n_kept; out["P"] = res.n_pillars
     print(json.dumps(out))
 
