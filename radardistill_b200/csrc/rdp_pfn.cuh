@@ -15,20 +15,15 @@
 //   P1  row -> pillar slot, pillar start table                                         (thread = row)
 //   P2  per-pillar fp64 xyz sum -> mean (one rounding), pillar centre                  (thread = pillar)
 //   C1  decorated features (same op order / roundings as the reference) -> smem        (thread = row)
-//   ST  thread = (channel quad, row group): the quad's 4 weight rows sit in registers; the threads of a row group walk
-//       the same pillar-aligned 1/16 of the tile's rows: x = W f as k-ascending fmaf chains (one 16 B feature load
-//       feeds 16 FMAs), y = fma(x, scale, shift), running max (+ lowest-index argmax), and a coalesced feature row
-//       is stored when a pillar's last row has been folded in.
-//       STATS: fp64 sum x, sum x^2 per thread and the Gram matrix of the features (4x4 register blocks)
+//   ST  lane = output channel, its weight row in registers; each warp streams a pillar-aligned quarter of the
+//       tile's rows: x = W f as a k-ascending fmaf chain (feature row broadcast from smem), y = fma(x, scale,
+//       shift), running max (+ lowest-index argmax), one coalesced 128 B store when a pillar's last row is in.
+//       STATS: fp64 sum x, sum x^2 per lane and the Gram matrix of the features (4x4 register blocks)
 //       BWD  : per (pillar, channel) route the gradient to the winning row and accumulate dbeta, G, A
 // Arithmetic is the canonical form of oracle/pillar_oracle.c (ORC_MEAN_F64): outputs are bit-identical to it.
 #pragma once
 
 #include "rdp_common.cuh"
-
-#ifndef RDP_APPLY_BLOCKS
-#define RDP_APPLY_BLOCKS 4
-#endif
 
 namespace rdp {
 
@@ -98,7 +93,7 @@ struct PfnSmem {
     static constexpr size_t S_BYTES = (MODE == PFN_MODE_STATS) ? sizeof(double) * kPfnThreads * 16 : 0;
     static constexpr size_t B_BYTES = 0;  // BWD: the end-of-kernel scratch aliases f + the prefetch buffers (see bwd_scratch())
     static constexpr size_t SCR = Z_BYTES > S_BYTES ? (Z_BYTES > B_BYTES ? Z_BYTES : B_BYTES) : (S_BYTES > B_BYTES ? S_BYTES : B_BYTES);
-    static constexpr int PCH = (MODE == PFN_MODE_BWD) ? 64 : 1;  // pillars per backward prefetch chunk
+    static constexpr int PCH = (MODE == PFN_MODE_BWD) ? 48 : 1;  // pillars per backward prefetch chunk
     PfnStage<Cfg> st[2];
     alignas(8) uint64_t full[2];
     alignas(8) uint64_t pre;                       // BWD: arrival of the tile's (grad, features, argpos) rows
@@ -115,8 +110,6 @@ struct PfnSmem {
     float scale[Cfg::COUT], shift[Cfg::COUT];
     float carry_v[Cfg::COUT];
     int carry_k[Cfg::COUT], carry_p[Cfg::COUT];
-    float part_v[Cfg::GROUPS * Cfg::COUT];          // big-pillar path: per row group partial maxima
-    int part_k[Cfg::GROUPS * Cfg::COUT], part_p[Cfg::GROUPS * Cfg::COUT];
     int wred[3][kPfnThreads / 32];
     double dred[kPfnThreads * 3];
 };
@@ -182,7 +175,7 @@ __device__ __forceinline__ int warp_max(int v) { return __reduce_max_sync(0xffff
 
 // ------------------------------------------------------------------------------------------- the tile kernel
 template <class Cfg, int MODE>
-__global__ void __launch_bounds__(kPfnThreads, (MODE == PFN_MODE_APPLY) ? RDP_APPLY_BLOCKS : 4) pfn_tile_kernel(const __grid_constant__ PfnArgs a) {
+__global__ void __launch_bounds__(kPfnThreads, (MODE == PFN_MODE_APPLY) ? 5 : 4) pfn_tile_kernel(const __grid_constant__ PfnArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     using Smem = PfnSmem<Cfg, MODE>;
     Smem &S = *reinterpret_cast<Smem *>(smem_raw);
@@ -209,16 +202,11 @@ __global__ void __launch_bounds__(kPfnThreads, (MODE == PFN_MODE_APPLY) ? RDP_AP
         mbar_init(&S.pre, 1);
         fence_mbar_init();
     }
-    // Forward modes: thread = (channel quad, row group).  The quad's four weight rows live in registers, so one 16-byte
-    // feature load from shared memory feeds 16 FMAs (the lane-per-channel form re-read every feature row from every lane
-    // and was bound by the shared-memory pipe).  Backward: lane = channel (+32 cc).
-    constexpr int QUADS = Cfg::QUADS, GROUPS = Cfg::GROUPS;
-    constexpr int WR = (MODE == PFN_MODE_BWD) ? CPL : 4;
-    const int quad = tid % QUADS, grp = tid / QUADS;
-    float W[WR][CS], sc[WR], sh[WR];
+    // lane = output channel (+32): its weight row(s) live in registers for the whole kernel
+    float W[CPL][CS], sc[CPL], sh[CPL];
 #pragma unroll
-    for (int cc = 0; cc < WR; ++cc) {
-        const int ch = (MODE == PFN_MODE_BWD) ? (lane + 32 * cc) : (quad * 4 + cc);
+    for (int cc = 0; cc < CPL; ++cc) {
+        const int ch = lane + 32 * cc;
 #pragma unroll
         for (int s = 0; s < CS; ++s) {
             const int k = a.kmap[s];
@@ -237,12 +225,12 @@ __global__ void __launch_bounds__(kPfnThreads, (MODE == PFN_MODE_APPLY) ? RDP_AP
     __syncthreads();
 
     // ---- accumulators that live for the whole CTA
-    double st_x[4], st_x2[4], st_m[16];
+    double st_x[CPL], st_x2[CPL], st_m[16];
     int gba = 0, gbb = 0;
     const int grg = tid % Cfg::RG, gblk = tid / Cfg::RG;
     if (MODE == PFN_MODE_STATS) {
 #pragma unroll
-        for (int cc = 0; cc < 4; ++cc) st_x[cc] = st_x2[cc] = 0.0;
+        for (int cc = 0; cc < CPL; ++cc) st_x[cc] = st_x2[cc] = 0.0;
 #pragma unroll
         for (int e = 0; e < 16; ++e) st_m[e] = 0.0;
         int rem = gblk;
@@ -266,25 +254,15 @@ __global__ void __launch_bounds__(kPfnThreads, (MODE == PFN_MODE_APPLY) ? RDP_AP
     };
 
     // C1: decorated features of rows [rowbase, rowbase + np) of `rows` -> S.f[0..np)
-    // C1: decorated features of rows [rowbase, rowbase + np) of `rows` -> S.f[0..np).  `g0 >= 0`: rows of a staged tile,
-    // the pillar slot is gid - g0 and the "last row of its pillar" flag comes from the next row; g0 < 0: big-pillar chunk
-    // (slot 0, never last).  In the APPLY modes slot CS of the feature row carries (slot << 1 | last) for the stream.
-    auto c1 = [&](const float *rows, int rowbase, int np, int g0) {
+    auto c1 = [&](const float *rows, int rowbase, int np) {
         for (int jj = tid; jj < np; jj += NT) {
             float r[COLS], f[Cfg::FW];
             const float *src = rows + (rowbase + jj) * RS;
 #pragma unroll
             for (int c = 0; c < COLS; ++c) r[c] = src[c];
-            int slot = 0, last = 0;
-            if (g0 >= 0) {
-                const int gid = __float_as_int(src[RS - 1]);
-                slot = gid - g0;
-                last = (jj == np - 1) || (__float_as_int(src[RS + RS - 1]) != gid);
-            }
-            if (want_arg) { const int row = __float_as_int(src[RS - 2]); S.kept[jj] = none_dropped ? row : a.orig2kept[row]; }
-            decorate<Cfg>(r, S.cen[slot * 2], S.cen[slot * 2 + 1], &S.mean[slot * 3], a, f);
-            // STATS: ones column (the Gram matrix then carries sum f as well); APPLY: the row's pillar slot and last flag
-            f[CS] = (MODE == PFN_MODE_STATS || MODE == PFN_MODE_BWD) ? 1.0f : __int_as_float((slot << 1) | last);
+            const int lp = S.lp[jj] >> 1;
+            decorate<Cfg>(r, S.cen[lp * 2], S.cen[lp * 2 + 1], &S.mean[lp * 3], a, f);
+            f[CS] = 1.0f;  // ones column: the Gram matrix then carries sum f (S1) as well
 #pragma unroll
             for (int k = CS + 1; k < Cfg::FW; ++k) f[k] = 0.0f;
             float4 *dst = reinterpret_cast<float4 *>(&S.f[jj * Cfg::FSTRIDE]);
@@ -293,7 +271,7 @@ __global__ void __launch_bounds__(kPfnThreads, (MODE == PFN_MODE_APPLY) ? RDP_AP
         }
     };
 
-    // x[c] = W[c] . f(row j) for the quad's four channels: k-ascending fmaf chains, one feature load per four k
+    // x[cc] = W[cc] . f(row j) as a k-ascending fmaf chain
     auto dot_row = [&](int j, float *x) {
         float f[Cfg::FW];
         const float4 *src = reinterpret_cast<const float4 *>(&S.f[j * Cfg::FSTRIDE]);
@@ -303,58 +281,89 @@ __global__ void __launch_bounds__(kPfnThreads, (MODE == PFN_MODE_APPLY) ? RDP_AP
             f[k4 * 4] = v.x; f[k4 * 4 + 1] = v.y; f[k4 * 4 + 2] = v.z; f[k4 * 4 + 3] = v.w;
         }
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int cc = 0; cc < CPL; ++cc) {
             float acc = 0.0f;
 #pragma unroll
-            for (int k = 0; k < CS; ++k) acc = fmaf(W[c][k], f[k], acc);
-            x[c] = acc;
+            for (int k = 0; k < CS; ++k) acc = fmaf(W[cc][k], f[k], acc);
+            x[cc] = acc;
         }
     };
 
-    // running max state of the pillar a thread is streaming (its four channels)
-    float m[4];
-    int mk[4], mp[4];
+    // running max state of the pillar a warp is streaming (lane = channel)
+    float m[CPL];
+    int mk[CPL], mp[CPL];
     auto reset_max = [&]() {
 #pragma unroll
-        for (int c = 0; c < 4; ++c) { m[c] = want_arg ? -1.0f : 0.0f; mk[c] = INF; mp[c] = 0; }
+        for (int cc = 0; cc < CPL; ++cc) { m[cc] = want_arg ? -1.0f : 0.0f; mk[cc] = INF; mp[cc] = 0; }
+    };
+    auto fold_max = [&](const float *x, int kj, int pos) {
+#pragma unroll
+        for (int cc = 0; cc < CPL; ++cc) {
+            const float y = fmaf(x[cc], sc[cc], sh[cc]);
+            if (!want_arg) {
+                m[cc] = fmaxf(m[cc], y);  // ReLU folds into the max with 0
+            } else {
+                const float z = fmaxf(y, 0.0f);
+                if (z > m[cc] || (z == m[cc] && kj < mk[cc])) { m[cc] = z; mk[cc] = kj; mp[cc] = pos; }
+            }
+        }
     };
 
-    // STREAM: the 8 (16) threads of a row group walk the same pillar-aligned rows [ra, rb) of S.f, each for its own
-    // channel quad.  APPLY keeps the running max and stores 16 bytes per thread -- a coalesced feature row per group --
-    // when a pillar's last row has been folded in (slot CS of the feature row = (pillar slot << 1) | last flag); STATS accumulates
-    // sum x / sum x^2.
-    auto stream = [&](int ra, int rb, int pillar0, int gb) {  // pillar0 = global id of pillar slot 0
+    // STREAM: warp w walks rows [ra, rb) of S.f; APPLY keeps the running max and stores a pillar when its last row
+    // has been folded in (S.lp[j] = (pillar slot << 1) | last-row flag); STATS accumulates sum x / sum x^2.
+    auto stream = [&](int ra, int rb, int ps, int gb) {
         if (is_apply) reset_max();
-        // pillars close in order, so the output pointers just advance from the first row's pillar
-        const int slot0 = (is_apply && ra < rb) ? (__float_as_int(S.f[ra * Cfg::FSTRIDE + CS]) >> 1) : 0;
-        float *fout = a.features + (size_t)(pillar0 + slot0) * COUT + quad * 4;
-        int32_t *aout = want_arg ? a.argpos + (size_t)(pillar0 + slot0) * COUT + quad * 4 : nullptr;
-        for (int j = ra; j < rb; ++j) {
-            float x[4];
-            dot_row(j, x);
+        // first pillar this warp closes = the pillar of its first row (ranges are pillar aligned)
+        const int slot0 = (ra < rb) ? (S.lp[ra] >> 1) : 0;
+        float *fout = a.features + (size_t)(ps + slot0) * COUT + lane;
+        int32_t *aout = want_arg ? a.argpos + (size_t)(ps + slot0) * COUT + lane : nullptr;
+        int j = ra;
+        for (; j + 1 < rb; j += 2) {  // two rows in flight: two independent fmaf chains per channel
+            float x0[CPL], x1[CPL];
+            dot_row(j, x0);
+            dot_row(j + 1, x1);
             if (MODE == PFN_MODE_STATS) {
 #pragma unroll
-                for (int c = 0; c < 4; ++c) { const double v = (double)x[c]; st_x[c] += v; st_x2[c] = fma(v, v, st_x2[c]); }
+                for (int cc = 0; cc < CPL; ++cc) {
+                    const double v0 = (double)x0[cc], v1 = (double)x1[cc];
+                    st_x[cc] += v0; st_x2[cc] = fma(v0, v0, st_x2[cc]);
+                    st_x[cc] += v1; st_x2[cc] = fma(v1, v1, st_x2[cc]);
+                }
             } else {
-                const int meta = __float_as_int(S.f[j * Cfg::FSTRIDE + CS]);
-                if (!want_arg) {
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) m[c] = fmaxf(m[c], fmaf(x[c], sc[c], sh[c]));  // ReLU folds into the max with 0
-                } else {
-                    const int kj = S.kept[j];
+                for (int h = 0; h < 2; ++h) {
+                    const int jj = j + h, meta = S.lp[jj];
+                    fold_max(h ? x1 : x0, want_arg ? S.kept[jj] : 0, gb + jj);
+                    if (meta & 1) {  // pillars close in order: the output row pointer just advances
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        const float z = fmaxf(fmaf(x[c], sc[c], sh[c]), 0.0f);
-                        if (z > m[c] || (z == m[c] && kj < mk[c])) { m[c] = z; mk[c] = kj; mp[c] = gb + j; }
+                        for (int cc = 0; cc < CPL; ++cc) {
+                            fout[32 * cc] = m[cc];
+                            if (want_arg) aout[32 * cc] = mp[cc];
+                        }
+                        fout += COUT;
+                        if (want_arg) aout += COUT;
+                        reset_max();
                     }
                 }
+            }
+        }
+        if (j < rb) {
+            float x0[CPL];
+            dot_row(j, x0);
+            if (MODE == PFN_MODE_STATS) {
+#pragma unroll
+                for (int cc = 0; cc < CPL; ++cc) { const double v0 = (double)x0[cc]; st_x[cc] += v0; st_x2[cc] = fma(v0, v0, st_x2[cc]); }
+            } else {
+                const int meta = S.lp[j];
+                fold_max(x0, want_arg ? S.kept[j] : 0, gb + j);
                 if (meta & 1) {
-                    *reinterpret_cast<float4 *>(fout) = make_float4(m[0], m[1], m[2], m[3]);
-                    fout += COUT;
-                    if (want_arg) {
-                        *reinterpret_cast<int4 *>(aout) = make_int4(mp[0], mp[1], mp[2], mp[3]);
-                        aout += COUT;
+#pragma unroll
+                    for (int cc = 0; cc < CPL; ++cc) {
+                        fout[32 * cc] = m[cc];
+                        if (want_arg) aout[32 * cc] = mp[cc];
                     }
+                    fout += COUT;
+                    if (want_arg) aout += COUT;
                     reset_max();
                 }
             }
@@ -396,42 +405,17 @@ __global__ void __launch_bounds__(kPfnThreads, (MODE == PFN_MODE_APPLY) ? RDP_AP
         PfnStage<Cfg> &T = S.st[s];
         const long long base = (long long)t * WIN;
 
-        // ---- A: head flags -> tile bounds (block reduction) and, in the same pass, every pillar that starts in the
-        //         window is reduced by the thread of its head row: fp64 xyz sum -> mean, pillar centre.
-        const int g0 = T.gid(0);  // pillar of window row 0: pillar slots of this tile are gid - g0 (< CAP)
+        // ---- P0: which pillars does this tile own?
         int jmin = INF, jend = INF, jlast = -1;
         for (int j = tid; j < CAP; j += NT) {
             const bool valid = base + j < N;
-            const int gid = T.gid(j);
-            const bool head = valid && (gid != T.gid(j - 1));
+            const bool head = valid && (T.gid(j) != T.gid(j - 1));
             if (j < WIN) {
                 if (head) { jmin = min(jmin, j); jlast = max(jlast, j); }
                 if (!valid) jend = min(jend, j);
             } else if (head || !valid) {
                 jend = min(jend, j);
             }
-#if !defined(RDP_ABLATE) || RDP_ABLATE < 3
-            if (head && j < WIN) {
-                double sx = 0.0, sy = 0.0, sz3 = 0.0;
-                int e = j;
-                for (; e < CAP && base + e < N && T.gid(e) == gid; ++e) {
-                    const float *r = T.row(e);
-                    sx += (double)r[1]; sy += (double)r[2]; sz3 += (double)r[3];
-                }
-                if (e < CAP || base + e >= N) {  // else: runs past the staged rows -> big-pillar path below
-                    const int slot = gid - g0;
-                    float mx, my, mz;
-                    mean3(sx, sy, sz3, e - j, &mx, &my, &mz);
-                    S.mean[slot * 3] = mx; S.mean[slot * 3 + 1] = my; S.mean[slot * 3 + 2] = mz;
-                    const float *r0 = T.row(j);
-                    pillar_centre(r0[1], r0[2], a, &S.cen[slot * 2], &S.cen[slot * 2 + 1]);
-                    if (is_apply && a.pillar_mean) {
-                        float *pm = a.pillar_mean + (size_t)gid * 3;
-                        pm[0] = mx; pm[1] = my; pm[2] = mz;
-                    }
-                }
-            }
-#endif
         }
         jmin = warp_min(jmin); jend = warp_min(jend); jlast = warp_max(jlast);
         if (lane == 0) { S.wred[0][warp] = jmin; S.wred[1][warp] = jend; S.wred[2][warp] = jlast; }
@@ -445,23 +429,47 @@ __global__ void __launch_bounds__(kPfnThreads, (MODE == PFN_MODE_APPLY) ? RDP_AP
         const int ps = T.gid(j0);
         const int nb = np > 0 ? T.gid(jstop - 1) - ps + 1 : 0;
         const int gb = (int)base + j0;
-        if (MODE == PFN_MODE_BWD && np > 0 && tid == 0) prefetch_bwd(ps, min(Smem::PCH, nb));  // lands while C1 runs
+        if (MODE == PFN_MODE_BWD && np > 0 && tid == 0) prefetch_bwd(ps, min(Smem::PCH, nb));  // lands while P1..C1 run
 
         if (np > 0) {
-#if !defined(RDP_ABLATE) || RDP_ABLATE < 2
-            c1(T.rows, j0 + 1, np, g0);
-#endif
+            // ---- P1: row -> (pillar slot, last-row flag); pillar start table
+            for (int jj = tid; jj < np; jj += NT) {
+                const int j = j0 + jj, gid = T.gid(j);
+                const int last = (jj == np - 1) || (T.gid(j + 1) != gid);
+                S.lp[jj] = ((gid - ps) << 1) | last;
+                if (gid != T.gid(j - 1)) S.start[gid - ps] = jj;
+                if (want_arg) { const int row = T.ord(j); S.kept[jj] = none_dropped ? row : a.orig2kept[row]; }
+            }
+            if (tid == 0) S.start[nb] = np;
+            __syncthreads();
+            // ---- P2: per-pillar mean and centre
+            for (int q = tid; q < nb; q += NT) {
+                const int b0 = S.start[q], b1 = S.start[q + 1];
+                double sx = 0.0, sy = 0.0, sz3 = 0.0;
+                for (int jj = b0; jj < b1; ++jj) {
+                    const float *r = T.row(j0 + jj);
+                    sx += (double)r[1]; sy += (double)r[2]; sz3 += (double)r[3];
+                }
+                float mx, my, mz;
+                mean3(sx, sy, sz3, b1 - b0, &mx, &my, &mz);
+                S.mean[q * 3] = mx; S.mean[q * 3 + 1] = my; S.mean[q * 3 + 2] = mz;
+                const float *r0 = T.row(j0 + b0);
+                pillar_centre(r0[1], r0[2], a, &S.cen[q * 2], &S.cen[q * 2 + 1]);
+                if (is_apply && a.pillar_mean) {
+                    float *pm = a.pillar_mean + (size_t)(ps + q) * 3;
+                    pm[0] = mx; pm[1] = my; pm[2] = mz;
+                }
+            }
+            __syncthreads();
+            c1(T.rows, j0 + 1, np);
             __syncthreads();
             if (MODE != PFN_MODE_BWD) {
-                // row group g streams a pillar-aligned 1/GROUPS of the rows
-                const int r_lo = (grp * np) / GROUPS, r_hi = ((grp + 1) * np) / GROUPS;
-                int ra = r_lo, rb = r_hi;  // advance both to the next pillar start
-                while (ra > 0 && ra < np && T.gid(j0 + ra) == T.gid(j0 + ra - 1)) ++ra;
-                while (rb < np && T.gid(j0 + rb) == T.gid(j0 + rb - 1)) ++rb;
-#if !defined(RDP_ABLATE) || RDP_ABLATE < 1
+                // warp w streams a pillar-aligned quarter of the rows
+                const int r_lo = (warp * np) / NW, r_hi = ((warp + 1) * np) / NW;
+                const int ra = (warp == 0) ? 0 : S.start[S.lp[r_lo] >> 1];
+                const int rb = (warp == NW - 1) ? np : S.start[S.lp[r_hi] >> 1];
                 if (MODE == PFN_MODE_STATS) gram(np);
-                stream(ra, rb, g0, gb);
-#endif
+                stream(ra, rb, ps, gb);
             } else {
                 // ---- E (backward): warp = pillar, lane = channel
                 float tB[CPL], tG[CPL], tA[CPL][CS];
@@ -563,32 +571,34 @@ __global__ void __launch_bounds__(kPfnThreads, (MODE == PFN_MODE_APPLY) ? RDP_AP
                 for (long long cs = a0; cs < e; cs += CAP) {
                     const int npc = (int)min((long long)CAP, e - cs);
                     for (int i = tid; i < npc * RS; i += NT) rows[i] = a.grows[(cs + 1) * RS + i];
-                    __syncthreads();
-                    c1(rows, 0, npc, -1);
-                    __syncthreads();
-                    if (MODE == PFN_MODE_STATS) gram(npc);
-                    stream((grp * npc) / GROUPS, ((grp + 1) * npc) / GROUPS, pb, (int)cs);
-                    if (is_apply) {
-                        // merge the row groups' running maxima into the carry, in group order (deterministic)
-#pragma unroll
-                        for (int c = 0; c < 4; ++c) {
-                            S.part_v[grp * COUT + quad * 4 + c] = m[c];
-                            S.part_k[grp * COUT + quad * 4 + c] = mk[c];
-                            S.part_p[grp * COUT + quad * 4 + c] = mp[c];
-                        }
-                        __syncthreads();
-                        if (tid < COUT) {
-                            float bm = S.carry_v[tid];
-                            int bk = S.carry_k[tid], bp = S.carry_p[tid];
-                            for (int g = 0; g < GROUPS; ++g) {
-                                const float v = S.part_v[g * COUT + tid];
-                                const int vk = S.part_k[g * COUT + tid];
-                                if (v > bm || (want_arg && v == bm && vk < bk)) { bm = v; bk = vk; bp = S.part_p[g * COUT + tid]; }
-                            }
-                            S.carry_v[tid] = bm; S.carry_k[tid] = bk; S.carry_p[tid] = bp;
-                        }
+                    for (int jj = tid; jj < npc; jj += NT) {
+                        S.lp[jj] = 0;  // slot 0, never "last": the carry below closes the pillar
+                        if (want_arg) { const int row = __float_as_int(a.grows[(cs + jj + 1) * RS + RS - 2]); S.kept[jj] = none_dropped ? row : a.orig2kept[row]; }
                     }
                     __syncthreads();
+                    c1(rows, 0, npc);
+                    __syncthreads();
+                    if (MODE == PFN_MODE_STATS) gram(npc);
+                    stream((warp * npc) / NW, ((warp + 1) * npc) / NW, pb, (int)cs);
+                    if (is_apply) {
+                        // merge the warps' running maxima into the carry, in warp order (deterministic)
+                        for (int w = 0; w < NW; ++w) {
+                            if (warp == w) {
+#pragma unroll
+                                for (int cc = 0; cc < CPL; ++cc) {
+                                    const int ch = lane + 32 * cc;
+                                    const float bm = S.carry_v[ch];
+                                    const int bk = S.carry_k[ch];
+                                    if (m[cc] > bm || (want_arg && m[cc] == bm && mk[cc] < bk)) {
+                                        S.carry_v[ch] = m[cc]; S.carry_k[ch] = mk[cc]; S.carry_p[ch] = mp[cc];
+                                    }
+                                }
+                            }
+                            __syncthreads();
+                        }
+                    } else {
+                        __syncthreads();
+                    }
                 }
                 if (is_apply && tid < COUT) {
                     a.features[(size_t)pb * COUT + tid] = S.carry_v[tid];
@@ -606,14 +616,14 @@ __global__ void __launch_bounds__(kPfnThreads, (MODE == PFN_MODE_APPLY) ? RDP_AP
         double *out = a.partials + (size_t)blockIdx.x * Cfg::STATS_DOUBLES;
         __syncthreads();
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            dscr[(grp * COUT + quad * 4 + c) * 2] = st_x[c];
-            dscr[(grp * COUT + quad * 4 + c) * 2 + 1] = st_x2[c];
+        for (int cc = 0; cc < CPL; ++cc) {
+            dscr[(warp * COUT + lane + 32 * cc) * 2] = st_x[cc];
+            dscr[(warp * COUT + lane + 32 * cc) * 2 + 1] = st_x2[cc];
         }
         __syncthreads();
         if (tid < COUT) {
             double sx = 0.0, sx2 = 0.0;
-            for (int g = 0; g < GROUPS; ++g) { sx += dscr[(g * COUT + tid) * 2]; sx2 += dscr[(g * COUT + tid) * 2 + 1]; }
+            for (int w = 0; w < NW; ++w) { sx += dscr[(w * COUT + tid) * 2]; sx2 += dscr[(w * COUT + tid) * 2 + 1]; }
             out[tid] = sx; out[COUT + tid] = sx2;
         }
         __syncthreads();
