@@ -166,6 +166,7 @@ def workload_config(mode, frames, n_lidar, n_radar):
 def build_modules(device, mode, ddp):
     import torch
     from radardistill_b200 import synth, vfe
+    from radardistill_b200.vfe import forward_pair
     torch.manual_seed(1234)
     lid = vfe.DynamicPillarVFESimple2D(model_cfg=Cfg(S2D_CFG), num_point_features=5, voxel_size=synth.VOXEL_SIZE,
                                        grid_size=synth.grid_size_of(), point_cloud_range=synth.PC_RANGE).to(device)
@@ -191,12 +192,8 @@ def build_modules(device, mode, ddp):
             self.vfe, self.radar_vfe, self.lidar_no_grad = vfe_mod, radar_vfe_mod, lidar_no_grad
 
         def forward(self, batch_dict):
-            if self.lidar_no_grad:
-                with torch.no_grad():
-                    batch_dict = self.vfe(batch_dict)
-            else:
-                batch_dict = self.vfe(batch_dict)
-            return self.radar_vfe(batch_dict)
+            # the two encoders are independent: radar on a side stream, LiDAR on the current one
+            return forward_pair(self.vfe, self.radar_vfe, batch_dict, first_no_grad=self.lidar_no_grad)
 
     pair = PairedEncoders(lid, rad, lidar_no_grad=(mode == "A"))
     call = pair

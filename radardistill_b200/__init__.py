@@ -6,7 +6,7 @@ Public surface (mirrors ``pcdet/models/backbones_3d/vfe``):
 The computation lives in ``librdp.so`` (C ABI: ``include/rdp.h``), built by ``radardistill_b200.build``.
 """
 from .vfe import (REGISTRY, DynamicPillarVFE, DynamicPillarVFESimple2D, PFNLayerV2, Radar_DynamicPillarVFESimple2D,
-                  Radar_DynamicPillarVFESimple2D_Test, VFETemplate, register)
+                  Radar_DynamicPillarVFESimple2D_Test, VFETemplate, forward_pair, register)
 from . import ops, synth  # noqa: F401
 
 __version__ = "0.1.0"

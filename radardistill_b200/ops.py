@@ -147,9 +147,38 @@ def _check_param(t: Optional[torch.Tensor], shape, name: str):
     return t.detach().contiguous() if not t.is_contiguous() else t.detach()
 
 
-def encode_forward(points: torch.Tensor, spec: EncoderSpec, batch_size: int, weight, bias, gamma, beta, running_mean,
-                   running_var, train_bn: bool, want_argmax: bool) -> EncodeResult:
-    """index + PFN forward on the current stream; one 64-byte read-back to learn N and P."""
+@dataclass
+class PendingEncode:
+    """Kernels of one forward have been enqueued on `stream`; `finish` waits for the 64-byte (N, P) publication."""
+    spec: EncoderSpec
+    batch_size: int
+    n_points: int
+    points: torch.Tensor
+    coords: torch.Tensor
+    inverse: torch.Tensor
+    counts: torch.Tensor
+    features: torch.Tensor
+    argpos: Optional[torch.Tensor]
+    bn_state: Optional[torch.Tensor]
+    workspace: torch.Tensor
+    counters: torch.Tensor
+    host: torch.Tensor
+    event: "torch.cuda.Event"
+    stream: "torch.cuda.Stream"
+    train_bn: bool = False
+
+
+_host_pool = {}
+
+
+def _take_host(device) -> torch.Tensor:
+    pool = _host_pool.setdefault(device.index, [])
+    return pool.pop() if pool else torch.empty(_lib.RDP_NUM_COUNTERS, dtype=torch.int32).pin_memory()
+
+
+def encode_launch(points: torch.Tensor, spec: EncoderSpec, batch_size: int, weight, bias, gamma, beta, running_mean,
+                  running_var, train_bn: bool, want_argmax: bool) -> PendingEncode:
+    """Enqueues index + PFN forward on the current stream and returns without synchronising."""
     lib = _lib.load()
     if not points.is_cuda:
         raise _lib.RdpError("the pillar encoder has no CPU path: `points` must be a CUDA tensor")
@@ -183,27 +212,43 @@ def encode_forward(points: torch.Tensor, spec: EncoderSpec, batch_size: int, wei
         counters = torch.empty(_lib.RDP_NUM_COUNTERS, dtype=torch.int32, device=dev)
         features = torch.empty((cap, spec.c_out), dtype=torch.float32, device=dev)
         argpos = torch.empty((cap, spec.c_out), dtype=torch.int32, device=dev) if want_argmax else None
-        pmean = None
         bn_state = None
         if train_bn:
             bn_state = torch.zeros(int(lib.rdp_bn_state_doubles(C.byref(layout))), dtype=torch.float64, device=dev)
-        st = _stream_ptr()
+        stream = torch.cuda.current_stream()
+        st = C.c_void_p(stream.cuda_stream)
         _lib.check(lib.rdp_index_fwd(_ptr(pts), n0, C.byref(geom), spec.coord_cols, _ptr(ws), nbytes.value, _ptr(coords),
                                      _ptr(inverse), _ptr(counts), _ptr(counters), st), "rdp_index_fwd")
         prm = _params_struct(spec, weight, bias, gamma, beta, running_mean, running_var, train_bn)
         _lib.check(lib.rdp_pfn_fwd(_ptr(pts), n0, C.byref(geom), C.byref(layout), C.byref(prm), _ptr(ws), nbytes.value,
-                                   _ptr(counters), _ptr(features), _ptr(argpos), _ptr(pmean), _ptr(bn_state), st),
-                   "rdp_pfn_fwd")
-        host = _pinned_counters(dev)  # written by a kernel (zero-copy): never queues behind bulk DMA on the copy engines
+                                   _ptr(counters), _ptr(features), _ptr(argpos), None, _ptr(bn_state), st), "rdp_pfn_fwd")
+        host = _take_host(dev)  # written by a kernel (zero-copy): never queues behind bulk DMA on the copy engines
         _lib.check(lib.rdp_publish_counters(_ptr(counters), C.c_void_p(host.data_ptr()), st), "rdp_publish_counters")
-        torch.cuda.current_stream().synchronize()
-        n_kept, n_pillars, err = int(host[_lib.CNT_N]), int(host[_lib.CNT_P]), int(host[_lib.CNT_ERRFLAGS])
+        event = torch.cuda.Event()
+        event.record(stream)
+    return PendingEncode(spec=spec, batch_size=int(batch_size), n_points=int(n0), points=pts, coords=coords, inverse=inverse,
+                         counts=counts, features=features, argpos=argpos, bn_state=bn_state, workspace=ws, counters=counters,
+                         host=host, event=event, stream=stream, train_bn=train_bn)
+
+
+def encode_finish(p: PendingEncode) -> EncodeResult:
+    """Waits for the forward's kernels, reads (N, P) and narrows the capacity-sized outputs."""
+    p.event.synchronize()
+    n_kept, n_pillars, err = int(p.host[_lib.CNT_N]), int(p.host[_lib.CNT_P]), int(p.host[_lib.CNT_ERRFLAGS])
+    _host_pool.setdefault(p.points.device.index, []).append(p.host)
     if err & 1:
-        raise ValueError(f"points[:, 0] holds a batch index outside [0, {batch_size})")
-    return EncodeResult(features=features[:n_pillars], coords=coords[:n_pillars], inverse=inverse[:n_kept],
-                        counts=counts[:n_pillars], argpos=None if argpos is None else argpos[:n_pillars],
-                        n_kept=n_kept, n_pillars=n_pillars, pillar_mean=pmean, bn_state=bn_state, workspace=ws,
-                        counters=counters, spec=spec, batch_size=int(batch_size), n_points=int(n0))
+        raise ValueError(f"points[:, 0] holds a batch index outside [0, {p.batch_size})")
+    return EncodeResult(features=p.features[:n_pillars], coords=p.coords[:n_pillars], inverse=p.inverse[:n_kept],
+                        counts=p.counts[:n_pillars], argpos=None if p.argpos is None else p.argpos[:n_pillars],
+                        n_kept=n_kept, n_pillars=n_pillars, pillar_mean=None, bn_state=p.bn_state, workspace=p.workspace,
+                        counters=p.counters, spec=p.spec, batch_size=p.batch_size, n_points=p.n_points)
+
+
+def encode_forward(points: torch.Tensor, spec: EncoderSpec, batch_size: int, weight, bias, gamma, beta, running_mean,
+                   running_var, train_bn: bool, want_argmax: bool) -> EncodeResult:
+    """index + PFN forward on the current stream; one 64-byte read-back to learn N and P."""
+    return encode_finish(encode_launch(points, spec, batch_size, weight, bias, gamma, beta, running_mean, running_var,
+                                       train_bn, want_argmax))
 
 
 def encode_backward(points: torch.Tensor, spec: EncoderSpec, batch_size: int, res: EncodeResult, features, grad_features,
@@ -230,21 +275,17 @@ def encode_backward(points: torch.Tensor, spec: EncoderSpec, batch_size: int, re
 
 
 class _PillarEncodeFn(torch.autograd.Function):
-    """Autograd node: saves (points, argmax, pillar means, BN state) -- never the (N, C) activations."""
+    """Autograd node: saves (points, argpos, BN state, workspace) -- never the (N, C) activations.  The forward kernels
+    were already enqueued (``pending``); this only waits for them and wires up the backward."""
 
     @staticmethod
-    def forward(ctx, points, weight, bias, gamma, beta, running_mean, running_var, spec, batch_size, train_bn, holder):
-        needs_grad = any(t is not None and t.requires_grad for t in (weight, bias, gamma, beta))
-        res = encode_forward(points, spec, batch_size, weight, bias, gamma, beta, running_mean, running_var, train_bn,
-                             want_argmax=needs_grad)
+    def forward(ctx, weight, bias, gamma, beta, running_mean, running_var, pending, holder):
+        res = encode_finish(pending)
         holder.append(res)
         # the node must not reference its own outputs (reference cycle => the ~1 GB of state would wait for the GC)
         ctx.res = dataclasses.replace(res, features=None, coords=None)
-        ctx.spec, ctx.batch_size, ctx.train_bn = spec, batch_size, train_bn
-        pts = points.detach()
-        if pts.dtype != torch.float32 or not pts.is_contiguous() or pts.data_ptr() % 16:
-            pts = pts.float().contiguous()
-        ctx.points = pts
+        ctx.spec, ctx.batch_size, ctx.train_bn = pending.spec, pending.batch_size, pending.train_bn
+        ctx.points = pending.points
         ctx.save_for_backward(weight, bias, gamma, beta, res.features)
         ctx.rm, ctx.rv = running_mean, running_var
         ctx.mark_non_differentiable(res.coords)
@@ -259,18 +300,36 @@ class _PillarEncodeFn(torch.autograd.Function):
         d_w, d_g, d_b = encode_backward(ctx.points, ctx.spec, ctx.batch_size, res, features, grad_features, weight, bias,
                                         gamma, beta, ctx.rm, ctx.rv, ctx.train_bn)
         use_norm = gamma is not None
-        return (None, d_w, (None if use_norm else d_b), d_g, (d_b if use_norm else None), None, None, None, None, None, None)
+        return (d_w, (None if use_norm else d_b), d_g, (d_b if use_norm else None), None, None, None, None)
+
+
+@dataclass
+class PendingModuleEncode:
+    pending: PendingEncode
+    params: tuple
+    needs_grad: bool
+
+
+def encode_async(points, spec: EncoderSpec, batch_size: int, weight, bias=None, gamma=None, beta=None, running_mean=None,
+                 running_var=None, train_bn: bool = False) -> PendingModuleEncode:
+    """Enqueues a (differentiable) encode on the current stream; pair with ``encode_wait``."""
+    if points.requires_grad:
+        raise NotImplementedError("gradients w.r.t. points are not produced (points are a leaf in the reference)")
+    needs_grad = torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in (weight, bias, gamma, beta))
+    pending = encode_launch(points, spec, batch_size, weight, bias, gamma, beta, running_mean, running_var, train_bn,
+                            want_argmax=needs_grad)
+    return PendingModuleEncode(pending, (weight, bias, gamma, beta, running_mean, running_var), needs_grad)
+
+
+def encode_wait(pm: PendingModuleEncode) -> EncodeResult:
+    if pm.needs_grad:
+        holder = []
+        feats, coords = _PillarEncodeFn.apply(*pm.params, pm.pending, holder)
+        return dataclasses.replace(holder[0], features=feats, coords=coords)
+    return encode_finish(pm.pending)
 
 
 def encode(points, spec: EncoderSpec, batch_size: int, weight, bias=None, gamma=None, beta=None, running_mean=None,
            running_var=None, train_bn: bool = False) -> EncodeResult:
     """Differentiable (w.r.t. the PFN parameters) pillar encoding.  Returns the full EncodeResult."""
-    if points.requires_grad:
-        raise NotImplementedError("gradients w.r.t. points are not produced (points are a leaf in the reference)")
-    holder = []
-    if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in (weight, bias, gamma, beta)):
-        feats, coords = _PillarEncodeFn.apply(points, weight, bias, gamma, beta, running_mean, running_var, spec, batch_size,
-                                              train_bn, holder)
-        return dataclasses.replace(holder[0], features=feats, coords=coords)
-    return encode_forward(points, spec, batch_size, weight, bias, gamma, beta, running_mean, running_var, train_bn,
-                          want_argmax=False)
+    return encode_wait(encode_async(points, spec, batch_size, weight, bias, gamma, beta, running_mean, running_var, train_bn))

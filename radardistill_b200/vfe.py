@@ -111,7 +111,9 @@ class _FusedDynamicPillarVFE(VFETemplate):
             return int(bs)
         return int(points[:, 0].max().item()) + 1 if points.shape[0] else 1  # host sync; pass batch_size to avoid it
 
-    def forward(self, batch_dict, **kwargs):
+    def launch(self, batch_dict):
+        """Enqueues this encoder's kernels on the current stream without synchronising; pair with ``finish``.
+        Lets independent encoders (LiDAR teacher / radar student) overlap on two streams -- see ``forward_pair``."""
         if self.double_flip:
             # the reference path uses `np` without importing it (dynamic_pillar_vfe.py:196-199) and cannot run
             raise NotImplementedError("DOUBLE_FLIP is dead code in the reference (NameError) and is not provided")
@@ -119,21 +121,59 @@ class _FusedDynamicPillarVFE(VFETemplate):
         pfn = self.pfn_layers[0]
         norm = pfn.norm if self.use_norm else None
         train_bn = bool(self.use_norm and norm.training)
-        res = ops.encode(points, self.spec, self._batch_size(batch_dict, points), pfn.linear.weight,
-                         bias=None if self.use_norm else pfn.linear.bias,
-                         gamma=norm.weight if norm is not None else None, beta=norm.bias if norm is not None else None,
-                         running_mean=norm.running_mean if norm is not None else None,
-                         running_var=norm.running_var if norm is not None else None, train_bn=train_bn)
+        pm = ops.encode_async(points, self.spec, self._batch_size(batch_dict, points), pfn.linear.weight,
+                              bias=None if self.use_norm else pfn.linear.bias,
+                              gamma=norm.weight if norm is not None else None, beta=norm.bias if norm is not None else None,
+                              running_mean=norm.running_mean if norm is not None else None,
+                              running_var=norm.running_var if norm is not None else None, train_bn=train_bn)
+        return pm, train_bn
+
+    def finish(self, batch_dict, token):
+        pm, train_bn = token
+        res = ops.encode_wait(pm)
         if train_bn:
             if res.n_kept == 1:
                 raise ValueError(f"Expected more than 1 value per channel when training, got input size "
                                  f"torch.Size([1, {self.spec.c_out}])")
-            norm.num_batches_tracked.add_(1)
+            self.pfn_layers[0].norm.num_batches_tracked.add_(1)
         self.last_result = res
         for k in self._feature_keys:
             batch_dict[k] = res.features
         batch_dict[self._coords_key] = res.coords
         return batch_dict
+
+    def forward(self, batch_dict, **kwargs):
+        return self.finish(batch_dict, self.launch(batch_dict))
+
+
+def forward_pair(first, second, batch_dict, side_stream=None, first_no_grad=False):
+    """Runs two independent encoders (e.g. ``vfe`` and ``radar_vfe``, pillarnet.py:28-33) concurrently: ``second`` is
+    enqueued on a side stream while ``first`` runs on the current one.  Results are identical to calling them in turn."""
+    main = torch.cuda.current_stream()
+    side = side_stream if side_stream is not None else _side_stream(main.device)
+    side.wait_stream(main)
+    with torch.cuda.stream(side):
+        tok2 = second.launch(batch_dict)
+    with torch.set_grad_enabled(torch.is_grad_enabled() and not first_no_grad):  # frozen teacher (FREEZE_PIPELINE)
+        tok1 = first.launch(batch_dict)
+        batch_dict = first.finish(batch_dict, tok1)
+    with torch.cuda.stream(side):
+        batch_dict = second.finish(batch_dict, tok2)
+    main.wait_stream(side)
+    for k in second._feature_keys + (second._coords_key,):
+        batch_dict[k].record_stream(main)
+    return batch_dict
+
+
+_side_streams = {}
+
+
+def _side_stream(device):
+    s = _side_streams.get(device.index)
+    if s is None:
+        s = torch.cuda.Stream(device)
+        _side_streams[device.index] = s
+    return s
 
 
 class DynamicPillarVFE(_FusedDynamicPillarVFE):

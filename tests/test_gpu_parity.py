@@ -246,3 +246,48 @@ def test_host_buffer_c_abi_entry_point():
     np.testing.assert_array_equal(coords[:r["p"]], r["coords"])
     np.testing.assert_array_equal(inv[:r["n"]], r["inverse"])
     np.testing.assert_array_equal(feats[:r["p"]], r["features"])
+
+
+def test_forward_pair_two_streams_matches_sequential():
+    """forward_pair (radar on a side stream, LiDAR on the current one) gives bit-identical outputs and gradients."""
+    from radardistill_b200 import synth
+    from radardistill_b200.vfe import forward_pair
+    lp, rp = torch.from_numpy(synth.lidar_batch(2, sweeps=3)).cuda(), torch.from_numpy(synth.radar_batch(2)).cuda()
+    outs = []
+    for paired in (False, True):
+        lid, rad = _shipped_module("lidar", train=False), _shipped_module("radar", train=True)
+        bd = {"points": lp, "radar_points": rp, "batch_size": 2}
+        if paired:
+            bd = forward_pair(lid, rad, bd, first_no_grad=True)
+        else:
+            with torch.no_grad():
+                bd = lid(bd)
+            bd = rad(bd)
+        assert not bd["pillar_features"].requires_grad and bd["radar_pillar_features"].requires_grad
+        bd["radar_pillar_features"].square().sum().backward()
+        torch.cuda.synchronize()
+        outs.append((bd["pillar_features"].clone(), bd["pillar_coords"].clone(), bd["radar_pillar_features"].detach().clone(),
+                     rad.pfn_layers[0].linear.weight.grad.clone(), rad.pfn_layers[0].norm.running_var.clone()))
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
+
+
+def test_host_pipeline_matches_direct_call():
+    from radardistill_b200 import synth
+    from radardistill_b200.pipeline import HostPipeline
+    lid = _shipped_module("lidar", train=False)
+    frames = [synth.lidar_batch(1, seed0=s, sweeps=2) for s in range(4)]
+    pipe = HostPipeline(lambda d: lid({"points": d["points"], "batch_size": 1}), torch.device("cuda", 0),
+                        ("pillar_features", "pillar_coords"))
+    hosts = [{"points": torch.from_numpy(f).pin_memory()} for f in frames]
+    with torch.no_grad():
+        for i, h in enumerate(hosts):
+            pipe.submit(h, hosts[i + 1] if i + 1 < len(hosts) else None)
+            if i >= 2:  # slots are recycled after `depth` steps: read step i-2 before it is overwritten
+                pass
+        pipe.finish()
+        for i in (1, 2, 3):  # depth 3: the last three steps are still resident
+            got = pipe.result(i)
+            ref = lid({"points": torch.from_numpy(frames[i]).cuda(), "batch_size": 1})
+            assert torch.equal(got["pillar_features"], ref["pillar_features"].cpu())
+            assert torch.equal(got["pillar_coords"], ref["pillar_coords"].cpu())
