@@ -151,11 +151,12 @@ def forward_pair(first, second, batch_dict, side_stream=None, first_no_grad=Fals
     enqueued on a side stream while ``first`` runs on the current one.  Results are identical to calling them in turn."""
     main = torch.cuda.current_stream()
     side = side_stream if side_stream is not None else _side_stream(main.device)
-    side.wait_stream(main)
+    side.wait_stream(main)   # inputs of `second` were produced on the current stream
+    with torch.set_grad_enabled(torch.is_grad_enabled() and not first_no_grad):  # frozen teacher (FREEZE_PIPELINE)
+        tok1 = first.launch(batch_dict)   # the long kernels go first: they keep the GPU busy while `second` is enqueued
     with torch.cuda.stream(side):
         tok2 = second.launch(batch_dict)
-    with torch.set_grad_enabled(torch.is_grad_enabled() and not first_no_grad):  # frozen teacher (FREEZE_PIPELINE)
-        tok1 = first.launch(batch_dict)
+    with torch.set_grad_enabled(torch.is_grad_enabled() and not first_no_grad):
         batch_dict = first.finish(batch_dict, tok1)
     with torch.cuda.stream(side):
         batch_dict = second.finish(batch_dict, tok2)
