@@ -315,6 +315,17 @@ group_rows_kernel(const float *__restrict__ pts, const int32_t *__restrict__ ran
         if (pos[k] < 0) continue;
         const int r = k * kIndexThreads + tid;
         const float *p = tile + r * cols;
+        if (rs == 8) {
+            // one 256-bit store (STG.256) = one full 32-byte sector per row: the scatter is bound by store requests
+            float v[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+                v[c] = c < cols ? p[c] : (c == 6 ? __int_as_float((int)(row0 + r)) : (c == 7 ? __int_as_float(rk[k]) : 0.0f));
+            asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(grows + ((size_t)pos[k] + 1) * 8), "f"(v[0]),
+                         "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+                         : "memory");
+            continue;
+        }
         float4 *d = reinterpret_cast<float4 *>(grows + ((size_t)pos[k] + 1) * rs);
         for (int c4 = 0; c4 < rs; c4 += 4) {
             float v[4];
