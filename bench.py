@@ -66,7 +66,7 @@ class ClockSampler:
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:
@@ -199,7 +199,7 @@ def build_modules(device, mode, ddp):
     call = pair
     if ddp:
         from torch.nn.parallel import DistributedDataParallel as DDP
-        call = DDP(pair, device_ids=[device.index])   # one reducer / one bucket for all PFN parameters
+        call = DDP(pair, device_ids=[device.index], gradient_as_bucket_view=True)   # one reducer / one bucket for all PFN parameters
     return lid, rad, call
 
 
@@ -252,10 +252,13 @@ def run_ours(args):
         torch.cuda.synchronize()
         return [s.elapsed_time(e) for s, e in evs]
 
+    clk = ClockSampler(local)
+    clk.__enter__()   # started before the warm-up so that nvidia-smi is already streaming when the timed steps run
     for _ in range(max(args.warmup, 3)):
         gpu_step(call, lidar_dev, radar_dev, mode, frames)
     barrier()
-    with ClockSampler(local) as clk:
+    clk.rows.clear()  # keep only samples taken during the timed region
+    if True:
         t_wall0 = time.perf_counter()
         ms = timed_steps(mode, args.steps)
         barrier()
@@ -271,6 +274,11 @@ def run_ours(args):
     else:
         total_rows = float(n_rows)
     value = total_rows / (step_ms * 1e-3)
+    if wall < 0.3:  # short timed region: keep the same load running (same count on every rank) until nvidia-smi has samples
+        for _ in range(int(0.3 / (step_ms * 1e-3)) + 1):
+            gpu_step(call, lidar_dev, radar_dev, mode, frames)
+        barrier()
+    clk.__exit__(None, None, None)
 
     # ---- mode A beside it (reference-faithful step) when the headline is mode B, N == 1 only
     extra = {}

@@ -21,8 +21,11 @@ void set_last_cuda_error(cudaError_t e, const char *where);
     } while (0)
 
 // ----------------------------------------------------------------------------- tiling constants
-constexpr int kIndexThreads = 256;
-constexpr int kIndexTileRows = 1024;  // points per CTA in the quantise / rank / fill kernels
+#ifndef RDP_INDEX_THREADS
+#define RDP_INDEX_THREADS 256
+#endif
+constexpr int kIndexThreads = RDP_INDEX_THREADS;
+constexpr int kIndexTileRows = 4 * RDP_INDEX_THREADS;  // points per CTA in the quantise / rank / fill kernels
 constexpr int kScanThreads = 256;
 constexpr int kScanGrid = 296;        // 2 CTAs per SM: every CTA of a chunked scan is co-resident
 constexpr int kPfnThreads = 128;

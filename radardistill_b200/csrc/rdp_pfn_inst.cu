@@ -18,8 +18,15 @@ using Cfg = CfgOf<RDP_CFG_ID>::type;
 template <int MODE>
 static cudaError_t launch_tile(const PfnArgs &a, int grid, cudaStream_t st) {
     const size_t smem = sizeof(PfnSmem<Cfg, MODE>);
-    cudaError_t e = cudaFuncSetAttribute(pfn_tile_kernel<Cfg, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    static bool configured[64] = {false};  // per device; the attribute is sticky, set it once
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64 || !configured[dev]) {
+        e = cudaFuncSetAttribute(pfn_tile_kernel<Cfg, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        if (dev >= 0 && dev < 64) configured[dev] = true;
+    }
     pfn_tile_kernel<Cfg, MODE><<<grid, kPfnThreads, smem, st>>>(a);
     return cudaGetLastError();
 }

@@ -176,6 +176,24 @@ def _take_host(device) -> torch.Tensor:
     return pool.pop() if pool else torch.empty(_lib.RDP_NUM_COUNTERS, dtype=torch.int32).pin_memory()
 
 
+_struct_cache = {}
+
+
+def _structs(spec: EncoderSpec, batch_size: int, n0: int):
+    """ctypes geometry / layout structs and the workspace size for (spec, batch_size, n0), cached."""
+    key = (spec, batch_size, n0)
+    hit = _struct_cache.get(key)
+    if hit is None:
+        lib = _lib.load()
+        geom, layout = spec.geom(batch_size), spec.layout_struct()
+        nbytes = C.c_size_t(0)
+        _lib.check(lib.rdp_workspace_bytes(n0, C.byref(geom), C.byref(layout), C.byref(nbytes)), "rdp_workspace_bytes")
+        if len(_struct_cache) > 256:
+            _struct_cache.clear()
+        hit = _struct_cache[key] = (geom, layout, nbytes.value)
+    return hit
+
+
 def encode_launch(points: torch.Tensor, spec: EncoderSpec, batch_size: int, weight, bias, gamma, beta, running_mean,
                   running_var, train_bn: bool, want_argmax: bool) -> PendingEncode:
     """Enqueues index + PFN forward on the current stream and returns without synchronising."""
@@ -201,9 +219,8 @@ def encode_launch(points: torch.Tensor, spec: EncoderSpec, batch_size: int, weig
     train_bn = bool(train_bn and use_norm)
 
     with torch.cuda.device(dev):
-        geom, layout = spec.geom(batch_size), spec.layout_struct()
-        nbytes = C.c_size_t(0)
-        _lib.check(lib.rdp_workspace_bytes(n0, C.byref(geom), C.byref(layout), C.byref(nbytes)), "rdp_workspace_bytes")
+        geom, layout, ws_bytes = _structs(spec, int(batch_size), int(n0))
+        nbytes = C.c_size_t(ws_bytes)
         cap = max(n0, 1)
         ws = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
         coords = torch.empty((cap, spec.coord_cols), dtype=torch.int32, device=dev)
