@@ -25,6 +25,7 @@ int carve_workspace(void *base, int64_t n_points, const rdp_geom_t *geom, const 
     ws->words = (cells + 31) / 32;
     ws->pcap = n < cells ? n : cells;
     ws->index_tiles = (n + kIndexTileRows - 1) / kIndexTileRows;
+    ws->pfn_tiles = (n + kPfnWin - 1) / kPfnWin;
     ws->partial_blocks = kPfnGridCap;
     int cin = kMaxCin, cout = kMaxCout;
     if (layout) { cin = layout->c_in; cout = layout->c_out; }
@@ -53,6 +54,8 @@ int carve_workspace(void *base, int64_t n_points, const rdp_geom_t *geom, const 
     ws->ends = reinterpret_cast<int32_t *>(take(sizeof(int32_t) * (size_t)(ws->pcap + 4)));
     const size_t pad = kPfnCap + 8;
     ws->grows = reinterpret_cast<float *>(take(sizeof(float) * (size_t)(n + pad + 1) * grouped_row_floats(geom->cols)));
+    ws->aux = reinterpret_cast<float *>(take(sizeof(float) * 8 * (size_t)(ws->pcap + kPfnWin + 8)));
+    ws->tile_first = reinterpret_cast<int32_t *>(take(sizeof(int32_t) * (size_t)(ws->pfn_tiles + 4)));
     ws->orig2kept = reinterpret_cast<int32_t *>(take(sizeof(int32_t) * (size_t)(n + 4)));
     ws->kept2orig = reinterpret_cast<int32_t *>(take(sizeof(int32_t) * (size_t)(n + 4)));
     ws->index_bytes = off;

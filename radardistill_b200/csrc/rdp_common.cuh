@@ -65,9 +65,11 @@ struct Workspace {
     double *totals;          // their fixed-order sum (reduce_partials_kernel)
     char *zero_begin;
     size_t zero_bytes;
+    float *aux;              // (pcap + pad) * 8 : per-pillar table [mean xyz | centre xy | first grouped row | rows | 0]
+    int32_t *tile_first;     // PFN tiles + 2   : first pillar that starts at or after grouped row 128 t
     int32_t *orig2kept;      // n     (only written / read when the range mask dropped rows)
     int32_t *kept2orig;      // n
-    int64_t words, n, pcap, index_tiles;
+    int64_t words, n, pcap, index_tiles, pfn_tiles;
     size_t index_bytes;      // bytes rdp_index_fwd needs (everything before `partials`)
     size_t total_bytes;
     int64_t partial_doubles_per_block;
@@ -110,6 +112,17 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gme
                      smem_u32(dst_smem)),
                  "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
+}
+
+// (sx, sy, sz) / cnt, each correctly rounded in fp64 and then rounded once to fp32 -- bit-identical to the three IEEE
+// divisions of the oracle, but with one reciprocal: y = RN(1/b), q = RN(a y), r = a - b q (exact, FMA), RN(q + r y) is the
+// correctly rounded quotient (Markstein); b is a small exact integer here.
+__device__ __forceinline__ void mean3(double sx, double sy, double sz, int cnt, float *mx, float *my, float *mz) {
+    const double b = (double)cnt, y = __drcp_rn(b);
+    const double qx = __dmul_rn(sx, y), qy = __dmul_rn(sy, y), qz = __dmul_rn(sz, y);
+    *mx = (float)__fma_rn(__fma_rn(-qx, b, sx), y, qx);
+    *my = (float)__fma_rn(__fma_rn(-qy, b, sy), y, qy);
+    *mz = (float)__fma_rn(__fma_rn(-qz, b, sz), y, qz);
 }
 
 // --- block-wide exclusive scan of one int per thread (blockDim.x == 256), returns exclusive prefix,

@@ -14,6 +14,7 @@
 //   K2b emit_coords    one thread per bitmap word -> coords[rank] in key order
 //   K3 rank_count      key[i] -> rank = word_prefix + popc(below) ; inverse[j] ; counts[rank]++
 //   K4 count_scan      exclusive scan of counts -> pillar start offsets
+//   K6 pillar_table    thread = pillar: fp64 mean of its grouped rows, pillar centre, first row, row count
 //   K5 group_rows      pos = start[rank]++ ; grouped_rows[pos] = row i, gpid[pos] = rank, gorder[pos] = i
 //                      (counting-sort fill; the order inside a pillar is arbitrary, every consumer is order
 //                      independent).  The PFN kernels then stream contiguous, pillar-aligned row tiles with TMA.
@@ -24,6 +25,7 @@ namespace rdp {
 struct GeomDev {
     float lo_x, lo_y, vx, vy;
     int nx, ny, batch, cols;
+    float off_x, off_y;
 };
 
 // ----------------------------------------------------------------------------- K1
@@ -238,7 +240,7 @@ rank_count_kernel(int32_t *__restrict__ keys, long long n0, const uint32_t *__re
 // ----------------------------------------------------------------------------- K4
 __global__ void __launch_bounds__(kScanThreads)
 count_scan_kernel(const int32_t *__restrict__ counts, uint64_t *__restrict__ state, int32_t *__restrict__ ends,
-                  int32_t *__restrict__ counters) {
+                  int32_t *__restrict__ tile_first, int32_t *__restrict__ counters) {
     __shared__ int s_scan[9];
     __shared__ uint32_t s_u32;
     __shared__ int s_ticket;
@@ -268,7 +270,13 @@ count_scan_kernel(const int32_t *__restrict__ counts, uint64_t *__restrict__ sta
         for (int q = 0; q < 4; ++q) {
             if (p + q < p1) {
                 ends[p + q] = (int)s;  // exclusive start; K5 advances it to the inclusive end
-                s += (uint32_t)c[q];
+                const uint32_t e = s + (uint32_t)c[q];
+                // PFN tile t owns the pillars that start in grouped rows [128 t, 128 t + 128): pillar p+q+1 is the first
+                // pillar starting at or after every tile boundary in (s, e]
+                for (uint32_t t = s / kPfnWin + 1; t * (uint32_t)kPfnWin <= e; ++t) tile_first[t] = (int)(p + q + 1);
+                if (p + q == 0) tile_first[0] = 0;
+                if (p + q == P - 1 && e % kPfnWin != 0) tile_first[e / kPfnWin + 1] = (int)P;
+                s = e;
             }
         }
     }
@@ -344,6 +352,31 @@ __global__ void publish_counters_kernel(const int32_t *__restrict__ counters, vo
     __threadfence_system();
 }
 
+// ----------------------------------------------------------------------------- K6
+// Per-pillar table for the PFN kernels: thread = pillar reads its (contiguous) grouped rows once and writes
+// [mean x, y, z | centre x, y | first grouped row | rows | 0] -- scatter_mean (:226) and the pillar centre (:215-216).
+// Mean: fp64 sum of the fp32 coordinates (order independent), correctly rounded quotient, one rounding to fp32.
+__global__ void __launch_bounds__(256)
+pillar_table_kernel(const float *__restrict__ grows, const int32_t *__restrict__ ends, const int32_t *__restrict__ counters,
+                    int rs, GeomDev g, float *__restrict__ aux) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= counters[RDP_CNT_P]) return;
+    const int s = p ? ends[p - 1] : 0, e = ends[p];
+    double sx = 0.0, sy = 0.0, sz = 0.0;
+    const float *r = grows + ((size_t)s + 1) * rs;
+    const float x0 = r[1], y0 = r[2];
+    for (int i = s; i < e; ++i, r += rs) { sx += (double)r[1]; sy += (double)r[2]; sz += (double)r[3]; }
+    float mx, my, mz;
+    mean3(sx, sy, sz, e - s, &mx, &my, &mz);
+    // centre of the cell: cx*vx + x_off with separate mul / add roundings (:215-216); the quantisation repeats
+    // quantize_mark_kernel's IEEE ops, so cx / cy equal the emitted coords
+    const float qx = floorf(__fdiv_rn(__fsub_rn(x0, g.lo_x), g.vx)), qy = floorf(__fdiv_rn(__fsub_rn(y0, g.lo_y), g.vy));
+    const float cenx = __fadd_rn(__fmul_rn((float)(int)qx, g.vx), g.off_x), ceny = __fadd_rn(__fmul_rn((float)(int)qy, g.vy), g.off_y);
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(aux + (size_t)p * 8), "f"(mx), "f"(my), "f"(mz), "f"(cenx),
+                 "f"(ceny), "f"(__int_as_float(s)), "f"(__int_as_float(e - s)), "f"(0.0f)
+                 : "memory");
+}
+
 static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 }  // namespace rdp
@@ -367,7 +400,8 @@ extern "C" int rdp_index_fwd(const float *points, int64_t n_points, const rdp_ge
     if (n_points == 0) return RDP_OK;
     RDP_CUDA_OK(cudaMemsetAsync(ws.zero_begin, 0, ws.zero_bytes, stream));
 
-    GeomDev g{geom->lo[0], geom->lo[1], geom->vsz[0], geom->vsz[1], geom->nx, geom->ny, geom->batch_size, geom->cols};
+    GeomDev g{geom->lo[0], geom->lo[1], geom->vsz[0], geom->vsz[1], geom->nx, geom->ny, geom->batch_size, geom->cols,
+              geom->off[0], geom->off[1]};
     const size_t smem = (size_t)kIndexTileRows * geom->cols * sizeof(float);
     if (smem > 200 * 1024) return RDP_ERR_UNSUPPORTED;
     if (smem > 48 * 1024) {
@@ -381,8 +415,10 @@ extern "C" int rdp_index_fwd(const float *points, int64_t n_points, const rdp_ge
         ws.bitmap, ws.word_prefix, ws.words, g, coord_cols, coords, counts);
     rank_count_kernel<<<tiles, kIndexThreads, 0, stream>>>(ws.keys, n_points, ws.bitmap, ws.word_prefix, ws.tile_keep,
                                                          inverse, counts, counters, ws.orig2kept, ws.kept2orig);
-    count_scan_kernel<<<kScanGrid, kScanThreads, 0, stream>>>(counts, ws.scan_state_b, ws.ends, counters);
+    count_scan_kernel<<<kScanGrid, kScanThreads, 0, stream>>>(counts, ws.scan_state_b, ws.ends, ws.tile_first, counters);
     group_rows_kernel<<<tiles, kIndexThreads, smem, stream>>>(points, ws.keys, n_points, geom->cols, ws.ends, ws.grows);
+    pillar_table_kernel<<<(unsigned)((ws.pcap + 255) / 256), 256, 0, stream>>>(ws.grows, ws.ends, counters,
+                                                                               grouped_row_floats(geom->cols), g, ws.aux);
     RDP_CUDA_OK(cudaGetLastError());
     return RDP_OK;
 }

@@ -39,7 +39,7 @@ static int build_kmap(const rdp_geom_t *g, const rdp_layout_t *l, int8_t *kmap, 
 static int fill_args(PfnArgs *a, const PfnLaunch *L, int64_t n_points, const rdp_geom_t *geom, const rdp_layout_t *layout,
                      const rdp_pfn_params_t *prm, const Workspace &ws, const int32_t *counters) {
     memset(a, 0, sizeof(*a));
-    a->grows = ws.grows; a->ends = ws.ends; a->counters = counters;
+    a->grows = ws.grows; a->aux = ws.aux; a->tile_first = ws.tile_first; a->ends = ws.ends; a->counters = counters;
     a->orig2kept = ws.orig2kept;
     a->weight = prm->weight; a->bias = prm->bias; a->gamma = prm->gamma; a->beta = prm->beta;
     a->rmean = prm->running_mean; a->rvar = prm->running_var;
@@ -82,6 +82,13 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const double *__re
     }
 }
 
+// scatter_mean's (P, 3) output (:226) for callers that want it: the first three columns of the pillar table
+__global__ void table_to_mean_kernel(const float *__restrict__ aux, const int32_t *__restrict__ counters, float *__restrict__ out) {
+    const long long total = 3ll * counters[RDP_CNT_P];
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x)
+        out[e] = aux[(e / 3) * 8 + (e % 3)];
+}
+
 static int pfn_grid(int64_t n_points) {
     const int64_t tiles = (n_points + kPfnWin - 1) / kPfnWin;
     return (int)(tiles < kPfnGridCap ? (tiles < 1 ? 1 : tiles) : kPfnGridCap);
@@ -114,7 +121,7 @@ extern "C" int rdp_pfn_fwd(const float *points, int64_t n_points, const rdp_geom
     if (rc != RDP_OK) return rc;
     a.features = features;
     a.argpos = argpos;
-    a.pillar_mean = pillar_mean;
+    if (pillar_mean) table_to_mean_kernel<<<148 * 4, 256, 0, st>>>(ws.aux, counters, pillar_mean);
     const int grid = pfn_grid(n_points);
     if (train) {
         if (L->stats_partial_doubles > ws.partial_doubles_per_block) return RDP_ERR_WORKSPACE;

@@ -31,6 +31,8 @@ constexpr int kMaxSuper = 24;
 
 struct PfnArgs {
     const float *grows;
+    const float *aux;               // per-pillar table [mean xyz | centre xy | first grouped row | rows | 0]
+    const int32_t *tile_first;      // first pillar starting at or after grouped row 128 t
     const int32_t *ends, *counters, *orig2kept;
     const float *weight, *bias, *gamma, *beta, *rmean, *rvar;
     const double *bn_state;  // train apply: folded scale / shift live here
@@ -72,6 +74,7 @@ struct PfnCfg {
     static constexpr int BWD_DOUBLES = COUT * BWD_PER;
     static constexpr int RS = (COLS + 2 + 3) / 4 * 4;  // floats per grouped row: the row, padding, original row id, pillar id
     static constexpr uint32_t ROW_BYTES = (kPfnCap + 1) * RS * 4;  // the window plus the row in front of it
+    static constexpr uint32_t AUX_BYTES = kPfnWin * 8 * 4;
     static_assert(CS <= kMaxSuper, "too many features");
     static_assert(ROW_BYTES % 16 == 0, "TMA sizes");
     static_assert(NBLK <= kPfnThreads && COUT % 32 == 0, "tiling");
@@ -81,6 +84,7 @@ struct PfnCfg {
 // Slot RS-2 of a row holds its original row index, slot RS-1 its pillar id (int bit patterns).
 template <class Cfg>
 struct PfnStage {
+    alignas(32) float aux[kPfnWin * 8];   // table entries of the (at most 128) pillars that start in the window
     alignas(16) float rows[(kPfnCap + 1) * Cfg::RS];
     __device__ __forceinline__ int gid(int j) const { return __float_as_int(rows[(j + 1) * Cfg::RS + Cfg::RS - 1]); }
     __device__ __forceinline__ int ord(int j) const { return __float_as_int(rows[(j + 1) * Cfg::RS + Cfg::RS - 2]); }
@@ -105,13 +109,11 @@ struct PfnSmem {
     int start[kPfnCap + 1];
     int lp[kPfnCap];                               // (pillar slot << 1) | last-row-of-pillar flag
     int kept[kPfnCap];
-    float mean[kPfnCap * 3];
-    float cen[kPfnCap * 2];
+    float bigaux[8];                               // big-pillar path: table entry of the pillar being streamed
+    int tf[2][2];                                  // per stage: first pillar of the tile, first pillar of the next
     float scale[Cfg::COUT], shift[Cfg::COUT];
     float carry_v[Cfg::COUT];
     int carry_k[Cfg::COUT], carry_p[Cfg::COUT];
-    int wred[3][kPfnThreads / 32];
-    double dred[kPfnThreads * 3];
 };
 
 // ------------------------------------------------------------------------------------------- features
@@ -148,26 +150,6 @@ __device__ __forceinline__ void fold_bn(double gamma, double beta, double mean, 
     const double s = __dmul_rn(gamma, inv_std);
     *scale = (float)s;
     *shift = (float)__dsub_rn(beta, __dmul_rn(mean, s));
-}
-
-// pillar centre of the cell that holds (x, y): cx*vx + x_off with separate mul / add roundings (:215-216);
-// the quantisation repeats quantize_mark_kernel's IEEE ops, so cx / cy equal the emitted coords.
-__device__ __forceinline__ void pillar_centre(float x, float y, const PfnArgs &a, float *cenx, float *ceny) {
-    const float qx = floorf(__fdiv_rn(__fsub_rn(x, a.lo[0]), a.vsz[0]));
-    const float qy = floorf(__fdiv_rn(__fsub_rn(y, a.lo[1]), a.vsz[1]));
-    *cenx = __fadd_rn(__fmul_rn((float)(int)qx, a.vsz[0]), a.off[0]);
-    *ceny = __fadd_rn(__fmul_rn((float)(int)qy, a.vsz[1]), a.off[1]);
-}
-
-// (sx, sy, sz) / cnt, each correctly rounded in fp64 and then rounded once to fp32 -- bit-identical to the three IEEE
-// divisions of the oracle, but with one reciprocal: y = RN(1/b), q = RN(a y), r = a - b q (exact, FMA), RN(q + r y) is the
-// correctly rounded quotient (Markstein); b is a small exact integer here.
-__device__ __forceinline__ void mean3(double sx, double sy, double sz, int cnt, float *mx, float *my, float *mz) {
-    const double b = (double)cnt, y = __drcp_rn(b);
-    const double qx = __dmul_rn(sx, y), qy = __dmul_rn(sy, y), qz = __dmul_rn(sz, y);
-    *mx = (float)__fma_rn(__fma_rn(-qx, b, sx), y, qx);
-    *my = (float)__fma_rn(__fma_rn(-qy, b, sy), y, qy);
-    *mz = (float)__fma_rn(__fma_rn(-qz, b, sz), y, qz);
 }
 
 __device__ __forceinline__ int warp_min(int v) { return __reduce_min_sync(0xffffffffu, v); }
@@ -247,21 +229,38 @@ __global__ void __launch_bounds__(kPfnThreads, (MODE == PFN_MODE_APPLY) ? 5 : 4)
         }
     }
 
-    auto issue = [&](int t, int s) {
+    // thread 0 only.  (pf, pn) = tile_first[t], tile_first[t + 1]; published to the CTA through S.tf before the arrive.
+    auto issue = [&](int t, int s, int pf, int pn) {
         PfnStage<Cfg> &T = S.st[s];
-        mbar_expect_tx(&S.full[s], Cfg::ROW_BYTES);
+        S.tf[s][0] = pf; S.tf[s][1] = pn;
+        mbar_expect_tx(&S.full[s], Cfg::ROW_BYTES + Cfg::AUX_BYTES);
         tma_bulk_g2s(T.rows, a.grows + (size_t)t * WIN * RS, Cfg::ROW_BYTES, &S.full[s]);  // grows row 0 = the row before position 0
+        tma_bulk_g2s(T.aux, a.aux + (size_t)pf * 8, Cfg::AUX_BYTES, &S.full[s]);
     };
 
-    // C1: decorated features of rows [rowbase, rowbase + np) of `rows` -> S.f[0..np)
-    auto c1 = [&](const float *rows, int rowbase, int np) {
+    // C1 (thread = row): decorated features of rows [rowbase, rowbase + np) of `rows` -> S.f[0..np), the row's
+    // (pillar slot << 1 | last-row flag) -> S.lp, pillar start table -> S.start.  `ps >= 0`: rows of a staged tile, the
+    // slot is gid - ps and `aux` the tile's table slice; ps < 0: chunk of one big pillar (slot 0, never last, S.bigaux).
+    auto c1 = [&](const float *rows, int rowbase, int np, int ps, const float *aux) {
         for (int jj = tid; jj < np; jj += NT) {
             float r[COLS], f[Cfg::FW];
             const float *src = rows + (rowbase + jj) * RS;
 #pragma unroll
             for (int c = 0; c < COLS; ++c) r[c] = src[c];
-            const int lp = S.lp[jj] >> 1;
-            decorate<Cfg>(r, S.cen[lp * 2], S.cen[lp * 2 + 1], &S.mean[lp * 3], a, f);
+            int slot = 0;
+            const float *ax = S.bigaux;
+            if (ps >= 0) {
+                const int gid = __float_as_int(src[RS - 1]);
+                slot = gid - ps;
+                ax = aux + slot * 8;
+                const int last = (jj == np - 1) || (__float_as_int(src[RS + RS - 1]) != gid);
+                S.lp[jj] = (slot << 1) | last;
+                if (__float_as_int(src[-1]) != gid) S.start[slot] = jj;
+            } else {
+                S.lp[jj] = 0;
+            }
+            if (want_arg) { const int row = __float_as_int(src[RS - 2]); S.kept[jj] = none_dropped ? row : a.orig2kept[row]; }
+            decorate<Cfg>(r, ax[3], ax[4], ax, a, f);
             f[CS] = 1.0f;  // ones column: the Gram matrix then carries sum f (S1) as well
 #pragma unroll
             for (int k = CS + 1; k < Cfg::FW; ++k) f[k] = 0.0f;
@@ -395,73 +394,41 @@ __global__ void __launch_bounds__(kPfnThreads, (MODE == PFN_MODE_APPLY) ? 5 : 4)
         tma_bulk_g2s(S.pre_arg, a.argpos + (size_t)p0 * COUT, bytes, &S.pre);
     };
 
-    if (t_begin < t_end && tid == 0) issue(t_begin, 0);
+    // thread 0 keeps tile_first two tiles ahead in registers so the TMA issue never waits on a global load
+    int tfa = 0, tfb = 0, tfc = 0;
+    if (t_begin < t_end && tid == 0) {
+        tfa = a.tile_first[t_begin]; tfb = a.tile_first[t_begin + 1];
+        tfc = (t_begin + 1 < t_end) ? a.tile_first[t_begin + 2] : tfb;
+        issue(t_begin, 0, tfa, tfb);
+    }
     uint32_t par0 = 0, par1 = 0, ppar = 0;
 
     for (int t = t_begin; t < t_end; ++t) {
         const int s = (t - t_begin) & 1;
-        if (tid == 0 && t + 1 < t_end) issue(t + 1, s ^ 1);
+        if (tid == 0 && t + 1 < t_end) {
+            issue(t + 1, s ^ 1, tfb, tfc);
+            tfb = tfc;
+            tfc = (t + 2 < t_end) ? a.tile_first[t + 3] : tfc;
+        }
         if (s == 0) { mbar_wait(&S.full[0], par0); par0 ^= 1; } else { mbar_wait(&S.full[1], par1); par1 ^= 1; }
         PfnStage<Cfg> &T = S.st[s];
         const long long base = (long long)t * WIN;
 
-        // ---- P0: which pillars does this tile own?
-        int jmin = INF, jend = INF, jlast = -1;
-        for (int j = tid; j < CAP; j += NT) {
-            const bool valid = base + j < N;
-            const bool head = valid && (T.gid(j) != T.gid(j - 1));
-            if (j < WIN) {
-                if (head) { jmin = min(jmin, j); jlast = max(jlast, j); }
-                if (!valid) jend = min(jend, j);
-            } else if (head || !valid) {
-                jend = min(jend, j);
-            }
-        }
-        jmin = warp_min(jmin); jend = warp_min(jend); jlast = warp_max(jlast);
-        if (lane == 0) { S.wred[0][warp] = jmin; S.wred[1][warp] = jend; S.wred[2][warp] = jlast; }
-        __syncthreads();
-        jmin = INF; jend = INF; jlast = -1;
-#pragma unroll
-        for (int w = 0; w < NW; ++w) { jmin = min(jmin, S.wred[0][w]); jend = min(jend, S.wred[1][w]); jlast = max(jlast, S.wred[2][w]); }
-        if (jmin == INF) { __syncthreads(); continue; }  // a pillar from an earlier tile covers the whole window
-        const bool big = (jend == INF);                   // the last pillar runs past the staged rows
-        const int j0 = jmin, jstop = big ? jlast : jend, np = jstop - j0;
-        const int ps = T.gid(j0);
-        const int nb = np > 0 ? T.gid(jstop - 1) - ps + 1 : 0;
+        // ---- tile bounds straight from the pillar table (built once per forward by pillar_table_kernel)
+        const int ps = S.tf[s][0], pe = S.tf[s][1];
+        if (pe == ps) { __syncthreads(); continue; }  // a pillar from an earlier tile covers the whole window
+        const int j0 = __float_as_int(T.aux[5]) - (int)base;                      // first row of the first pillar
+        const float *alast = T.aux + (pe - ps - 1) * 8;
+        const int last_start = __float_as_int(alast[5]) - (int)base, last_rows = __float_as_int(alast[6]);
+        const bool big = last_start + last_rows > CAP;                             // the last pillar runs past the staged rows
+        const int jstop = big ? last_start : last_start + last_rows, np = jstop - j0;
+        const int nb = big ? pe - ps - 1 : pe - ps;
         const int gb = (int)base + j0;
-        if (MODE == PFN_MODE_BWD && np > 0 && tid == 0) prefetch_bwd(ps, min(Smem::PCH, nb));  // lands while P1..C1 run
+        if (MODE == PFN_MODE_BWD && np > 0 && tid == 0) prefetch_bwd(ps, min(Smem::PCH, nb));  // lands while C1 runs
 
         if (np > 0) {
-            // ---- P1: row -> (pillar slot, last-row flag); pillar start table
-            for (int jj = tid; jj < np; jj += NT) {
-                const int j = j0 + jj, gid = T.gid(j);
-                const int last = (jj == np - 1) || (T.gid(j + 1) != gid);
-                S.lp[jj] = ((gid - ps) << 1) | last;
-                if (gid != T.gid(j - 1)) S.start[gid - ps] = jj;
-                if (want_arg) { const int row = T.ord(j); S.kept[jj] = none_dropped ? row : a.orig2kept[row]; }
-            }
             if (tid == 0) S.start[nb] = np;
-            __syncthreads();
-            // ---- P2: per-pillar mean and centre
-            for (int q = tid; q < nb; q += NT) {
-                const int b0 = S.start[q], b1 = S.start[q + 1];
-                double sx = 0.0, sy = 0.0, sz3 = 0.0;
-                for (int jj = b0; jj < b1; ++jj) {
-                    const float *r = T.row(j0 + jj);
-                    sx += (double)r[1]; sy += (double)r[2]; sz3 += (double)r[3];
-                }
-                float mx, my, mz;
-                mean3(sx, sy, sz3, b1 - b0, &mx, &my, &mz);
-                S.mean[q * 3] = mx; S.mean[q * 3 + 1] = my; S.mean[q * 3 + 2] = mz;
-                const float *r0 = T.row(j0 + b0);
-                pillar_centre(r0[1], r0[2], a, &S.cen[q * 2], &S.cen[q * 2 + 1]);
-                if (is_apply && a.pillar_mean) {
-                    float *pm = a.pillar_mean + (size_t)(ps + q) * 3;
-                    pm[0] = mx; pm[1] = my; pm[2] = mz;
-                }
-            }
-            __syncthreads();
-            c1(T.rows, j0 + 1, np);
+            c1(T.rows, j0 + 1, np, ps, T.aux);
             __syncthreads();
             if (MODE != PFN_MODE_BWD) {
                 // warp w streams a pillar-aligned quarter of the rows
@@ -523,27 +490,9 @@ __global__ void __launch_bounds__(kPfnThreads, (MODE == PFN_MODE_APPLY) ? 5 : 4)
         if (big) {
             // ---- big pillar pb = rows [a0, e): straight from global memory
             __syncthreads();
-            const int pb = T.gid(jlast);
-            const long long a0 = base + jlast;
-            const long long e = a.ends[pb];
-            double sx = 0.0, sy = 0.0, sz3 = 0.0;
-            for (long long g = a0 + tid; g < e; g += NT) {
-                const float *r = a.grows + (g + 1) * RS;
-                sx += (double)r[1]; sy += (double)r[2]; sz3 += (double)r[3];
-            }
-            S.dred[tid * 3] = sx; S.dred[tid * 3 + 1] = sy; S.dred[tid * 3 + 2] = sz3;
-            __syncthreads();
-            if (tid < 3) {
-                double tsum = 0.0;  // fp64 adds of fp32 values in this range are exact: order is immaterial
-                for (int j = 0; j < NT; ++j) tsum += S.dred[j * 3 + tid];
-                const float mv = (float)__ddiv_rn(tsum, (double)(e - a0));
-                S.mean[tid] = mv;
-                if (is_apply && a.pillar_mean) a.pillar_mean[(size_t)pb * 3 + tid] = mv;
-            }
-            if (tid == 32) {
-                const float *r0 = a.grows + (a0 + 1) * RS;
-                pillar_centre(r0[1], r0[2], a, &S.cen[0], &S.cen[1]);
-            }
+            const int pb = pe - 1;
+            const long long a0 = base + last_start, e = a0 + last_rows;
+            if (tid < 8) S.bigaux[tid] = alast[tid];
             if (tid < COUT) { S.carry_v[tid] = want_arg ? -1.0f : 0.0f; S.carry_k[tid] = INF; S.carry_p[tid] = 0; }
             __syncthreads();
             if (MODE == PFN_MODE_BWD) {
@@ -556,7 +505,7 @@ __global__ void __launch_bounds__(kPfnThreads, (MODE == PFN_MODE_APPLY) ? 5 : 4)
                         float r[COLS], f[Cfg::FW];
 #pragma unroll
                         for (int c = 0; c < COLS; ++c) r[c] = src[c];
-                        decorate<Cfg>(r, S.cen[0], S.cen[1], &S.mean[0], a, f);
+                        decorate<Cfg>(r, S.bigaux[3], S.bigaux[4], S.bigaux, a, f);
                         float x = 0.0f;
 #pragma unroll
                         for (int k = 0; k < CS; ++k) x = fmaf(W[cc][k], f[k], x);
@@ -571,12 +520,8 @@ __global__ void __launch_bounds__(kPfnThreads, (MODE == PFN_MODE_APPLY) ? 5 : 4)
                 for (long long cs = a0; cs < e; cs += CAP) {
                     const int npc = (int)min((long long)CAP, e - cs);
                     for (int i = tid; i < npc * RS; i += NT) rows[i] = a.grows[(cs + 1) * RS + i];
-                    for (int jj = tid; jj < npc; jj += NT) {
-                        S.lp[jj] = 0;  // slot 0, never "last": the carry below closes the pillar
-                        if (want_arg) { const int row = __float_as_int(a.grows[(cs + jj + 1) * RS + RS - 2]); S.kept[jj] = none_dropped ? row : a.orig2kept[row]; }
-                    }
                     __syncthreads();
-                    c1(rows, 0, npc);
+                    c1(rows, 0, npc, -1, nullptr);
                     __syncthreads();
                     if (MODE == PFN_MODE_STATS) gram(npc);
                     stream((warp * npc) / NW, ((warp + 1) * npc) / NW, pb, (int)cs);
