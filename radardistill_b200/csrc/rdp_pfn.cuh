@@ -97,7 +97,7 @@ struct PfnSmem {
     static constexpr size_t S_BYTES = (MODE == PFN_MODE_STATS) ? sizeof(double) * kPfnThreads * 16 : 0;
     static constexpr size_t B_BYTES = 0;  // BWD: the end-of-kernel scratch aliases f + the prefetch buffers (see bwd_scratch())
     static constexpr size_t SCR = Z_BYTES > S_BYTES ? (Z_BYTES > B_BYTES ? Z_BYTES : B_BYTES) : (S_BYTES > B_BYTES ? S_BYTES : B_BYTES);
-    static constexpr int PCH = (MODE == PFN_MODE_BWD) ? 48 : 1;  // pillars per backward prefetch chunk
+    static constexpr int PCH = (MODE == PFN_MODE_BWD) ? 32 : 1;  // pillars per backward prefetch chunk
     PfnStage<Cfg> st[2];
     alignas(8) uint64_t full[2];
     alignas(8) uint64_t pre;                       // BWD: arrival of the tile's (grad, features, argpos) rows
