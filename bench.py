@@ -361,11 +361,17 @@ def run_ours(args):
         alg = row_bytes * n_kept + 4 * spec.c_out * n_pil           # rows read once + feature rows written once
         alg_fwd = row_bytes * len(lidar) + 4 * n_kept + n_pil * (4 * spec.c_out + 4 * spec.coord_cols + 4)  # SURVEY 8(d) B_fwd
         peak, peak_src = peaks()
+        traffic, traffic_src = None, None
+        tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
+        if os.path.exists(tp):  # dram__bytes_read + dram__bytes_write of one launch from the committed ncu --set full capture
+            tj = json.load(open(tp))["pfn_tile_apply_eval"]
+            if tj["rows"] == n_kept and tj["pillars"] == n_pil:
+                traffic, traffic_src = tj["dram_bytes_read"] + tj["dram_bytes_write"], tj["source"]
         dur = sum(durs) / len(durs)
         idx = sum(idx_durs) / len(idx_durs)
         roof = {"bound": "hbm", "kernel": "pfn_fwd_kernel<Simple2D 6 cols, 32 ch, APPLY> (LiDAR batch, eval BN)",
                 "achieved": alg / (dur * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": alg / (dur * 1e-3) / 1e9 / peak,
-                "traffic": None, "peak_source": peak_src, "kernel_ms": dur, "algorithmic_bytes": int(alg),
+                "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "kernel_ms": dur, "algorithmic_bytes": int(alg),
                 "frac_of_8000_nominal": alg / (dur * 1e-3) / 1e9 / 8000.0,
                 "whole_forward": {"algorithmic_bytes": int(alg_fwd), "ms": idx + dur, "index_ms": idx,
                                   "achieved": alg_fwd / ((idx + dur) * 1e-3) / 1e9,
