@@ -25,6 +25,10 @@
 
 #include "rdp_common.cuh"
 
+#ifndef RDP_LPR
+#define RDP_LPR 16   // lanes that share one feature row in the forward stream (32 / 16 / 8)
+#endif
+
 namespace rdp {
 
 constexpr int kMaxSuper = 24;
@@ -184,11 +188,17 @@ __global__ void __launch_bounds__(kPfnThreads, (MODE == PFN_MODE_APPLY) ? 5 : 4)
         mbar_init(&S.pre, 1);
         fence_mbar_init();
     }
-    // lane = output channel (+32): its weight row(s) live in registers for the whole kernel
-    float W[CPL][CS], sc[CPL], sh[CPL];
+    // Forward stream: LPR lanes share one feature row; lane sl of the sub-group owns channels sl + LPR q, whose weight
+    // rows live in registers for the whole kernel.  With LPR = 16 a 16-byte feature load feeds two rows' worth of lanes
+    // (two addresses per warp instruction), which halves the shared-memory wavefronts per row -- the pipe that bounds the
+    // lane-per-channel form (ncu: l1tex lsu wavefronts 80 %).  Backward: lane = channel (+32 cc).
+    constexpr int LPR = RDP_LPR, SUB = 32 / LPR, NS = NW * SUB;
+    constexpr int WN = (MODE == PFN_MODE_BWD) ? CPL : COUT / LPR;
+    const int sl = lane % LPR, sid = warp * SUB + lane / LPR;
+    float W[WN][CS], sc[WN], sh[WN];
 #pragma unroll
-    for (int cc = 0; cc < CPL; ++cc) {
-        const int ch = lane + 32 * cc;
+    for (int cc = 0; cc < WN; ++cc) {
+        const int ch = (MODE == PFN_MODE_BWD) ? (lane + 32 * cc) : (sl + LPR * cc);
 #pragma unroll
         for (int s = 0; s < CS; ++s) {
             const int k = a.kmap[s];
@@ -207,12 +217,12 @@ __global__ void __launch_bounds__(kPfnThreads, (MODE == PFN_MODE_APPLY) ? 5 : 4)
     __syncthreads();
 
     // ---- accumulators that live for the whole CTA
-    double st_x[CPL], st_x2[CPL], st_m[16];
+    double st_x[WN], st_x2[WN], st_m[16];
     int gba = 0, gbb = 0;
     const int grg = tid % Cfg::RG, gblk = tid / Cfg::RG;
     if (MODE == PFN_MODE_STATS) {
 #pragma unroll
-        for (int cc = 0; cc < CPL; ++cc) st_x[cc] = st_x2[cc] = 0.0;
+        for (int cc = 0; cc < WN; ++cc) st_x[cc] = st_x2[cc] = 0.0;
 #pragma unroll
         for (int e = 0; e < 16; ++e) st_m[e] = 0.0;
         int rem = gblk;
@@ -280,7 +290,7 @@ __global__ void __launch_bounds__(kPfnThreads, (MODE == PFN_MODE_APPLY) ? 5 : 4)
             f[k4 * 4] = v.x; f[k4 * 4 + 1] = v.y; f[k4 * 4 + 2] = v.z; f[k4 * 4 + 3] = v.w;
         }
 #pragma unroll
-        for (int cc = 0; cc < CPL; ++cc) {
+        for (int cc = 0; cc < WN; ++cc) {
             float acc = 0.0f;
 #pragma unroll
             for (int k = 0; k < CS; ++k) acc = fmaf(W[cc][k], f[k], acc);
@@ -288,84 +298,68 @@ __global__ void __launch_bounds__(kPfnThreads, (MODE == PFN_MODE_APPLY) ? 5 : 4)
         }
     };
 
-    // running max state of the pillar a warp is streaming (lane = channel)
-    float m[CPL];
-    int mk[CPL], mp[CPL];
+    // running max state of the pillar a sub-group is streaming (lane = its channels)
+    float m[WN];
+    int mk[WN], mp[WN];
     auto reset_max = [&]() {
 #pragma unroll
-        for (int cc = 0; cc < CPL; ++cc) { m[cc] = want_arg ? -1.0f : 0.0f; mk[cc] = INF; mp[cc] = 0; }
+        for (int cc = 0; cc < WN; ++cc) { m[cc] = want_arg ? -1.0f : 0.0f; mk[cc] = INF; mp[cc] = 0; }
     };
-    auto fold_max = [&](const float *x, int kj, int pos) {
+    float *fout = nullptr;
+    int32_t *aout = nullptr;
+    // one row: BN (+ReLU) -> running max / lowest-index argmax (or the fp64 statistics); stores the pillar when `meta`
+    // carries the last-row flag (pillars close in order: the output row pointer just advances)
+    auto fold_row = [&](const float *x, int j, int gb) {
+        if (MODE == PFN_MODE_STATS) {
 #pragma unroll
-        for (int cc = 0; cc < CPL; ++cc) {
+            for (int cc = 0; cc < WN; ++cc) { const double v = (double)x[cc]; st_x[cc] += v; st_x2[cc] = fma(v, v, st_x2[cc]); }
+            return;
+        }
+        const int meta = S.lp[j];
+        const int kj = want_arg ? S.kept[j] : 0;
+#pragma unroll
+        for (int cc = 0; cc < WN; ++cc) {
             const float y = fmaf(x[cc], sc[cc], sh[cc]);
             if (!want_arg) {
                 m[cc] = fmaxf(m[cc], y);  // ReLU folds into the max with 0
             } else {
                 const float z = fmaxf(y, 0.0f);
-                if (z > m[cc] || (z == m[cc] && kj < mk[cc])) { m[cc] = z; mk[cc] = kj; mp[cc] = pos; }
+                if (z > m[cc] || (z == m[cc] && kj < mk[cc])) { m[cc] = z; mk[cc] = kj; mp[cc] = gb + j; }
             }
+        }
+        if (meta & 1) {
+#pragma unroll
+            for (int cc = 0; cc < WN; ++cc) {
+                fout[LPR * cc] = m[cc];
+                if (want_arg) aout[LPR * cc] = mp[cc];
+            }
+            fout += COUT;
+            if (want_arg) aout += COUT;
+            reset_max();
         }
     };
 
-    // STREAM: warp w walks rows [ra, rb) of S.f; APPLY keeps the running max and stores a pillar when its last row
-    // has been folded in (S.lp[j] = (pillar slot << 1) | last-row flag); STATS accumulates sum x / sum x^2.
+    // STREAM: every sub-group of LPR lanes walks its own pillar-aligned rows [ra, rb) of S.f, two rows in flight
+    // (sub-groups of a warp with shorter ranges simply leave the loop earlier).
     auto stream = [&](int ra, int rb, int ps, int gb) {
-        if (is_apply) reset_max();
-        // first pillar this warp closes = the pillar of its first row (ranges are pillar aligned)
-        const int slot0 = (ra < rb) ? (S.lp[ra] >> 1) : 0;
-        float *fout = a.features + (size_t)(ps + slot0) * COUT + lane;
-        int32_t *aout = want_arg ? a.argpos + (size_t)(ps + slot0) * COUT + lane : nullptr;
+        if (is_apply) {
+            reset_max();
+            const int slot0 = (ra < rb) ? (S.lp[ra] >> 1) : 0;  // first pillar this sub-group closes
+            fout = a.features + (size_t)(ps + slot0) * COUT + sl;
+            aout = want_arg ? a.argpos + (size_t)(ps + slot0) * COUT + sl : nullptr;
+        }
         int j = ra;
         for (; j + 1 < rb; j += 2) {  // two rows in flight: two independent fmaf chains per channel
-            float x0[CPL], x1[CPL];
+            float x0[WN], x1[WN];
             dot_row(j, x0);
             dot_row(j + 1, x1);
-            if (MODE == PFN_MODE_STATS) {
-#pragma unroll
-                for (int cc = 0; cc < CPL; ++cc) {
-                    const double v0 = (double)x0[cc], v1 = (double)x1[cc];
-                    st_x[cc] += v0; st_x2[cc] = fma(v0, v0, st_x2[cc]);
-                    st_x[cc] += v1; st_x2[cc] = fma(v1, v1, st_x2[cc]);
-                }
-            } else {
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int jj = j + h, meta = S.lp[jj];
-                    fold_max(h ? x1 : x0, want_arg ? S.kept[jj] : 0, gb + jj);
-                    if (meta & 1) {  // pillars close in order: the output row pointer just advances
-#pragma unroll
-                        for (int cc = 0; cc < CPL; ++cc) {
-                            fout[32 * cc] = m[cc];
-                            if (want_arg) aout[32 * cc] = mp[cc];
-                        }
-                        fout += COUT;
-                        if (want_arg) aout += COUT;
-                        reset_max();
-                    }
-                }
-            }
+            fold_row(x0, j, gb);
+            fold_row(x1, j + 1, gb);
         }
         if (j < rb) {
-            float x0[CPL];
+            float x0[WN];
             dot_row(j, x0);
-            if (MODE == PFN_MODE_STATS) {
-#pragma unroll
-                for (int cc = 0; cc < CPL; ++cc) { const double v0 = (double)x0[cc]; st_x[cc] += v0; st_x2[cc] = fma(v0, v0, st_x2[cc]); }
-            } else {
-                const int meta = S.lp[j];
-                fold_max(x0, want_arg ? S.kept[j] : 0, gb + j);
-                if (meta & 1) {
-#pragma unroll
-                    for (int cc = 0; cc < CPL; ++cc) {
-                        fout[32 * cc] = m[cc];
-                        if (want_arg) aout[32 * cc] = mp[cc];
-                    }
-                    fout += COUT;
-                    if (want_arg) aout += COUT;
-                    reset_max();
-                }
-            }
+            fold_row(x0, j, gb);
         }
     };
 
@@ -431,10 +425,10 @@ __global__ void __launch_bounds__(kPfnThreads, (MODE == PFN_MODE_APPLY) ? 5 : 4)
             c1(T.rows, j0 + 1, np, ps, T.aux);
             __syncthreads();
             if (MODE != PFN_MODE_BWD) {
-                // warp w streams a pillar-aligned quarter of the rows
-                const int r_lo = (warp * np) / NW, r_hi = ((warp + 1) * np) / NW;
-                const int ra = (warp == 0) ? 0 : S.start[S.lp[r_lo] >> 1];
-                const int rb = (warp == NW - 1) ? np : S.start[S.lp[r_hi] >> 1];
+                // sub-group `sid` streams a pillar-aligned 1/NS of the rows
+                const int r_lo = (sid * np) / NS, r_hi = ((sid + 1) * np) / NS;
+                const int ra = (sid == 0) ? 0 : S.start[S.lp[r_lo] >> 1];
+                const int rb = (sid == NS - 1) ? np : S.start[S.lp[r_hi] >> 1];
                 if (MODE == PFN_MODE_STATS) gram(np);
                 stream(ra, rb, ps, gb);
             } else {
@@ -524,14 +518,14 @@ __global__ void __launch_bounds__(kPfnThreads, (MODE == PFN_MODE_APPLY) ? 5 : 4)
                     c1(rows, 0, npc, -1, nullptr);
                     __syncthreads();
                     if (MODE == PFN_MODE_STATS) gram(npc);
-                    stream((warp * npc) / NW, ((warp + 1) * npc) / NW, pb, (int)cs);
+                    stream((sid * npc) / NS, ((sid + 1) * npc) / NS, pb, (int)cs);
                     if (is_apply) {
-                        // merge the warps' running maxima into the carry, in warp order (deterministic)
-                        for (int w = 0; w < NW; ++w) {
-                            if (warp == w) {
+                        // merge the sub-groups' running maxima into the carry, in stream order (deterministic)
+                        for (int w = 0; w < NS; ++w) {
+                            if (sid == w) {
 #pragma unroll
-                                for (int cc = 0; cc < CPL; ++cc) {
-                                    const int ch = lane + 32 * cc;
+                                for (int cc = 0; cc < WN; ++cc) {
+                                    const int ch = sl + LPR * cc;
                                     const float bm = S.carry_v[ch];
                                     const int bk = S.carry_k[ch];
                                     if (m[cc] > bm || (want_arg && m[cc] == bm && mk[cc] < bk)) {
@@ -560,15 +554,17 @@ __global__ void __launch_bounds__(kPfnThreads, (MODE == PFN_MODE_APPLY) ? 5 : 4)
         // layout: [sum x (COUT) | sum x^2 (COUT) | NBLK blocks of 16]
         double *out = a.partials + (size_t)blockIdx.x * Cfg::STATS_DOUBLES;
         __syncthreads();
+        if (MODE == PFN_MODE_STATS) {
 #pragma unroll
-        for (int cc = 0; cc < CPL; ++cc) {
-            dscr[(warp * COUT + lane + 32 * cc) * 2] = st_x[cc];
-            dscr[(warp * COUT + lane + 32 * cc) * 2 + 1] = st_x2[cc];
+            for (int cc = 0; cc < WN; ++cc) {
+                dscr[(sid * COUT + sl + LPR * cc) * 2] = st_x[cc];
+                dscr[(sid * COUT + sl + LPR * cc) * 2 + 1] = st_x2[cc];
+            }
         }
         __syncthreads();
         if (tid < COUT) {
             double sx = 0.0, sx2 = 0.0;
-            for (int w = 0; w < NW; ++w) { sx += dscr[(w * COUT + tid) * 2]; sx2 += dscr[(w * COUT + tid) * 2 + 1]; }
+            for (int w = 0; w < NS; ++w) { sx += dscr[(w * COUT + tid) * 2]; sx2 += dscr[(w * COUT + tid) * 2 + 1]; }
             out[tid] = sx; out[COUT + tid] = sx2;
         }
         __syncthreads();
