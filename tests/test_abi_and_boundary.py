@@ -105,3 +105,25 @@ def test_state_dict_matches_the_reference_class():
     assert list(a.keys()) == list(b.keys())
     assert all(tuple(a[k].shape) == tuple(b[k].shape) and a[k].dtype == b[k].dtype for k in a)
     ours.load_state_dict(a, strict=True)
+
+
+def test_torch_library_ops_are_registered_with_fake_kernels():
+    """torch.ops.rdp.* exist, carry schemas, and their fake kernels give the data-dependent sizes unbacked symbols."""
+    from torch._subclasses.fake_tensor import FakeTensorMode
+    from torch.fx.experimental.symbolic_shapes import ShapeEnv
+    from radardistill_b200 import torch_ops
+    spec = ops.make_spec(6, synth.VOXEL_SIZE, synth.grid_size_of(), synth.PC_RANGE, _lib.LAYOUT_SIMPLE2D, True, True, True, False, 32)
+    ints, floats = torch_ops.spec_to_lists(spec)
+    assert torch_ops.spec_from_lists(ints, floats) == spec
+    assert "Tensor points" in str(torch.ops.rdp.pillar_encode.default._schema)
+    with FakeTensorMode(shape_env=ShapeEnv()):
+        pts, w = torch.empty((500, 7), device="cuda"), torch.empty((32, 15), device="cuda")
+        v = lambda: torch.empty(32, device="cuda")
+        out = torch.ops.rdp.pillar_encode(pts, w, None, v(), v(), v(), v(), ints, floats, 2, True, True)
+        feats, coords, inverse, counts, argpos, bn_state = out[:6]
+        assert feats.shape[1] == 32 and coords.shape[1] == 3 and feats.dtype == torch.float32 and coords.dtype == torch.int32
+        assert feats.shape[0] == coords.shape[0] == counts.shape[0] == argpos.shape[0]      # one symbol: P
+        assert bn_state.shape[0] == 4 * 32 + 1 + 15 + 15 * 15
+        g = torch.ops.rdp.pillar_encode_backward(pts, feats, feats, argpos, bn_state, out[6], out[7], w, None, v(), v(), v(), v(),
+                                                 ints, floats, 2, True)
+        assert [tuple(t.shape) for t in g] == [(32, 15), (32,), (32,)]

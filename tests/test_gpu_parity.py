@@ -291,3 +291,24 @@ def test_host_pipeline_matches_direct_call():
             ref = lid({"points": torch.from_numpy(frames[i]).cuda(), "batch_size": 1})
             assert torch.equal(got["pillar_features"], ref["pillar_features"].cpu())
             assert torch.equal(got["pillar_coords"], ref["pillar_coords"].cpu())
+
+
+def test_torch_library_op_matches_module():
+    """torch.ops.rdp.pillar_encode (+ its registered autograd) == the drop-in module, bit for bit."""
+    from radardistill_b200 import synth, torch_ops
+    pts = torch.from_numpy(synth.radar_batch(3)).cuda()
+    m = _shipped_module("radar", train=True)
+    pfn, n = m.pfn_layers[0], m.pfn_layers[0].norm
+    w = pfn.linear.weight.detach().clone().requires_grad_(True)
+    gamma, beta = n.weight.detach().clone().requires_grad_(True), n.bias.detach().clone().requires_grad_(True)
+    ints, floats = torch_ops.spec_to_lists(m.spec)
+    out = torch.ops.rdp.pillar_encode(pts, w, None, gamma, beta, n.running_mean.clone(), n.running_var.clone(), ints, floats, 3,
+                                      True, True)
+    feats, coords, new_rm = out[0], out[1], out[8]
+    ref = m({"radar_points": pts, "batch_size": 3})
+    assert torch.equal(coords, ref["radar_pillar_coords"]) and torch.equal(feats, ref["radar_pillar_features"])
+    assert torch.equal(new_rm, n.running_mean)
+    g = torch.randn(feats.shape, generator=torch.Generator().manual_seed(1)).cuda()
+    feats.backward(g)
+    ref["radar_pillar_features"].backward(g)
+    assert torch.equal(w.grad, pfn.linear.weight.grad) and torch.equal(gamma.grad, n.weight.grad) and torch.equal(beta.grad, n.bias.grad)
