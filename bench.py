@@ -253,7 +253,8 @@ def run_ours(args):
         return [s.elapsed_time(e) for s, e in evs]
 
     clk = ClockSampler(local)
-    clk.__enter__()   # started before the warm-up so that nvidia-smi is already streaming when the timed steps run
+    if rank == 0:     # one sampler per job: the step is host-bound, eight pollers would perturb what they measure
+        clk.__enter__()   # started before the warm-up so that nvidia-smi is already streaming when the timed steps run
     for _ in range(max(args.warmup, 3)):
         gpu_step(call, lidar_dev, radar_dev, mode, frames)
     barrier()
@@ -278,7 +279,8 @@ def run_ours(args):
         for _ in range(int(0.3 / (step_ms * 1e-3)) + 1):
             gpu_step(call, lidar_dev, radar_dev, mode, frames)
         barrier()
-    clk.__exit__(None, None, None)
+    if rank == 0:
+        clk.__exit__(None, None, None)
 
     # ---- mode A beside it (reference-faithful step) when the headline is mode B, N == 1 only
     extra = {}
