@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define RDP_ABI_VERSION 1
+#define RDP_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define RDP_API __attribute__((visibility("default")))
@@ -108,6 +108,18 @@ RDP_API int rdp_workspace_bytes(int64_t n_points, const rdp_geom_t *geom, const 
 RDP_API int rdp_index_fwd(const float *points, int64_t n_points, const rdp_geom_t *geom, int32_t coord_cols,
                   void *workspace, size_t workspace_bytes,
                   int32_t *coords, int32_t *inverse, int32_t *counts, int32_t *counters, void *stream);
+
+/*
+ * rdp_index_fwd that also tells the host N and P as early as they exist: right after the bitmap scan (two kernels
+ * into the call) a one-warp kernel copies counters[] to `host_mapped` (pinned, device-visible host memory; NULL to
+ * skip) and `event` (a cudaEvent_t passed as void*; NULL to skip) is recorded on `stream`.  A host thread that
+ * waits on the event learns the output sizes while the remaining index kernels (and whatever the caller enqueues
+ * behind them) are still running -- the reference's size read-backs (:204-206 boolean mask, :212 unique) stall the
+ * stream instead.  Everything else is rdp_index_fwd.
+ */
+RDP_API int rdp_index_fwd_publish(const float *points, int64_t n_points, const rdp_geom_t *geom, int32_t coord_cols,
+                                  void *workspace, size_t workspace_bytes, int32_t *coords, int32_t *inverse,
+                                  int32_t *counts, int32_t *counters, int32_t *host_mapped, void *event, void *stream);
 
 /*
  * scatter_mean -> decorated features -> Linear + BatchNorm1d + ReLU -> scatter_max.

@@ -162,7 +162,10 @@ class PillarOracle:
         bmean, bvar = np.zeros(co, np.float64), np.ones(co, np.float64)
         scale, shift = np.ones(co, np.float32), self.bias.copy()
         if cfg.use_norm:
-            if training:
+            if training and self.mean_mode == MEAN_F64:   # canonical: from the fp64 feature moments
+                L.orc_bn_batch_stats_moments(_p(f), C.c_int64(n), C.c_int(cin), _p(self.weight), C.c_int(co),
+                                             _p(bmean), _p(bvar))
+            elif training:                                # reference semantics: moments of the fp32 x values
                 L.orc_bn_batch_stats(_p(x), C.c_int64(n), C.c_int(co), _p(bmean), _p(bvar))
             else:
                 bmean, bvar = self.running_mean.astype(np.float64), self.running_var.astype(np.float64)

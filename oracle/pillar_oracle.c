@@ -286,6 +286,43 @@ void orc_bn_batch_stats(const float *x, int64_t n, int cout, double *mean, doubl
     free(s);
 }
 
+/*
+ * Canonical (ORC_MEAN_F64) train-mode statistics: x = W f is linear, so the batch moments of x follow from the
+ * first and second moments of the features, accumulated in fp64 (products of two fp32 values are exact in fp64):
+ *   S1[k] = sum_j f[j][k],  S2[k][l] = sum_j f[j][k] f[j][l],
+ *   mean_c = (w_c . S1) / n,  E[x^2]_c = (w_c^T S2 w_c) / n,  var_c = E[x^2]_c - mean_c^2   (biased, as BatchNorm1d).
+ * Differs from summing the rounded fp32 x values (orc_bn_batch_stats) by the fp32 rounding of x only (~1e-7
+ * relative); this is what the CUDA kernels compute (one pass over the rows without the linear layer).
+ */
+void orc_bn_batch_stats_moments(const float *f, int64_t n, int cin, const float *W, int cout, double *mean, double *var) {
+    double *S1 = (double *)calloc((size_t)(cin + cin * cin), sizeof(double)), *S2 = S1 + cin;
+    for (int64_t j = 0; j < n; ++j) {
+        const float *fj = f + j * cin;
+        for (int k = 0; k < cin; ++k) {
+            const double a = (double)fj[k];
+            S1[k] += a;
+            for (int l = k; l < cin; ++l) S2[k * cin + l] += a * (double)fj[l];
+        }
+    }
+    for (int k = 0; k < cin; ++k)
+        for (int l = 0; l < k; ++l) S2[k * cin + l] = S2[l * cin + k];
+    for (int c = 0; c < cout; ++c) {
+        const float *w = W + c * cin;
+        double m = 0.0, e2 = 0.0;
+        for (int k = 0; k < cin; ++k) m += (double)w[k] * S1[k];
+        for (int k = 0; k < cin; ++k) {
+            double row = 0.0;
+            for (int l = 0; l < cin; ++l) row += S2[k * cin + l] * (double)w[l];
+            e2 += (double)w[k] * row;
+        }
+        m = n > 0 ? m / (double)n : 0.0;
+        double vv = n > 0 ? e2 / (double)n - m * m : 0.0;
+        mean[c] = m;
+        var[c] = vv > 0.0 ? vv : 0.0;
+    }
+    free(S1);
+}
+
 /* y = x*scale + shift with scale = gamma/sqrt(var+eps), shift = beta - mean*scale (fp64, one rounding). */
 void orc_bn_fold(const float *gamma, const float *beta, const double *mean, const double *var, double eps,
                  int cout, float *scale, float *shift) {

@@ -8,12 +8,12 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("RDP_LIB_PATH", os.path.join(_HERE, "librdp.so"))  # override: kernel-variant experiments
 
-RDP_ABI_VERSION = 1
+RDP_ABI_VERSION = 2
 RDP_NUM_COUNTERS = 16
 CNT_N, CNT_P, CNT_ERRFLAGS = 0, 1, 2
 LAYOUT_SIMPLE2D, LAYOUT_DYNPILLAR = 0, 1
 
-EXPORTS = ["rdp_abi_version", "rdp_status_string", "rdp_last_cuda_error", "rdp_workspace_bytes", "rdp_index_fwd",
+EXPORTS = ["rdp_abi_version", "rdp_status_string", "rdp_last_cuda_error", "rdp_workspace_bytes", "rdp_index_fwd", "rdp_index_fwd_publish",
            "rdp_pfn_fwd", "rdp_bn_state_doubles", "rdp_pfn_bwd", "rdp_argmax_kept", "rdp_publish_counters",
            "rdp_encode_host"]
 
@@ -61,6 +61,8 @@ def load() -> C.CDLL:
     vp = C.c_void_p
     lib.rdp_index_fwd.restype = C.c_int
     lib.rdp_index_fwd.argtypes = [vp, C.c_int64, C.POINTER(Geom), C.c_int32, vp, C.c_size_t, vp, vp, vp, vp, vp]
+    lib.rdp_index_fwd_publish.restype = C.c_int
+    lib.rdp_index_fwd_publish.argtypes = [vp, C.c_int64, C.POINTER(Geom), C.c_int32, vp, C.c_size_t, vp, vp, vp, vp, vp, vp, vp]
     lib.rdp_pfn_fwd.restype = C.c_int
     lib.rdp_pfn_fwd.argtypes = [vp, C.c_int64, C.POINTER(Geom), C.POINTER(Layout), C.POINTER(PfnParams), vp, C.c_size_t,
                                 vp, vp, vp, vp, vp, vp]

@@ -383,10 +383,18 @@ static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t
 
 using namespace rdp;
 
-extern "C" int rdp_index_fwd(const float *points, int64_t n_points, const rdp_geom_t *geom, int32_t coord_cols,
-                             void *workspace, size_t workspace_bytes, int32_t *coords, int32_t *inverse,
-                             int32_t *counts, int32_t *counters, void *stream_v) {
+extern "C" int rdp_index_fwd_publish(const float *points, int64_t n_points, const rdp_geom_t *geom, int32_t coord_cols,
+                                     void *workspace, size_t workspace_bytes, int32_t *coords, int32_t *inverse,
+                                     int32_t *counts, int32_t *counters, int32_t *host_mapped, void *event_v, void *stream_v) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+    cudaEvent_t event = static_cast<cudaEvent_t>(event_v);
+    // N, P and the error flags are final after the bitmap scan (K2): publish them there, so the host learns the output
+    // sizes ~50 us into the call and can enqueue whatever follows while the remaining kernels run.
+    auto publish = [&]() -> int {
+        if (host_mapped) publish_counters_kernel<<<1, 32, 0, stream>>>(counters, host_mapped);
+        if (event) RDP_CUDA_OK(cudaEventRecord(event, stream));
+        return RDP_OK;
+    };
     if (!geom || !counters || n_points < 0 || (coord_cols != 3 && coord_cols != 4)) return RDP_ERR_INVALID_ARG;
     if (n_points > 0 && (!points || !workspace || !coords || !inverse || !counts)) return RDP_ERR_INVALID_ARG;
     if (!aligned16(points) || !aligned16(coords) || !aligned16(inverse) || !aligned16(workspace)) return RDP_ERR_INVALID_ARG;
@@ -397,7 +405,7 @@ extern "C" int rdp_index_fwd(const float *points, int64_t n_points, const rdp_ge
     if (n_points > 0 && ws.index_bytes > workspace_bytes) return RDP_ERR_WORKSPACE;
 
     RDP_CUDA_OK(cudaMemsetAsync(counters, 0, sizeof(int32_t) * RDP_NUM_COUNTERS, stream));
-    if (n_points == 0) return RDP_OK;
+    if (n_points == 0) return publish();
     RDP_CUDA_OK(cudaMemsetAsync(ws.zero_begin, 0, ws.zero_bytes, stream));
 
     GeomDev g{geom->lo[0], geom->lo[1], geom->vsz[0], geom->vsz[1], geom->nx, geom->ny, geom->batch_size, geom->cols,
@@ -411,6 +419,7 @@ extern "C" int rdp_index_fwd(const float *points, int64_t n_points, const rdp_ge
     const int tiles = (int)ws.index_tiles;
     quantize_mark_kernel<<<tiles, kIndexThreads, smem, stream>>>(points, n_points, g, ws.bitmap, ws.keys, ws.tile_keep, counters);
     bitmap_rank_kernel<<<kScanGrid, kScanThreads, 0, stream>>>(ws.bitmap, ws.words, ws.scan_state_a, ws.word_prefix, counters);
+    if (int rc2 = publish()) return rc2;
     emit_coords_kernel<<<(unsigned)((ws.words + kScanThreads - 1) / kScanThreads), kScanThreads, 0, stream>>>(
         ws.bitmap, ws.word_prefix, ws.words, g, coord_cols, coords, counts);
     rank_count_kernel<<<tiles, kIndexThreads, 0, stream>>>(ws.keys, n_points, ws.bitmap, ws.word_prefix, ws.tile_keep,
@@ -421,6 +430,13 @@ extern "C" int rdp_index_fwd(const float *points, int64_t n_points, const rdp_ge
                                                                                grouped_row_floats(geom->cols), g, ws.aux);
     RDP_CUDA_OK(cudaGetLastError());
     return RDP_OK;
+}
+
+extern "C" int rdp_index_fwd(const float *points, int64_t n_points, const rdp_geom_t *geom, int32_t coord_cols,
+                             void *workspace, size_t workspace_bytes, int32_t *coords, int32_t *inverse,
+                             int32_t *counts, int32_t *counters, void *stream_v) {
+    return rdp_index_fwd_publish(points, n_points, geom, coord_cols, workspace, workspace_bytes, coords, inverse, counts, counters,
+                                 nullptr, nullptr, stream_v);
 }
 
 extern "C" int rdp_publish_counters(const int32_t *counters, int32_t *host_mapped, void *stream_v) {

@@ -73,7 +73,7 @@ struct PfnCfg {
     static constexpr int ZSTRIDE = COUT + 4;
     static constexpr int NBLK = T4 * (T4 + 1) / 2;                 // upper-triangle 4x4 blocks of the Gram matrix
     static constexpr int RG = kPfnThreads / NBLK;                  // row groups in the Gram phase
-    static constexpr int STATS_DOUBLES = 2 * COUT + 16 * NBLK;
+    static constexpr int STATS_DOUBLES = 16 * NBLK;   // Gram blocks of [features | 1] (batch moments of x follow from them)
     static constexpr int BWD_PER = CS + 2;
     static constexpr int BWD_DOUBLES = COUT * BWD_PER;
     static constexpr int RS = (COLS + 2 + 3) / 4 * 4;  // floats per grouped row: the row, padding, original row id, pillar id
@@ -202,7 +202,7 @@ __global__ void __launch_bounds__(kPfnThreads, (MODE == PFN_MODE_APPLY) ? 5 : 4)
 #pragma unroll
         for (int s = 0; s < CS; ++s) {
             const int k = a.kmap[s];
-            W[cc][s] = (k >= 0) ? __ldg(a.weight + ch * a.c_in + k) : 0.0f;
+            W[cc][s] = (k >= 0 && is_apply) ? __ldg(a.weight + ch * a.c_in + k) : 0.0f;
         }
         sc[cc] = 1.0f;
         sh[cc] = 0.0f;
@@ -217,23 +217,21 @@ __global__ void __launch_bounds__(kPfnThreads, (MODE == PFN_MODE_APPLY) ? 5 : 4)
     __syncthreads();
 
     // ---- accumulators that live for the whole CTA
-    double st_x[WN], st_x2[WN], st_m[16];
+    double st_m[16];
     int gba = 0, gbb = 0;
     const int grg = tid % Cfg::RG, gblk = tid / Cfg::RG;
     if (MODE == PFN_MODE_STATS) {
-#pragma unroll
-        for (int cc = 0; cc < WN; ++cc) st_x[cc] = st_x2[cc] = 0.0;
 #pragma unroll
         for (int e = 0; e < 16; ++e) st_m[e] = 0.0;
         int rem = gblk;
         while (gba < Cfg::T4 && rem >= Cfg::T4 - gba) { rem -= Cfg::T4 - gba; ++gba; }
         gbb = gba + rem;  // block (gba, gbb), gba <= gbb, valid when gblk < NBLK
     }
-    double dB[CPL], dG[CPL], dA[CPL][CS];
+    double dB[CPL], dA[CPL][CS];
     if (MODE == PFN_MODE_BWD) {
 #pragma unroll
         for (int cc = 0; cc < CPL; ++cc) {
-            dB[cc] = dG[cc] = 0.0;
+            dB[cc] = 0.0;
 #pragma unroll
             for (int k = 0; k < CS; ++k) dA[cc][k] = 0.0;
         }
@@ -310,11 +308,6 @@ __global__ void __launch_bounds__(kPfnThreads, (MODE == PFN_MODE_APPLY) ? 5 : 4)
     // one row: BN (+ReLU) -> running max / lowest-index argmax (or the fp64 statistics); stores the pillar when `meta`
     // carries the last-row flag (pillars close in order: the output row pointer just advances)
     auto fold_row = [&](const float *x, int j, int gb) {
-        if (MODE == PFN_MODE_STATS) {
-#pragma unroll
-            for (int cc = 0; cc < WN; ++cc) { const double v = (double)x[cc]; st_x[cc] += v; st_x2[cc] = fma(v, v, st_x2[cc]); }
-            return;
-        }
         const int meta = S.lp[j];
         const int kj = want_arg ? S.kept[j] : 0;
 #pragma unroll
@@ -424,19 +417,20 @@ __global__ void __launch_bounds__(kPfnThreads, (MODE == PFN_MODE_APPLY) ? 5 : 4)
             if (tid == 0) S.start[nb] = np;
             c1(T.rows, j0 + 1, np, ps, T.aux);
             __syncthreads();
-            if (MODE != PFN_MODE_BWD) {
+            if (MODE == PFN_MODE_STATS) {
+                gram(np);   // train-mode batch statistics come from the feature moments alone: no linear layer in this pass
+            } else if (MODE != PFN_MODE_BWD) {
                 // sub-group `sid` streams a pillar-aligned 1/NS of the rows
                 const int r_lo = (sid * np) / NS, r_hi = ((sid + 1) * np) / NS;
                 const int ra = (sid == 0) ? 0 : S.start[S.lp[r_lo] >> 1];
                 const int rb = (sid == NS - 1) ? np : S.start[S.lp[r_hi] >> 1];
-                if (MODE == PFN_MODE_STATS) gram(np);
                 stream(ra, rb, ps, gb);
             } else {
                 // ---- E (backward): warp = pillar, lane = channel
-                float tB[CPL], tG[CPL], tA[CPL][CS];
+                float tB[CPL], tA[CPL][CS];
 #pragma unroll
                 for (int cc = 0; cc < CPL; ++cc) {
-                    tB[cc] = tG[cc] = 0.0f;
+                    tB[cc] = 0.0f;
 #pragma unroll
                     for (int k = 0; k < CS; ++k) tA[cc][k] = 0.0f;
                 }
@@ -461,11 +455,7 @@ __global__ void __launch_bounds__(kPfnThreads, (MODE == PFN_MODE_APPLY) ? 5 : 4)
                             const float4 v = src[k4];
                             f[k4 * 4] = v.x; f[k4 * 4 + 1] = v.y; f[k4 * 4 + 2] = v.z; f[k4 * 4 + 3] = v.w;
                         }
-                        float x = 0.0f;
-#pragma unroll
-                        for (int k = 0; k < CS; ++k) x = fmaf(W[cc][k], f[k], x);
-                        tB[cc] += gy;
-                        tG[cc] = fmaf(gy, x, tG[cc]);
+                        tB[cc] += gy;   // G = sum gy x = w . A (x is linear in f): folded in bwd_finalize_kernel
 #pragma unroll
                         for (int k = 0; k < CS; ++k) tA[cc][k] = fmaf(gy, f[k], tA[cc][k]);
                     }
@@ -474,7 +464,6 @@ __global__ void __launch_bounds__(kPfnThreads, (MODE == PFN_MODE_APPLY) ? 5 : 4)
 #pragma unroll
                 for (int cc = 0; cc < CPL; ++cc) {
                     dB[cc] += (double)tB[cc];
-                    dG[cc] += (double)tG[cc];
 #pragma unroll
                     for (int k = 0; k < CS; ++k) dA[cc][k] += (double)tA[cc][k];
                 }
@@ -500,11 +489,7 @@ __global__ void __launch_bounds__(kPfnThreads, (MODE == PFN_MODE_APPLY) ? 5 : 4)
 #pragma unroll
                         for (int c = 0; c < COLS; ++c) r[c] = src[c];
                         decorate<Cfg>(r, S.bigaux[3], S.bigaux[4], S.bigaux, a, f);
-                        float x = 0.0f;
-#pragma unroll
-                        for (int k = 0; k < CS; ++k) x = fmaf(W[cc][k], f[k], x);
                         dB[cc] += (double)gy;
-                        dG[cc] = fma((double)gy, (double)x, dG[cc]);
 #pragma unroll
                         for (int k = 0; k < CS; ++k) dA[cc][k] = fma((double)gy, (double)f[k], dA[cc][k]);
                     }
@@ -518,7 +503,7 @@ __global__ void __launch_bounds__(kPfnThreads, (MODE == PFN_MODE_APPLY) ? 5 : 4)
                     c1(rows, 0, npc, -1, nullptr);
                     __syncthreads();
                     if (MODE == PFN_MODE_STATS) gram(npc);
-                    stream((sid * npc) / NS, ((sid + 1) * npc) / NS, pb, (int)cs);
+                    else stream((sid * npc) / NS, ((sid + 1) * npc) / NS, pb, (int)cs);
                     if (is_apply) {
                         // merge the sub-groups' running maxima into the carry, in stream order (deterministic)
                         for (int w = 0; w < NS; ++w) {
@@ -551,22 +536,8 @@ __global__ void __launch_bounds__(kPfnThreads, (MODE == PFN_MODE_APPLY) ? 5 : 4)
 
     // ---- per-CTA partial sums
     if (MODE == PFN_MODE_STATS) {
-        // layout: [sum x (COUT) | sum x^2 (COUT) | NBLK blocks of 16]
+        // layout: NBLK blocks of 16
         double *out = a.partials + (size_t)blockIdx.x * Cfg::STATS_DOUBLES;
-        __syncthreads();
-        if (MODE == PFN_MODE_STATS) {
-#pragma unroll
-            for (int cc = 0; cc < WN; ++cc) {
-                dscr[(sid * COUT + sl + LPR * cc) * 2] = st_x[cc];
-                dscr[(sid * COUT + sl + LPR * cc) * 2 + 1] = st_x2[cc];
-            }
-        }
-        __syncthreads();
-        if (tid < COUT) {
-            double sx = 0.0, sx2 = 0.0;
-            for (int w = 0; w < NS; ++w) { sx += dscr[(w * COUT + tid) * 2]; sx2 += dscr[(w * COUT + tid) * 2 + 1]; }
-            out[tid] = sx; out[COUT + tid] = sx2;
-        }
         __syncthreads();
 #pragma unroll
         for (int e = 0; e < 16; ++e) dscr[tid * 16 + e] = st_m[e];
@@ -575,7 +546,7 @@ __global__ void __launch_bounds__(kPfnThreads, (MODE == PFN_MODE_APPLY) ? 5 : 4)
             const int blk = e / 16, el = e % 16;
             double sacc = 0.0;
             for (int g = 0; g < Cfg::RG; ++g) sacc += dscr[(blk * Cfg::RG + g) * 16 + el];
-            out[2 * COUT + e] = sacc;
+            out[e] = sacc;
         }
     }
     if (MODE == PFN_MODE_BWD) {
@@ -585,7 +556,7 @@ __global__ void __launch_bounds__(kPfnThreads, (MODE == PFN_MODE_APPLY) ? 5 : 4)
 #pragma unroll
         for (int cc = 0; cc < CPL; ++cc) {
             double *dst = dscr + ((size_t)warp * COUT + lane + 32 * cc) * PER;
-            dst[0] = dB[cc]; dst[1] = dG[cc];
+            dst[0] = dB[cc]; dst[1] = 0.0;
 #pragma unroll
             for (int k = 0; k < CS; ++k) dst[2 + k] = dA[cc][k];
         }
@@ -613,12 +584,33 @@ __global__ void __launch_bounds__(256) bn_finalize_kernel(const __grid_constant_
     for (int e = tid; e < TOT; e += blockDim.x) tot[e] = totals[e];  // reduce_partials_kernel's fixed-order sums
     __syncthreads();
     const int cin = a.c_in;
+    // Gram entry of super features (fa <= fb): block (fa/4, fb/4), element (fa%4, fb%4); column CS is the ones column
+    auto gram_at = [&](int fa, int fb) {
+        const int ba = fa / 4, bb = fb / 4;
+        const int blk = ba * T4 - ba * (ba - 1) / 2 + (bb - ba);
+        return tot[blk * 16 + (fa % 4) * 4 + (fb % 4)];
+    };
     if (tid < COUT) {
+        // batch moments of x = W f from the feature moments (oracle: orc_bn_batch_stats_moments):
+        //   mean_c = w_c . S1 / n,  E[x^2]_c = w_c^T S2 w_c / n,  var_c = E[x^2]_c - mean_c^2  (biased)
         const double n = (double)N;
         double mean = 0.0, var = 0.0;
         if (N > 0) {
-            mean = __ddiv_rn(tot[tid], n);
-            var = __dsub_rn(__ddiv_rn(tot[COUT + tid], n), __dmul_rn(mean, mean));
+            double m = 0.0, e2 = 0.0;
+            for (int fa = 0; fa < CS; ++fa) {
+                const int ka = a.kmap[fa];
+                if (ka < 0) continue;
+                const double wa = (double)a.weight[tid * cin + ka];
+                m += wa * gram_at(fa, CS);
+                double row = 0.0;
+                for (int fb = 0; fb < CS; ++fb) {
+                    const int kb = a.kmap[fb];
+                    if (kb >= 0) row += (fa <= fb ? gram_at(fa, fb) : gram_at(fb, fa)) * (double)a.weight[tid * cin + kb];
+                }
+                e2 += wa * row;
+            }
+            mean = __ddiv_rn(m, n);
+            var = __dsub_rn(__ddiv_rn(e2, n), __dmul_rn(mean, mean));
             if (!(var > 0.0)) var = 0.0;
         }
         bn_state[tid] = mean;
@@ -634,12 +626,6 @@ __global__ void __launch_bounds__(256) bn_finalize_kernel(const __grid_constant_
     }
     if (tid == 0) bn_state[4 * COUT] = (double)N;
     double *S1 = bn_state + 4 * COUT + 1, *S2 = S1 + cin;
-    // Gram entry of super features (fa <= fb): block (fa/4, fb/4), element (fa%4, fb%4)
-    auto gram_at = [&](int fa, int fb) {
-        const int ba = fa / 4, bb = fb / 4;
-        const int blk = ba * T4 - ba * (ba - 1) / 2 + (bb - ba);
-        return tot[2 * COUT + blk * 16 + (fa % 4) * 4 + (fb % 4)];
-    };
     for (int e = tid; e < CS * CS; e += blockDim.x) {
         const int fa = e / CS, fb = e % CS;
         const int ka = a.kmap[fa], kb = a.kmap[fb];
@@ -674,7 +660,13 @@ __global__ void __launch_bounds__(256) bwd_finalize_kernel(const __grid_constant
     if (tid < COUT) {
         double mu, is;
         stat(tid, &mu, &is);
-        const double db = tot[tid * PER], G = tot[tid * PER + 1];
+        // G_c = sum_p gy x_win = w_c . A_c  (x = W f is linear in the features), in fp64
+        double G = 0.0;
+        for (int s = 0; s < CS; ++s) {
+            const int k = a.kmap[s];
+            if (k >= 0) G = fma((double)a.weight[tid * cin + k], tot[tid * PER + 2 + s], G);
+        }
+        const double db = tot[tid * PER];
         const double dg = (G - mu * db) * is;
         dgam[tid] = dg;
         d_beta[tid] = (float)db;

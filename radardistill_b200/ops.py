@@ -171,9 +171,16 @@ class PendingEncode:
 _host_pool = {}
 
 
-def _take_host(device) -> torch.Tensor:
+def _take_host(device, stream):
+    """A (pinned counters buffer, CUDA event) pair; the event exists (has been recorded once) so that librdp can record
+    it by handle from inside rdp_index_fwd_publish."""
     pool = _host_pool.setdefault(device.index, [])
-    return pool.pop() if pool else torch.empty(_lib.RDP_NUM_COUNTERS, dtype=torch.int32).pin_memory()
+    if pool:
+        return pool.pop()
+    host = torch.empty(_lib.RDP_NUM_COUNTERS, dtype=torch.int32).pin_memory()
+    event = torch.cuda.Event()
+    event.record(stream)
+    return host, event
 
 
 _struct_cache = {}
@@ -234,25 +241,28 @@ def encode_launch(points: torch.Tensor, spec: EncoderSpec, batch_size: int, weig
             bn_state = torch.zeros(int(lib.rdp_bn_state_doubles(C.byref(layout))), dtype=torch.float64, device=dev)
         stream = torch.cuda.current_stream()
         st = C.c_void_p(stream.cuda_stream)
-        _lib.check(lib.rdp_index_fwd(_ptr(pts), n0, C.byref(geom), spec.coord_cols, _ptr(ws), nbytes.value, _ptr(coords),
-                                     _ptr(inverse), _ptr(counts), _ptr(counters), st), "rdp_index_fwd")
+        # (N, P) are published to pinned host memory (zero-copy kernel store: never queues behind bulk DMA) right after
+        # the bitmap scan, and `event` is recorded there: encode_finish returns while the rest of the forward still runs
+        host, event = _take_host(dev, stream)
+        _lib.check(lib.rdp_index_fwd_publish(_ptr(pts), n0, C.byref(geom), spec.coord_cols, _ptr(ws), nbytes.value,
+                                             _ptr(coords), _ptr(inverse), _ptr(counts), _ptr(counters),
+                                             C.c_void_p(host.data_ptr()), C.c_void_p(event.cuda_event), st),
+                   "rdp_index_fwd_publish")
         prm = _params_struct(spec, weight, bias, gamma, beta, running_mean, running_var, train_bn)
         _lib.check(lib.rdp_pfn_fwd(_ptr(pts), n0, C.byref(geom), C.byref(layout), C.byref(prm), _ptr(ws), nbytes.value,
                                    _ptr(counters), _ptr(features), _ptr(argpos), None, _ptr(bn_state), st), "rdp_pfn_fwd")
-        host = _take_host(dev)  # written by a kernel (zero-copy): never queues behind bulk DMA on the copy engines
-        _lib.check(lib.rdp_publish_counters(_ptr(counters), C.c_void_p(host.data_ptr()), st), "rdp_publish_counters")
-        event = torch.cuda.Event()
-        event.record(stream)
     return PendingEncode(spec=spec, batch_size=int(batch_size), n_points=int(n0), points=pts, coords=coords, inverse=inverse,
                          counts=counts, features=features, argpos=argpos, bn_state=bn_state, workspace=ws, counters=counters,
                          host=host, event=event, stream=stream, train_bn=train_bn)
 
 
 def encode_finish(p: PendingEncode) -> EncodeResult:
-    """Waits for the forward's kernels, reads (N, P) and narrows the capacity-sized outputs."""
+    """Waits for the early (N, P) publication -- not for the forward's kernels, which may still be running on
+    `p.stream` -- and narrows the capacity-sized outputs."""
     p.event.synchronize()
-    n_kept, n_pillars, err = int(p.host[_lib.CNT_N]), int(p.host[_lib.CNT_P]), int(p.host[_lib.CNT_ERRFLAGS])
-    _host_pool.setdefault(p.points.device.index, []).append(p.host)
+    hv = p.host.tolist()
+    n_kept, n_pillars, err = hv[_lib.CNT_N], hv[_lib.CNT_P], hv[_lib.CNT_ERRFLAGS]
+    _host_pool.setdefault(p.points.device.index, []).append((p.host, p.event))
     if err & 1:
         raise ValueError(f"points[:, 0] holds a batch index outside [0, {p.batch_size})")
     return EncodeResult(features=p.features[:n_pillars], coords=p.coords[:n_pillars], inverse=p.inverse[:n_kept],
