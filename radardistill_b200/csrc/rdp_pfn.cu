@@ -1,4 +1,5 @@
 // rdp_pfn.cu -- host side of rdp_pfn_fwd / rdp_pfn_bwd: argument marshalling and config dispatch.
+#include <cstdlib>
 #include <cstring>
 
 #include "rdp_pfn_host.h"
@@ -131,7 +132,14 @@ extern "C" int rdp_pfn_fwd(const float *points, int64_t n_points, const rdp_geom
         a.bn_state = bn_state;
         a.fold_from_state = 1;
     }
-    RDP_CUDA_OK(L->tile(a, argpos ? PFN_MODE_APPLY_ARG : PFN_MODE_APPLY, grid, st));
+    static const bool legacy = getenv("RDP_PFN_LEGACY") != nullptr;   // A/B switch for kernel experiments
+    if (legacy) {
+        RDP_CUDA_OK(L->tile(a, argpos ? PFN_MODE_APPLY_ARG : PFN_MODE_APPLY, grid, st));
+    } else {
+        const int64_t tiles = (n_points + kPfnWin - 1) / kPfnWin;
+        const int rgrid = (int)(tiles < kRowsGridCap ? (tiles < 1 ? 1 : tiles) : kRowsGridCap);
+        RDP_CUDA_OK(L->rows(a, argpos ? 1 : 0, rgrid, st));
+    }
     return RDP_OK;
 }
 
