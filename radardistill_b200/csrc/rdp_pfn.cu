@@ -132,8 +132,11 @@ extern "C" int rdp_pfn_fwd(const float *points, int64_t n_points, const rdp_geom
         a.bn_state = bn_state;
         a.fold_from_state = 1;
     }
-    static const bool legacy = getenv("RDP_PFN_LEGACY") != nullptr;   // A/B switch for kernel experiments
-    if (legacy) {
+    // forward form: the lane = channel tile stream (default) or the thread = row kernel (RDP_PFN_ROWS=1; bit-identical,
+    // measured slower so far -- see DESIGN.md); the row kernel's 256-bit stores need 32-byte aligned outputs
+    static const bool use_rows = getenv("RDP_PFN_ROWS") != nullptr;
+    const bool aligned32 = !(reinterpret_cast<uintptr_t>(features) & 31u) && !(reinterpret_cast<uintptr_t>(argpos) & 31u);
+    if (!use_rows || !aligned32) {
         RDP_CUDA_OK(L->tile(a, argpos ? PFN_MODE_APPLY_ARG : PFN_MODE_APPLY, grid, st));
     } else {
         const int64_t tiles = (n_points + kPfnWin - 1) / kPfnWin;
@@ -172,8 +175,16 @@ extern "C" int rdp_pfn_bwd(const float *points, int64_t n_points, const rdp_geom
     a.grad = grad_features;
     a.feat_out = features;
     a.argpos = const_cast<int32_t *>(argpos);
-    const int grid = pfn_grid(n_points);
-    RDP_CUDA_OK(L->tile(a, PFN_MODE_BWD, grid, st));
+    // backward form: the tile kernel (default) or the pillar-streaming kernel (RDP_BWD_STREAM=1; same results, measured
+    // slower so far -- see DESIGN.md)
+    static const bool use_stream = getenv("RDP_BWD_STREAM") != nullptr;
+    int grid = pfn_grid(n_points);
+    if (!use_stream) {
+        RDP_CUDA_OK(L->tile(a, PFN_MODE_BWD, grid, st));
+    } else {
+        grid = kBwdGrid;   // persistent: every warp streams a contiguous pillar range (P is only known on the device)
+        RDP_CUDA_OK(L->bwd_stream(a, grid, st));
+    }
     reduce_partials_kernel<<<(L->bwd_partial_doubles + 31) / 32, 256, 0, st>>>(ws.partials, grid, L->bwd_partial_doubles, ws.totals);
     RDP_CUDA_OK(L->bwd_finalize(a, ws.totals, bn_state, train ? 1 : 0, d_weight, d_gamma, d_beta, st));
     return RDP_OK;

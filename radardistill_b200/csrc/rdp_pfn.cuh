@@ -101,13 +101,13 @@ struct PfnSmem {
     static constexpr size_t S_BYTES = (MODE == PFN_MODE_STATS) ? sizeof(double) * kPfnThreads * 16 : 0;
     static constexpr size_t B_BYTES = 0;  // BWD: the end-of-kernel scratch aliases f + the prefetch buffers (see bwd_scratch())
     static constexpr size_t SCR = Z_BYTES > S_BYTES ? (Z_BYTES > B_BYTES ? Z_BYTES : B_BYTES) : (S_BYTES > B_BYTES ? S_BYTES : B_BYTES);
-    static constexpr int PCH = (MODE == PFN_MODE_BWD) ? 32 : 1;  // pillars per backward prefetch chunk
+    static constexpr int PCH = (MODE == PFN_MODE_BWD) ? 16 : 1;  // pillars per backward prefetch chunk (two chunks in flight)
     PfnStage<Cfg> st[2];
     alignas(8) uint64_t full[2];
-    alignas(8) uint64_t pre;                       // BWD: arrival of the tile's (grad, features, argpos) rows
-    alignas(16) float pre_grad[(MODE == PFN_MODE_BWD) ? PCH * Cfg::COUT : 4];
-    alignas(16) float pre_out[(MODE == PFN_MODE_BWD) ? PCH * Cfg::COUT : 4];
-    alignas(16) int pre_arg[(MODE == PFN_MODE_BWD) ? PCH * Cfg::COUT : 4];
+    alignas(8) uint64_t pre[2];                    // BWD: arrival of a chunk's (grad, features, argpos) rows, double buffered
+    alignas(16) float pre_grad[2][(MODE == PFN_MODE_BWD) ? PCH * Cfg::COUT : 4];
+    alignas(16) float pre_out[2][(MODE == PFN_MODE_BWD) ? PCH * Cfg::COUT : 4];
+    alignas(16) int pre_arg[2][(MODE == PFN_MODE_BWD) ? PCH * Cfg::COUT : 4];
     alignas(16) float f[kPfnCap * Cfg::FSTRIDE];   // decorated features of the tile's rows
     alignas(16) unsigned char scr[SCR];            // STATS / BWD: fp64 reduction scratch at kernel end
     int start[kPfnCap + 1];
@@ -171,21 +171,25 @@ __global__ void __launch_bounds__(kPfnThreads, (MODE == PFN_MODE_APPLY) ? 5 : 4)
     const long long N = a.counters[RDP_CNT_N];
     const bool none_dropped = (N == a.n0);
     const int ntiles = (int)((N + WIN - 1) / WIN);
-    const int per = (ntiles + (int)gridDim.x - 1) / (int)gridDim.x;
-    const int t_begin = min(ntiles, (int)blockIdx.x * per), t_end = min(ntiles, t_begin + per);
+    // Tile order: CTA b takes tiles b, b + grid, b + 2 grid, ... -- at any moment the grid works on one contiguous window
+    // of the row array and of the outputs (DRAM pages are used completely) instead of one private stream per CTA.
+    const int G = (int)gridDim.x;
+    const int nk = (ntiles > (int)blockIdx.x) ? (ntiles - (int)blockIdx.x + G - 1) / G : 0;   // tiles of this CTA
+    auto tile_of = [&](int k) { return (int)blockIdx.x + k * G; };
     constexpr bool want_arg = (MODE == PFN_MODE_APPLY_ARG);   // compile-time: the eval kernel carries no argmax state
     constexpr bool is_apply = (MODE == PFN_MODE_APPLY) || (MODE == PFN_MODE_APPLY_ARG);
     // fp64 reduction scratch used once at the end of the kernel; in BWD it aliases the (then idle) prefetch + feature buffers
-    double *dscr = (MODE == PFN_MODE_BWD) ? reinterpret_cast<double *>(S.pre_grad) : reinterpret_cast<double *>(S.scr);
+    double *dscr = (MODE == PFN_MODE_BWD) ? reinterpret_cast<double *>(&S.pre_grad[0][0]) : reinterpret_cast<double *>(S.scr);
     static_assert(MODE != PFN_MODE_BWD ||
-                  sizeof(double) * (kPfnThreads / 32) * Cfg::BWD_DOUBLES <= 3 * sizeof(float) * Smem::PCH * Cfg::COUT + sizeof(S.f),
+                  sizeof(double) * (kPfnThreads / 32) * Cfg::BWD_DOUBLES <= 6 * sizeof(float) * Smem::PCH * Cfg::COUT + sizeof(S.f),
                   "backward scratch must fit in pre_grad | pre_out | pre_arg | f");
 
     // ---- per-CTA constants
     if (tid == 0) {
         mbar_init(&S.full[0], 1);
         mbar_init(&S.full[1], 1);
-        mbar_init(&S.pre, 1);
+        mbar_init(&S.pre[0], 1);
+        mbar_init(&S.pre[1], 1);
         fence_mbar_init();
     }
     // Forward stream: LPR lanes share one feature row; lane sl of the sub-group owns channels sl + LPR q, whose weight
@@ -373,29 +377,30 @@ __global__ void __launch_bounds__(kPfnThreads, (MODE == PFN_MODE_APPLY) ? 5 : 4)
     };
 
     // BWD: the upstream gradient, forward output and argmax rows of pillars [p0, p0 + n) -> smem, asynchronously
-    auto prefetch_bwd = [&](int p0, int n) {
+    auto prefetch_bwd = [&](int b, int p0, int n) {
         const uint32_t bytes = (uint32_t)n * COUT * 4;
-        mbar_expect_tx(&S.pre, 3 * bytes);
-        tma_bulk_g2s(S.pre_grad, a.grad + (size_t)p0 * COUT, bytes, &S.pre);
-        tma_bulk_g2s(S.pre_out, a.feat_out + (size_t)p0 * COUT, bytes, &S.pre);
-        tma_bulk_g2s(S.pre_arg, a.argpos + (size_t)p0 * COUT, bytes, &S.pre);
+        mbar_expect_tx(&S.pre[b], 3 * bytes);
+        tma_bulk_g2s(S.pre_grad[b], a.grad + (size_t)p0 * COUT, bytes, &S.pre[b]);
+        tma_bulk_g2s(S.pre_out[b], a.feat_out + (size_t)p0 * COUT, bytes, &S.pre[b]);
+        tma_bulk_g2s(S.pre_arg[b], a.argpos + (size_t)p0 * COUT, bytes, &S.pre[b]);
     };
 
     // thread 0 keeps tile_first two tiles ahead in registers so the TMA issue never waits on a global load
-    int tfa = 0, tfb = 0, tfc = 0;
-    if (t_begin < t_end && tid == 0) {
-        tfa = a.tile_first[t_begin]; tfb = a.tile_first[t_begin + 1];
-        tfc = (t_begin + 1 < t_end) ? a.tile_first[t_begin + 2] : tfb;
-        issue(t_begin, 0, tfa, tfb);
+    int nfa = 0, nfb = 0;   // (tile_first[t], tile_first[t + 1]) of the tile after the next
+    if (nk > 0 && tid == 0) {
+        issue(tile_of(0), 0, a.tile_first[tile_of(0)], a.tile_first[tile_of(0) + 1]);
+        if (nk > 1) { nfa = a.tile_first[tile_of(1)]; nfb = a.tile_first[tile_of(1) + 1]; }
     }
-    uint32_t par0 = 0, par1 = 0, ppar = 0;
+    uint32_t par0 = 0, par1 = 0;
+    int cj = 0;             // BWD: chunks consumed so far (buffer cj & 1, phase (cj >> 1) & 1)
+    bool pending = false;   // BWD: the first chunk of the tile being entered was requested during the previous tile
 
-    for (int t = t_begin; t < t_end; ++t) {
-        const int s = (t - t_begin) & 1;
-        if (tid == 0 && t + 1 < t_end) {
-            issue(t + 1, s ^ 1, tfb, tfc);
-            tfb = tfc;
-            tfc = (t + 2 < t_end) ? a.tile_first[t + 3] : tfc;
+    for (int k = 0; k < nk; ++k) {
+        const int t = tile_of(k);
+        const int s = k & 1;
+        if (tid == 0 && k + 1 < nk) {
+            issue(tile_of(k + 1), s ^ 1, nfa, nfb);
+            if (k + 2 < nk) { nfa = a.tile_first[tile_of(k + 2)]; nfb = a.tile_first[tile_of(k + 2) + 1]; }
         }
         if (s == 0) { mbar_wait(&S.full[0], par0); par0 ^= 1; } else { mbar_wait(&S.full[1], par1); par1 ^= 1; }
         PfnStage<Cfg> &T = S.st[s];
@@ -411,7 +416,14 @@ __global__ void __launch_bounds__(kPfnThreads, (MODE == PFN_MODE_APPLY) ? 5 : 4)
         const int jstop = big ? last_start : last_start + last_rows, np = jstop - j0;
         const int nb = big ? pe - ps - 1 : pe - ps;
         const int gb = (int)base + j0;
-        if (MODE == PFN_MODE_BWD && np > 0 && tid == 0) prefetch_bwd(ps, min(Smem::PCH, nb));  // lands while C1 runs
+        if (MODE == PFN_MODE_BWD) {
+            if (!pending && nb > 0 && tid == 0) prefetch_bwd(cj & 1, ps, min(Smem::PCH, nb));
+            if (pending && nb == 0) {   // only a big pillar starts here: drain the chunk that was requested for this tile
+                mbar_wait(&S.pre[cj & 1], (uint32_t)(cj >> 1) & 1u);
+                ++cj;
+            }
+            pending = false;
+        }
 
         if (np > 0) {
             if (tid == 0) S.start[nb] = np;
@@ -436,18 +448,27 @@ __global__ void __launch_bounds__(kPfnThreads, (MODE == PFN_MODE_APPLY) ? 5 : 4)
                 }
                 for (int q0 = 0; q0 < nb; q0 += Smem::PCH) {
                   const int nq = min(Smem::PCH, nb - q0);
-                  if (q0 > 0) {  // rare: more pillars in the tile than one prefetch chunk holds
-                      __syncthreads();
-                      if (tid == 0) prefetch_bwd(ps + q0, nq);
+                  if (q0 > 0) __syncthreads();   // every warp is done with the buffer the next request lands in
+                  // request the chunk after this one -- the rest of this tile, else the head of the next tile -- so that one
+                  // chunk is always in flight while another is folded in (the tile form was bound by exactly this latency)
+                  if (q0 + Smem::PCH < nb) {
+                      if (tid == 0) prefetch_bwd((cj + 1) & 1, ps + q0 + Smem::PCH, min(Smem::PCH, nb - q0 - Smem::PCH));
+                  } else if (k + 1 < nk) {
+                      const int ps1 = S.tf[s ^ 1][0], pe1 = S.tf[s ^ 1][1];
+                      if (pe1 > ps1) {
+                          pending = true;
+                          if (tid == 0) prefetch_bwd((cj + 1) & 1, ps1, min(Smem::PCH, pe1 - ps1));
+                      }
                   }
-                  mbar_wait(&S.pre, ppar);
-                  ppar ^= 1;
+                  const int b = cj & 1;
+                  mbar_wait(&S.pre[b], (uint32_t)(cj >> 1) & 1u);
+                  ++cj;
                   for (int q = warp; q < nq; q += NW) {
 #pragma unroll
                     for (int cc = 0; cc < CPL; ++cc) {
                         const int o = q * COUT + lane + 32 * cc;
-                        const float gy = S.pre_out[o] > 0.0f ? S.pre_grad[o] : 0.0f;
-                        const int jj = S.pre_arg[o] - gb;
+                        const float gy = S.pre_out[b][o] > 0.0f ? S.pre_grad[b][o] : 0.0f;
+                        const int jj = S.pre_arg[b][o] - gb;
                         float f[Cfg::FW];
                         const float4 *src = reinterpret_cast<const float4 *>(&S.f[jj * Cfg::FSTRIDE]);
 #pragma unroll

@@ -58,6 +58,21 @@ static cudaError_t rows(const PfnArgs &a, int want_arg, int grid, cudaStream_t s
     return want_arg ? launch_rows<true>(a, grid, st) : launch_rows<false>(a, grid, st);
 }
 
+static cudaError_t bwd_stream(const PfnArgs &a, int grid, cudaStream_t st) {
+    const size_t smem = sizeof(double) * (kBwdThreads / 32) * Cfg::BWD_DOUBLES;
+    static bool configured[64] = {false};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64 || !configured[dev]) {
+        e = cudaFuncSetAttribute(pfn_bwd_stream_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        if (dev >= 0 && dev < 64) configured[dev] = true;
+    }
+    pfn_bwd_stream_kernel<Cfg><<<grid, kBwdThreads, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
 static cudaError_t bn_finalize(const PfnArgs &a, const double *totals, double *bn_state, float *rm, float *rv, double momentum,
                                cudaStream_t st) {
     bn_finalize_kernel<Cfg><<<1, 256, 0, st>>>(a, totals, bn_state, rm, rv, momentum);
@@ -76,7 +91,7 @@ static cudaError_t bwd_finalize(const PfnArgs &a, const double *totals, const do
 #define RDP_CAT(a, b) RDP_CAT2(a, b)
 const PfnLaunch *RDP_CAT(rdp_pfn_cfg_, RDP_CFG_ID)() {
     static const PfnLaunch L = {Cfg::COLS, Cfg::LAYOUT, Cfg::DIST ? 1 : 0, Cfg::COUT, Cfg::CS,
-                                Cfg::STATS_DOUBLES, Cfg::BWD_DOUBLES, tile, rows, bn_finalize, bwd_finalize};
+                                Cfg::STATS_DOUBLES, Cfg::BWD_DOUBLES, tile, rows, bwd_stream, bn_finalize, bwd_finalize};
     return &L;
 }
 

@@ -10,12 +10,14 @@
 // quad -- one uniform-address LDS.128 feeds 4 x 2 FFMAs -- and the per-row bookkeeping of the stream disappears:
 //
 //   A  thread t of a 128-thread CTA takes rows t and t + 128 of a 256-row chunk of the pillar-grouped row array:
-//      row (32 B) + its pillar's table entry straight from global memory (coalesced / L1), decorate in registers,
-//      x_c = sum_k fmaf(W[c][k], f[k], x_c), y_c = fma(x_c, scale_c, shift_c) for all channels, y -> smem tile
-//      X[row][channel]; pillar head / last-row flags by warp ballot.
-//   B  segmented max over the rows of each pillar: thread = (row group, channel quad) walks the pillars that START in
-//      its 16 rows (LDS.128 + 4 FMNMX per row) and writes each pillar's 128-byte feature row with 16-byte stores
-//      (8 lanes = one full line).  A pillar left open at the end of the chunk is carried in shared memory.
+//      row (32 B) + its pillar's table entry from global memory (coalesced / L1) -- fetched into registers one chunk
+//      ahead, so the loads fly under the previous chunk's arithmetic -- decorate in registers,
+//      x_c = sum_k fmaf(W[c][k], f[k], x_c), z_c = max(fma(x_c, scale_c, shift_c), 0) for all channels; pillar head /
+//      last-row flags by warp ballot.  A row that is a whole pillar (two thirds of the LiDAR pillars) stores its
+//      feature row directly (256-bit stores, one full sector each); the other rows go to the smem tile X[row][channel].
+//   B  segmented max over the rows of each multi-row pillar: thread = (row group, channel quad) walks the pillars that
+//      START in its 16 rows (LDS.128 + 4 FMNMX per row) and writes each pillar's 128-byte feature row with 16-byte
+//      stores (8 lanes = one full line).  A pillar left open at the end of the chunk is carried in shared memory.
 //
 // A persistent CTA owns a contiguous, pillar-aligned range of rows (the PFN tiles of tile_first) and walks it chunk by
 // chunk, so a pillar of any length is handled by the carry; there is no separate big-pillar path.
@@ -32,6 +34,13 @@ constexpr int kRowsChunk = kRowsThreads * kRowsPerThread;
 #define RDP_ROWS_GRID_PER_SM 5
 #endif
 constexpr int kRowsGridCap = 148 * RDP_ROWS_GRID_PER_SM;
+#ifndef RDP_ROWS_AUX_AHEAD
+#define RDP_ROWS_AUX_AHEAD 288
+#endif
+constexpr int kRowsAuxAhead = RDP_ROWS_AUX_AHEAD;
+#ifndef RDP_ROWS_REGPIPE
+#define RDP_ROWS_REGPIPE 0   // 1: also hold the next chunk's rows / table entries in registers (costs ~36 registers)
+#endif   // pillars of look-ahead for the table prefetch (~2 chunks of LiDAR rows)
 
 template <class Cfg, bool ARG>
 struct RowsSmem {
@@ -48,6 +57,12 @@ struct RowsSmem {
     alignas(16) int carry_k[2][ARG ? Cfg::COUT : 4], carry_p[2][ARG ? Cfg::COUT : 4];
 };
 
+__device__ __forceinline__ void st_global_v8(float *p, const float *v) {
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]),
+                 "f"(v[5]), "f"(v[6]), "f"(v[7])
+                 : "memory");
+}
+
 template <class Cfg, bool ARG>
 __global__ void __launch_bounds__(kRowsThreads, RDP_ROWS_GRID_PER_SM) pfn_rows_kernel(const __grid_constant__ PfnArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -57,6 +72,7 @@ __global__ void __launch_bounds__(kRowsThreads, RDP_ROWS_GRID_PER_SM) pfn_rows_k
     constexpr int NT = kRowsThreads, R = kRowsPerThread, CHUNK = kRowsChunk, WIN = kPfnWin, INF = 0x7fffffff;
     constexpr int QUADS = COUT / 4, GROUPS = NT / QUADS, RPG = CHUNK / GROUPS;  // phase B: rows per (row group)
     static_assert(RPG == 16 || RPG == 32, "row groups must align with the 32-bit flag words");
+    static_assert(COUT % 8 == 0 && COLS <= RS - 2, "layout");
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long long N = a.counters[RDP_CNT_N];
     const int P = a.counters[RDP_CNT_P];
@@ -90,38 +106,90 @@ __global__ void __launch_bounds__(kRowsThreads, RDP_ROWS_GRID_PER_SM) pfn_rows_k
         return pf >= P ? N : (long long)__float_as_int(__ldg(a.aux + (size_t)pf * 8 + 5));
     };
     const long long row_begin = (t_begin < t_end) ? tile_row(t_begin) : 0, row_end = (t_begin < t_end) ? tile_row(t_end) : 0;
-    __syncthreads();
 
-    int par = 0;
-    for (long long c0 = row_begin; c0 < row_end; c0 += CHUNK, par ^= 1) {
-        const int nrow = (int)min((long long)CHUNK, row_end - c0);
-
-        // =========================================================================== A: thread = row
-        float f[R][Cfg::FW];
-        bool valid[R];
+    // ---- register pipeline: rows of chunk i+1 are requested before chunk i's arithmetic, their table entries (whose
+    //      address needs the row's pillar id) before chunk i's phase B
+    struct RowIn { float4 v[RS / 4]; int gprev, gnext; };
+    struct AuxIn { float4 m4, c4; };   // [mean x y z | centre x] [centre y | first row | rows | 0]
+    auto fetch_rows = [&](long long c0, int nrow, RowIn (&o)[R]) {
 #pragma unroll
         for (int i = 0; i < R; ++i) {
             const int r = tid + i * NT;
-            const long long g = c0 + r;
-            valid[i] = r < nrow;
-            bool head = false, last = false;
-            if (valid[i]) {
-                float row[RS];
+            if (r < nrow) {
+                const long long g = c0 + r;
                 const float4 *src = reinterpret_cast<const float4 *>(a.grows + (size_t)(g + 1) * RS);
 #pragma unroll
+                for (int q = 0; q < RS / 4; ++q) o[i].v[q] = src[q];
+                o[i].gprev = __float_as_int(a.grows[(size_t)g * RS + RS - 1]);   // the row in front of row 0 is a sentinel (pillar -1)
+                o[i].gnext = (g + 1 < N) ? __float_as_int(a.grows[(size_t)(g + 2) * RS + RS - 1]) : -1;
+            }
+        }
+    };
+    auto fetch_aux = [&](int nrow, const RowIn (&in)[R], AuxIn (&o)[R]) {
+#pragma unroll
+        for (int i = 0; i < R; ++i) {
+            if (tid + i * NT < nrow) {
+                const float4 *ax = reinterpret_cast<const float4 *>(a.aux + (size_t)__float_as_int(in[i].v[RS / 4 - 1].w) * 8);
+                o[i].m4 = ax[0];
+                o[i].c4 = ax[1];
+            }
+        }
+    };
+    RowIn nx[R];
+    AuxIn na[R];
+    long long c0 = row_begin;
+    int nrow = (int)min((long long)CHUNK, row_end - c0);
+    if (RDP_ROWS_REGPIPE && c0 < row_end) {
+        fetch_rows(c0, nrow, nx);
+        fetch_aux(nrow, nx, na);
+    }
+    __syncthreads();
+
+    int par = 0;
+    while (c0 < row_end) {
+        RowIn cur[R];
+        AuxIn ca[R];
+        const long long c1 = c0 + CHUNK;
+        const int nrow1 = (c1 < row_end) ? (int)min((long long)CHUNK, row_end - c1) : 0;
+        if (RDP_ROWS_REGPIPE) {
+#pragma unroll
+            for (int i = 0; i < R; ++i) { cur[i] = nx[i]; ca[i] = na[i]; }
+            if (nrow1) fetch_rows(c1, nrow1, nx);
+        } else {   // the L2 prefetch below (issued two chunks ago) has the lines waiting in L2
+            fetch_rows(c0, nrow, cur);
+            fetch_aux(nrow, cur, ca);
+        }
+        // L2 prefetch two chunks ahead: the row lines (address known) and the table lines of the pillars about that far
+        // ahead of this thread's row, so the register pipeline above only ever waits for L2, not for DRAM
+        if (c0 + 2 * CHUNK < row_end && tid < CHUNK * RS * 4 / 128)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(a.grows + (size_t)(c0 + 2 * CHUNK + 1) * RS + tid * 32));
+        if (tid < nrow) {
+            const int gahead = min(__float_as_int(cur[0].v[RS / 4 - 1].w) + kRowsAuxAhead, P - 1);
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(a.aux + (size_t)gahead * 8));
+        }
+
+        // =========================================================================== A: thread = row
+        float f[R][Cfg::FW];
+        bool valid[R], single[R];
+        int gidv[R];
+#pragma unroll
+        for (int i = 0; i < R; ++i) {
+            const int r = tid + i * NT;
+            valid[i] = r < nrow;
+            bool head = false, last = false;
+            gidv[i] = 0;
+            if (valid[i]) {
+                float row[RS];
+#pragma unroll
                 for (int q = 0; q < RS / 4; ++q) {
-                    const float4 v = src[q];
-                    row[4 * q] = v.x; row[4 * q + 1] = v.y; row[4 * q + 2] = v.z; row[4 * q + 3] = v.w;
+                    row[4 * q] = cur[i].v[q].x; row[4 * q + 1] = cur[i].v[q].y; row[4 * q + 2] = cur[i].v[q].z; row[4 * q + 3] = cur[i].v[q].w;
                 }
                 const int gid = __float_as_int(row[RS - 1]);
-                const int gprev = __float_as_int(a.grows[(size_t)g * RS + RS - 1]);       // row -1 is the sentinel (pillar -1)
-                const int gnext = (g + 1 < N) ? __float_as_int(a.grows[(size_t)(g + 2) * RS + RS - 1]) : -1;
-                head = gid != gprev;
-                last = gid != gnext;
-                const float4 *ax = reinterpret_cast<const float4 *>(a.aux + (size_t)gid * 8);
-                const float4 m4 = ax[0], c4 = ax[1];  // [mean x y z | centre x] [centre y | start | rows | 0]
-                const float mean[3] = {m4.x, m4.y, m4.z};
-                decorate<Cfg>(row, m4.w, c4.x, mean, a, f[i]);
+                gidv[i] = gid;
+                head = gid != cur[i].gprev;
+                last = gid != cur[i].gnext;
+                const float mean[3] = {ca[i].m4.x, ca[i].m4.y, ca[i].m4.z};
+                decorate<Cfg>(row, ca[i].m4.w, ca[i].c4.x, mean, a, f[i]);
                 S.gid[r] = gid;
                 if (ARG) {
                     const int orig = __float_as_int(row[RS - 2]);
@@ -131,19 +199,20 @@ __global__ void __launch_bounds__(kRowsThreads, RDP_ROWS_GRID_PER_SM) pfn_rows_k
 #pragma unroll
                 for (int k = 0; k < CS; ++k) f[i][k] = 0.0f;
             }
+            single[i] = head && last;   // the row is a whole pillar: its feature row leaves from here
             const uint32_t hb = __ballot_sync(0xffffffffu, head), lb = __ballot_sync(0xffffffffu, last);
             if (lane == 0) { S.heads[i * (NT / 32) + warp] = hb; S.lasts[i * (NT / 32) + warp] = lb; }
         }
 
-        // x = W f (k-ascending fmaf chain), y = fma(x, scale, shift) [ARG: z = max(y, 0)]  -> X[row][channel]
+        // x = W f (k-ascending fmaf chain), z = max(fma(x, scale, shift), 0): single-row pillars -> global, others -> X
         auto linear = [&](auto rows_tag) {
             constexpr int RR = decltype(rows_tag)::value;
 #pragma unroll
-            for (int c4 = 0; c4 < QUADS; ++c4) {
-                float y[RR][4];
+            for (int c8 = 0; c8 < COUT / 8; ++c8) {
+                float y[RR][8];
 #pragma unroll
-                for (int cc = 0; cc < 4; ++cc) {
-                    const int c = c4 * 4 + cc;
+                for (int cc = 0; cc < 8; ++cc) {
+                    const int c = c8 * 8 + cc;
                     float acc[RR];
 #pragma unroll
                     for (int i = 0; i < RR; ++i) acc[i] = 0.0f;
@@ -158,76 +227,98 @@ __global__ void __launch_bounds__(kRowsThreads, RDP_ROWS_GRID_PER_SM) pfn_rows_k
 #pragma unroll
                         for (int i = 0; i < RR; ++i) acc[i] = fmaf(wv[k], f[i][k], acc[i]);
 #pragma unroll
-                    for (int i = 0; i < RR; ++i) {
-                        const float yy = fmaf(acc[i], wv[CS], wv[CS + 1]);
-                        y[i][cc] = ARG ? fmaxf(yy, 0.0f) : yy;
-                    }
+                    for (int i = 0; i < RR; ++i) y[i][cc] = fmaxf(fmaf(acc[i], wv[CS], wv[CS + 1]), 0.0f);
                 }
 #pragma unroll
-                for (int i = 0; i < RR; ++i)
-                    *reinterpret_cast<float4 *>(&S.x[(tid + i * NT) * XS + c4 * 4]) = make_float4(y[i][0], y[i][1], y[i][2], y[i][3]);
+                for (int i = 0; i < RR; ++i) {
+                    if (single[i]) {
+                        st_global_v8(a.features + (size_t)gidv[i] * COUT + c8 * 8, y[i]);
+                    } else {
+                        float4 *dst = reinterpret_cast<float4 *>(&S.x[(tid + i * NT) * XS + c8 * 8]);
+                        dst[0] = make_float4(y[i][0], y[i][1], y[i][2], y[i][3]);
+                        dst[1] = make_float4(y[i][4], y[i][5], y[i][6], y[i][7]);
+                    }
+                }
             }
         };
         if (__any_sync(0xffffffffu, valid[R - 1])) linear(std::integral_constant<int, R>{});
         else if (__any_sync(0xffffffffu, valid[0])) linear(std::integral_constant<int, 1>{});
+        if (ARG) {
+#pragma unroll
+            for (int i = 0; i < R; ++i) {
+                if (single[i]) {   // the only row of its pillar wins every channel
+                    const float pv = __int_as_float((int)c0 + tid + i * NT);
+                    const float pos[8] = {pv, pv, pv, pv, pv, pv, pv, pv};
+#pragma unroll
+                    for (int c8 = 0; c8 < COUT / 8; ++c8)
+                        st_global_v8(reinterpret_cast<float *>(a.argpos) + (size_t)gidv[i] * COUT + c8 * 8, pos);
+                }
+            }
+        }
+        if (RDP_ROWS_REGPIPE && nrow1) fetch_aux(nrow1, nx, na);
         __syncthreads();
 
         // =========================================================================== B: thread = (row group, quad)
         {
             const int g = tid / QUADS, q = tid % QUADS;
             const int gr0 = g * RPG;
-            uint32_t own = S.heads[gr0 >> 5] >> (gr0 & 31);
-            if (RPG < 32) own &= (1u << RPG) - 1u;
-            const bool carry_in = (g == 0) && !(S.heads[0] & 1u);   // the chunk starts inside a pillar: continue it from the carry
-            int r = -1;
-            if (carry_in) r = 0;
-            else if (own) r = gr0 + __ffs(own) - 1;
-            if (r >= 0 && r < nrow) {
+            uint32_t hw = S.heads[gr0 >> 5] >> (gr0 & 31), lw = S.lasts[gr0 >> 5] >> (gr0 & 31);
+            if (RPG < 32) { hw &= (1u << RPG) - 1u; lw &= (1u << RPG) - 1u; }
+            uint32_t own = hw & ~lw;                                 // heads of multi-row pillars that start in my rows
+            bool carry_in = (g == 0) && !(S.heads[0] & 1u);           // the chunk starts inside a pillar: continue it from the carry
+            // rows from r through the first last-row flag at or after r; -1 if the pillar is still open at the end of the chunk
+            auto seg_len = [&](int r) -> int {
+                int w = r >> 5;
+                uint32_t b = S.lasts[w] >> (r & 31);
+                if (b) return __ffs(b);
+                int len = 32 - (r & 31);
+                for (++w; w < CHUNK / 32; ++w) {
+                    b = S.lasts[w];
+                    if (b) return len + __ffs(b);
+                    len += 32;
+                }
+                return -1;
+            };
+            while (carry_in || own) {
+                int r;
                 float m[4];
                 int mk[4], mp[4];
                 if (carry_in) {
+                    r = 0;
                     const float4 cv = *reinterpret_cast<const float4 *>(&S.carry_v[par][4 * q]);
                     m[0] = cv.x; m[1] = cv.y; m[2] = cv.z; m[3] = cv.w;
-                    if (ARG) {
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) { mk[e] = S.carry_k[par][4 * q + e]; mp[e] = S.carry_p[par][4 * q + e]; }
-                    }
+                    for (int e = 0; e < 4; ++e) { mk[e] = ARG ? S.carry_k[par][4 * q + e] : INF; mp[e] = ARG ? S.carry_p[par][4 * q + e] : 0; }
+                    carry_in = false;
                 } else {
+                    const int bit = __ffs(own) - 1;
+                    own &= own - 1;
+                    r = gr0 + bit;
 #pragma unroll
                     for (int e = 0; e < 4; ++e) { m[e] = ARG ? -1.0f : 0.0f; mk[e] = INF; mp[e] = 0; }
                 }
-                int pid = S.gid[r];
-                const int stop = gr0 + RPG;   // heads at or after this row belong to later groups
-                uint32_t lw = S.lasts[r >> 5];
-                bool open = true;
-                for (;;) {
-                    const float4 v = *reinterpret_cast<const float4 *>(&S.x[r * XS + 4 * q]);
+                const int pid = S.gid[r];
+                int len = seg_len(r);
+                const bool open = len < 0;
+                if (open) len = nrow - r;
+                const float *xp = &S.x[r * XS + 4 * q];
+                for (int k = 0; k < len; ++k, xp += XS) {
+                    const float4 v = *reinterpret_cast<const float4 *>(xp);
                     const float vv[4] = {v.x, v.y, v.z, v.w};
                     if (!ARG) {
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) m[e] = fmaxf(m[e], vv[e]);   // ReLU folds into the max with 0
+                        for (int e = 0; e < 4; ++e) m[e] = fmaxf(m[e], vv[e]);
                     } else {
-                        const int kj = S.kept[r], pos = (int)c0 + r;
+                        const int kj = S.kept[r + k], pos = (int)c0 + r + k;
 #pragma unroll
                         for (int e = 0; e < 4; ++e)
                             if (vv[e] > m[e] || (vv[e] == m[e] && kj < mk[e])) { m[e] = vv[e]; mk[e] = kj; mp[e] = pos; }
                     }
-                    const bool is_last = (lw >> (r & 31)) & 1u;
-                    if (is_last) {
-                        *reinterpret_cast<float4 *>(a.features + (size_t)pid * COUT + 4 * q) = make_float4(m[0], m[1], m[2], m[3]);
-                        if (ARG) *reinterpret_cast<int4 *>(a.argpos + (size_t)pid * COUT + 4 * q) = make_int4(mp[0], mp[1], mp[2], mp[3]);
-                        ++pid;
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) { m[e] = ARG ? -1.0f : 0.0f; mk[e] = INF; mp[e] = 0; }
-                        open = false;
-                        if (r + 1 >= stop) break;
-                    } else {
-                        open = true;
-                    }
-                    if (++r >= nrow) break;
-                    if ((r & 31) == 0) lw = S.lasts[r >> 5];
                 }
-                if (open) {   // the pillar continues in the next chunk of this CTA
+                if (!open) {
+                    *reinterpret_cast<float4 *>(a.features + (size_t)pid * COUT + 4 * q) = make_float4(m[0], m[1], m[2], m[3]);
+                    if (ARG) *reinterpret_cast<int4 *>(a.argpos + (size_t)pid * COUT + 4 * q) = make_int4(mp[0], mp[1], mp[2], mp[3]);
+                } else {   // the pillar continues in the next chunk of this CTA
                     *reinterpret_cast<float4 *>(&S.carry_v[par ^ 1][4 * q]) = make_float4(m[0], m[1], m[2], m[3]);
                     if (ARG) {
 #pragma unroll
@@ -237,6 +328,9 @@ __global__ void __launch_bounds__(kRowsThreads, RDP_ROWS_GRID_PER_SM) pfn_rows_k
             }
         }
         __syncthreads();
+        c0 = c1;
+        nrow = nrow1;
+        par ^= 1;
     }
 }
 
