@@ -11,10 +11,10 @@
 //
 //   K1 quantize_mark   points (TMA bulk tile -> smem) -> key[i], bitmap |= bit(key)          [HBM: read rows]
 //   K2 bitmap_rank     popcount scan of the bitmap -> word_prefix, P
-//   K2b emit_coords    one thread per bitmap word -> coords[rank] in key order
+//   K2b zero_counts    counts[0, P) = 0
 //   K3 rank_count      key[i] -> rank = word_prefix + popc(below) ; inverse[j] ; counts[rank]++
 //   K4 count_scan      exclusive scan of counts -> pillar start offsets
-//   K6 pillar_table    thread = pillar: fp64 mean of its grouped rows, pillar centre, first row, row count
+//   K6 pillar_table    thread = pillar: fp64 mean of its grouped rows, pillar centre, first row, row count; coords
 //   K5 group_rows      pos = start[rank]++ ; grouped_rows[pos] = row i, gpid[pos] = rank, gorder[pos] = i
 //                      (counting-sort fill; the order inside a pillar is arbitrary, every consumer is order
 //                      independent).  The PFN kernels then stream contiguous, pillar-aligned row tiles with TMA.
@@ -139,35 +139,10 @@ bitmap_rank_kernel(const uint32_t *__restrict__ bitmap, long long words,
 }
 
 // ----------------------------------------------------------------------------- K2b
-// One thread per bitmap word: coords of its set bits in key order (:243-248); zeroes counts[rank] for K3.
-__global__ void __launch_bounds__(kScanThreads)
-emit_coords_kernel(const uint32_t *__restrict__ bitmap, const uint32_t *__restrict__ word_prefix, long long words, GeomDev g,
-                   int coord_cols, int32_t *__restrict__ coords, int32_t *__restrict__ counts) {
-    const long long w = (long long)blockIdx.x * kScanThreads + threadIdx.x;
-    if (w >= words) return;
-    uint32_t bits = bitmap[w];
-    if (!bits) return;
-    uint32_t rank = word_prefix[w];
-    const int sxy = g.nx * g.ny;
-    const long long key0 = w * 32;  // decode the word's first key once; later bits only carry
-    const int b0 = (int)(key0 / sxy);
-    const int rem = (int)(key0 - (long long)b0 * sxy);
-    const int cx0 = rem / g.ny, cy0 = rem - cx0 * g.ny;
-    while (bits) {
-        const int bit = __ffs(bits) - 1;
-        bits &= bits - 1;
-        int cy = cy0 + bit, cx = cx0, b = b0;
-        while (cy >= g.ny) { cy -= g.ny; ++cx; }
-        while (cx >= g.nx) { cx -= g.nx; ++b; }
-        if (coord_cols == 3) {
-            int32_t *o = coords + (size_t)rank * 3;
-            o[0] = b; o[1] = cy; o[2] = cx;  // [b, y, x]  (:248)
-        } else {
-            *reinterpret_cast<int4 *>(coords + (size_t)rank * 4) = make_int4(b, 0, cy, cx);  // (:138)
-        }
-        counts[rank] = 0;
-        ++rank;
-    }
+// counts[0, P) = 0 for K3's atomics (P is only known on the device).
+__global__ void __launch_bounds__(256) zero_counts_kernel(int32_t *__restrict__ counts, const int32_t *__restrict__ counters) {
+    const int P = counters[RDP_CNT_P];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P; i += gridDim.x * blockDim.x) counts[i] = 0;
 }
 
 // ----------------------------------------------------------------------------- K3
@@ -358,13 +333,14 @@ __global__ void publish_counters_kernel(const int32_t *__restrict__ counters, vo
 // Mean: fp64 sum of the fp32 coordinates (order independent), correctly rounded quotient, one rounding to fp32.
 __global__ void __launch_bounds__(256)
 pillar_table_kernel(const float *__restrict__ grows, const int32_t *__restrict__ ends, const int32_t *__restrict__ counters,
-                    int rs, GeomDev g, float *__restrict__ aux) {
+                    int rs, GeomDev g, float *__restrict__ aux, int coord_cols, int32_t *__restrict__ coords) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= counters[RDP_CNT_P]) return;
     const int s = p ? ends[p - 1] : 0, e = ends[p];
     double sx = 0.0, sy = 0.0, sz = 0.0;
     const float *r = grows + ((size_t)s + 1) * rs;
     const float x0 = r[1], y0 = r[2];
+    const int b0 = __float2int_rz(r[0]);
     for (int i = s; i < e; ++i, r += rs) { sx += (double)r[1]; sy += (double)r[2]; sz += (double)r[3]; }
     float mx, my, mz;
     mean3(sx, sy, sz, e - s, &mx, &my, &mz);
@@ -372,6 +348,13 @@ pillar_table_kernel(const float *__restrict__ grows, const int32_t *__restrict__
     // quantize_mark_kernel's IEEE ops, so cx / cy equal the emitted coords
     const float qx = floorf(__fdiv_rn(__fsub_rn(x0, g.lo_x), g.vx)), qy = floorf(__fdiv_rn(__fsub_rn(y0, g.lo_y), g.vy));
     const float cenx = __fadd_rn(__fmul_rn((float)(int)qx, g.vx), g.off_x), ceny = __fadd_rn(__fmul_rn((float)(int)qy, g.vy), g.off_y);
+    // pillar coords (:243-248): the pillars are in key order, and key = b*nx*ny + cx*ny + cy decodes to exactly these
+    if (coord_cols == 3) {
+        int32_t *o = coords + (size_t)p * 3;
+        o[0] = b0; o[1] = (int)qy; o[2] = (int)qx;   // [b, y, x]  (:248)
+    } else {
+        *reinterpret_cast<int4 *>(coords + (size_t)p * 4) = make_int4(b0, 0, (int)qy, (int)qx);  // (:138)
+    }
     asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(aux + (size_t)p * 8), "f"(mx), "f"(my), "f"(mz), "f"(cenx),
                  "f"(ceny), "f"(__int_as_float(s)), "f"(__int_as_float(e - s)), "f"(0.0f)
                  : "memory");
@@ -420,14 +403,13 @@ extern "C" int rdp_index_fwd_publish(const float *points, int64_t n_points, cons
     quantize_mark_kernel<<<tiles, kIndexThreads, smem, stream>>>(points, n_points, g, ws.bitmap, ws.keys, ws.tile_keep, counters);
     bitmap_rank_kernel<<<kScanGrid, kScanThreads, 0, stream>>>(ws.bitmap, ws.words, ws.scan_state_a, ws.word_prefix, counters);
     if (int rc2 = publish()) return rc2;
-    emit_coords_kernel<<<(unsigned)((ws.words + kScanThreads - 1) / kScanThreads), kScanThreads, 0, stream>>>(
-        ws.bitmap, ws.word_prefix, ws.words, g, coord_cols, coords, counts);
+    zero_counts_kernel<<<148 * 2, 256, 0, stream>>>(counts, counters);
     rank_count_kernel<<<tiles, kIndexThreads, 0, stream>>>(ws.keys, n_points, ws.bitmap, ws.word_prefix, ws.tile_keep,
                                                          inverse, counts, counters, ws.orig2kept, ws.kept2orig);
     count_scan_kernel<<<kScanGrid, kScanThreads, 0, stream>>>(counts, ws.scan_state_b, ws.ends, ws.tile_first, counters);
     group_rows_kernel<<<tiles, kIndexThreads, smem, stream>>>(points, ws.keys, n_points, geom->cols, ws.ends, ws.grows);
     pillar_table_kernel<<<(unsigned)((ws.pcap + 255) / 256), 256, 0, stream>>>(ws.grows, ws.ends, counters,
-                                                                               grouped_row_floats(geom->cols), g, ws.aux);
+                                                                               grouped_row_floats(geom->cols), g, ws.aux, coord_cols, coords);
     RDP_CUDA_OK(cudaGetLastError());
     return RDP_OK;
 }

@@ -28,19 +28,18 @@
 namespace rdp {
 
 constexpr int kRowsThreads = 128;
-constexpr int kRowsPerThread = 2;
+#ifndef RDP_ROWS_R
+#define RDP_ROWS_R 2
+#endif
+constexpr int kRowsPerThread = RDP_ROWS_R;
 constexpr int kRowsChunk = kRowsThreads * kRowsPerThread;
 #ifndef RDP_ROWS_GRID_PER_SM
 #define RDP_ROWS_GRID_PER_SM 5
 #endif
 constexpr int kRowsGridCap = 148 * RDP_ROWS_GRID_PER_SM;
-#ifndef RDP_ROWS_AUX_AHEAD
-#define RDP_ROWS_AUX_AHEAD 288
-#endif
-constexpr int kRowsAuxAhead = RDP_ROWS_AUX_AHEAD;
 #ifndef RDP_ROWS_REGPIPE
 #define RDP_ROWS_REGPIPE 0   // 1: also hold the next chunk's rows / table entries in registers (costs ~36 registers)
-#endif   // pillars of look-ahead for the table prefetch (~2 chunks of LiDAR rows)
+#endif
 
 template <class Cfg, bool ARG>
 struct RowsSmem {
@@ -71,7 +70,7 @@ __global__ void __launch_bounds__(kRowsThreads, RDP_ROWS_GRID_PER_SM) pfn_rows_k
     constexpr int COUT = Cfg::COUT, CS = Cfg::CS, COLS = Cfg::COLS, RS = Cfg::RS, WS = Smem::WS, XS = Smem::XS;
     constexpr int NT = kRowsThreads, R = kRowsPerThread, CHUNK = kRowsChunk, WIN = kPfnWin, INF = 0x7fffffff;
     constexpr int QUADS = COUT / 4, GROUPS = NT / QUADS, RPG = CHUNK / GROUPS;  // phase B: rows per (row group)
-    static_assert(RPG == 16 || RPG == 32, "row groups must align with the 32-bit flag words");
+    static_assert(RPG == 8 || RPG == 16 || RPG == 32, "row groups must align with the 32-bit flag words");
     static_assert(COUT % 8 == 0 && COLS <= RS - 2, "layout");
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long long N = a.counters[RDP_CNT_N];
@@ -155,19 +154,10 @@ __global__ void __launch_bounds__(kRowsThreads, RDP_ROWS_GRID_PER_SM) pfn_rows_k
 #pragma unroll
             for (int i = 0; i < R; ++i) { cur[i] = nx[i]; ca[i] = na[i]; }
             if (nrow1) fetch_rows(c1, nrow1, nx);
-        } else {   // the L2 prefetch below (issued two chunks ago) has the lines waiting in L2
+        } else {
             fetch_rows(c0, nrow, cur);
             fetch_aux(nrow, cur, ca);
         }
-        // L2 prefetch two chunks ahead: the row lines (address known) and the table lines of the pillars about that far
-        // ahead of this thread's row, so the register pipeline above only ever waits for L2, not for DRAM
-        if (c0 + 2 * CHUNK < row_end && tid < CHUNK * RS * 4 / 128)
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(a.grows + (size_t)(c0 + 2 * CHUNK + 1) * RS + tid * 32));
-        if (tid < nrow) {
-            const int gahead = min(__float_as_int(cur[0].v[RS / 4 - 1].w) + kRowsAuxAhead, P - 1);
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(a.aux + (size_t)gahead * 8));
-        }
-
         // =========================================================================== A: thread = row
         float f[R][Cfg::FW];
         bool valid[R], single[R];
