@@ -10,8 +10,11 @@ Workload (BASELINE.json configs[2]/[3]): paired radar + LiDAR pillar encoding, f
           (teacher pre-training, tools/cfgs/nuscenes_models/pillarnet.yaml);
   mode A (reference-faithful distillation step, radar_distill_train.yaml:68): LiDAR encoder frozen
           (eval BN, forward only), radar encoder train-mode forward + backward.  Reported under "mode_a".
-value  = points/s over all ranks with inputs resident in HBM (CUDA events per step, L2 flushed between steps)
-e2e    = the same through the module API from pinned HOST buffers: H2D of the points, D2H of the features/coords
+value  = points/s over all ranks with inputs resident in HBM (CUDA events per step, L2 flushed between steps); the
+         backward is driven by a dense upstream gradient (what SparseEnc hands back), resident like the inputs
+e2e    = the same through the module API from pinned HOST buffers: every step uploads its points (H2D) and reads the
+         step's result -- the parameter gradients -- back (D2H); "e2e_host_outputs" additionally downloads the
+         pillar features / coords (what a host-side consumer of rdp_encode_host would receive)
 --impl reference: the CPU oracle port (oracle/pillar_oracle.c, all host threads) on the same workload.
 Multi-GPU: frames shard over ranks (weak scaling, 8 frames per GPU); the only collective is DDP's gradient
 all-reduce of the PFN parameters.
@@ -205,14 +208,35 @@ def build_modules(device, mode, ddp):
 
 
 
-def gpu_step(call, lidar_dev, radar_dev, mode, frames):
-    """One step: both encoders over the batch (+ backward of a sum loss), as PillarNet.forward does (pillarnet.py:28-33)."""
+def gpu_step(call, lidar_dev, radar_dev, mode, frames, upstream):
+    """One step: both encoders over the batch as PillarNet.forward runs them (pillarnet.py:28-33), then the backward
+    from a dense upstream gradient d(loss)/d(pillar_features) -- what the SparseEnc backbone's backward hands to the
+    encoder (spconv_backbone_2d.py:262) -- into the PFN parameters."""
+    import torch
+    for p in upstream["params"]:   # optimizer.zero_grad(set_to_none=True) of the training loop (train_utils.py:55)
+        p.grad = None
     bd = call({"points": lidar_dev, "radar_points": radar_dev, "batch_size": frames})
-    loss = bd["radar_pillar_features"].sum()
+    outs = [bd["radar_pillar_features"]]
+    grads = [upstream["radar"][:outs[0].shape[0]]]
     if mode == "B":
-        loss = loss + bd["pillar_features"].sum()
-    loss.backward()
+        outs.append(bd["pillar_features"])
+        grads.append(upstream["lidar"][:outs[1].shape[0]])
+    torch.autograd.backward(outs, grads)
     return bd
+
+
+def make_upstream(device, n_lidar, n_radar, params=(), c_out=32):
+    import torch
+    g = torch.Generator(device=device)
+    g.manual_seed(99)
+    return {"lidar": torch.randn((n_lidar, c_out), device=device, generator=g),
+            "radar": torch.randn((n_radar, c_out), device=device, generator=g), "params": list(params)}
+
+
+def grads_vector(mods):
+    """The step's result: every PFN parameter gradient, flattened (1 056 floats for the two shipped encoders)."""
+    import torch
+    return torch.cat([p.grad.reshape(-1) for m in mods for p in m.parameters() if p.grad is not None])
 
 
 def run_ours(args):
@@ -234,6 +258,7 @@ def run_ours(args):
     lid, rad, call = build_modules(device, mode, ddp)
     lidar_dev, radar_dev = torch.from_numpy(lidar).to(device), torch.from_numpy(radar).to(device)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
+    upstream = make_upstream(device, len(lidar), len(radar), list(lid.parameters()) + list(rad.parameters()))
 
     def barrier():
         if ddp:
@@ -246,7 +271,7 @@ def run_ours(args):
             flush.fill_(1)
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s.record()
-            gpu_step(call, lidar_dev, radar_dev, m, frames)
+            gpu_step(call, lidar_dev, radar_dev, m, frames, upstream)
             e.record()
             evs.append((s, e))
         torch.cuda.synchronize()
@@ -256,7 +281,7 @@ def run_ours(args):
     if rank == 0:     # one sampler per job: the step is host-bound, eight pollers would perturb what they measure
         clk.__enter__()   # started before the warm-up so that nvidia-smi is already streaming when the timed steps run
     for _ in range(max(args.warmup, 3)):
-        gpu_step(call, lidar_dev, radar_dev, mode, frames)
+        gpu_step(call, lidar_dev, radar_dev, mode, frames, upstream)
     barrier()
     clk.rows.clear()  # keep only samples taken during the timed region
     if True:
@@ -277,7 +302,7 @@ def run_ours(args):
     value = total_rows / (step_ms * 1e-3)
     if wall < 0.3:  # short timed region: keep the same load running (same count on every rank) until nvidia-smi has samples
         for _ in range(int(0.3 / (step_ms * 1e-3)) + 1):
-            gpu_step(call, lidar_dev, radar_dev, mode, frames)
+            gpu_step(call, lidar_dev, radar_dev, mode, frames, upstream)
         barrier()
     if rank == 0:
         clk.__exit__(None, None, None)
@@ -286,47 +311,66 @@ def run_ours(args):
     extra = {}
     if mode == "B" and not ddp:
         lidA, radA, callA = build_modules(device, "A", False)
+        upstreamA = dict(upstream, params=list(lidA.parameters()) + list(radA.parameters()))
         for _ in range(3):
-            gpu_step(callA, lidar_dev, radar_dev, "A", frames)
+            gpu_step(callA, lidar_dev, radar_dev, "A", frames, upstreamA)
         evs = []
         for _ in range(args.steps):
             flush.fill_(1)
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            s.record(); gpu_step(callA, lidar_dev, radar_dev, "A", frames); e.record()
+            s.record(); gpu_step(callA, lidar_dev, radar_dev, "A", frames, upstreamA); e.record()
             evs.append((s, e))
         torch.cuda.synchronize()
         msA = sum(s.elapsed_time(e) for s, e in evs) / len(evs)
         extra["mode_a"] = {"value": n_rows / (msA * 1e-3), "unit": "points/s", "ms_per_step": msA,
                            "what": "LiDAR frozen eval-BN forward + radar train-BN forward+backward (radar_distill_train.yaml)"}
 
-    # ---- e2e: pinned host buffers in, pinned host buffers out, through the package's host pipeline
+    # ---- e2e: pinned host buffers in, the step's result out, through the package's host pipeline
     #      (radardistill_b200.pipeline.HostPipeline: uploads / downloads overlap the kernels; every step's H2D of its
-    #      points and D2H of its features + coords complete inside the timed region)
+    #      points and D2H of its result complete inside the timed region).  Result of a training step = the parameter
+    #      gradients; the second pass also downloads the pillar features + coords.
     from radardistill_b200.pipeline import HostPipeline
     lidar_pin, radar_pin = torch.from_numpy(lidar).pin_memory(), torch.from_numpy(radar).pin_memory()
     host_in = {"points": lidar_pin, "radar_points": radar_pin}
-    pipe = HostPipeline(lambda d: gpu_step(call, d["points"], d["radar_points"], mode, frames), device,
-                        ("pillar_features", "pillar_coords", "radar_pillar_features", "radar_pillar_coords"))
-    for _ in range(3):
-        d2h = pipe.submit(host_in, host_in)
-    pipe.finish()
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(args.steps):
-        d2h = pipe.submit(host_in, host_in if i + 1 < args.steps else None)
-    pipe.finish()
-    barrier()
-    e2e_dt = (time.perf_counter() - t0) / args.steps
-    if ddp:
-        t = torch.tensor([e2e_dt], device=device, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_dt = float(t.item())
-    e2e = {"value": total_rows / e2e_dt, "unit": "points/s", "h2d_bytes_per_step": int(lidar.nbytes + radar.nbytes),
-           "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_dt * 1e3,
-           "how": "HostPipeline: pinned H2D on an input stream, D2H on an output stream, overlapped with the kernels"}
+    mods = (lid, rad)
 
-    # ---- roofline of the dominant kernel: pfn_fwd_kernel<APPLY> on the LiDAR batch (one launch per rdp_pfn_fwd in
-    #      eval mode), timed live with CUDA events on the launching stream, L2 flushed before every launch.
+    def e2e_step(d):
+        bd = gpu_step(call, d["points"], d["radar_points"], mode, frames, upstream)
+        bd["param_grads"] = grads_vector(mods).unsqueeze(1)
+        return bd
+
+    def time_e2e(keys):
+        pipe = HostPipeline(e2e_step, device, keys)
+        for _ in range(3):
+            d2h = pipe.submit(host_in, host_in)
+        pipe.finish()
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            d2h = pipe.submit(host_in, host_in if i + 1 < args.steps else None)
+        pipe.finish()
+        barrier()
+        dt = (time.perf_counter() - t0) / args.steps
+        if ddp:
+            t = torch.tensor([dt], device=device, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        return dt, int(d2h)
+
+    e2e_dt, d2h = time_e2e(("param_grads",))
+    e2e = {"value": total_rows / e2e_dt, "unit": "points/s", "h2d_bytes_per_step": int(lidar.nbytes + radar.nbytes),
+           "d2h_bytes_per_step": d2h, "ms_per_step": e2e_dt * 1e3,
+           "how": "HostPipeline: pinned H2D of the points on an input stream, D2H of the step's parameter gradients on an "
+                  "output stream, overlapped with the kernels of the neighbouring steps"}
+    out_dt, out_d2h = time_e2e(("param_grads", "pillar_features", "pillar_coords", "radar_pillar_features", "radar_pillar_coords"))
+    e2e_out = {"value": total_rows / out_dt, "unit": "points/s", "h2d_bytes_per_step": int(lidar.nbytes + radar.nbytes),
+               "d2h_bytes_per_step": out_d2h, "ms_per_step": out_dt * 1e3,
+               "how": "as e2e, plus the D2H of the pillar features and coords of both encoders (PCIe bound)"}
+
+    # ---- roofline: the PFN kernels on the LiDAR batch, each timed live with CUDA events on the launching stream, L2
+    #      flushed before every launch.  Headline = pfn_tile_kernel<APPLY> (one launch per eval-mode rdp_pfn_fwd: the
+    #      kernel both step modes spend the most forward time in); the train-mode forward and the backward calls
+    #      (several launches each, dominated by one tile kernel) are listed beside it.
     roof = None
     if rank == 0:
         import ctypes as C
@@ -334,50 +378,83 @@ def run_ours(args):
         norm = lid.pfn_layers[0].norm
         lib = _lib.load()
         geom, layout = spec.geom(frames), spec.layout_struct()
-        res = ops.encode_forward(lidar_dev, spec, frames, lid.pfn_layers[0].linear.weight, None, norm.weight, norm.bias,
-                                 norm.running_mean, norm.running_var, False, False)
-        prm = ops._params_struct(spec, lid.pfn_layers[0].linear.weight.detach(), None, norm.weight.detach(), norm.bias.detach(),
-                                 norm.running_mean, norm.running_var, False)
+        w = lid.pfn_layers[0].linear.weight.detach()
+        res = ops.encode_forward(lidar_dev, spec, frames, w, None, norm.weight, norm.bias, norm.running_mean.clone(),
+                                 norm.running_var.clone(), True, True)   # train-mode state for the backward timing
+        torch.cuda.synchronize()
+        P_ = ops._ptr
         feats = torch.empty((len(lidar), spec.c_out), dtype=torch.float32, device=device)
+        argp = torch.empty((len(lidar), spec.c_out), dtype=torch.int32, device=device)
+        dw, dg, db = (torch.empty(sh, device=device) for sh in ((spec.c_out, spec.c_in), (spec.c_out,), (spec.c_out,)))
         st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-        durs, idx_durs = [], []
+        rm, rv = norm.running_mean.clone(), norm.running_var.clone()
+        prm_eval = ops._params_struct(spec, w, None, norm.weight.detach(), norm.bias.detach(), rm, rv, False)
+        prm_train = ops._params_struct(spec, w, None, norm.weight.detach(), norm.bias.detach(), rm, rv, True)
+
+        def call_index():
+            _lib.check(lib.rdp_index_fwd(P_(lidar_dev), len(lidar), C.byref(geom), spec.coord_cols, P_(res.workspace),
+                                         res.workspace.numel(), P_(res.coords), P_(res.inverse), P_(res.counts),
+                                         P_(res.counters), st), "rdp_index_fwd")
+
+        def call_fwd(prm, arg, state):
+            _lib.check(lib.rdp_pfn_fwd(P_(lidar_dev), len(lidar), C.byref(geom), C.byref(layout), C.byref(prm), P_(res.workspace),
+                                       res.workspace.numel(), P_(res.counters), P_(feats), arg, None, state, st), "rdp_pfn_fwd")
+
+        def call_bwd():
+            _lib.check(lib.rdp_pfn_bwd(P_(lidar_dev), len(lidar), C.byref(geom), C.byref(layout), C.byref(prm_train),
+                                       P_(res.workspace), res.workspace.numel(), P_(res.counters), P_(upstream["lidar"]),
+                                       P_(feats), P_(argp), P_(res.bn_state), P_(dw), P_(dg), P_(db), st), "rdp_pfn_bwd")
+
+        def timed(fn, reps):
+            ts = []
+            for i in range(reps + 3):
+                flush.fill_(1)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(); fn(); e1.record()
+                torch.cuda.synchronize()
+                if i >= 3:
+                    ts.append(e0.elapsed_time(e1))
+            return sum(ts) / len(ts)
+
         reps = max(args.steps, 10)
-        for i in range(reps + 3):
-            flush.fill_(1)
-            s0, s1, s2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
-            s0.record()
-            # index pass (5 kernels) re-run so the PFN launch sees a cold L2 state comparable to the real step
-            _lib.check(lib.rdp_index_fwd(ops._ptr(lidar_dev), len(lidar), C.byref(geom), spec.coord_cols, ops._ptr(res.workspace),
-                                         res.workspace.numel(), ops._ptr(res.coords), ops._ptr(res.inverse), ops._ptr(res.counts),
-                                         ops._ptr(res.counters), st), "rdp_index_fwd")
-            s1.record()
-            _lib.check(lib.rdp_pfn_fwd(ops._ptr(lidar_dev), len(lidar), C.byref(geom), C.byref(layout), C.byref(prm),
-                                       ops._ptr(res.workspace), res.workspace.numel(), ops._ptr(res.counters),
-                                       ops._ptr(feats), None, None, None, st), "rdp_pfn_fwd")
-            s2.record()
-            torch.cuda.synchronize()
-            if i >= 3:
-                idx_durs.append(s0.elapsed_time(s1)); durs.append(s1.elapsed_time(s2))
+        idx = timed(call_index, reps)
+        dur = timed(lambda: call_fwd(prm_eval, None, None), reps)
+        dur_train = timed(lambda: call_fwd(prm_train, P_(argp), P_(res.bn_state)), reps)
+        dur_bwd = timed(call_bwd, reps)
         n_kept, n_pil = res.n_kept, res.n_pillars
         row_bytes = 4 * spec.cols
         alg = row_bytes * n_kept + 4 * spec.c_out * n_pil           # rows read once + feature rows written once
         alg_fwd = row_bytes * len(lidar) + 4 * n_kept + n_pil * (4 * spec.c_out + 4 * spec.coord_cols + 4)  # SURVEY 8(d) B_fwd
+        alg_train = 2 * row_bytes * n_kept + 8 * spec.c_out * n_pil  # moments pass re-reads the rows; features + argmax written
+        alg_bwd = 8 * spec.c_out * n_pil + row_bytes * n_kept + 4 * n_kept   # SURVEY 8(d) B_bwd
         peak, peak_src = peaks()
-        traffic, traffic_src = None, None
+        traffic, traffic_src, tj_all = None, None, {}
         tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
-        if os.path.exists(tp):  # dram__bytes_read + dram__bytes_write of one launch from the committed ncu --set full capture
-            tj = json.load(open(tp))["pfn_tile_apply_eval"]
-            if tj["rows"] == n_kept and tj["pillars"] == n_pil:
+        if os.path.exists(tp):  # dram__bytes_read + dram__bytes_write per launch from the committed ncu --set full captures
+            tj_all = json.load(open(tp))
+            tj = tj_all.get("pfn_tile_apply_eval", {})
+            if tj.get("rows") == n_kept and tj.get("pillars") == n_pil:
                 traffic, traffic_src = tj["dram_bytes_read"] + tj["dram_bytes_write"], tj["source"]
-        dur = sum(durs) / len(durs)
-        idx = sum(idx_durs) / len(idx_durs)
+
+        def entry(name, alg_bytes, ms, key=None):
+            e = {"kernel": name, "algorithmic_bytes": int(alg_bytes), "ms": ms, "achieved": alg_bytes / (ms * 1e-3) / 1e9,
+                 "frac": alg_bytes / (ms * 1e-3) / 1e9 / peak}
+            t = tj_all.get(key) if key else None
+            if t and t.get("rows") == n_kept and t.get("pillars") == n_pil:
+                e["traffic"] = t["dram_bytes_read"] + t["dram_bytes_write"]
+            return e
+
         roof = {"bound": "hbm", "kernel": "pfn_tile_kernel<PfnCfg<6 cols, Simple2D, 32 ch>, APPLY> (LiDAR batch of 8 frames, eval BN)",
                 "achieved": alg / (dur * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": alg / (dur * 1e-3) / 1e9 / peak,
                 "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "kernel_ms": dur, "algorithmic_bytes": int(alg),
                 "frac_of_8000_nominal": alg / (dur * 1e-3) / 1e9 / 8000.0,
                 "whole_forward": {"algorithmic_bytes": int(alg_fwd), "ms": idx + dur, "index_ms": idx,
                                   "achieved": alg_fwd / ((idx + dur) * 1e-3) / 1e9,
-                                  "frac": alg_fwd / ((idx + dur) * 1e-3) / 1e9 / peak}}
+                                  "frac": alg_fwd / ((idx + dur) * 1e-3) / 1e9 / peak},
+                "other_calls": [
+                    entry("rdp_index_fwd: 7 index kernels + publish", row_bytes * len(lidar) + 4 * n_kept + n_pil * (4 * spec.coord_cols + 4), idx),
+                    entry("rdp_pfn_fwd train: pfn_tile<STATS> + reduce + bn_finalize + pfn_tile<APPLY_ARG>", alg_train, dur_train, "pfn_train_fwd"),
+                    entry("rdp_pfn_bwd: pfn_tile<BWD> + reduce + bwd_finalize", alg_bwd, dur_bwd, "pfn_tile_bwd")]}
 
     if rank == 0:
         cpu = None
@@ -389,12 +466,15 @@ def run_ours(args):
             cpu = {"value": v, "unit": "points/s", "cores": cores, "kind": "port",
                    "sample": f"{fr} of the {frames} paired frames ({len(l2)} LiDAR + {len(r2)} radar rows) x 3 steps, C oracle "
                              f"(oracle/pillar_oracle.c), {cores} threads in the per-point loops, {dt:.2f} s/step"}
-        launches_lidar = 5 + (3 if mode == "B" else 1) + (2 if mode == "B" else 0)  # index 5, pfn stats+finalize+apply | apply, bwd 2
-        launches = (launches_lidar + 10) * args.steps
+        # librdp kernels per step: index 8 (quantise, scan, zero, rank, scan, group, table, publish); forward 4 in train mode
+        # (moments, reduce, finalize, apply) or 1; backward 3 (tile, reduce, finalize).  Radar encoder always trains.
+        launches_lidar = 8 + (4 + 3 if mode == "B" else 1)
+        launches = (launches_lidar + 15) * args.steps
         line = {"metric": "pillar-encoder points/s (fwd+bwd)", "value": value, "unit": "points/s", "n_gpus": world,
                 "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": step_ms, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": workload_config(mode, frames, len(lidar), len(radar)), "e2e": e2e, "gpu_launches": launches,
+                "config": workload_config(mode, frames, len(lidar), len(radar)), "e2e": e2e, "e2e_host_outputs": e2e_out,
+                "gpu_launches": launches,
                 "clocks": clk.summary(), "roofline": roof, "cpu_baseline": cpu, "wall_s_timed_region": wall}
         line.update(extra)
         print(json.dumps(line), flush=True)

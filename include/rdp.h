@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define RDP_ABI_VERSION 2
+#define RDP_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define RDP_API __attribute__((visibility("default")))
@@ -86,6 +86,8 @@ typedef struct rdp_pfn_params {
     double eps;           /* 1e-3  (:29)                                                     */
     double momentum;      /* 0.01  (:29)                                                     */
     int32_t train_bn;     /* 1: batch statistics + running-stat update; 0: running stats     */
+    int64_t *num_batches_tracked; /* norm.num_batches_tracked (device, int64): += 1 by a train-mode forward over more
+                                     than one point, as BatchNorm1d does; may be NULL                               */
 } rdp_pfn_params_t;
 
 RDP_API int rdp_abi_version(void);
@@ -127,8 +129,10 @@ RDP_API int rdp_index_fwd_publish(const float *points, int64_t n_points, const r
  * Must follow rdp_index_fwd on the same points / workspace / stream.
  *   features    (cap n_points, c_out) fp32      rows [0,P)
  *   argpos      (cap n_points, c_out) int32     winning row of every (pillar, channel) as a position in the
- *                                               workspace's pillar-grouped order (lowest kept index on ties);
- *                                               input of rdp_pfn_bwd / rdp_argmax_kept.  NULL if not wanted.
+ *                                               workspace's pillar-grouped order (lowest kept index on ties),
+ *                                               bit-complemented (negative) where the ReLU clamped the maximum to 0
+ *                                               (no gradient flows, :38); input of rdp_pfn_bwd / rdp_argmax_kept.
+ *                                               NULL if not wanted.
  *   pillar_mean (cap n_points, 3) fp32          per-pillar xyz mean (scatter_mean, :226); NULL if not wanted
  *   bn_state    (rdp_bn_state_doubles(layout)) fp64: batch mean/var, folded scale/shift and the feature
  *               moments the backward needs; required when train_bn, else may be NULL
@@ -141,10 +145,21 @@ RDP_API int rdp_pfn_fwd(const float *points, int64_t n_points, const rdp_geom_t 
 RDP_API int64_t rdp_bn_state_doubles(const rdp_layout_t *layout);
 
 /*
+ * rdp_index_fwd_publish followed by rdp_pfn_fwd in one call (one trip through the host binding per forward).
+ * Same buffers and meaning as the two functions; replaces dynamic_pillar_vfe.py:201-249.
+ */
+RDP_API int rdp_encode_fwd(const float *points, int64_t n_points, const rdp_geom_t *geom, const rdp_layout_t *layout,
+                           const rdp_pfn_params_t *params, void *workspace, size_t workspace_bytes,
+                           int32_t *coords, int32_t *inverse, int32_t *counts, int32_t *counters,
+                           float *features, int32_t *argpos, double *bn_state,
+                           int32_t *host_mapped, void *event, void *stream);
+
+/*
  * Parameter gradients of the PFN (autograd of :35-46): argmax routing, ReLU', BatchNorm backward
  * (batch statistics when params->train_bn, running statistics otherwise), dW = g_x^T f.
  * Points are a non-differentiable leaf in the reference, so no point gradient is produced.
- *   grad_features (P, c_out) fp32 ; features / argpos / bn_state as written by rdp_pfn_fwd; same workspace
+ *   grad_features (P, c_out) fp32 ; argpos / bn_state as written by rdp_pfn_fwd; same workspace.  `features` is not
+ *   read (the ReLU mask travels in the sign of argpos) and may be NULL.
  *   d_weight (c_out, c_in), d_gamma (c_out) [NULL without norm], d_beta (c_out) [bias grad without norm]
  */
 RDP_API int rdp_pfn_bwd(const float *points, int64_t n_points, const rdp_geom_t *geom, const rdp_layout_t *layout,

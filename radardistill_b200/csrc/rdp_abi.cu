@@ -101,6 +101,18 @@ extern "C" int64_t rdp_bn_state_doubles(const rdp_layout_t *layout) {
     return 4 * cout + 1 + cin + cin * cin;
 }
 
+extern "C" int rdp_encode_fwd(const float *points, int64_t n_points, const rdp_geom_t *geom, const rdp_layout_t *layout,
+                              const rdp_pfn_params_t *params, void *workspace, size_t workspace_bytes, int32_t *coords,
+                              int32_t *inverse, int32_t *counts, int32_t *counters, float *features, int32_t *argpos,
+                              double *bn_state, int32_t *host_mapped, void *event, void *stream) {
+    if (!layout) return RDP_ERR_INVALID_ARG;
+    int rc = rdp_index_fwd_publish(points, n_points, geom, layout->coord_cols, workspace, workspace_bytes, coords, inverse, counts,
+                                   counters, host_mapped, event, stream);
+    if (rc != RDP_OK) return rc;
+    return rdp_pfn_fwd(points, n_points, geom, layout, params, workspace, workspace_bytes, counters, features, argpos, nullptr,
+                       bn_state, stream);
+}
+
 extern "C" int rdp_encode_host(const float *points, int64_t n_points, const rdp_geom_t *geom, const rdp_layout_t *layout,
                                const rdp_pfn_params_t *hp, float *features, int32_t *coords, int32_t *inverse,
                                int32_t *counts, int64_t *n_kept, int64_t *n_pillars) {
@@ -149,6 +161,7 @@ extern "C" int rdp_encode_host(const float *points, int64_t n_points, const rdp_
     dp.running_mean = up(hp->running_mean, cout);
     dp.running_var = up(hp->running_var, cout);
     dp.train_bn = 0;
+    dp.num_batches_tracked = nullptr;
     rc = rdp_index_fwd(d_pts, n_points, geom, kc, d_ws, ws_bytes, d_coords, d_inv, d_cnt, d_counters, st);
     if (rc == RDP_OK)
         rc = rdp_pfn_fwd(d_pts, n_points, geom, layout, &dp, d_ws, ws_bytes, d_counters, d_feat, nullptr, nullptr, nullptr, st);

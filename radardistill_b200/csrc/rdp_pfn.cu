@@ -60,7 +60,8 @@ __global__ void argpos_to_kept_kernel(const int32_t *__restrict__ argpos, const 
     const long long total = (long long)counters[RDP_CNT_P] * cout;
     const bool none_dropped = ((long long)counters[RDP_CNT_N] == n0);
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-        const int row = __float_as_int(grows[((size_t)argpos[e] + 1) * rs + rs - 2]);
+        const int ap = argpos[e];
+        const int row = __float_as_int(grows[((size_t)(ap >= 0 ? ap : ~ap) + 1) * rs + rs - 2]);
         out[e] = none_dropped ? row : orig2kept[row];
     }
 }
@@ -128,7 +129,8 @@ extern "C" int rdp_pfn_fwd(const float *points, int64_t n_points, const rdp_geom
         if (L->stats_partial_doubles > ws.partial_doubles_per_block) return RDP_ERR_WORKSPACE;
         RDP_CUDA_OK(L->tile(a, PFN_MODE_STATS, grid, st));
         reduce_partials_kernel<<<(L->stats_partial_doubles + 31) / 32, 256, 0, st>>>(ws.partials, grid, L->stats_partial_doubles, ws.totals);
-        RDP_CUDA_OK(L->bn_finalize(a, ws.totals, bn_state, prm->running_mean, prm->running_var, prm->momentum, st));
+        RDP_CUDA_OK(L->bn_finalize(a, ws.totals, bn_state, prm->running_mean, prm->running_var, prm->momentum,
+                                   reinterpret_cast<long long *>(prm->num_batches_tracked), st));
         a.bn_state = bn_state;
         a.fold_from_state = 1;
     }
@@ -160,7 +162,8 @@ extern "C" int rdp_pfn_bwd(const float *points, int64_t n_points, const rdp_geom
         if (d_gamma) RDP_CUDA_OK(cudaMemsetAsync(d_gamma, 0, sizeof(float) * layout->c_out, st));
         return RDP_OK;
     }
-    if (!points || !workspace || !grad_features || !features || !argpos) return RDP_ERR_INVALID_ARG;
+    (void)features;   // the ReLU mask travels in the sign of argpos; kept in the signature for ABI stability
+    if (!points || !workspace || !grad_features || !argpos) return RDP_ERR_INVALID_ARG;
     if (train && !bn_state) return RDP_ERR_INVALID_ARG;
     const PfnLaunch *L = lookup(geom, layout);
     if (!L) return RDP_ERR_UNSUPPORTED;
@@ -173,7 +176,6 @@ extern "C" int rdp_pfn_bwd(const float *points, int64_t n_points, const rdp_geom
     rc = fill_args(&a, L, n_points, geom, layout, prm, ws, counters);
     if (rc != RDP_OK) return rc;
     a.grad = grad_features;
-    a.feat_out = features;
     a.argpos = const_cast<int32_t *>(argpos);
     // backward form: the tile kernel (default) or the pillar-streaming kernel (RDP_BWD_STREAM=1; same results, measured
     // slower so far -- see DESIGN.md)

@@ -41,10 +41,11 @@ struct PfnArgs {
     const float *weight, *bias, *gamma, *beta, *rmean, *rvar;
     const double *bn_state;  // train apply: folded scale / shift live here
     float *features;
-    int32_t *argpos;         // winning GROUPED position per (pillar, channel); see argpos_to_kept_kernel
+    int32_t *argpos;         // winning GROUPED position per (pillar, channel), bit-complemented (negative) when the
+                             // pillar's maximum was clamped by the ReLU (zero gradient); see argpos_to_kept_kernel
     float *pillar_mean;
     double *partials;
-    const float *grad, *feat_out;  // backward inputs
+    const float *grad;       // backward input: upstream gradient (P, Cout)
     long long n0;
     double eps;
     float lo[3], vsz[3], off[3];
@@ -101,12 +102,11 @@ struct PfnSmem {
     static constexpr size_t S_BYTES = (MODE == PFN_MODE_STATS) ? sizeof(double) * kPfnThreads * 16 : 0;
     static constexpr size_t B_BYTES = 0;  // BWD: the end-of-kernel scratch aliases f + the prefetch buffers (see bwd_scratch())
     static constexpr size_t SCR = Z_BYTES > S_BYTES ? (Z_BYTES > B_BYTES ? Z_BYTES : B_BYTES) : (S_BYTES > B_BYTES ? S_BYTES : B_BYTES);
-    static constexpr int PCH = (MODE == PFN_MODE_BWD) ? 16 : 1;  // pillars per backward prefetch chunk (two chunks in flight)
+    static constexpr int PCH = (MODE == PFN_MODE_BWD) ? 24 : 1;  // pillars per backward prefetch chunk (two chunks in flight)
     PfnStage<Cfg> st[2];
     alignas(8) uint64_t full[2];
-    alignas(8) uint64_t pre[2];                    // BWD: arrival of a chunk's (grad, features, argpos) rows, double buffered
+    alignas(8) uint64_t pre[2];                    // BWD: arrival of a chunk's (grad, argpos) rows, double buffered
     alignas(16) float pre_grad[2][(MODE == PFN_MODE_BWD) ? PCH * Cfg::COUT : 4];
-    alignas(16) float pre_out[2][(MODE == PFN_MODE_BWD) ? PCH * Cfg::COUT : 4];
     alignas(16) int pre_arg[2][(MODE == PFN_MODE_BWD) ? PCH * Cfg::COUT : 4];
     alignas(16) float f[kPfnCap * Cfg::FSTRIDE];   // decorated features of the tile's rows
     alignas(16) unsigned char scr[SCR];            // STATS / BWD: fp64 reduction scratch at kernel end
@@ -181,8 +181,8 @@ __global__ void __launch_bounds__(kPfnThreads, (MODE == PFN_MODE_APPLY) ? 5 : 4)
     // fp64 reduction scratch used once at the end of the kernel; in BWD it aliases the (then idle) prefetch + feature buffers
     double *dscr = (MODE == PFN_MODE_BWD) ? reinterpret_cast<double *>(&S.pre_grad[0][0]) : reinterpret_cast<double *>(S.scr);
     static_assert(MODE != PFN_MODE_BWD ||
-                  sizeof(double) * (kPfnThreads / 32) * Cfg::BWD_DOUBLES <= 6 * sizeof(float) * Smem::PCH * Cfg::COUT + sizeof(S.f),
-                  "backward scratch must fit in pre_grad | pre_out | pre_arg | f");
+                  sizeof(double) * (kPfnThreads / 32) * Cfg::BWD_DOUBLES <= 4 * sizeof(float) * Smem::PCH * Cfg::COUT + sizeof(S.f),
+                  "backward scratch must fit in pre_grad | pre_arg | f");
 
     // ---- per-CTA constants
     if (tid == 0) {
@@ -328,7 +328,7 @@ __global__ void __launch_bounds__(kPfnThreads, (MODE == PFN_MODE_APPLY) ? 5 : 4)
 #pragma unroll
             for (int cc = 0; cc < WN; ++cc) {
                 fout[LPR * cc] = m[cc];
-                if (want_arg) aout[LPR * cc] = mp[cc];
+                if (want_arg) aout[LPR * cc] = (m[cc] > 0.0f) ? mp[cc] : ~mp[cc];   // negative: ReLU clamped the pillar (no gradient)
             }
             fout += COUT;
             if (want_arg) aout += COUT;
@@ -379,9 +379,8 @@ __global__ void __launch_bounds__(kPfnThreads, (MODE == PFN_MODE_APPLY) ? 5 : 4)
     // BWD: the upstream gradient, forward output and argmax rows of pillars [p0, p0 + n) -> smem, asynchronously
     auto prefetch_bwd = [&](int b, int p0, int n) {
         const uint32_t bytes = (uint32_t)n * COUT * 4;
-        mbar_expect_tx(&S.pre[b], 3 * bytes);
+        mbar_expect_tx(&S.pre[b], 2 * bytes);
         tma_bulk_g2s(S.pre_grad[b], a.grad + (size_t)p0 * COUT, bytes, &S.pre[b]);
-        tma_bulk_g2s(S.pre_out[b], a.feat_out + (size_t)p0 * COUT, bytes, &S.pre[b]);
         tma_bulk_g2s(S.pre_arg[b], a.argpos + (size_t)p0 * COUT, bytes, &S.pre[b]);
     };
 
@@ -467,8 +466,9 @@ __global__ void __launch_bounds__(kPfnThreads, (MODE == PFN_MODE_APPLY) ? 5 : 4)
 #pragma unroll
                     for (int cc = 0; cc < CPL; ++cc) {
                         const int o = q * COUT + lane + 32 * cc;
-                        const float gy = S.pre_out[b][o] > 0.0f ? S.pre_grad[b][o] : 0.0f;
-                        const int jj = S.pre_arg[b][o] - gb;
+                        const int ap = S.pre_arg[b][o];   // negative: the forward marked the pillar as ReLU-clamped (:38)
+                        const float gy = ap >= 0 ? S.pre_grad[b][o] : 0.0f;
+                        const int jj = (ap >= 0 ? ap : ~ap) - gb;
                         float f[Cfg::FW];
                         const float4 *src = reinterpret_cast<const float4 *>(&S.f[jj * Cfg::FSTRIDE]);
 #pragma unroll
@@ -504,8 +504,9 @@ __global__ void __launch_bounds__(kPfnThreads, (MODE == PFN_MODE_APPLY) ? 5 : 4)
 #pragma unroll
                     for (int cc = 0; cc < CPL; ++cc) {
                         const size_t o = (size_t)pb * COUT + lane + 32 * cc;
-                        const float gy = a.feat_out[o] > 0.0f ? a.grad[o] : 0.0f;
-                        const float *src = a.grows + ((size_t)a.argpos[o] + 1) * RS;
+                        const int ap = a.argpos[o];
+                        const float gy = ap >= 0 ? a.grad[o] : 0.0f;
+                        const float *src = a.grows + ((size_t)(ap >= 0 ? ap : ~ap) + 1) * RS;
                         float r[COLS], f[Cfg::FW];
 #pragma unroll
                         for (int c = 0; c < COLS; ++c) r[c] = src[c];
@@ -547,7 +548,7 @@ __global__ void __launch_bounds__(kPfnThreads, (MODE == PFN_MODE_APPLY) ? 5 : 4)
                 }
                 if (is_apply && tid < COUT) {
                     a.features[(size_t)pb * COUT + tid] = S.carry_v[tid];
-                    if (want_arg) a.argpos[(size_t)pb * COUT + tid] = S.carry_p[tid];
+                    if (want_arg) a.argpos[(size_t)pb * COUT + tid] = (S.carry_v[tid] > 0.0f) ? S.carry_p[tid] : ~S.carry_p[tid];
                 }
                 fence_proxy_async();  // generic-proxy writes to the stage buffer before a later TMA reuses it
             }
@@ -597,7 +598,8 @@ __global__ void __launch_bounds__(kPfnThreads, (MODE == PFN_MODE_APPLY) ? 5 : 4)
 // bn_state = [mean(COUT) | var(COUT) | scale(COUT) | shift(COUT) | n | S1(CIN) | S2(CIN*CIN)]
 template <class Cfg>
 __global__ void __launch_bounds__(256) bn_finalize_kernel(const __grid_constant__ PfnArgs a, const double *totals, double *bn_state,
-                                                         float *running_mean, float *running_var, double momentum) {
+                                                         float *running_mean, float *running_var, double momentum,
+                                                         long long *num_batches_tracked) {
     constexpr int COUT = Cfg::COUT, CS = Cfg::CS, TOT = Cfg::STATS_DOUBLES, T4 = Cfg::T4;
     __shared__ double tot[TOT];
     const int tid = threadIdx.x;
@@ -645,7 +647,10 @@ __global__ void __launch_bounds__(256) bn_finalize_kernel(const __grid_constant_
             running_var[tid] = (float)((1.0 - momentum) * (double)running_var[tid] + momentum * var * (n / (n - 1.0)));
         }
     }
-    if (tid == 0) bn_state[4 * COUT] = (double)N;
+    if (tid == 0) {
+        bn_state[4 * COUT] = (double)N;
+        if (num_batches_tracked) *num_batches_tracked += 1;   // BatchNorm1d counts every train-mode forward (:29)
+    }
     double *S1 = bn_state + 4 * COUT + 1, *S2 = S1 + cin;
     for (int e = tid; e < CS * CS; e += blockDim.x) {
         const int fa = e / CS, fb = e % CS;

@@ -5,7 +5,7 @@
 //     dbeta_c = sum_p gy[p][c]            A_c[k] = sum_p gy[p][c] f[argmax(p, c)][k]
 // (G_c = w_c . A_c, the rest is closed form: bwd_finalize_kernel).  So the kernel is a stream over pillars:
 //   warp = a contiguous range of pillars, lane = channel (+32 per extra channel block);
-//   per pillar: coalesced 128-byte rows of grad / forward output / argpos, the pillar's table entry (warp uniform),
+//   per pillar: coalesced 128-byte rows of grad / argpos (its sign carries the ReLU mask), the pillar's table entry (warp uniform),
 //   each lane's winner row straight from the grouped row array (a pillar has ~2 rows: the 32 lanes hit 1-2 lines),
 //   features re-decorated in registers, 14 FMAs into fp32 accumulators that are folded into fp64 every 32 pillars.
 // No shared-memory staging, no block barriers in the stream: the tile form spent its time waiting for the
@@ -61,8 +61,8 @@ __global__ void __launch_bounds__(kBwdThreads, RDP_BWD_CTAS_PER_SM) pfn_bwd_stre
         }
     };
 
-    // stage 1 of a batch of U pillars: the coalesced (grad, output, argpos) rows
-    struct S1 { float g[U][CPL], out[U][CPL]; int pos[U][CPL]; };
+    // stage 1 of a batch of U pillars: the coalesced (grad, argpos) rows
+    struct S1 { float g[U][CPL]; int pos[U][CPL]; };
     auto load1 = [&](int p0, S1 &o) {
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -71,7 +71,6 @@ __global__ void __launch_bounds__(kBwdThreads, RDP_BWD_CTAS_PER_SM) pfn_bwd_stre
             for (int cc = 0; cc < CPL; ++cc) {
                 const size_t off = (size_t)p * COUT + lane + 32 * cc;
                 o.g[u][cc] = __ldg(a.grad + off);
-                o.out[u][cc] = __ldg(a.feat_out + off);
                 o.pos[u][cc] = __ldg(a.argpos + off);
             }
         }
@@ -92,8 +91,9 @@ __global__ void __launch_bounds__(kBwdThreads, RDP_BWD_CTAS_PER_SM) pfn_bwd_stre
             const int p = min(p0 + u, p_end - 1);
 #pragma unroll
             for (int cc = 0; cc < CPL; ++cc) {
-                gy[u][cc] = (live && nxt.out[u][cc] > 0.0f) ? nxt.g[u][cc] : 0.0f;   // ReLU' (:38) on the routed gradient
-                const float4 *src = reinterpret_cast<const float4 *>(a.grows + ((size_t)nxt.pos[u][cc] + 1) * RS);
+                const int ap = nxt.pos[u][cc];   // negative: the forward marked the pillar as ReLU-clamped (:38)
+                gy[u][cc] = (live && ap >= 0) ? nxt.g[u][cc] : 0.0f;
+                const float4 *src = reinterpret_cast<const float4 *>(a.grows + ((size_t)(ap >= 0 ? ap : ~ap) + 1) * RS);
 #pragma unroll
                 for (int q = 0; q < RS / 4; ++q) rowv[u][cc][q] = __ldg(src + q);
             }

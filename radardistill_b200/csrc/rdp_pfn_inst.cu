@@ -74,8 +74,8 @@ static cudaError_t bwd_stream(const PfnArgs &a, int grid, cudaStream_t st) {
 }
 
 static cudaError_t bn_finalize(const PfnArgs &a, const double *totals, double *bn_state, float *rm, float *rv, double momentum,
-                               cudaStream_t st) {
-    bn_finalize_kernel<Cfg><<<1, 256, 0, st>>>(a, totals, bn_state, rm, rv, momentum);
+                               long long *num_batches_tracked, cudaStream_t st) {
+    bn_finalize_kernel<Cfg><<<1, 256, 0, st>>>(a, totals, bn_state, rm, rv, momentum, num_batches_tracked);
     return cudaGetLastError();
 }
 

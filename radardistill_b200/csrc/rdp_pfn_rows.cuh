@@ -221,8 +221,15 @@ __global__ void __launch_bounds__(kRowsThreads, RDP_ROWS_GRID_PER_SM) pfn_rows_k
                 }
 #pragma unroll
                 for (int i = 0; i < RR; ++i) {
-                    if (single[i]) {
+                    if (single[i]) {   // the only row of its pillar wins every channel
                         st_global_v8(a.features + (size_t)gidv[i] * COUT + c8 * 8, y[i]);
+                        if (ARG) {
+                            const int pos = (int)c0 + tid + i * NT;
+                            float pv[8];
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) pv[e] = __int_as_float(y[i][e] > 0.0f ? pos : ~pos);
+                            st_global_v8(reinterpret_cast<float *>(a.argpos) + (size_t)gidv[i] * COUT + c8 * 8, pv);
+                        }
                     } else {
                         float4 *dst = reinterpret_cast<float4 *>(&S.x[(tid + i * NT) * XS + c8 * 8]);
                         dst[0] = make_float4(y[i][0], y[i][1], y[i][2], y[i][3]);
@@ -233,18 +240,6 @@ __global__ void __launch_bounds__(kRowsThreads, RDP_ROWS_GRID_PER_SM) pfn_rows_k
         };
         if (__any_sync(0xffffffffu, valid[R - 1])) linear(std::integral_constant<int, R>{});
         else if (__any_sync(0xffffffffu, valid[0])) linear(std::integral_constant<int, 1>{});
-        if (ARG) {
-#pragma unroll
-            for (int i = 0; i < R; ++i) {
-                if (single[i]) {   // the only row of its pillar wins every channel
-                    const float pv = __int_as_float((int)c0 + tid + i * NT);
-                    const float pos[8] = {pv, pv, pv, pv, pv, pv, pv, pv};
-#pragma unroll
-                    for (int c8 = 0; c8 < COUT / 8; ++c8)
-                        st_global_v8(reinterpret_cast<float *>(a.argpos) + (size_t)gidv[i] * COUT + c8 * 8, pos);
-                }
-            }
-        }
         if (RDP_ROWS_REGPIPE && nrow1) fetch_aux(nrow1, nx, na);
         __syncthreads();
 
@@ -307,7 +302,11 @@ __global__ void __launch_bounds__(kRowsThreads, RDP_ROWS_GRID_PER_SM) pfn_rows_k
                 }
                 if (!open) {
                     *reinterpret_cast<float4 *>(a.features + (size_t)pid * COUT + 4 * q) = make_float4(m[0], m[1], m[2], m[3]);
-                    if (ARG) *reinterpret_cast<int4 *>(a.argpos + (size_t)pid * COUT + 4 * q) = make_int4(mp[0], mp[1], mp[2], mp[3]);
+                    if (ARG) {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) mp[e] = (m[e] > 0.0f) ? mp[e] : ~mp[e];   // negative: clamped by the ReLU
+                        *reinterpret_cast<int4 *>(a.argpos + (size_t)pid * COUT + 4 * q) = make_int4(mp[0], mp[1], mp[2], mp[3]);
+                    }
                 } else {   // the pillar continues in the next chunk of this CTA
                     *reinterpret_cast<float4 *>(&S.carry_v[par ^ 1][4 * q]) = make_float4(m[0], m[1], m[2], m[3]);
                     if (ARG) {

@@ -9,7 +9,6 @@ replaces the body of the reference ``forward`` between reading ``points`` and wr
 from __future__ import annotations
 
 import ctypes as C
-import dataclasses
 from dataclasses import dataclass
 from typing import Optional
 
@@ -72,24 +71,68 @@ def make_spec(num_point_features: int, voxel_size, grid_size, point_cloud_range,
                        coord_cols=coord_cols, lo=lo, vsz=vsz, off=off, nx=int(grid_size[0]), ny=int(grid_size[1]))
 
 
-@dataclass
 class EncodeResult:
-    features: torch.Tensor            # (P, c_out) fp32
-    coords: torch.Tensor              # (P, coord_cols) int32
-    inverse: torch.Tensor             # (N,) int32   pillar of each KEPT point (torch.unique's inverse)
-    counts: torch.Tensor              # (P,) int32
-    argpos: Optional[torch.Tensor]    # (P, c_out) int32 winning row as a position in the grouped order (internal)
-    n_kept: int
-    n_pillars: int
-    # state for the backward / inspection
-    pillar_mean: Optional[torch.Tensor] = None
-    bn_state: Optional[torch.Tensor] = None
-    workspace: Optional[torch.Tensor] = None
-    counters: Optional[torch.Tensor] = None
-    spec: Optional["EncoderSpec"] = None
-    batch_size: int = 1
-    n_points: int = 0
-    _argmax: Optional[torch.Tensor] = None
+    """Outputs + saved state of one forward.  ``features`` / ``coords`` are what the modules publish; ``inverse``,
+    ``counts``, ``bn_state``, ``counters`` and ``workspace`` are views into the one scratch allocation of the call and
+    are only materialised when somebody asks for them (they are inspection / backward state, not hot-path outputs)."""
+    __slots__ = ("features", "coords", "argpos", "n_kept", "n_pillars", "spec", "batch_size", "n_points", "train_bn",
+                 "_buf", "_plan", "_argmax", "_views", "params_struct")
+
+    def __init__(self, features, coords, argpos, n_kept, n_pillars, spec, batch_size, n_points, buf, plan, train_bn=False,
+                 params_struct=None):
+        self.features, self.coords, self.argpos = features, coords, argpos
+        self.n_kept, self.n_pillars, self.spec, self.batch_size, self.n_points = n_kept, n_pillars, spec, batch_size, n_points
+        self._buf, self._plan, self.train_bn, self.params_struct = buf, plan, train_bn, params_struct
+        self._argmax, self._views = None, {}
+
+    def without_outputs(self):
+        """Copy for the autograd node: must not reference the node's own outputs (reference cycle => ~1 GB waits for the GC)."""
+        r = EncodeResult(None, None, self.argpos, self.n_kept, self.n_pillars, self.spec, self.batch_size, self.n_points,
+                         self._buf, self._plan, self.train_bn, self.params_struct)
+        return r
+
+    def with_outputs(self, features, coords):
+        r = EncodeResult(features, coords, self.argpos, self.n_kept, self.n_pillars, self.spec, self.batch_size,
+                         self.n_points, self._buf, self._plan, self.train_bn, self.params_struct)
+        r._views = self._views
+        return r
+
+    def _view(self, name, off, nbytes, dtype, narrow):
+        v = self._views.get(name)
+        if v is None:
+            v = self._buf[off:off + nbytes].view(dtype)
+            if narrow is not None:
+                v = v[:narrow]
+            self._views[name] = v
+        return v
+
+    def _state_ptrs(self):
+        """(workspace ptr, workspace bytes, counters ptr, bn_state ptr | None) for the backward call."""
+        base = self._buf.data_ptr()
+        return base, self._plan.ws_bytes, base + self._plan.off_counters, (base + self._plan.off_bn) if self.train_bn else None
+
+    @property
+    def workspace(self) -> torch.Tensor:
+        return self._view("workspace", 0, self._plan.ws_bytes, torch.uint8, None)
+
+    @property
+    def counters(self) -> torch.Tensor:
+        return self._view("counters", self._plan.off_counters, 4 * _lib.RDP_NUM_COUNTERS, torch.int32, None)
+
+    @property
+    def inverse(self) -> torch.Tensor:
+        """(N,) int32: pillar of each KEPT point (torch.unique's inverse, :212)."""
+        return self._view("inverse", self._plan.off_inverse, 4 * (self._plan.cap + 4), torch.int32, self.n_kept)
+
+    @property
+    def counts(self) -> torch.Tensor:
+        return self._view("counts", self._plan.off_counts, 4 * (self._plan.cap + 4), torch.int32, self.n_pillars)
+
+    @property
+    def bn_state(self) -> Optional[torch.Tensor]:
+        if not self.train_bn:
+            return None
+        return self._view("bn_state", self._plan.off_bn, 8 * self._plan.bn_doubles, torch.float64, None)
 
     @property
     def argmax(self) -> Optional[torch.Tensor]:
@@ -100,116 +143,144 @@ class EncodeResult:
             lib = _lib.load()
             out = torch.empty((max(self.n_pillars, 1), self.spec.c_out), dtype=torch.int32, device=self.argpos.device)
             with torch.cuda.device(self.argpos.device):
-                geom, layout = self.spec.geom(self.batch_size), self.spec.layout_struct()
-                _lib.check(lib.rdp_argmax_kept(self.n_points, C.byref(geom), C.byref(layout), _ptr(self.workspace),
-                                               self.workspace.numel(), _ptr(self.counters), _ptr(self.argpos), _ptr(out),
+                base = self._buf.data_ptr()
+                _lib.check(lib.rdp_argmax_kept(self.n_points, C.byref(self._plan.geom), C.byref(self._plan.layout),
+                                               C.c_void_p(base), self._plan.ws_bytes,
+                                               C.c_void_p(base + self._plan.off_counters), _ptr(self.argpos), _ptr(out),
                                                _stream_ptr()), "rdp_argmax_kept")
             self._argmax = out[:self.n_pillars]
         return self._argmax
+
+
+class ExternalState:
+    """Backward state handed around as separate tensors (the torch.library ops return them individually)."""
+    __slots__ = ("argpos", "train_bn", "params_struct", "_plan", "workspace", "counters", "bn_state")
+
+    def __init__(self, spec, batch_size, n_points, argpos, workspace, counters, bn_state):
+        self.argpos, self.workspace, self.counters, self.bn_state = argpos, workspace, counters, bn_state
+        self.train_bn, self.params_struct = bn_state is not None, None
+        self._plan = _plan(spec, int(batch_size), int(n_points), self.train_bn)
+
+    def _state_ptrs(self):
+        return (self.workspace.data_ptr(), self.workspace.numel(), self.counters.data_ptr(),
+                None if self.bn_state is None else self.bn_state.data_ptr())
 
 
 def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
+def _raw_stream(dev_index: int) -> int:
+    try:
+        return torch._C._cuda_getCurrentRawStream(dev_index)
+    except AttributeError:  # pragma: no cover
+        return torch.cuda.current_stream(dev_index).cuda_stream
+
+
 def _stream_ptr():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    return C.c_void_p(_raw_stream(torch.cuda.current_device()))
 
 
-_pinned = {}
+class _Plan:
+    """Everything about a (spec, batch_size, n_points, train_bn) call that does not change from step to step: the ctypes
+    geometry / layout structs, the workspace size and the carving of the call's single scratch allocation
+    [ librdp workspace | counters | bn_state | inverse | counts ]."""
+    __slots__ = ("spec", "geom", "layout", "ws_bytes", "cap", "bn_doubles", "off_counters", "off_bn", "off_inverse",
+                 "off_counts", "total_bytes")
 
 
-def _pinned_counters(device) -> torch.Tensor:
-    key = (device.index, torch.cuda.current_stream().cuda_stream)
-    t = _pinned.get(key)
-    if t is None:
-        t = torch.empty(_lib.RDP_NUM_COUNTERS, dtype=torch.int32).pin_memory()
-        _pinned[key] = t
-    return t
+_plan_cache = {}
 
 
-def _params_struct(spec: EncoderSpec, weight, bias, gamma, beta, running_mean, running_var, train_bn: bool) -> PfnParams:
-    p = PfnParams()
-    p.weight, p.bias = weight.data_ptr(), (bias.data_ptr() if bias is not None else None)
-    p.gamma = gamma.data_ptr() if gamma is not None else None
-    p.beta = beta.data_ptr() if beta is not None else None
-    p.running_mean = running_mean.data_ptr() if running_mean is not None else None
-    p.running_var = running_var.data_ptr() if running_var is not None else None
-    p.eps, p.momentum, p.train_bn = spec.eps, spec.momentum, int(train_bn)
+def _plan(spec: "EncoderSpec", batch_size: int, n0: int, train_bn: bool) -> _Plan:
+    key = (id(spec), batch_size, n0, train_bn)
+    pl = _plan_cache.get(key)
+    if pl is not None and pl.spec is spec:
+        return pl
+    lib = _lib.load()
+    pl = _Plan()
+    pl.spec, pl.geom, pl.layout = spec, spec.geom(batch_size), spec.layout_struct()
+    nbytes = C.c_size_t(0)
+    _lib.check(lib.rdp_workspace_bytes(n0, C.byref(pl.geom), C.byref(pl.layout), C.byref(nbytes)), "rdp_workspace_bytes")
+    up = lambda v: (v + 255) // 256 * 256
+    pl.ws_bytes, pl.cap = up(nbytes.value), max(n0, 1)
+    pl.bn_doubles = int(lib.rdp_bn_state_doubles(C.byref(pl.layout))) if train_bn else 0
+    pl.off_counters = pl.ws_bytes
+    pl.off_bn = pl.off_counters + 256
+    pl.off_inverse = pl.off_bn + up(8 * pl.bn_doubles)
+    pl.off_counts = pl.off_inverse + up(4 * (pl.cap + 4))
+    pl.total_bytes = pl.off_counts + up(4 * (pl.cap + 4))
+    if len(_plan_cache) > 512:
+        _plan_cache.clear()
+    _plan_cache[key] = pl
+    return pl
+
+
+_prm_cache = {}
+
+
+def _params_struct(spec: "EncoderSpec", weight, bias, gamma, beta, running_mean, running_var, train_bn: bool,
+                   num_batches_tracked=None) -> PfnParams:
+    """ctypes parameter struct for these tensors, cached by their addresses (they rarely move between steps)."""
+    key = (weight.data_ptr(), 0 if bias is None else bias.data_ptr(), 0 if gamma is None else gamma.data_ptr(),
+           0 if beta is None else beta.data_ptr(), 0 if running_mean is None else running_mean.data_ptr(),
+           0 if running_var is None else running_var.data_ptr(), bool(train_bn),
+           0 if num_batches_tracked is None else num_batches_tracked.data_ptr(), spec.eps, spec.momentum)
+    p = _prm_cache.get(key)
+    if p is None:
+        p = PfnParams()
+        p.weight, p.bias, p.gamma, p.beta = key[0], key[1] or None, key[2] or None, key[3] or None
+        p.running_mean, p.running_var = key[4] or None, key[5] or None
+        p.eps, p.momentum, p.train_bn = spec.eps, spec.momentum, int(train_bn)
+        p.num_batches_tracked = key[7] or None
+        if len(_prm_cache) > 512:
+            _prm_cache.clear()
+        _prm_cache[key] = p
     return p
 
 
 def _check_param(t: Optional[torch.Tensor], shape, name: str):
     if t is None:
         return None
-    if not t.is_cuda or t.dtype != torch.float32 or tuple(t.shape) != tuple(shape):
+    if not t.is_cuda or t.dtype != torch.float32 or tuple(t.shape) != tuple(shape) or not t.is_contiguous():
+        if t.is_cuda and t.dtype == torch.float32 and tuple(t.shape) == tuple(shape):
+            return t.detach().contiguous()
         raise ValueError(f"{name}: expected a CUDA float32 tensor of shape {tuple(shape)}, got {t.dtype} {tuple(t.shape)} on {t.device}")
-    return t.detach().contiguous() if not t.is_contiguous() else t.detach()
+    return t
 
 
-@dataclass
 class PendingEncode:
-    """Kernels of one forward have been enqueued on `stream`; `finish` waits for the 64-byte (N, P) publication."""
-    spec: EncoderSpec
-    batch_size: int
-    n_points: int
-    points: torch.Tensor
-    coords: torch.Tensor
-    inverse: torch.Tensor
-    counts: torch.Tensor
-    features: torch.Tensor
-    argpos: Optional[torch.Tensor]
-    bn_state: Optional[torch.Tensor]
-    workspace: torch.Tensor
-    counters: torch.Tensor
-    host: torch.Tensor
-    event: "torch.cuda.Event"
-    stream: "torch.cuda.Stream"
-    train_bn: bool = False
+    """Kernels of one forward have been enqueued on the current stream; `finish` waits for the early (N, P) publication."""
+    __slots__ = ("spec", "batch_size", "n_points", "points", "coords", "features", "argpos", "buf", "plan", "host", "event",
+                 "train_bn", "prm")
 
 
 _host_pool = {}
 
 
-def _take_host(device, stream):
-    """A (pinned counters buffer, CUDA event) pair; the event exists (has been recorded once) so that librdp can record
-    it by handle from inside rdp_index_fwd_publish."""
-    pool = _host_pool.setdefault(device.index, [])
+def _take_host(dev_index: int, stream_handle: int):
+    """A (pinned counters buffer, its numpy view, CUDA event) triple; the event exists (has been recorded once) so that
+    librdp can record it by handle from inside the forward call."""
+    pool = _host_pool.get(dev_index)
     if pool:
         return pool.pop()
     host = torch.empty(_lib.RDP_NUM_COUNTERS, dtype=torch.int32).pin_memory()
     event = torch.cuda.Event()
-    event.record(stream)
-    return host, event
-
-
-_struct_cache = {}
-
-
-def _structs(spec: EncoderSpec, batch_size: int, n0: int):
-    """ctypes geometry / layout structs and the workspace size for (spec, batch_size, n0), cached."""
-    key = (spec, batch_size, n0)
-    hit = _struct_cache.get(key)
-    if hit is None:
-        lib = _lib.load()
-        geom, layout = spec.geom(batch_size), spec.layout_struct()
-        nbytes = C.c_size_t(0)
-        _lib.check(lib.rdp_workspace_bytes(n0, C.byref(geom), C.byref(layout), C.byref(nbytes)), "rdp_workspace_bytes")
-        if len(_struct_cache) > 256:
-            _struct_cache.clear()
-        hit = _struct_cache[key] = (geom, layout, nbytes.value)
-    return hit
+    event.record(torch.cuda.current_stream(dev_index))
+    return host, host.numpy(), event
 
 
 def encode_launch(points: torch.Tensor, spec: EncoderSpec, batch_size: int, weight, bias, gamma, beta, running_mean,
-                  running_var, train_bn: bool, want_argmax: bool) -> PendingEncode:
-    """Enqueues index + PFN forward on the current stream and returns without synchronising."""
+                  running_var, train_bn: bool, want_argmax: bool, num_batches_tracked=None) -> PendingEncode:
+    """Enqueues index + PFN forward on the current stream (one call into librdp) and returns without synchronising."""
     lib = _lib.load()
     if not points.is_cuda:
         raise _lib.RdpError("the pillar encoder has no CPU path: `points` must be a CUDA tensor")
     if points.dim() != 2 or points.shape[1] != spec.cols:
         raise ValueError(f"points must be (N, {spec.cols}), got {tuple(points.shape)}")
-    pts = points.detach()
+    pts = points
+    if pts.requires_grad:
+        pts = pts.detach()
     if pts.dtype != torch.float32:
         pts = pts.float()
     if not pts.is_contiguous() or pts.data_ptr() % 16:
@@ -224,51 +295,50 @@ def encode_launch(points: torch.Tensor, spec: EncoderSpec, batch_size: int, weig
     running_mean = _check_param(running_mean, (spec.c_out,), "norm.running_mean")
     running_var = _check_param(running_var, (spec.c_out,), "norm.running_var")
     train_bn = bool(train_bn and use_norm)
+    batch_size = int(batch_size)
+    pl = _plan(spec, batch_size, int(n0), train_bn)
 
-    with torch.cuda.device(dev):
-        geom, layout, ws_bytes = _structs(spec, int(batch_size), int(n0))
-        nbytes = C.c_size_t(ws_bytes)
-        cap = max(n0, 1)
-        ws = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
-        coords = torch.empty((cap, spec.coord_cols), dtype=torch.int32, device=dev)
-        inverse = torch.empty(cap + 4, dtype=torch.int32, device=dev)
-        counts = torch.empty(cap + 4, dtype=torch.int32, device=dev)
-        counters = torch.empty(_lib.RDP_NUM_COUNTERS, dtype=torch.int32, device=dev)
-        features = torch.empty((cap, spec.c_out), dtype=torch.float32, device=dev)
-        argpos = torch.empty((cap, spec.c_out), dtype=torch.int32, device=dev) if want_argmax else None
-        bn_state = None
-        if train_bn:
-            bn_state = torch.zeros(int(lib.rdp_bn_state_doubles(C.byref(layout))), dtype=torch.float64, device=dev)
-        stream = torch.cuda.current_stream()
-        st = C.c_void_p(stream.cuda_stream)
+    switch = torch.cuda.current_device() != dev.index
+    if switch:
+        prev = torch.cuda.current_device()
+        torch.cuda.set_device(dev)
+    try:
+        buf = torch.empty(pl.total_bytes, dtype=torch.uint8, device=dev)
+        coords = torch.empty((pl.cap, spec.coord_cols), dtype=torch.int32, device=dev)
+        features = torch.empty((pl.cap, spec.c_out), dtype=torch.float32, device=dev)
+        argpos = torch.empty((pl.cap, spec.c_out), dtype=torch.int32, device=dev) if want_argmax else None
+        st = _raw_stream(dev.index)
         # (N, P) are published to pinned host memory (zero-copy kernel store: never queues behind bulk DMA) right after
         # the bitmap scan, and `event` is recorded there: encode_finish returns while the rest of the forward still runs
-        host, event = _take_host(dev, stream)
-        _lib.check(lib.rdp_index_fwd_publish(_ptr(pts), n0, C.byref(geom), spec.coord_cols, _ptr(ws), nbytes.value,
-                                             _ptr(coords), _ptr(inverse), _ptr(counts), _ptr(counters),
-                                             C.c_void_p(host.data_ptr()), C.c_void_p(event.cuda_event), st),
-                   "rdp_index_fwd_publish")
-        prm = _params_struct(spec, weight, bias, gamma, beta, running_mean, running_var, train_bn)
-        _lib.check(lib.rdp_pfn_fwd(_ptr(pts), n0, C.byref(geom), C.byref(layout), C.byref(prm), _ptr(ws), nbytes.value,
-                                   _ptr(counters), _ptr(features), _ptr(argpos), None, _ptr(bn_state), st), "rdp_pfn_fwd")
-    return PendingEncode(spec=spec, batch_size=int(batch_size), n_points=int(n0), points=pts, coords=coords, inverse=inverse,
-                         counts=counts, features=features, argpos=argpos, bn_state=bn_state, workspace=ws, counters=counters,
-                         host=host, event=event, stream=stream, train_bn=train_bn)
+        host, host_np, event = _take_host(dev.index, st)
+        prm = _params_struct(spec, weight, bias, gamma, beta, running_mean, running_var, train_bn,
+                             num_batches_tracked if train_bn else None)
+        base = buf.data_ptr()
+        _lib.check(lib.rdp_encode_fwd(pts.data_ptr(), n0, C.byref(pl.geom), C.byref(pl.layout), C.byref(prm), base, pl.ws_bytes,
+                                      coords.data_ptr(), base + pl.off_inverse, base + pl.off_counts, base + pl.off_counters,
+                                      features.data_ptr(), None if argpos is None else argpos.data_ptr(),
+                                      (base + pl.off_bn) if train_bn else None, host.data_ptr(), event.cuda_event, st),
+                   "rdp_encode_fwd")
+    finally:
+        if switch:
+            torch.cuda.set_device(prev)
+    p = PendingEncode()
+    p.spec, p.batch_size, p.n_points, p.points, p.coords, p.features, p.argpos = spec, batch_size, int(n0), pts, coords, features, argpos
+    p.buf, p.plan, p.host, p.event, p.train_bn, p.prm = buf, pl, (host, host_np), event, train_bn, prm
+    return p
 
 
 def encode_finish(p: PendingEncode) -> EncodeResult:
-    """Waits for the early (N, P) publication -- not for the forward's kernels, which may still be running on
-    `p.stream` -- and narrows the capacity-sized outputs."""
+    """Waits for the early (N, P) publication -- not for the forward's kernels, which may still be running on the
+    launching stream -- and narrows the capacity-sized outputs."""
     p.event.synchronize()
-    hv = p.host.tolist()
-    n_kept, n_pillars, err = hv[_lib.CNT_N], hv[_lib.CNT_P], hv[_lib.CNT_ERRFLAGS]
-    _host_pool.setdefault(p.points.device.index, []).append((p.host, p.event))
+    host, host_np = p.host
+    n_kept, n_pillars, err = int(host_np[_lib.CNT_N]), int(host_np[_lib.CNT_P]), int(host_np[_lib.CNT_ERRFLAGS])
+    _host_pool.setdefault(p.points.device.index, []).append((host, host_np, p.event))
     if err & 1:
         raise ValueError(f"points[:, 0] holds a batch index outside [0, {p.batch_size})")
-    return EncodeResult(features=p.features[:n_pillars], coords=p.coords[:n_pillars], inverse=p.inverse[:n_kept],
-                        counts=p.counts[:n_pillars], argpos=None if p.argpos is None else p.argpos[:n_pillars],
-                        n_kept=n_kept, n_pillars=n_pillars, pillar_mean=None, bn_state=p.bn_state, workspace=p.workspace,
-                        counters=p.counters, spec=p.spec, batch_size=p.batch_size, n_points=p.n_points)
+    return EncodeResult(p.features[:n_pillars], p.coords[:n_pillars], None if p.argpos is None else p.argpos[:n_pillars],
+                        n_kept, n_pillars, p.spec, p.batch_size, p.n_points, p.buf, p.plan, p.train_bn, p.prm)
 
 
 def encode_forward(points: torch.Tensor, spec: EncoderSpec, batch_size: int, weight, bias, gamma, beta, running_mean,
@@ -284,67 +354,79 @@ def encode_backward(points: torch.Tensor, spec: EncoderSpec, batch_size: int, re
     lib = _lib.load()
     dev = points.device
     use_norm = gamma is not None
-    with torch.cuda.device(dev):
-        geom, layout = spec.geom(batch_size), spec.layout_struct()
+    train_bn = bool(train_bn and use_norm)
+    pl = res._plan
+    switch = torch.cuda.current_device() != dev.index
+    if switch:
+        prev = torch.cuda.current_device()
+        torch.cuda.set_device(dev)
+    try:
         d_w = torch.empty((spec.c_out, spec.c_in), dtype=torch.float32, device=dev)
         d_g = torch.empty(spec.c_out, dtype=torch.float32, device=dev) if use_norm else None
         d_b = torch.empty(spec.c_out, dtype=torch.float32, device=dev)
-        g = grad_features.contiguous().float()
-        prm = _params_struct(spec, weight.detach(), None if bias is None else bias.detach(),
-                             None if gamma is None else gamma.detach(), None if beta is None else beta.detach(),
-                             running_mean, running_var, bool(train_bn and use_norm))
-        feats = features if features.is_contiguous() else features.contiguous()
-        _lib.check(lib.rdp_pfn_bwd(_ptr(points), points.shape[0], C.byref(geom), C.byref(layout), C.byref(prm),
-                                   _ptr(res.workspace), res.workspace.numel(), _ptr(res.counters), _ptr(g),
-                                   _ptr(feats), _ptr(res.argpos), _ptr(res.bn_state), _ptr(d_w),
-                                   _ptr(d_g), _ptr(d_b), _stream_ptr()), "rdp_pfn_bwd")
+        g = grad_features
+        if g.dtype != torch.float32 or not g.is_contiguous():
+            g = g.contiguous().float()
+        prm = res.params_struct
+        if prm is None or bool(prm.train_bn) != train_bn:
+            prm = _params_struct(spec, weight, bias, gamma, beta, running_mean, running_var, train_bn)
+        ws_ptr, ws_bytes, cnt_ptr, bn_ptr = res._state_ptrs()
+        _lib.check(lib.rdp_pfn_bwd(points.data_ptr(), points.shape[0], C.byref(pl.geom), C.byref(pl.layout), C.byref(prm),
+                                   ws_ptr, ws_bytes, cnt_ptr, g.data_ptr(), None, res.argpos.data_ptr(), bn_ptr, d_w.data_ptr(),
+                                   None if d_g is None else d_g.data_ptr(), d_b.data_ptr(), _raw_stream(dev.index)),
+                   "rdp_pfn_bwd")
+    finally:
+        if switch:
+            torch.cuda.set_device(prev)
     return d_w, d_g, d_b
 
 
 class _PillarEncodeFn(torch.autograd.Function):
     """Autograd node: saves (points, argpos, BN state, workspace) -- never the (N, C) activations.  The forward kernels
-    were already enqueued (``pending``); this only waits for them and wires up the backward."""
+    were already enqueued (``pending``); this only waits for the (N, P) publication and wires up the backward."""
 
     @staticmethod
     def forward(ctx, weight, bias, gamma, beta, running_mean, running_var, pending, holder):
         res = encode_finish(pending)
         holder.append(res)
         # the node must not reference its own outputs (reference cycle => the ~1 GB of state would wait for the GC)
-        ctx.res = dataclasses.replace(res, features=None, coords=None)
+        ctx.res = res.without_outputs()
         ctx.spec, ctx.batch_size, ctx.train_bn = pending.spec, pending.batch_size, pending.train_bn
         ctx.points = pending.points
-        ctx.save_for_backward(weight, bias, gamma, beta, res.features)
+        ctx.save_for_backward(weight, bias, gamma, beta)
         ctx.rm, ctx.rv = running_mean, running_var
         ctx.mark_non_differentiable(res.coords)
         return res.features, res.coords
 
     @staticmethod
     def backward(ctx, grad_features, _grad_coords):
-        weight, bias, gamma, beta, features = ctx.saved_tensors
+        weight, bias, gamma, beta = ctx.saved_tensors
         res = ctx.res
         if res.argpos is None:
             raise RuntimeError("backward through a forward that ran without requires_grad parameters")
-        d_w, d_g, d_b = encode_backward(ctx.points, ctx.spec, ctx.batch_size, res, features, grad_features, weight, bias,
+        d_w, d_g, d_b = encode_backward(ctx.points, ctx.spec, ctx.batch_size, res, None, grad_features, weight, bias,
                                         gamma, beta, ctx.rm, ctx.rv, ctx.train_bn)
         use_norm = gamma is not None
         return (d_w, (None if use_norm else d_b), d_g, (d_b if use_norm else None), None, None, None, None)
 
 
-@dataclass
 class PendingModuleEncode:
-    pending: PendingEncode
-    params: tuple
-    needs_grad: bool
+    __slots__ = ("pending", "params", "needs_grad")
+
+    def __init__(self, pending, params, needs_grad):
+        self.pending, self.params, self.needs_grad = pending, params, needs_grad
 
 
 def encode_async(points, spec: EncoderSpec, batch_size: int, weight, bias=None, gamma=None, beta=None, running_mean=None,
-                 running_var=None, train_bn: bool = False) -> PendingModuleEncode:
+                 running_var=None, train_bn: bool = False, num_batches_tracked=None) -> PendingModuleEncode:
     """Enqueues a (differentiable) encode on the current stream; pair with ``encode_wait``."""
     if points.requires_grad:
         raise NotImplementedError("gradients w.r.t. points are not produced (points are a leaf in the reference)")
-    needs_grad = torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in (weight, bias, gamma, beta))
+    needs_grad = torch.is_grad_enabled() and (weight.requires_grad or (bias is not None and bias.requires_grad) or
+                                              (gamma is not None and gamma.requires_grad) or
+                                              (beta is not None and beta.requires_grad))
     pending = encode_launch(points, spec, batch_size, weight, bias, gamma, beta, running_mean, running_var, train_bn,
-                            want_argmax=needs_grad)
+                            want_argmax=needs_grad, num_batches_tracked=num_batches_tracked)
     return PendingModuleEncode(pending, (weight, bias, gamma, beta, running_mean, running_var), needs_grad)
 
 
@@ -352,7 +434,7 @@ def encode_wait(pm: PendingModuleEncode) -> EncodeResult:
     if pm.needs_grad:
         holder = []
         feats, coords = _PillarEncodeFn.apply(*pm.params, pm.pending, holder)
-        return dataclasses.replace(holder[0], features=feats, coords=coords)
+        return holder[0].with_outputs(feats, coords)
     return encode_finish(pm.pending)
 
 

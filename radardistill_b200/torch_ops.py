@@ -21,7 +21,7 @@ from typing import List, Optional, Tuple
 import torch
 
 from . import ops
-from .ops import EncoderSpec, EncodeResult
+from .ops import EncoderSpec
 
 
 def spec_to_lists(spec: EncoderSpec) -> Tuple[List[int], List[float]]:
@@ -52,9 +52,11 @@ def pillar_encode(points: torch.Tensor, weight: torch.Tensor, bias: Optional[tor
     rm = running_mean.clone() if running_mean is not None else None   # the kernels update their copies in train mode
     rv = running_var.clone() if running_var is not None else None
     r = ops.encode_forward(points, spec, batch_size, weight, bias, gamma, beta, rm, rv, train_bn, want_argmax)
-    return (r.features, r.coords, r.inverse, r.counts,
+    # ops.encode_forward carves inverse / counts / counters / bn_state out of the call's one scratch allocation; custom-op
+    # outputs must not alias each other, so the small ones are copied and the allocation itself is the `workspace` output
+    return (r.features, r.coords, r.inverse.clone(), r.counts.clone(),
             r.argpos if r.argpos is not None else _empty(dev, torch.int32),
-            r.bn_state if r.bn_state is not None else _empty(dev, torch.float64), r.workspace, r.counters,
+            r.bn_state.clone() if r.bn_state is not None else _empty(dev, torch.float64), r._buf, r.counters.clone(),
             rm if rm is not None else _empty(dev), rv if rv is not None else _empty(dev))
 
 
@@ -80,9 +82,8 @@ def pillar_encode_backward(points: torch.Tensor, grad_features: torch.Tensor, fe
                            running_mean: Optional[torch.Tensor], running_var: Optional[torch.Tensor], spec_ints: List[int],
                            spec_floats: List[float], batch_size: int, train_bn: bool) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
     spec = spec_from_lists(spec_ints, spec_floats)
-    res = EncodeResult(features=features, coords=None, inverse=None, counts=None, argpos=argpos, n_kept=0,
-                       n_pillars=int(features.shape[0]), bn_state=bn_state if bn_state.numel() else None, workspace=workspace,
-                       counters=counters, spec=spec, batch_size=batch_size, n_points=int(points.shape[0]))
+    res = ops.ExternalState(spec, batch_size, int(points.shape[0]), argpos, workspace, counters,
+                            bn_state if bn_state.numel() else None)
     d_w, d_g, d_b = ops.encode_backward(points, spec, batch_size, res, features, grad_features, weight, bias, gamma, beta,
                                         running_mean, running_var, train_bn)
     return d_w, (d_g if d_g is not None else _empty(points.device)), d_b

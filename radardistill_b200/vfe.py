@@ -125,7 +125,8 @@ class _FusedDynamicPillarVFE(VFETemplate):
                               bias=None if self.use_norm else pfn.linear.bias,
                               gamma=norm.weight if norm is not None else None, beta=norm.bias if norm is not None else None,
                               running_mean=norm.running_mean if norm is not None else None,
-                              running_var=norm.running_var if norm is not None else None, train_bn=train_bn)
+                              running_var=norm.running_var if norm is not None else None, train_bn=train_bn,
+                              num_batches_tracked=norm.num_batches_tracked if train_bn else None)
         return pm, train_bn
 
     def finish(self, batch_dict, token):
@@ -135,7 +136,8 @@ class _FusedDynamicPillarVFE(VFETemplate):
             if res.n_kept == 1:
                 raise ValueError(f"Expected more than 1 value per channel when training, got input size "
                                  f"torch.Size([1, {self.spec.c_out}])")
-            self.pfn_layers[0].norm.num_batches_tracked.add_(1)
+            if res.n_points == 0:   # no kernel ran; otherwise bn_finalize_kernel has counted the batch (BatchNorm1d, :29)
+                self.pfn_layers[0].norm.num_batches_tracked.add_(1)
         self.last_result = res
         for k in self._feature_keys:
             batch_dict[k] = res.features
