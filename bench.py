@@ -200,7 +200,7 @@ def build_modules(device, mode, ddp):
 
     pair = PairedEncoders(lid, rad, lidar_no_grad=(mode == "A"))
     call = pair
-    if ddp:
+    if ddp == "ddp":
         from torch.nn.parallel import DistributedDataParallel as DDP
         call = DDP(pair, device_ids=[device.index], gradient_as_bucket_view=True)   # one reducer / one bucket for all PFN parameters
     return lid, rad, call
@@ -222,6 +222,8 @@ def gpu_step(call, lidar_dev, radar_dev, mode, frames, upstream):
         outs.append(bd["pillar_features"])
         grads.append(upstream["lidar"][:outs[1].shape[0]])
     torch.autograd.backward(outs, grads)
+    if upstream.get("reducer") is not None:   # the step's one collective: gradient all-reduce of the PFN parameters
+        upstream["reducer"].reduce()
     return bd
 
 
@@ -255,10 +257,13 @@ def run_ours(args):
     mode, frames = args.mode, FRAMES_PER_GPU
     lidar, radar = make_clouds(rank, frames)
     n_rows = len(lidar) + len(radar)
-    lid, rad, call = build_modules(device, mode, ddp)
+    lid, rad, call = build_modules(device, mode, args.dp if ddp else False)
     lidar_dev, radar_dev = torch.from_numpy(lidar).to(device), torch.from_numpy(radar).to(device)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
     upstream = make_upstream(device, len(lidar), len(radar), list(lid.parameters()) + list(rad.parameters()))
+    if ddp and args.dp == "lean":
+        from radardistill_b200.sharding import GradientAllReduce
+        upstream["reducer"] = GradientAllReduce(upstream["params"])
 
     def barrier():
         if ddp:
@@ -473,7 +478,10 @@ def run_ours(args):
         line = {"metric": "pillar-encoder points/s (fwd+bwd)", "value": value, "unit": "points/s", "n_gpus": world,
                 "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": step_ms, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": workload_config(mode, frames, len(lidar), len(radar)), "e2e": e2e, "e2e_host_outputs": e2e_out,
+                "config": dict(workload_config(mode, frames, len(lidar), len(radar)),
+                               data_parallel=("none" if not ddp else ("GradientAllReduce: one NCCL all_reduce of the flat PFN gradients "
+                                              "per step" if args.dp == "lean" else "torch DistributedDataParallel"))),
+                "e2e": e2e, "e2e_host_outputs": e2e_out,
                 "gpu_launches": launches,
                 "clocks": clk.summary(), "roofline": roof, "cpu_baseline": cpu, "wall_s_timed_region": wall}
         line.update(extra)
@@ -490,6 +498,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default="B", choices=["A", "B"])
+    ap.add_argument("--dp", default="lean", choices=["lean", "ddp"],
+                    help="N > 1: gradient all-reduce by radardistill_b200.sharding.GradientAllReduce (one all_reduce of a flat "
+                         "buffer per step) or by torch DistributedDataParallel")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

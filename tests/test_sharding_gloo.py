@@ -56,6 +56,15 @@ def _worker(rank, world, port, global_batch, out_q):
         g = torch.from_numpy(b["d_weight"].copy())
         dist.all_reduce(g)
         g /= world
+        # the package's reducer: one all-reduce of the flat PFN gradients, p.grad <- average over ranks
+        w = torch.nn.Parameter(torch.zeros(32, 15)); gm = torch.nn.Parameter(torch.zeros(32)); frozen = torch.nn.Parameter(torch.zeros(3), requires_grad=False)
+        w.grad = torch.full((32, 15), float(rank + 1)); gm.grad = torch.arange(32, dtype=torch.float32) * (rank + 1)
+        red = sharding.GradientAllReduce([w, gm, frozen])
+        red.reduce()
+        assert red.flat.numel() == 32 * 15 + 32
+        assert torch.equal(w.grad, torch.full((32, 15), (1 + world) / 2.0))
+        assert torch.allclose(gm.grad, torch.arange(32, dtype=torch.float32) * (1 + world) / 2.0)
+        assert w.grad.data_ptr() == red.flat.data_ptr()   # gradients are views of the flat buffer
         # max-over-ranks timing, as bench.py reports it
         t = torch.tensor([0.010 * (rank + 1)], dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
