@@ -46,6 +46,8 @@ constexpr int kMaxCout = 64;
 constexpr int kCntTicketA = 4;   // bitmap scan ticket
 constexpr int kCntTicketB = 5;   // count scan ticket
 constexpr int kCntPfnBlocks = 6; // blocks used by the last stats launch
+constexpr int kCntDoneStats = 8; // CTAs of bn_finalize_kernel that have reduced their chunk (reset by the last one)
+constexpr int kCntDoneBwd = 9;   // same for bwd_finalize_kernel
 
 // ----------------------------------------------------------------------------- workspace layout
 struct Workspace {

@@ -66,24 +66,6 @@ __global__ void argpos_to_kept_kernel(const int32_t *__restrict__ argpos, const 
     }
 }
 
-// Sums the per-CTA partial vectors partials[b][e] over b in a fixed order (deterministic): lane = element,
-// warp w adds CTAs w, w+8, ..., then the 8 warp sums are combined in warp order.
-__global__ void __launch_bounds__(256) reduce_partials_kernel(const double *__restrict__ partials, int nblocks, int el,
-                                                             double *__restrict__ totals) {
-    __shared__ double sm[8][32];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, e = blockIdx.x * 32 + lane;
-    double acc = 0.0;
-    if (e < el)
-        for (int b = warp; b < nblocks; b += 8) acc += partials[(size_t)b * el + e];
-    sm[warp][lane] = acc;
-    __syncthreads();
-    if (warp == 0 && e < el) {
-        double t = 0.0;
-        for (int w = 0; w < 8; ++w) t += sm[w][lane];
-        totals[e] = t;
-    }
-}
-
 // scatter_mean's (P, 3) output (:226) for callers that want it: the first three columns of the pillar table
 __global__ void table_to_mean_kernel(const float *__restrict__ aux, const int32_t *__restrict__ counters, float *__restrict__ out) {
     const long long total = 3ll * counters[RDP_CNT_P];
@@ -128,8 +110,8 @@ extern "C" int rdp_pfn_fwd(const float *points, int64_t n_points, const rdp_geom
     if (train) {
         if (L->stats_partial_doubles > ws.partial_doubles_per_block) return RDP_ERR_WORKSPACE;
         RDP_CUDA_OK(L->tile(a, PFN_MODE_STATS, grid, st));
-        reduce_partials_kernel<<<(L->stats_partial_doubles + 31) / 32, 256, 0, st>>>(ws.partials, grid, L->stats_partial_doubles, ws.totals);
-        RDP_CUDA_OK(L->bn_finalize(a, ws.totals, bn_state, prm->running_mean, prm->running_var, prm->momentum,
+        RDP_CUDA_OK(L->bn_finalize(a, ws.partials, grid, ws.totals, const_cast<int32_t *>(counters) + kCntDoneStats, bn_state,
+                                   prm->running_mean, prm->running_var, prm->momentum,
                                    reinterpret_cast<long long *>(prm->num_batches_tracked), st));
         a.bn_state = bn_state;
         a.fold_from_state = 1;
@@ -187,8 +169,8 @@ extern "C" int rdp_pfn_bwd(const float *points, int64_t n_points, const rdp_geom
         grid = kBwdGrid;   // persistent: every warp streams a contiguous pillar range (P is only known on the device)
         RDP_CUDA_OK(L->bwd_stream(a, grid, st));
     }
-    reduce_partials_kernel<<<(L->bwd_partial_doubles + 31) / 32, 256, 0, st>>>(ws.partials, grid, L->bwd_partial_doubles, ws.totals);
-    RDP_CUDA_OK(L->bwd_finalize(a, ws.totals, bn_state, train ? 1 : 0, d_weight, d_gamma, d_beta, st));
+    RDP_CUDA_OK(L->bwd_finalize(a, ws.partials, grid, ws.totals, const_cast<int32_t *>(counters) + kCntDoneBwd, bn_state,
+                                train ? 1 : 0, d_weight, d_gamma, d_beta, st));
     return RDP_OK;
 }
 

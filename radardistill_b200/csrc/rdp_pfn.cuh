@@ -593,18 +593,52 @@ __global__ void __launch_bounds__(kPfnThreads, (MODE == PFN_MODE_APPLY) ? 5 : 4)
 }
 
 // ------------------------------------------------------------------------------------------- BN finalize (train)
+// Fixed-order sum of the per-CTA partial vectors (deterministic): CTA b of the launch owns elements [32 b, 32 b + 32);
+// lane = element, warp w adds producer CTAs w, w + 8, ..., the 8 warp sums are combined in warp order.  Returns true in
+// the CTA that finishes last (ticket counter `done`, reset for the next launch): `totals` is then complete and that CTA
+// goes on to the closed-form epilogue -- one launch instead of a reduction kernel followed by a finalize kernel.
+__device__ __forceinline__ bool reduce_partials_last(const double *__restrict__ partials, int nblocks, int el, double *__restrict__ totals,
+                                                     int32_t *done) {
+    __shared__ double sm[8][32];
+    __shared__ int s_last;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, e = blockIdx.x * 32 + lane;
+    double acc = 0.0;
+    if (e < el)
+        for (int b = warp; b < nblocks; b += 8) acc += partials[(size_t)b * el + e];
+    sm[warp][lane] = acc;
+    __syncthreads();
+    if (warp == 0 && e < el) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += sm[w][lane];
+        totals[e] = t;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int ticket = atomicAdd(done, 1);
+        s_last = (ticket == (int)gridDim.x - 1);
+        if (s_last) *done = 0;
+    }
+    __syncthreads();
+    if (s_last) __threadfence();
+    return s_last != 0;
+}
+
 // Reduces the per-CTA partials in a fixed order (deterministic), folds the batch statistics into scale/shift,
 // updates the running statistics, and expands the feature moments for the backward.
 // bn_state = [mean(COUT) | var(COUT) | scale(COUT) | shift(COUT) | n | S1(CIN) | S2(CIN*CIN)]
 template <class Cfg>
-__global__ void __launch_bounds__(256) bn_finalize_kernel(const __grid_constant__ PfnArgs a, const double *totals, double *bn_state,
+__global__ void __launch_bounds__(256) bn_finalize_kernel(const __grid_constant__ PfnArgs a, const double *partials, int nblocks,
+                                                         double *totals, int32_t *done, double *bn_state,
                                                          float *running_mean, float *running_var, double momentum,
                                                          long long *num_batches_tracked) {
     constexpr int COUT = Cfg::COUT, CS = Cfg::CS, TOT = Cfg::STATS_DOUBLES, T4 = Cfg::T4;
     __shared__ double tot[TOT];
+    __shared__ double part_m[COUT][8], part_e[COUT][8];
     const int tid = threadIdx.x;
+    if (!reduce_partials_last(partials, nblocks, TOT, totals, done)) return;
     const long long N = a.counters[RDP_CNT_N];
-    for (int e = tid; e < TOT; e += blockDim.x) tot[e] = totals[e];  // reduce_partials_kernel's fixed-order sums
+    for (int e = tid; e < TOT; e += blockDim.x) tot[e] = totals[e];
     __syncthreads();
     const int cin = a.c_in;
     // Gram entry of super features (fa <= fb): block (fa/4, fb/4), element (fa%4, fb%4); column CS is the ones column
@@ -613,25 +647,34 @@ __global__ void __launch_bounds__(256) bn_finalize_kernel(const __grid_constant_
         const int blk = ba * T4 - ba * (ba - 1) / 2 + (bb - ba);
         return tot[blk * 16 + (fa % 4) * 4 + (fb % 4)];
     };
+    // batch moments of x = W f from the feature moments (oracle: orc_bn_batch_stats_moments):
+    //   mean_c = w_c . S1 / n,  E[x^2]_c = w_c^T S2 w_c / n,  var_c = E[x^2]_c - mean_c^2  (biased)
+    // 8 threads per channel take the rows fa = j, j + 8, ... of the quadratic form; the 8 partial sums are added in order.
+    for (int item = tid; item < COUT * 8; item += blockDim.x) {
+        const int c = item >> 3, j = item & 7;
+        double m = 0.0, e2 = 0.0;
+        for (int fa = j; fa < CS; fa += 8) {
+            const int ka = a.kmap[fa];
+            if (ka < 0) continue;
+            const double wa = (double)a.weight[c * cin + ka];
+            m += wa * gram_at(fa, CS);
+            double row = 0.0;
+            for (int fb = 0; fb < CS; ++fb) {
+                const int kb = a.kmap[fb];
+                if (kb >= 0) row += (fa <= fb ? gram_at(fa, fb) : gram_at(fb, fa)) * (double)a.weight[c * cin + kb];
+            }
+            e2 += wa * row;
+        }
+        part_m[c][j] = m;
+        part_e[c][j] = e2;
+    }
+    __syncthreads();
     if (tid < COUT) {
-        // batch moments of x = W f from the feature moments (oracle: orc_bn_batch_stats_moments):
-        //   mean_c = w_c . S1 / n,  E[x^2]_c = w_c^T S2 w_c / n,  var_c = E[x^2]_c - mean_c^2  (biased)
         const double n = (double)N;
         double mean = 0.0, var = 0.0;
         if (N > 0) {
             double m = 0.0, e2 = 0.0;
-            for (int fa = 0; fa < CS; ++fa) {
-                const int ka = a.kmap[fa];
-                if (ka < 0) continue;
-                const double wa = (double)a.weight[tid * cin + ka];
-                m += wa * gram_at(fa, CS);
-                double row = 0.0;
-                for (int fb = 0; fb < CS; ++fb) {
-                    const int kb = a.kmap[fb];
-                    if (kb >= 0) row += (fa <= fb ? gram_at(fa, fb) : gram_at(fb, fa)) * (double)a.weight[tid * cin + kb];
-                }
-                e2 += wa * row;
-            }
+            for (int j = 0; j < 8; ++j) { m += part_m[tid][j]; e2 += part_e[tid][j]; }
             mean = __ddiv_rn(m, n);
             var = __dsub_rn(__ddiv_rn(e2, n), __dmul_rn(mean, mean));
             if (!(var > 0.0)) var = 0.0;
@@ -666,13 +709,15 @@ __global__ void __launch_bounds__(256) bn_finalize_kernel(const __grid_constant_
 //   dW_ck    = (gamma_c/sigma_c) [ A_ck - dbeta_c/N S1_k - dgamma_c/N ((S2 w_c)_k - mu_c S1_k)/sigma_c ]   (train)
 //   dW_ck    = (gamma_c/sigma_c) A_ck                                                                    (eval BN)
 template <class Cfg>
-__global__ void __launch_bounds__(256) bwd_finalize_kernel(const __grid_constant__ PfnArgs a, const double *totals, const double *bn_state,
+__global__ void __launch_bounds__(256) bwd_finalize_kernel(const __grid_constant__ PfnArgs a, const double *partials, int nblocks,
+                                                          double *totals, int32_t *done, const double *bn_state,
                                                           int train_bn, float *d_weight, float *d_gamma, float *d_beta) {
     constexpr int COUT = Cfg::COUT, CS = Cfg::CS, PER = Cfg::BWD_PER;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *tot = reinterpret_cast<double *>(smem_raw);  // COUT*PER
     double *dgam = tot + COUT * PER;                       // COUT
     const int tid = threadIdx.x, cin = a.c_in;
+    if (!reduce_partials_last(partials, nblocks, COUT * PER, totals, done)) return;
     for (int e = tid; e < COUT * PER; e += blockDim.x) tot[e] = totals[e];
     __syncthreads();
     const double n = (double)a.counters[RDP_CNT_N];

@@ -12,10 +12,11 @@ struct PfnLaunch {
     cudaError_t (*tile)(const PfnArgs &a, int mode, int grid, cudaStream_t st);
     cudaError_t (*rows)(const PfnArgs &a, int want_arg, int grid, cudaStream_t st);   // pfn_rows_kernel (rdp_pfn_rows.cuh)
     cudaError_t (*bwd_stream)(const PfnArgs &a, int grid, cudaStream_t st);            // pfn_bwd_stream_kernel (rdp_pfn_bwd.cuh)
-    cudaError_t (*bn_finalize)(const PfnArgs &a, const double *totals, double *bn_state, float *rm, float *rv, double momentum,
-                               long long *num_batches_tracked, cudaStream_t st);
-    cudaError_t (*bwd_finalize)(const PfnArgs &a, const double *totals, const double *bn_state, int train_bn, float *dW, float *dg, float *db,
-                                cudaStream_t st);
+    // one launch each: fixed-order reduction of the per-CTA partials, then (last CTA) the closed-form epilogue
+    cudaError_t (*bn_finalize)(const PfnArgs &a, const double *partials, int nblocks, double *totals, int32_t *done, double *bn_state,
+                               float *rm, float *rv, double momentum, long long *num_batches_tracked, cudaStream_t st);
+    cudaError_t (*bwd_finalize)(const PfnArgs &a, const double *partials, int nblocks, double *totals, int32_t *done,
+                                const double *bn_state, int train_bn, float *dW, float *dg, float *db, cudaStream_t st);
 };
 
 // (id, cols, layout, with_distance, c_out) -- one translation unit each (rdp_pfn_inst.cu, -DRDP_CFG_ID=id)

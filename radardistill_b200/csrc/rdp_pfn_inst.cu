@@ -73,17 +73,19 @@ static cudaError_t bwd_stream(const PfnArgs &a, int grid, cudaStream_t st) {
     return cudaGetLastError();
 }
 
-static cudaError_t bn_finalize(const PfnArgs &a, const double *totals, double *bn_state, float *rm, float *rv, double momentum,
-                               long long *num_batches_tracked, cudaStream_t st) {
-    bn_finalize_kernel<Cfg><<<1, 256, 0, st>>>(a, totals, bn_state, rm, rv, momentum, num_batches_tracked);
+static cudaError_t bn_finalize(const PfnArgs &a, const double *partials, int nblocks, double *totals, int32_t *done, double *bn_state,
+                               float *rm, float *rv, double momentum, long long *num_batches_tracked, cudaStream_t st) {
+    bn_finalize_kernel<Cfg><<<(Cfg::STATS_DOUBLES + 31) / 32, 256, 0, st>>>(a, partials, nblocks, totals, done, bn_state, rm, rv,
+                                                                            momentum, num_batches_tracked);
     return cudaGetLastError();
 }
 
 constexpr size_t kBwdFinSmem = sizeof(double) * (Cfg::BWD_DOUBLES + Cfg::COUT);
 
-static cudaError_t bwd_finalize(const PfnArgs &a, const double *totals, const double *bn_state, int train_bn, float *dW, float *dg,
-                                float *db, cudaStream_t st) {
-    bwd_finalize_kernel<Cfg><<<1, 256, kBwdFinSmem, st>>>(a, totals, bn_state, train_bn, dW, dg, db);
+static cudaError_t bwd_finalize(const PfnArgs &a, const double *partials, int nblocks, double *totals, int32_t *done,
+                                const double *bn_state, int train_bn, float *dW, float *dg, float *db, cudaStream_t st) {
+    bwd_finalize_kernel<Cfg><<<(Cfg::BWD_DOUBLES + 31) / 32, 256, kBwdFinSmem, st>>>(a, partials, nblocks, totals, done, bn_state,
+                                                                                     train_bn, dW, dg, db);
     return cudaGetLastError();
 }
 

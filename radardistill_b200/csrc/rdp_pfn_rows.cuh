@@ -248,7 +248,8 @@ __global__ void __launch_bounds__(kRowsThreads, RDP_ROWS_GRID_PER_SM) pfn_rows_k
             const int g = tid / QUADS, q = tid % QUADS;
             const int gr0 = g * RPG;
             uint32_t hw = S.heads[gr0 >> 5] >> (gr0 & 31), lw = S.lasts[gr0 >> 5] >> (gr0 & 31);
-            if (RPG < 32) { hw &= (1u << RPG) - 1u; lw &= (1u << RPG) - 1u; }
+            constexpr uint32_t gmask = RPG < 32 ? ((1u << (RPG & 31)) - 1u) : 0xffffffffu;
+            hw &= gmask; lw &= gmask;
             uint32_t own = hw & ~lw;                                 // heads of multi-row pillars that start in my rows
             bool carry_in = (g == 0) && !(S.heads[0] & 1u);           // the chunk starts inside a pillar: continue it from the carry
             // rows from r through the first last-row flag at or after r; -1 if the pillar is still open at the end of the chunk
