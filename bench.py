@@ -458,8 +458,8 @@ def run_ours(args):
                                   "frac": alg_fwd / ((idx + dur) * 1e-3) / 1e9 / peak},
                 "other_calls": [
                     entry("rdp_index_fwd: 7 index kernels + publish", row_bytes * len(lidar) + 4 * n_kept + n_pil * (4 * spec.coord_cols + 4), idx),
-                    entry("rdp_pfn_fwd train: pfn_tile<STATS> + reduce + bn_finalize + pfn_tile<APPLY_ARG>", alg_train, dur_train, "pfn_train_fwd"),
-                    entry("rdp_pfn_bwd: pfn_tile<BWD> + reduce + bwd_finalize", alg_bwd, dur_bwd, "pfn_tile_bwd")]}
+                    entry("rdp_pfn_fwd train: pfn_tile<STATS> + bn_finalize + pfn_tile<APPLY_ARG>", alg_train, dur_train, "pfn_train_fwd"),
+                    entry("rdp_pfn_bwd: pfn_tile<BWD> + bwd_finalize", alg_bwd, dur_bwd, "pfn_tile_bwd")]}
 
     if rank == 0:
         cpu = None
@@ -471,10 +471,10 @@ def run_ours(args):
             cpu = {"value": v, "unit": "points/s", "cores": cores, "kind": "port",
                    "sample": f"{fr} of the {frames} paired frames ({len(l2)} LiDAR + {len(r2)} radar rows) x 3 steps, C oracle "
                              f"(oracle/pillar_oracle.c), {cores} threads in the per-point loops, {dt:.2f} s/step"}
-        # librdp kernels per step: index 8 (quantise, scan, zero, rank, scan, group, table, publish); forward 4 in train mode
-        # (moments, reduce, finalize, apply) or 1; backward 3 (tile, reduce, finalize).  Radar encoder always trains.
-        launches_lidar = 8 + (4 + 3 if mode == "B" else 1)
-        launches = (launches_lidar + 15) * args.steps
+        # librdp kernels per step: index 8 (quantise, scan, publish, zero, rank, scan, group, table); forward 3 in train mode
+        # (moments, finalize, apply) or 1; backward 2 (tile, finalize).  The radar encoder always trains.
+        launches_lidar = 8 + (3 + 2 if mode == "B" else 1)
+        launches = (launches_lidar + 13) * args.steps
         line = {"metric": "pillar-encoder points/s (fwd+bwd)", "value": value, "unit": "points/s", "n_gpus": world,
                 "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": step_ms, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
