@@ -9,9 +9,10 @@
 // Here a thread owns whole rows (two of them), so the only operand that has to be fetched per FFMA group is a weight
 // quad -- one uniform-address LDS.128 feeds 4 x 2 FFMAs -- and the per-row bookkeeping of the stream disappears:
 //
-//   A  thread t of a 128-thread CTA takes rows t and t + 128 of a 256-row chunk of the pillar-grouped row array:
-//      row (32 B) + its pillar's table entry from global memory (coalesced / L1) -- fetched into registers one chunk
-//      ahead, so the loads fly under the previous chunk's arithmetic -- decorate in registers,
+//   A  thread t of a 128-thread CTA takes rows t and t + 128 of a 256-row window of the pillar-grouped row array.  The
+//      window's rows (+ one row either side) and the table entries of the pillars that intersect it (tile_first gives
+//      the first one) arrive by two TMA bulk copies issued one window ahead, so no thread ever waits on a global
+//      load; decorate in registers,
 //      x_c = sum_k fmaf(W[c][k], f[k], x_c), z_c = max(fma(x_c, scale_c, shift_c), 0) for all channels; pillar head /
 //      last-row flags by warp ballot.  A row that is a whole pillar (two thirds of the LiDAR pillars) stores its
 //      feature row directly (256-bit stores, one full sector each); the other rows go to the smem tile X[row][channel].
@@ -28,30 +29,30 @@
 namespace rdp {
 
 constexpr int kRowsThreads = 128;
-#ifndef RDP_ROWS_R
-#define RDP_ROWS_R 2
-#endif
-constexpr int kRowsPerThread = RDP_ROWS_R;
-constexpr int kRowsChunk = kRowsThreads * kRowsPerThread;
+constexpr int kRowsPerThread = 2;
+constexpr int kRowsChunk = kRowsThreads * kRowsPerThread;   // 256 rows = two PFN tile windows
+static_assert(kRowsChunk == 2 * kPfnWin, "tile_first is indexed per 128-row window");
 #ifndef RDP_ROWS_GRID_PER_SM
-#define RDP_ROWS_GRID_PER_SM 5
+#define RDP_ROWS_GRID_PER_SM 3
 #endif
 constexpr int kRowsGridCap = 148 * RDP_ROWS_GRID_PER_SM;
-#ifndef RDP_ROWS_REGPIPE
-#define RDP_ROWS_REGPIPE 0   // 1: also hold the next chunk's rows / table entries in registers (costs ~36 registers)
-#endif
 
 template <class Cfg, bool ARG>
 struct RowsSmem {
     static constexpr int WS = (Cfg::CS + 2 + 3) / 4 * 4;  // floats per channel: weights | scale | shift | pad
     static constexpr int XS = Cfg::COUT + 4;              // tile row stride: 16-byte stores / loads stay conflict free
+    static constexpr int SROWS = kRowsChunk + 2;          // staged rows: the one in front of the window, the window, the one behind
+    static constexpr int SAUX = kRowsChunk + 2;           // staged table entries: every pillar that intersects the window
+    alignas(128) float rows[2][SROWS * Cfg::RS];
+    alignas(128) float aux[2][SAUX * 8];
     alignas(16) float w[Cfg::COUT * WS];
     alignas(16) float x[kRowsChunk * XS];
-    int gid[kRowsChunk];
+    alignas(8) uint64_t full[2];
+    int pa[2];                                            // first staged pillar of each stage
     int kept[ARG ? kRowsChunk : 1];
     uint32_t heads[kRowsChunk / 32], lasts[kRowsChunk / 32];
-    // running max of a pillar left open at the end of a chunk; double buffered by chunk parity (one group may still be
-    // reading the incoming carry while another writes the outgoing one)
+    // running max of a pillar left open at the end of a window; double buffered by window parity (one group may still
+    // be reading the incoming carry while another writes the outgoing one)
     alignas(16) float carry_v[2][Cfg::COUT];
     alignas(16) int carry_k[2][ARG ? Cfg::COUT : 4], carry_p[2][ARG ? Cfg::COUT : 4];
 };
@@ -64,11 +65,11 @@ __device__ __forceinline__ void st_global_v8(float *p, const float *v) {
 
 template <class Cfg, bool ARG>
 __global__ void __launch_bounds__(kRowsThreads, RDP_ROWS_GRID_PER_SM) pfn_rows_kernel(const __grid_constant__ PfnArgs a) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     using Smem = RowsSmem<Cfg, ARG>;
     Smem &S = *reinterpret_cast<Smem *>(smem_raw);
     constexpr int COUT = Cfg::COUT, CS = Cfg::CS, COLS = Cfg::COLS, RS = Cfg::RS, WS = Smem::WS, XS = Smem::XS;
-    constexpr int NT = kRowsThreads, R = kRowsPerThread, CHUNK = kRowsChunk, WIN = kPfnWin, INF = 0x7fffffff;
+    constexpr int NT = kRowsThreads, R = kRowsPerThread, CHUNK = kRowsChunk, INF = 0x7fffffff;
     constexpr int QUADS = COUT / 4, GROUPS = NT / QUADS, RPG = CHUNK / GROUPS;  // phase B: rows per (row group)
     static_assert(RPG == 8 || RPG == 16 || RPG == 32, "row groups must align with the 32-bit flag words");
     static_assert(COUT % 8 == 0 && COLS <= RS - 2, "layout");
@@ -77,6 +78,11 @@ __global__ void __launch_bounds__(kRowsThreads, RDP_ROWS_GRID_PER_SM) pfn_rows_k
     const int P = a.counters[RDP_CNT_P];
     const bool none_dropped = (N == a.n0);
 
+    if (tid == 0) {
+        mbar_init(&S.full[0], 1);
+        mbar_init(&S.full[1], 1);
+        fence_mbar_init();
+    }
     // ---- weights, folded BatchNorm scale / shift -> smem  (w[c][0..CS) | scale | shift)
     for (int e = tid; e < COUT * WS; e += NT) {
         const int c = e / WS, s = e % WS;
@@ -95,69 +101,53 @@ __global__ void __launch_bounds__(kRowsThreads, RDP_ROWS_GRID_PER_SM) pfn_rows_k
         S.w[e] = v;
     }
 
-    // ---- this CTA's rows: PFN tiles [t_begin, t_end) -> grouped rows [row_begin, row_end), both pillar boundaries
-    const int ntiles = (int)((N + WIN - 1) / WIN);
-    const int per = (ntiles + (int)gridDim.x - 1) / (int)gridDim.x;
-    const int t_begin = min(ntiles, (int)blockIdx.x * per), t_end = min(ntiles, t_begin + per);
+    // ---- this CTA's rows: windows [u_begin, u_end) own the pillars that START in them -> grouped rows
+    //      [row_begin, row_end), both pillar boundaries; they are walked window by window (256-row aligned)
+    const int ntiles = (int)((N + kPfnWin - 1) / kPfnWin);
+    const int nwin = (int)((N + CHUNK - 1) / CHUNK);
+    const int per = (nwin + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int u_begin = min(nwin, (int)blockIdx.x * per), u_end = min(nwin, u_begin + per);
     auto tile_row = [&](int t) -> long long {
         if (t >= ntiles) return N;
         const int pf = a.tile_first[t];
         return pf >= P ? N : (long long)__float_as_int(__ldg(a.aux + (size_t)pf * 8 + 5));
     };
-    const long long row_begin = (t_begin < t_end) ? tile_row(t_begin) : 0, row_end = (t_begin < t_end) ? tile_row(t_end) : 0;
+    const long long row_begin = (u_begin < u_end) ? tile_row(2 * u_begin) : 0, row_end = (u_begin < u_end) ? tile_row(2 * u_end) : 0;
+    const int u0 = (int)(row_begin / CHUNK);                                            // first window holding rows of mine
+    const int u1 = (row_end > row_begin) ? (int)((row_end + CHUNK - 1) / CHUNK) : u0;    // one past the last
 
-    // ---- register pipeline: rows of chunk i+1 are requested before chunk i's arithmetic, their table entries (whose
-    //      address needs the row's pillar id) before chunk i's phase B
-    struct RowIn { float4 v[RS / 4]; int gprev, gnext; };
-    struct AuxIn { float4 m4, c4; };   // [mean x y z | centre x] [centre y | first row | rows | 0]
-    auto fetch_rows = [&](long long c0, int nrow, RowIn (&o)[R]) {
-#pragma unroll
-        for (int i = 0; i < R; ++i) {
-            const int r = tid + i * NT;
-            if (r < nrow) {
-                const long long g = c0 + r;
-                const float4 *src = reinterpret_cast<const float4 *>(a.grows + (size_t)(g + 1) * RS);
-#pragma unroll
-                for (int q = 0; q < RS / 4; ++q) o[i].v[q] = src[q];
-                o[i].gprev = __float_as_int(a.grows[(size_t)g * RS + RS - 1]);   // the row in front of row 0 is a sentinel (pillar -1)
-                o[i].gnext = (g + 1 < N) ? __float_as_int(a.grows[(size_t)(g + 2) * RS + RS - 1]) : -1;
-            }
-        }
+    // thread 0: TMA of window u into stage s.  pa = first pillar staged = the one covering the window's first row.
+    auto issue = [&](int u, int s, int pa) {
+        const long long g0 = (long long)u * CHUNK;
+        const uint32_t nrows = (uint32_t)min((long long)Smem::SROWS, N + 2 - g0);   // array rows g0 .. (row g0 - 1 is the sentinel / neighbour)
+        const uint32_t naux = (uint32_t)min(Smem::SAUX, P - pa);
+        S.pa[s] = pa;
+        mbar_expect_tx(&S.full[s], nrows * RS * 4 + naux * 32);
+        tma_bulk_g2s(S.rows[s], a.grows + (size_t)g0 * RS, nrows * RS * 4, &S.full[s]);
+        tma_bulk_g2s(S.aux[s], a.aux + (size_t)pa * 8, naux * 32, &S.full[s]);
     };
-    auto fetch_aux = [&](int nrow, const RowIn (&in)[R], AuxIn (&o)[R]) {
-#pragma unroll
-        for (int i = 0; i < R; ++i) {
-            if (tid + i * NT < nrow) {
-                const float4 *ax = reinterpret_cast<const float4 *>(a.aux + (size_t)__float_as_int(in[i].v[RS / 4 - 1].w) * 8);
-                o[i].m4 = ax[0];
-                o[i].c4 = ax[1];
-            }
-        }
-    };
-    RowIn nx[R];
-    AuxIn na[R];
-    long long c0 = row_begin;
-    int nrow = (int)min((long long)CHUNK, row_end - c0);
-    if (RDP_ROWS_REGPIPE && c0 < row_end) {
-        fetch_rows(c0, nrow, nx);
-        fetch_aux(nrow, nx, na);
+    auto first_pillar = [&](int u) { return max(min(a.tile_first[2 * u], P) - 1, 0); };
+    int pa_next = 0;
+    if (tid == 0 && u0 < u1) {
+        issue(u0, 0, first_pillar(u0));
+        if (u0 + 1 < u1) pa_next = first_pillar(u0 + 1);
     }
     __syncthreads();
 
-    int par = 0;
-    while (c0 < row_end) {
-        RowIn cur[R];
-        AuxIn ca[R];
-        const long long c1 = c0 + CHUNK;
-        const int nrow1 = (c1 < row_end) ? (int)min((long long)CHUNK, row_end - c1) : 0;
-        if (RDP_ROWS_REGPIPE) {
-#pragma unroll
-            for (int i = 0; i < R; ++i) { cur[i] = nx[i]; ca[i] = na[i]; }
-            if (nrow1) fetch_rows(c1, nrow1, nx);
-        } else {
-            fetch_rows(c0, nrow, cur);
-            fetch_aux(nrow, cur, ca);
+    uint32_t par0 = 0, par1 = 0;
+    for (int u = u0; u < u1; ++u) {
+        const int s = (u - u0) & 1, par = s;
+        if (tid == 0 && u + 1 < u1) {
+            issue(u + 1, s ^ 1, pa_next);
+            if (u + 2 < u1) pa_next = first_pillar(u + 2);
         }
+        if (s == 0) { mbar_wait(&S.full[0], par0); par0 ^= 1; } else { mbar_wait(&S.full[1], par1); par1 ^= 1; }
+        const long long c0 = (long long)u * CHUNK;
+        const int lo = (int)(max(c0, row_begin) - c0), hi = (int)(min(c0 + CHUNK, row_end) - c0);   // my rows of this window
+        const float *srows = S.rows[s];
+        const float *saux = S.aux[s];
+        const int pa = S.pa[s];
+
         // =========================================================================== A: thread = row
         float f[R][Cfg::FW];
         bool valid[R], single[R];
@@ -165,22 +155,26 @@ __global__ void __launch_bounds__(kRowsThreads, RDP_ROWS_GRID_PER_SM) pfn_rows_k
 #pragma unroll
         for (int i = 0; i < R; ++i) {
             const int r = tid + i * NT;
-            valid[i] = r < nrow;
+            valid[i] = r >= lo && r < hi;
             bool head = false, last = false;
             gidv[i] = 0;
             if (valid[i]) {
                 float row[RS];
+                const float4 *src = reinterpret_cast<const float4 *>(srows + (r + 1) * RS);
 #pragma unroll
                 for (int q = 0; q < RS / 4; ++q) {
-                    row[4 * q] = cur[i].v[q].x; row[4 * q + 1] = cur[i].v[q].y; row[4 * q + 2] = cur[i].v[q].z; row[4 * q + 3] = cur[i].v[q].w;
+                    const float4 v = src[q];
+                    row[4 * q] = v.x; row[4 * q + 1] = v.y; row[4 * q + 2] = v.z; row[4 * q + 3] = v.w;
                 }
                 const int gid = __float_as_int(row[RS - 1]);
                 gidv[i] = gid;
-                head = gid != cur[i].gprev;
-                last = gid != cur[i].gnext;
-                const float mean[3] = {ca[i].m4.x, ca[i].m4.y, ca[i].m4.z};
-                decorate<Cfg>(row, ca[i].m4.w, ca[i].c4.x, mean, a, f[i]);
-                S.gid[r] = gid;
+                head = gid != __float_as_int(srows[r * RS + RS - 1]);                       // the row in front (sentinel: pillar -1)
+                last = (c0 + r + 1 >= N) || gid != __float_as_int(srows[(r + 2) * RS + RS - 1]);
+                const float4 *ax = reinterpret_cast<const float4 *>(saux + (gid - pa) * 8);   // [mean x y z | centre x] [centre y | ...]
+                const float4 m4 = ax[0];
+                const float ceny = saux[(gid - pa) * 8 + 4];
+                const float mean[3] = {m4.x, m4.y, m4.z};
+                decorate<Cfg>(row, m4.w, ceny, mean, a, f[i]);
                 if (ARG) {
                     const int orig = __float_as_int(row[RS - 2]);
                     S.kept[r] = none_dropped ? orig : a.orig2kept[orig];
@@ -240,7 +234,6 @@ __global__ void __launch_bounds__(kRowsThreads, RDP_ROWS_GRID_PER_SM) pfn_rows_k
         };
         if (__any_sync(0xffffffffu, valid[R - 1])) linear(std::integral_constant<int, R>{});
         else if (__any_sync(0xffffffffu, valid[0])) linear(std::integral_constant<int, 1>{});
-        if (RDP_ROWS_REGPIPE && nrow1) fetch_aux(nrow1, nx, na);
         __syncthreads();
 
         // =========================================================================== B: thread = (row group, quad)
@@ -251,8 +244,8 @@ __global__ void __launch_bounds__(kRowsThreads, RDP_ROWS_GRID_PER_SM) pfn_rows_k
             constexpr uint32_t gmask = RPG < 32 ? ((1u << (RPG & 31)) - 1u) : 0xffffffffu;
             hw &= gmask; lw &= gmask;
             uint32_t own = hw & ~lw;                                 // heads of multi-row pillars that start in my rows
-            bool carry_in = (g == 0) && !(S.heads[0] & 1u);           // the chunk starts inside a pillar: continue it from the carry
-            // rows from r through the first last-row flag at or after r; -1 if the pillar is still open at the end of the chunk
+            bool carry_in = (g == 0) && lo == 0 && hi > 0 && !(S.heads[0] & 1u);   // the window starts inside a pillar of mine: continue it
+            // rows from r through the first last-row flag at or after r; -1 if the pillar is still open at the end of the window
             auto seg_len = [&](int r) -> int {
                 int w = r >> 5;
                 uint32_t b = S.lasts[w] >> (r & 31);
@@ -283,10 +276,10 @@ __global__ void __launch_bounds__(kRowsThreads, RDP_ROWS_GRID_PER_SM) pfn_rows_k
 #pragma unroll
                     for (int e = 0; e < 4; ++e) { m[e] = ARG ? -1.0f : 0.0f; mk[e] = INF; mp[e] = 0; }
                 }
-                const int pid = S.gid[r];
+                const int pid = __float_as_int(srows[(r + 1) * RS + RS - 1]);
                 int len = seg_len(r);
                 const bool open = len < 0;
-                if (open) len = nrow - r;
+                if (open) len = hi - r;
                 const float *xp = &S.x[r * XS + 4 * q];
                 for (int k = 0; k < len; ++k, xp += XS) {
                     const float4 v = *reinterpret_cast<const float4 *>(xp);
@@ -308,7 +301,7 @@ __global__ void __launch_bounds__(kRowsThreads, RDP_ROWS_GRID_PER_SM) pfn_rows_k
                         for (int e = 0; e < 4; ++e) mp[e] = (m[e] > 0.0f) ? mp[e] : ~mp[e];   // negative: clamped by the ReLU
                         *reinterpret_cast<int4 *>(a.argpos + (size_t)pid * COUT + 4 * q) = make_int4(mp[0], mp[1], mp[2], mp[3]);
                     }
-                } else {   // the pillar continues in the next chunk of this CTA
+                } else {   // the pillar continues in the next window of this CTA
                     *reinterpret_cast<float4 *>(&S.carry_v[par ^ 1][4 * q]) = make_float4(m[0], m[1], m[2], m[3]);
                     if (ARG) {
 #pragma unroll
@@ -318,9 +311,6 @@ __global__ void __launch_bounds__(kRowsThreads, RDP_ROWS_GRID_PER_SM) pfn_rows_k
             }
         }
         __syncthreads();
-        c0 = c1;
-        nrow = nrow1;
-        par ^= 1;
     }
 }
 

@@ -100,7 +100,9 @@ class _FusedDynamicPillarVFE(VFETemplate):
         self.x_offset, self.y_offset, self.z_offset = self.spec.off
         self.scale_xy = int(grid_size[0]) * int(grid_size[1])
         self.scale_y = int(grid_size[1])
-        self.last_result = None  # EncodeResult of the latest forward (inverse / counts / argmax for inspection)
+        # EncodeResult of the latest forward (inverse / counts / argmax for inspection); kept out of nn.Module.__setattr__,
+        # which costs ~15 us per assignment on the hot path
+        object.__setattr__(self, "last_result", None)
 
     def get_output_feature_dim(self):
         return self.num_filters[-1]
@@ -138,7 +140,7 @@ class _FusedDynamicPillarVFE(VFETemplate):
                                  f"torch.Size([1, {self.spec.c_out}])")
             if res.n_points == 0:   # no kernel ran; otherwise bn_finalize_kernel has counted the batch (BatchNorm1d, :29)
                 self.pfn_layers[0].norm.num_batches_tracked.add_(1)
-        self.last_result = res
+        object.__setattr__(self, "last_result", res)
         for k in self._feature_keys:
             batch_dict[k] = res.features
         batch_dict[self._coords_key] = res.coords
@@ -154,14 +156,24 @@ def forward_pair(first, second, batch_dict, side_stream=None, first_no_grad=Fals
     main = torch.cuda.current_stream()
     side = side_stream if side_stream is not None else _side_stream(main.device)
     side.wait_stream(main)   # inputs of `second` were produced on the current stream
-    with torch.set_grad_enabled(torch.is_grad_enabled() and not first_no_grad):  # frozen teacher (FREEZE_PIPELINE)
+    grad_on = torch.is_grad_enabled()
+    try:
+        if first_no_grad and grad_on:   # frozen teacher (FREEZE_PIPELINE)
+            torch.set_grad_enabled(False)
         tok1 = first.launch(batch_dict)   # the long kernels go first: they keep the GPU busy while `second` is enqueued
-    with torch.cuda.stream(side):
+        torch.set_grad_enabled(grad_on)
+        torch.cuda.set_stream(side)       # plain stream switches: the `with torch.cuda.stream(...)` manager costs ~25 us a time
         tok2 = second.launch(batch_dict)
-    with torch.set_grad_enabled(torch.is_grad_enabled() and not first_no_grad):
+        torch.cuda.set_stream(main)
+        if first_no_grad and grad_on:
+            torch.set_grad_enabled(False)
         batch_dict = first.finish(batch_dict, tok1)
-    with torch.cuda.stream(side):
+        torch.set_grad_enabled(grad_on)
+        torch.cuda.set_stream(side)
         batch_dict = second.finish(batch_dict, tok2)
+    finally:
+        torch.cuda.set_stream(main)
+        torch.set_grad_enabled(grad_on)
     main.wait_stream(side)
     for k in second._feature_keys + (second._coords_key,):
         batch_dict[k].record_stream(main)
