@@ -10,7 +10,7 @@
 // sort with one-bit counters; no comparison sort, no ordering of floats, fully deterministic.
 //
 //   K1 quantize_mark   points (TMA bulk tile -> smem) -> key[i], bitmap |= bit(key)          [HBM: read rows]
-//   K2 bitmap_rank     popcount scan of the bitmap -> word_prefix, P
+//   K2 bitmap_rank     popcount scan of the bitmap -> word_prefix, P; publishes (N, P) to the host
 //   K2b zero_counts    counts[0, P) = 0
 //   K3 rank_count      key[i] -> rank = word_prefix + popc(below) ; inverse[j] ; counts[rank]++
 //   K4 count_scan      exclusive scan of counts -> pillar start offsets
@@ -96,7 +96,8 @@ quantize_mark_kernel(const float *__restrict__ pts, long long n0, GeomDev g, uin
 // the exclusive rank of every word.
 __global__ void __launch_bounds__(kScanThreads)
 bitmap_rank_kernel(const uint32_t *__restrict__ bitmap, long long words,
-                   uint64_t *__restrict__ state, uint32_t *__restrict__ word_prefix, int32_t *__restrict__ counters) {
+                   uint64_t *__restrict__ state, uint32_t *__restrict__ word_prefix, int32_t *__restrict__ counters,
+                   volatile int32_t *host_mapped) {
     __shared__ int s_scan[9];
     __shared__ uint32_t s_u32;
     __shared__ int s_ticket;
@@ -116,7 +117,16 @@ bitmap_rank_kernel(const uint32_t *__restrict__ bitmap, long long words,
     int tot;
     block_excl_scan_256((int)local, s_scan, &tot);
     uint32_t base = chunk_exclusive_prefix(state, ticket, (uint32_t)tot, &s_u32);
-    if (ticket == (int)gridDim.x - 1 && tid == 0) counters[RDP_CNT_P] = (int)(base + (uint32_t)tot);
+    if (ticket == (int)gridDim.x - 1 && tid == 0) {
+        // N (K1) and P are final here: publish them to the host (zero-copy store into pinned memory) before sweep 2,
+        // so the host learns the output sizes ~50 us into the forward
+        const int P = (int)(base + (uint32_t)tot);
+        counters[RDP_CNT_P] = P;
+        if (host_mapped) {
+            for (int i = 0; i < RDP_NUM_COUNTERS; ++i) host_mapped[i] = (i == RDP_CNT_P) ? P : counters[i];
+            __threadfence_system();
+        }
+    }
 
     // sweep 2
     for (long long wt = w0; wt < w1; wt += kScanThreads * 4) {
@@ -401,8 +411,9 @@ extern "C" int rdp_index_fwd_publish(const float *points, int64_t n_points, cons
     }
     const int tiles = (int)ws.index_tiles;
     quantize_mark_kernel<<<tiles, kIndexThreads, smem, stream>>>(points, n_points, g, ws.bitmap, ws.keys, ws.tile_keep, counters);
-    bitmap_rank_kernel<<<kScanGrid, kScanThreads, 0, stream>>>(ws.bitmap, ws.words, ws.scan_state_a, ws.word_prefix, counters);
-    if (int rc2 = publish()) return rc2;
+    bitmap_rank_kernel<<<kScanGrid, kScanThreads, 0, stream>>>(ws.bitmap, ws.words, ws.scan_state_a, ws.word_prefix, counters,
+                                                              host_mapped);
+    if (event) RDP_CUDA_OK(cudaEventRecord(event, stream));
     zero_counts_kernel<<<148 * 2, 256, 0, stream>>>(counts, counters);
     rank_count_kernel<<<tiles, kIndexThreads, 0, stream>>>(ws.keys, n_points, ws.bitmap, ws.word_prefix, ws.tile_keep,
                                                          inverse, counts, counters, ws.orig2kept, ws.kept2orig);
