@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define RDP_ABI_VERSION 3
+#define RDP_ABI_VERSION 4
 
 #if defined(__GNUC__)
 #define RDP_API __attribute__((visibility("default")))
@@ -124,6 +124,18 @@ RDP_API int rdp_index_fwd_publish(const float *points, int64_t n_points, const r
                                   int32_t *counts, int32_t *counters, int32_t *host_mapped, void *event, void *stream);
 
 /*
+ * Device-side input preparation (replaces the batch-index padding of collate_batch, pcdet/datasets/dataset_distill.py:237-244,
+ * and its 4 bytes per point of upload): `points` holds the frames back to back WITHOUT the batch column, i.e.
+ * (n_points, cols - 1) fp32, and frame b owns rows [frame_offsets[b], frame_offsets[b + 1]) (int32, device,
+ * batch_size + 1 entries, ascending, frame_offsets[0] == 0, frame_offsets[batch_size] == n_points).  geom->cols still
+ * counts the batch column: every output (and the workspace's grouped rows) is identical to what rdp_index_fwd_publish
+ * produces for the padded rows.  frame_offsets == NULL is rdp_index_fwd_publish.
+ */
+RDP_API int rdp_index_fwd_frames(const float *points, const int32_t *frame_offsets, int64_t n_points, const rdp_geom_t *geom,
+                                 int32_t coord_cols, void *workspace, size_t workspace_bytes, int32_t *coords, int32_t *inverse,
+                                 int32_t *counts, int32_t *counters, int32_t *host_mapped, void *event, void *stream);
+
+/*
  * scatter_mean -> decorated features -> Linear + BatchNorm1d + ReLU -> scatter_max.
  * Replaces dynamic_pillar_vfe.py:214-240 with PFNLayerV2.forward :35-46 (last layer).
  * Must follow rdp_index_fwd on the same points / workspace / stream.
@@ -153,6 +165,12 @@ RDP_API int rdp_encode_fwd(const float *points, int64_t n_points, const rdp_geom
                            int32_t *coords, int32_t *inverse, int32_t *counts, int32_t *counters,
                            float *features, int32_t *argpos, double *bn_state,
                            int32_t *host_mapped, void *event, void *stream);
+/* The same over frames without a batch column (rdp_index_fwd_frames + rdp_pfn_fwd). */
+RDP_API int rdp_encode_fwd_frames(const float *points, const int32_t *frame_offsets, int64_t n_points, const rdp_geom_t *geom,
+                                  const rdp_layout_t *layout, const rdp_pfn_params_t *params, void *workspace,
+                                  size_t workspace_bytes, int32_t *coords, int32_t *inverse, int32_t *counts,
+                                  int32_t *counters, float *features, int32_t *argpos, double *bn_state,
+                                  int32_t *host_mapped, void *event, void *stream);
 
 /*
  * Parameter gradients of the PFN (autograd of :35-46): argmax routing, ReLU', BatchNorm backward

@@ -8,12 +8,12 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("RDP_LIB_PATH", os.path.join(_HERE, "librdp.so"))  # override: kernel-variant experiments
 
-RDP_ABI_VERSION = 3
+RDP_ABI_VERSION = 4
 RDP_NUM_COUNTERS = 16
 CNT_N, CNT_P, CNT_ERRFLAGS = 0, 1, 2
 LAYOUT_SIMPLE2D, LAYOUT_DYNPILLAR = 0, 1
 
-EXPORTS = ["rdp_abi_version", "rdp_status_string", "rdp_last_cuda_error", "rdp_workspace_bytes", "rdp_index_fwd", "rdp_index_fwd_publish",
+EXPORTS = ["rdp_abi_version", "rdp_status_string", "rdp_last_cuda_error", "rdp_workspace_bytes", "rdp_index_fwd", "rdp_index_fwd_publish", "rdp_index_fwd_frames", "rdp_encode_fwd_frames",
            "rdp_pfn_fwd", "rdp_encode_fwd", "rdp_bn_state_doubles", "rdp_pfn_bwd", "rdp_argmax_kept", "rdp_publish_counters",
            "rdp_encode_host"]
 
@@ -69,6 +69,11 @@ def load() -> C.CDLL:
     lib.rdp_encode_fwd.restype = C.c_int
     lib.rdp_encode_fwd.argtypes = [vp, C.c_int64, C.POINTER(Geom), C.POINTER(Layout), C.POINTER(PfnParams), vp, C.c_size_t,
                                    vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.rdp_index_fwd_frames.restype = C.c_int
+    lib.rdp_index_fwd_frames.argtypes = [vp, vp, C.c_int64, C.POINTER(Geom), C.c_int32, vp, C.c_size_t, vp, vp, vp, vp, vp, vp, vp]
+    lib.rdp_encode_fwd_frames.restype = C.c_int
+    lib.rdp_encode_fwd_frames.argtypes = [vp, vp, C.c_int64, C.POINTER(Geom), C.POINTER(Layout), C.POINTER(PfnParams), vp, C.c_size_t,
+                                          vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.rdp_bn_state_doubles.restype = C.c_int64
     lib.rdp_bn_state_doubles.argtypes = [C.POINTER(Layout)]
     lib.rdp_pfn_bwd.restype = C.c_int

@@ -105,9 +105,18 @@ extern "C" int rdp_encode_fwd(const float *points, int64_t n_points, const rdp_g
                               const rdp_pfn_params_t *params, void *workspace, size_t workspace_bytes, int32_t *coords,
                               int32_t *inverse, int32_t *counts, int32_t *counters, float *features, int32_t *argpos,
                               double *bn_state, int32_t *host_mapped, void *event, void *stream) {
+    return rdp_encode_fwd_frames(points, nullptr, n_points, geom, layout, params, workspace, workspace_bytes, coords, inverse, counts,
+                                 counters, features, argpos, bn_state, host_mapped, event, stream);
+}
+
+extern "C" int rdp_encode_fwd_frames(const float *points, const int32_t *frame_offsets, int64_t n_points, const rdp_geom_t *geom,
+                                     const rdp_layout_t *layout, const rdp_pfn_params_t *params, void *workspace,
+                                     size_t workspace_bytes, int32_t *coords, int32_t *inverse, int32_t *counts, int32_t *counters,
+                                     float *features, int32_t *argpos, double *bn_state, int32_t *host_mapped, void *event,
+                                     void *stream) {
     if (!layout) return RDP_ERR_INVALID_ARG;
-    int rc = rdp_index_fwd_publish(points, n_points, geom, layout->coord_cols, workspace, workspace_bytes, coords, inverse, counts,
-                                   counters, host_mapped, event, stream);
+    int rc = rdp_index_fwd_frames(points, frame_offsets, n_points, geom, layout->coord_cols, workspace, workspace_bytes, coords,
+                                  inverse, counts, counters, host_mapped, event, stream);
     if (rc != RDP_OK) return rc;
     return rdp_pfn_fwd(points, n_points, geom, layout, params, workspace, workspace_bytes, counters, features, argpos, nullptr,
                        bn_state, stream);

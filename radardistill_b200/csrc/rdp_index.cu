@@ -28,10 +28,21 @@ struct GeomDev {
     float off_x, off_y;
 };
 
+// Frame of input row i when the rows carry no batch column: offsets[b] <= i < offsets[b + 1] (offsets has batch + 1 entries).
+__device__ __forceinline__ int frame_of(const int32_t *__restrict__ offsets, int batch, long long i) {
+    int lo = 0, hi = batch - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if ((long long)offsets[mid] <= i) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
 // ----------------------------------------------------------------------------- K1
 __global__ void __launch_bounds__(kIndexThreads)
 quantize_mark_kernel(const float *__restrict__ pts, long long n0, GeomDev g, uint32_t *__restrict__ bitmap,
-                     int32_t *__restrict__ keys, int32_t *__restrict__ tile_keep, int32_t *__restrict__ counters) {
+                     int32_t *__restrict__ keys, int32_t *__restrict__ tile_keep, int32_t *__restrict__ counters,
+                     const int32_t *__restrict__ offsets) {
     extern __shared__ __align__(128) float tile[];
     __shared__ __align__(8) uint64_t bar;
     __shared__ int s_keep;
@@ -39,11 +50,16 @@ quantize_mark_kernel(const float *__restrict__ pts, long long n0, GeomDev g, uin
     const int tid = threadIdx.x;
     const long long row0 = (long long)blockIdx.x * kIndexTileRows;
     const int rows = (int)min((long long)kIndexTileRows, n0 - row0);
-    const int floats = rows * g.cols;
+    // offsets != null: the rows are (x, y, z, features...) without the batch column and frame b owns rows
+    // [offsets[b], offsets[b + 1])  (what the dataset hands over before collate_batch pads the index in, dataset_distill.py:237-244)
+    const int in_cols = offsets ? g.cols - 1 : g.cols, xc = offsets ? 0 : 1;
+    const int floats = rows * in_cols;
     const uint32_t bulk_bytes = (uint32_t)(floats * 4) & ~15u;
-    const float *src = pts + row0 * g.cols;
+    const float *src = pts + row0 * in_cols;
+    __shared__ int s_b0;
 
     if (tid == 0) {
+        s_b0 = offsets ? frame_of(offsets, g.batch, row0) : 0;
         s_keep = 0;
         mbar_init(&bar, 1);
         fence_mbar_init();
@@ -64,12 +80,18 @@ quantize_mark_kernel(const float *__restrict__ pts, long long n0, GeomDev g, uin
     for (int k = 0; k < kIndexTileRows / kIndexThreads; ++k) {
         const int r = k * kIndexThreads + tid;
         if (r < rows) {
-            const float *p = tile + r * g.cols;
+            const float *p = tile + r * in_cols;
             // IEEE fp32 subtract + divide + floor, as torch.floor((xy - lo) / vsz)  (:201-202)
-            const float qx = floorf(__fdiv_rn(__fsub_rn(p[1], g.lo_x), g.vx));
-            const float qy = floorf(__fdiv_rn(__fsub_rn(p[2], g.lo_y), g.vy));
+            const float qx = floorf(__fdiv_rn(__fsub_rn(p[xc], g.lo_x), g.vx));
+            const float qy = floorf(__fdiv_rn(__fsub_rn(p[xc + 1], g.lo_y), g.vy));
             bool ok = (qx >= 0.0f) && (qx < (float)g.nx) && (qy >= 0.0f) && (qy < (float)g.ny);  // NaN/inf fail
-            const int b = __float2int_rz(p[0]);  // .int() truncates
+            int b;
+            if (offsets) {
+                b = s_b0;
+                while (b + 1 < g.batch && row0 + r >= (long long)offsets[b + 1]) ++b;
+            } else {
+                b = __float2int_rz(p[0]);  // .int() truncates
+            }
             if (ok && (b < 0 || b >= g.batch)) { ok = false; bad_batch = true; }
             int key = -1;
             if (ok) {
@@ -272,17 +294,20 @@ count_scan_kernel(const int32_t *__restrict__ counts, uint64_t *__restrict__ sta
 // 16-byte stores only (the scatter is bound by store requests, not bytes).
 __global__ void __launch_bounds__(kIndexThreads)
 group_rows_kernel(const float *__restrict__ pts, const int32_t *__restrict__ ranks, long long n0, int cols,
-                  int32_t *__restrict__ ends, float *__restrict__ grows) {
+                  int32_t *__restrict__ ends, float *__restrict__ grows, const int32_t *__restrict__ offsets, int batch) {
     extern __shared__ __align__(128) float tile[];
     __shared__ __align__(8) uint64_t bar;
     const int tid = threadIdx.x;
     const int rs = grouped_row_floats(cols);
     const long long row0 = (long long)blockIdx.x * kIndexTileRows;
     const int rows = (int)min((long long)kIndexTileRows, n0 - row0);
-    const int floats = rows * cols;
+    const int in_cols = offsets ? cols - 1 : cols;   // without a batch column the grouped row gets the frame id written in
+    const int floats = rows * in_cols;
     const uint32_t bulk_bytes = (uint32_t)(floats * 4) & ~15u;
-    const float *src = pts + row0 * cols;
+    const float *src = pts + row0 * in_cols;
+    __shared__ int s_b0;
     if (tid == 0) {
+        s_b0 = offsets ? frame_of(offsets, batch, row0) : 0;
         mbar_init(&bar, 1);
         fence_mbar_init();
     }
@@ -307,13 +332,20 @@ group_rows_kernel(const float *__restrict__ pts, const int32_t *__restrict__ ran
     for (int k = 0; k < kIndexTileRows / kIndexThreads; ++k) {
         if (pos[k] < 0) continue;
         const int r = k * kIndexThreads + tid;
-        const float *p = tile + r * cols;
+        float fb = 0.0f;
+        const float *p = tile + r * in_cols;
+        if (offsets) {
+            int b = s_b0;
+            while (b + 1 < batch && row0 + r >= (long long)offsets[b + 1]) ++b;
+            fb = (float)b;
+            p -= 1;   // logical column c >= 1 is input column c - 1; column 0 is fb
+        }
         if (rs == 8) {
             // one 256-bit store (STG.256) = one full 32-byte sector per row: the scatter is bound by store requests
             float v[8];
 #pragma unroll
             for (int c = 0; c < 8; ++c)
-                v[c] = c < cols ? p[c] : (c == 6 ? __int_as_float((int)(row0 + r)) : (c == 7 ? __int_as_float(rk[k]) : 0.0f));
+                v[c] = c < cols ? ((offsets && c == 0) ? fb : p[c]) : (c == 6 ? __int_as_float((int)(row0 + r)) : (c == 7 ? __int_as_float(rk[k]) : 0.0f));
             asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(grows + ((size_t)pos[k] + 1) * 8), "f"(v[0]),
                          "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
                          : "memory");
@@ -325,7 +357,7 @@ group_rows_kernel(const float *__restrict__ pts, const int32_t *__restrict__ ran
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const int c = c4 + i;
-                v[i] = c < cols ? p[c] : (c == rs - 2 ? __int_as_float((int)(row0 + r)) : (c == rs - 1 ? __int_as_float(rk[k]) : 0.0f));
+                v[i] = c < cols ? ((offsets && c == 0) ? fb : p[c]) : (c == rs - 2 ? __int_as_float((int)(row0 + r)) : (c == rs - 1 ? __int_as_float(rk[k]) : 0.0f));
             }
             d[c4 >> 2] = make_float4(v[0], v[1], v[2], v[3]);
         }
@@ -376,9 +408,9 @@ static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t
 
 using namespace rdp;
 
-extern "C" int rdp_index_fwd_publish(const float *points, int64_t n_points, const rdp_geom_t *geom, int32_t coord_cols,
-                                     void *workspace, size_t workspace_bytes, int32_t *coords, int32_t *inverse,
-                                     int32_t *counts, int32_t *counters, int32_t *host_mapped, void *event_v, void *stream_v) {
+extern "C" int rdp_index_fwd_frames(const float *points, const int32_t *frame_offsets, int64_t n_points, const rdp_geom_t *geom,
+                                    int32_t coord_cols, void *workspace, size_t workspace_bytes, int32_t *coords, int32_t *inverse,
+                                    int32_t *counts, int32_t *counters, int32_t *host_mapped, void *event_v, void *stream_v) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
     cudaEvent_t event = static_cast<cudaEvent_t>(event_v);
     // N, P and the error flags are final after the bitmap scan (K2): publish them there, so the host learns the output
@@ -410,7 +442,8 @@ extern "C" int rdp_index_fwd_publish(const float *points, int64_t n_points, cons
         RDP_CUDA_OK(cudaFuncSetAttribute(group_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
     const int tiles = (int)ws.index_tiles;
-    quantize_mark_kernel<<<tiles, kIndexThreads, smem, stream>>>(points, n_points, g, ws.bitmap, ws.keys, ws.tile_keep, counters);
+    quantize_mark_kernel<<<tiles, kIndexThreads, smem, stream>>>(points, n_points, g, ws.bitmap, ws.keys, ws.tile_keep, counters,
+                                                                 frame_offsets);
     bitmap_rank_kernel<<<kScanGrid, kScanThreads, 0, stream>>>(ws.bitmap, ws.words, ws.scan_state_a, ws.word_prefix, counters,
                                                               host_mapped);
     if (event) RDP_CUDA_OK(cudaEventRecord(event, stream));
@@ -418,11 +451,19 @@ extern "C" int rdp_index_fwd_publish(const float *points, int64_t n_points, cons
     rank_count_kernel<<<tiles, kIndexThreads, 0, stream>>>(ws.keys, n_points, ws.bitmap, ws.word_prefix, ws.tile_keep,
                                                          inverse, counts, counters, ws.orig2kept, ws.kept2orig);
     count_scan_kernel<<<kScanGrid, kScanThreads, 0, stream>>>(counts, ws.scan_state_b, ws.ends, ws.tile_first, counters);
-    group_rows_kernel<<<tiles, kIndexThreads, smem, stream>>>(points, ws.keys, n_points, geom->cols, ws.ends, ws.grows);
+    group_rows_kernel<<<tiles, kIndexThreads, smem, stream>>>(points, ws.keys, n_points, geom->cols, ws.ends, ws.grows, frame_offsets,
+                                                              geom->batch_size);
     pillar_table_kernel<<<(unsigned)((ws.pcap + 255) / 256), 256, 0, stream>>>(ws.grows, ws.ends, counters,
                                                                                grouped_row_floats(geom->cols), g, ws.aux, coord_cols, coords);
     RDP_CUDA_OK(cudaGetLastError());
     return RDP_OK;
+}
+
+extern "C" int rdp_index_fwd_publish(const float *points, int64_t n_points, const rdp_geom_t *geom, int32_t coord_cols,
+                                     void *workspace, size_t workspace_bytes, int32_t *coords, int32_t *inverse,
+                                     int32_t *counts, int32_t *counters, int32_t *host_mapped, void *event_v, void *stream_v) {
+    return rdp_index_fwd_frames(points, nullptr, n_points, geom, coord_cols, workspace, workspace_bytes, coords, inverse, counts,
+                                counters, host_mapped, event_v, stream_v);
 }
 
 extern "C" int rdp_index_fwd(const float *points, int64_t n_points, const rdp_geom_t *geom, int32_t coord_cols,

@@ -271,13 +271,23 @@ def _take_host(dev_index: int, stream_handle: int):
 
 
 def encode_launch(points: torch.Tensor, spec: EncoderSpec, batch_size: int, weight, bias, gamma, beta, running_mean,
-                  running_var, train_bn: bool, want_argmax: bool, num_batches_tracked=None) -> PendingEncode:
-    """Enqueues index + PFN forward on the current stream (one call into librdp) and returns without synchronising."""
+                  running_var, train_bn: bool, want_argmax: bool, num_batches_tracked=None,
+                  frame_offsets: Optional[torch.Tensor] = None) -> PendingEncode:
+    """Enqueues index + PFN forward on the current stream (one call into librdp) and returns without synchronising.
+
+    ``frame_offsets`` (int32 CUDA, ``batch_size + 1`` entries): ``points`` then holds the frames back to back WITHOUT the
+    batch column, ``(N, cols - 1)``, frame b owning rows ``[offsets[b], offsets[b + 1])`` -- the batch-index padding of
+    ``collate_batch`` (dataset_distill.py:237-244) and its 4 bytes per point of upload are skipped."""
     lib = _lib.load()
     if not points.is_cuda:
         raise _lib.RdpError("the pillar encoder has no CPU path: `points` must be a CUDA tensor")
-    if points.dim() != 2 or points.shape[1] != spec.cols:
-        raise ValueError(f"points must be (N, {spec.cols}), got {tuple(points.shape)}")
+    in_cols = spec.cols - (1 if frame_offsets is not None else 0)
+    if points.dim() != 2 or points.shape[1] != in_cols:
+        raise ValueError(f"points must be (N, {in_cols}), got {tuple(points.shape)}")
+    if frame_offsets is not None:
+        if (not frame_offsets.is_cuda or frame_offsets.dtype != torch.int32 or frame_offsets.dim() != 1
+                or frame_offsets.shape[0] != int(batch_size) + 1 or not frame_offsets.is_contiguous()):
+            raise ValueError(f"frame_offsets must be a contiguous CUDA int32 tensor with batch_size + 1 = {int(batch_size) + 1} entries")
     pts = points
     if pts.requires_grad:
         pts = pts.detach()
@@ -314,11 +324,13 @@ def encode_launch(points: torch.Tensor, spec: EncoderSpec, batch_size: int, weig
         prm = _params_struct(spec, weight, bias, gamma, beta, running_mean, running_var, train_bn,
                              num_batches_tracked if train_bn else None)
         base = buf.data_ptr()
-        _lib.check(lib.rdp_encode_fwd(pts.data_ptr(), n0, C.byref(pl.geom), C.byref(pl.layout), C.byref(prm), base, pl.ws_bytes,
-                                      coords.data_ptr(), base + pl.off_inverse, base + pl.off_counts, base + pl.off_counters,
-                                      features.data_ptr(), None if argpos is None else argpos.data_ptr(),
-                                      (base + pl.off_bn) if train_bn else None, host.data_ptr(), event.cuda_event, st),
-                   "rdp_encode_fwd")
+        _lib.check(lib.rdp_encode_fwd_frames(pts.data_ptr(), None if frame_offsets is None else frame_offsets.data_ptr(), n0,
+                                             C.byref(pl.geom), C.byref(pl.layout), C.byref(prm), base, pl.ws_bytes,
+                                             coords.data_ptr(), base + pl.off_inverse, base + pl.off_counts,
+                                             base + pl.off_counters, features.data_ptr(),
+                                             None if argpos is None else argpos.data_ptr(),
+                                             (base + pl.off_bn) if train_bn else None, host.data_ptr(), event.cuda_event, st),
+                   "rdp_encode_fwd_frames")
     finally:
         if switch:
             torch.cuda.set_device(prev)
@@ -418,7 +430,7 @@ class PendingModuleEncode:
 
 
 def encode_async(points, spec: EncoderSpec, batch_size: int, weight, bias=None, gamma=None, beta=None, running_mean=None,
-                 running_var=None, train_bn: bool = False, num_batches_tracked=None) -> PendingModuleEncode:
+                 running_var=None, train_bn: bool = False, num_batches_tracked=None, frame_offsets=None) -> PendingModuleEncode:
     """Enqueues a (differentiable) encode on the current stream; pair with ``encode_wait``."""
     if points.requires_grad:
         raise NotImplementedError("gradients w.r.t. points are not produced (points are a leaf in the reference)")
@@ -426,7 +438,7 @@ def encode_async(points, spec: EncoderSpec, batch_size: int, weight, bias=None, 
                                               (gamma is not None and gamma.requires_grad) or
                                               (beta is not None and beta.requires_grad))
     pending = encode_launch(points, spec, batch_size, weight, bias, gamma, beta, running_mean, running_var, train_bn,
-                            want_argmax=needs_grad, num_batches_tracked=num_batches_tracked)
+                            want_argmax=needs_grad, num_batches_tracked=num_batches_tracked, frame_offsets=frame_offsets)
     return PendingModuleEncode(pending, (weight, bias, gamma, beta, running_mean, running_var), needs_grad)
 
 

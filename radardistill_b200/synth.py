@@ -110,6 +110,16 @@ def collate(frames) -> np.ndarray:
     return np.ascontiguousarray(np.concatenate(rows, 0))
 
 
+def collate_frames(frames):
+    """The frames back to back WITHOUT a batch column, plus int32 frame offsets (batch + 1 entries): the input of the
+    device-side input prep (``rdp_index_fwd_frames``) -- no padding pass on the host, 4 bytes per point less to upload."""
+    offs = np.zeros(len(frames) + 1, np.int32)
+    for b, f in enumerate(frames):
+        offs[b + 1] = offs[b] + len(f)
+    pts = np.ascontiguousarray(np.concatenate([f.astype(np.float32) for f in frames], 0)) if frames else np.zeros((0, 1), np.float32)
+    return pts, offs
+
+
 def lidar_batch(batch: int, seed0: int = 0, **kw) -> np.ndarray:
     return collate([lidar_frame(seed0 + b, **kw) for b in range(batch)])
 

@@ -120,15 +120,19 @@ class _FusedDynamicPillarVFE(VFETemplate):
             # the reference path uses `np` without importing it (dynamic_pillar_vfe.py:196-199) and cannot run
             raise NotImplementedError("DOUBLE_FLIP is dead code in the reference (NameError) and is not provided")
         points = batch_dict[self._points_key]
+        # optional device-side input prep: `<points key>_offsets` (int32, batch_size + 1) => `points` is (N, C) without the
+        # batch column, frames back to back (what the dataset produces before collate_batch pads the frame index in)
+        offsets = batch_dict.get(self._points_key + "_offsets", None)
         pfn = self.pfn_layers[0]
         norm = pfn.norm if self.use_norm else None
         train_bn = bool(self.use_norm and norm.training)
-        pm = ops.encode_async(points, self.spec, self._batch_size(batch_dict, points), pfn.linear.weight,
+        bs = (int(offsets.shape[0]) - 1) if offsets is not None else self._batch_size(batch_dict, points)
+        pm = ops.encode_async(points, self.spec, bs, pfn.linear.weight,
                               bias=None if self.use_norm else pfn.linear.bias,
                               gamma=norm.weight if norm is not None else None, beta=norm.bias if norm is not None else None,
                               running_mean=norm.running_mean if norm is not None else None,
                               running_var=norm.running_var if norm is not None else None, train_bn=train_bn,
-                              num_batches_tracked=norm.num_batches_tracked if train_bn else None)
+                              num_batches_tracked=norm.num_batches_tracked if train_bn else None, frame_offsets=offsets)
         return pm, train_bn
 
     def finish(self, batch_dict, token):

@@ -312,3 +312,39 @@ def test_torch_library_op_matches_module():
     feats.backward(g)
     ref["radar_pillar_features"].backward(g)
     assert torch.equal(w.grad, pfn.linear.weight.grad) and torch.equal(gamma.grad, n.weight.grad) and torch.equal(beta.grad, n.bias.grad)
+
+
+@pytest.mark.parametrize("kind,train", [("lidar", False), ("radar", True)])
+def test_frames_without_batch_column_match_padded_rows(kind, train):
+    """Device-side input prep (rdp_index_fwd_frames): frames back to back + offsets give the same bits as collate_batch's
+    padded rows -- coords, inverse, counts, features, argmax and parameter gradients."""
+    from radardistill_b200 import synth
+    frames = [synth.lidar_frame(s, sweeps=2, beams=16, azimuths=256) if kind == "lidar" else synth.radar_frame(s, n_points=700 + 37 * s)
+              for s in range(5)]
+    frames[3] = frames[3][:0]                       # an empty frame in the middle
+    padded = synth.collate(frames)
+    raw, offs = synth.collate_frames(frames)
+    key = "points" if kind == "lidar" else "radar_points"
+    outs = []
+    for use_offsets in (False, True):
+        m = _shipped_module(kind, train)
+        if use_offsets:
+            bd = {key: torch.from_numpy(raw).cuda(), key + "_offsets": torch.from_numpy(offs).cuda()}
+        else:
+            bd = {key: torch.from_numpy(padded).cuda(), "batch_size": len(frames)}
+        out = m(bd)
+        fk = [k for k in out if k.endswith("pillar_features")][0]
+        ck = [k for k in out if k.endswith("_coords")][0]
+        res = m.last_result
+        rec = dict(f=out[fk].detach().cpu().numpy(), c=out[ck].cpu().numpy(), inv=res.inverse.cpu().numpy(), cnt=res.counts.cpu().numpy())
+        if train:
+            rec["arg"] = res.argmax.cpu().numpy()
+            out[fk].backward(torch.ones_like(out[fk]))
+            rec["dw"] = m.pfn_layers[0].linear.weight.grad.cpu().numpy()
+        outs.append(rec)
+    a, b = outs
+    for k in a:
+        if k in ("f", "dw") and train:     # train-mode statistics / gradient sums are fp64 sums in run-dependent order
+            assert H.norm_rel_err(b[k], a[k]) <= 1e-6
+        else:
+            np.testing.assert_array_equal(b[k], a[k])
