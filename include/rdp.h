@@ -195,6 +195,15 @@ RDP_API int rdp_argmax_kept(int64_t n_points, const rdp_geom_t *geom, const rdp_
                             int32_t *argmax_kept, void *stream);
 
 /*
+ * Dense cell -> pillar lookup for the consumer's first sparse convolution (spconv_backbone_2d.py:262-271 builds a
+ * SparseConvTensor from features + coords; its SubMConv2d rule book needs "which pillar sits at (b, y, x)"):
+ *   lookup (batch_size, ny, nx) int32: row of features / coords at that cell, or -1.
+ * Reads the occupancy bitmap + rank prefix rdp_index_fwd left in `workspace` (valid until the workspace is reused).
+ */
+RDP_API int rdp_pillar_lookup(int64_t n_points, const rdp_geom_t *geom, void *workspace, size_t workspace_bytes,
+                              int32_t *lookup, void *stream);
+
+/*
  * Copies counters[] to `host_mapped` (pinned, device-visible host memory: cudaHostAlloc / torch pin_memory under UVA)
  * from a one-warp kernel instead of a DMA transfer, so the 64-byte read-back never queues behind bulk copies on the
  * copy engines.  The values are visible on the host once `stream` has been synchronised.

@@ -14,7 +14,7 @@ CNT_N, CNT_P, CNT_ERRFLAGS = 0, 1, 2
 LAYOUT_SIMPLE2D, LAYOUT_DYNPILLAR = 0, 1
 
 EXPORTS = ["rdp_abi_version", "rdp_status_string", "rdp_last_cuda_error", "rdp_workspace_bytes", "rdp_index_fwd", "rdp_index_fwd_publish", "rdp_index_fwd_frames", "rdp_encode_fwd_frames",
-           "rdp_pfn_fwd", "rdp_encode_fwd", "rdp_bn_state_doubles", "rdp_pfn_bwd", "rdp_argmax_kept", "rdp_publish_counters",
+           "rdp_pfn_fwd", "rdp_encode_fwd", "rdp_bn_state_doubles", "rdp_pfn_bwd", "rdp_argmax_kept", "rdp_pillar_lookup", "rdp_publish_counters",
            "rdp_encode_host"]
 
 
@@ -81,6 +81,8 @@ def load() -> C.CDLL:
                                 vp, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.rdp_argmax_kept.restype = C.c_int
     lib.rdp_argmax_kept.argtypes = [C.c_int64, C.POINTER(Geom), C.POINTER(Layout), vp, C.c_size_t, vp, vp, vp, vp]
+    lib.rdp_pillar_lookup.restype = C.c_int
+    lib.rdp_pillar_lookup.argtypes = [C.c_int64, C.POINTER(Geom), vp, C.c_size_t, vp, vp]
     lib.rdp_publish_counters.restype = C.c_int
     lib.rdp_publish_counters.argtypes = [vp, vp, vp]
     lib.rdp_encode_host.restype = C.c_int

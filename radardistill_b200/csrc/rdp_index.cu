@@ -402,6 +402,33 @@ pillar_table_kernel(const float *__restrict__ grows, const int32_t *__restrict__
                  : "memory");
 }
 
+// ----------------------------------------------------------------------------- pillar-id lookup
+// Dense (B, ny, nx) map cell -> pillar row (or -1): what the first SubMConv2d of SparseEnc needs to build its rule
+// book (spconv_backbone_2d.py:262-271) without a hash pass of its own -- the occupancy bitmap + rank prefix already are
+// that table.  32 x 32 tiles: keys are x-major (b*nx*ny + cx*ny + cy), the output is y-major, so the tile is transposed
+// through shared memory and both sides stay coalesced.
+__global__ void __launch_bounds__(256) pillar_lookup_kernel(const uint32_t *__restrict__ bitmap, const uint32_t *__restrict__ word_prefix,
+                                                            int nx, int ny, int32_t *__restrict__ lookup) {
+    __shared__ int tile[32][33];
+    const int b = blockIdx.z, x0 = blockIdx.x * 32, y0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+    for (int j = ty; j < 32; j += 8) {
+        const int x = x0 + j, y = y0 + tx;
+        int v = -1;
+        if (x < nx && y < ny) {
+            const long long key = ((long long)b * nx + x) * ny + y;
+            const uint32_t w = bitmap[key >> 5], bit = 1u << (key & 31);
+            if (w & bit) v = (int)(word_prefix[key >> 5] + __popc(w & (bit - 1u)));
+        }
+        tile[j][tx] = v;
+    }
+    __syncthreads();
+    for (int j = ty; j < 32; j += 8) {
+        const int y = y0 + j, x = x0 + tx;
+        if (x < nx && y < ny) lookup[((size_t)b * ny + y) * nx + x] = tile[tx][j];
+    }
+}
+
 static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 }  // namespace rdp
@@ -471,6 +498,25 @@ extern "C" int rdp_index_fwd(const float *points, int64_t n_points, const rdp_ge
                              int32_t *counts, int32_t *counters, void *stream_v) {
     return rdp_index_fwd_publish(points, n_points, geom, coord_cols, workspace, workspace_bytes, coords, inverse, counts, counters,
                                  nullptr, nullptr, stream_v);
+}
+
+extern "C" int rdp_pillar_lookup(int64_t n_points, const rdp_geom_t *geom, void *workspace, size_t workspace_bytes, int32_t *lookup,
+                                 void *stream_v) {
+    if (!geom || !lookup || n_points < 0) return RDP_ERR_INVALID_ARG;
+    Workspace ws;
+    int rc = carve_workspace(workspace, n_points, geom, nullptr, &ws);
+    if (rc != RDP_OK) return rc;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+    if (n_points == 0) {   // rdp_index_fwd did not touch the workspace: every cell is empty
+        RDP_CUDA_OK(cudaMemsetAsync(lookup, 0xff, sizeof(int32_t) * (size_t)geom->batch_size * geom->nx * geom->ny, stream));
+        return RDP_OK;
+    }
+    if (!workspace || ws.index_bytes > workspace_bytes) return RDP_ERR_WORKSPACE;
+    dim3 grid((geom->nx + 31) / 32, (geom->ny + 31) / 32, geom->batch_size);
+    if (grid.y > 65535 || grid.z > 65535) return RDP_ERR_UNSUPPORTED;
+    pillar_lookup_kernel<<<grid, 256, 0, stream>>>(ws.bitmap, ws.word_prefix, geom->nx, geom->ny, lookup);
+    RDP_CUDA_OK(cudaGetLastError());
+    return RDP_OK;
 }
 
 extern "C" int rdp_publish_counters(const int32_t *counters, int32_t *host_mapped, void *stream_v) {

@@ -134,6 +134,18 @@ class EncodeResult:
             return None
         return self._view("bn_state", self._plan.off_bn, 8 * self._plan.bn_doubles, torch.float64, None)
 
+    def pillar_lookup(self) -> torch.Tensor:
+        """Dense ``(batch_size, ny, nx)`` int32 map cell -> row of ``features`` / ``coords`` (-1 = empty): the table
+        SparseEnc's first SubMConv2d needs for its rule book (spconv_backbone_2d.py:262-271), read off the occupancy
+        bitmap the index kernels left in the workspace."""
+        dev = self._buf.device
+        out = torch.empty((self.batch_size, self.spec.ny, self.spec.nx), dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.load().rdp_pillar_lookup(self.n_points, C.byref(self._plan.geom), self._buf.data_ptr(),
+                                                     self._plan.ws_bytes, out.data_ptr(), _raw_stream(dev.index)),
+                       "rdp_pillar_lookup")
+        return out
+
     @property
     def argmax(self) -> Optional[torch.Tensor]:
         """scatter_max's argmax in the reference's numbering: (P, c_out) int32 index among the KEPT points."""

@@ -348,3 +348,18 @@ def test_frames_without_batch_column_match_padded_rows(kind, train):
             assert H.norm_rel_err(b[k], a[k]) <= 1e-6
         else:
             np.testing.assert_array_equal(b[k], a[k])
+
+
+def test_pillar_lookup_is_the_inverse_of_coords():
+    """rdp_pillar_lookup: lookup[b, y, x] == row p  <=>  coords[p] == [b, y, x]; every other cell is -1."""
+    from radardistill_b200 import synth
+    pts = synth.lidar_batch(3, sweeps=2, beams=16, azimuths=256)
+    m = _shipped_module("lidar", train=False)
+    with torch.no_grad():
+        out = m({"points": torch.from_numpy(pts).cuda(), "batch_size": 3})
+    coords = out["pillar_coords"].cpu().numpy().astype(np.int64)
+    lut = m.last_result.pillar_lookup().cpu().numpy()
+    assert lut.shape == (3, m.spec.ny, m.spec.nx) and lut.dtype == np.int32
+    ref = np.full(lut.shape, -1, np.int32)
+    ref[coords[:, 0], coords[:, 1], coords[:, 2]] = np.arange(len(coords), dtype=np.int32)
+    np.testing.assert_array_equal(lut, ref)
