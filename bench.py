@@ -242,13 +242,37 @@ def grads_vector(mods):
     return torch.cat([p.grad.reshape(-1) for m in mods for p in m.parameters() if p.grad is not None])
 
 
+def pin_cpus(local: int, local_world: int):
+    """Gives every rank its own physical cores (all hyperthreads of each): the ranks' launch threads then never share a core.
+    Returns the CPU set, or None if the topology cannot be read."""
+    try:
+        allowed = sorted(os.sched_getaffinity(0))
+        cores = {}
+        for c in allowed:
+            with open(f"/sys/devices/system/cpu/cpu{c}/topology/thread_siblings_list") as f:
+                sib = f.read().strip()
+            cores.setdefault(sib, []).append(c)
+        groups = sorted(cores.values(), key=lambda g: g[0])
+        per = len(groups) // local_world
+        if per < 1:
+            return None
+        mine = sorted(c for g in groups[local * per:(local + 1) * per] for c in g)
+        os.sched_setaffinity(0, mine)
+        return mine
+    except Exception:
+        return None
+
+
 def run_ours(args):
-    import torch
-    import torch.distributed as dist
-    from radardistill_b200 import _lib, ops
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    pinned = None
+    if world > 1 and args.pin_cpus:   # before torch spawns its threads
+        pinned = pin_cpus(local, int(os.environ.get("LOCAL_WORLD_SIZE", str(world))))
+    import torch
+    import torch.distributed as dist
+    from radardistill_b200 import _lib, ops
     ddp = world > 1
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
@@ -511,6 +535,7 @@ def run_ours(args):
                 "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": step_ms, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": dict(workload_config(mode, frames, len(lidar), len(radar)),
+                               cpus_pinned=(pinned if pinned is None else len(pinned)),
                                data_parallel=("none" if not ddp else ("GradientAllReduce: one NCCL all_reduce of the flat PFN gradients "
                                               "per step" if args.dp == "lean" else "torch DistributedDataParallel"))),
                 "e2e": e2e, "e2e_host_outputs": e2e_out,
@@ -530,6 +555,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default="B", choices=["A", "B"])
+    ap.add_argument("--pin-cpus", type=int, default=1,
+                    help="N > 1: give every rank its own physical cores (sched_setaffinity); 0 = leave the scheduler alone")
     ap.add_argument("--dp", default="lean", choices=["lean", "ddp"],
                     help="N > 1: gradient all-reduce by radardistill_b200.sharding.GradientAllReduce (one all_reduce of a flat "
                          "buffer per step) or by torch DistributedDataParallel")
