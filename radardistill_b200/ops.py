@@ -434,6 +434,63 @@ class _PillarEncodeFn(torch.autograd.Function):
         return (d_w, (None if use_norm else d_b), d_g, (d_b if use_norm else None), None, None, None, None)
 
 
+class _PairEncodeFn(torch.autograd.Function):
+    """One autograd node for two independent encoders (``vfe.forward_pair``): `a` ran on the current stream, `b` on
+    ``side``.  Halves the per-step autograd bookkeeping of the pair; the two backward launches still overlap on the two
+    streams.  Same gradients as two ``_PillarEncodeFn`` nodes."""
+
+    @staticmethod
+    def forward(ctx, wa, ba, ga, bea, wb, bb, gb, beb, pma, pmb, side, holder):
+        ra, rb = encode_finish(pma.pending), encode_finish(pmb.pending)
+        holder.extend((ra, rb))
+        ctx.ra, ctx.rb = ra.without_outputs(), rb.without_outputs()
+        ctx.pa, ctx.pb, ctx.side = pma, pmb, side
+        ctx.save_for_backward(wa, ba, ga, bea, wb, bb, gb, beb)
+        ctx.mark_non_differentiable(ra.coords, rb.coords)
+        ctx.set_materialize_grads(False)
+        return ra.features, ra.coords, rb.features, rb.coords
+
+    @staticmethod
+    def backward(ctx, gfa, _gca, gfb, _gcb):
+        wa, ba, ga, bea, wb, bb, gb, beb = ctx.saved_tensors
+
+        def one(pm, res, gf, w, b, g, be):
+            if gf is None:
+                return (None, None, None, None)
+            if res.argpos is None:
+                raise RuntimeError("backward through a forward that ran without requires_grad parameters")
+            p = pm.pending
+            d_w, d_g, d_b = encode_backward(p.points, p.spec, p.batch_size, res, None, gf, w, b, g, be, pm.params[4], pm.params[5],
+                                            p.train_bn)
+            return (d_w, None, d_g, d_b) if g is not None else (d_w, d_b, None, None)
+
+        main = torch.cuda.current_stream()
+        side = ctx.side
+        grads_b = (None, None, None, None)
+        if gfb is not None:   # the short one goes out first, on the side stream
+            side.wait_stream(main)
+            gfb.record_stream(side)
+            torch.cuda.set_stream(side)
+            try:
+                grads_b = one(ctx.pb, ctx.rb, gfb, wb, bb, gb, beb)
+            finally:
+                torch.cuda.set_stream(main)
+        grads_a = one(ctx.pa, ctx.ra, gfa, wa, ba, ga, bea)
+        if gfb is not None:
+            main.wait_stream(side)
+            for t in grads_b:
+                if t is not None:
+                    t.record_stream(main)
+        return grads_a + grads_b + (None, None, None, None)
+
+
+def encode_wait_pair(pma: "PendingModuleEncode", pmb: "PendingModuleEncode", side):
+    """``encode_wait`` for two pending encodes that both need gradients: one autograd node for the pair."""
+    holder = []
+    fa, ca, fb, cb = _PairEncodeFn.apply(*pma.params[:4], *pmb.params[:4], pma, pmb, side, holder)
+    return holder[0].with_outputs(fa, ca), holder[1].with_outputs(fb, cb)
+
+
 class PendingModuleEncode:
     __slots__ = ("pending", "params", "needs_grad")
 

@@ -137,7 +137,9 @@ class _FusedDynamicPillarVFE(VFETemplate):
 
     def finish(self, batch_dict, token):
         pm, train_bn = token
-        res = ops.encode_wait(pm)
+        return self._publish(batch_dict, ops.encode_wait(pm), train_bn)
+
+    def _publish(self, batch_dict, res, train_bn):
         if train_bn:
             if res.n_kept == 1:
                 raise ValueError(f"Expected more than 1 value per channel when training, got input size "
@@ -169,12 +171,17 @@ def forward_pair(first, second, batch_dict, side_stream=None, first_no_grad=Fals
         torch.cuda.set_stream(side)       # plain stream switches: the `with torch.cuda.stream(...)` manager costs ~25 us a time
         tok2 = second.launch(batch_dict)
         torch.cuda.set_stream(main)
-        if first_no_grad and grad_on:
-            torch.set_grad_enabled(False)
-        batch_dict = first.finish(batch_dict, tok1)
-        torch.set_grad_enabled(grad_on)
-        torch.cuda.set_stream(side)
-        batch_dict = second.finish(batch_dict, tok2)
+        if tok1[0].needs_grad and tok2[0].needs_grad:   # one autograd node for the pair
+            res1, res2 = ops.encode_wait_pair(tok1[0], tok2[0], side)
+            batch_dict = first._publish(batch_dict, res1, tok1[1])
+            batch_dict = second._publish(batch_dict, res2, tok2[1])
+        else:
+            if first_no_grad and grad_on:
+                torch.set_grad_enabled(False)
+            batch_dict = first.finish(batch_dict, tok1)
+            torch.set_grad_enabled(grad_on)
+            torch.cuda.set_stream(side)
+            batch_dict = second.finish(batch_dict, tok2)
     finally:
         torch.cuda.set_stream(main)
         torch.set_grad_enabled(grad_on)

@@ -363,3 +363,34 @@ def test_pillar_lookup_is_the_inverse_of_coords():
     ref = np.full(lut.shape, -1, np.int32)
     ref[coords[:, 0], coords[:, 1], coords[:, 2]] = np.arange(len(coords), dtype=np.int32)
     np.testing.assert_array_equal(lut, ref)
+
+
+@pytest.mark.parametrize("use_both", [True, False])
+def test_forward_pair_single_autograd_node_matches_sequential(use_both):
+    """Both encoders trainable: forward_pair wires ONE autograd node for the pair; outputs and gradients must equal two
+    separate calls bit for bit (train-mode sums: to 1e-6), also when only one of the two outputs reaches the loss."""
+    from radardistill_b200 import synth
+    from radardistill_b200.vfe import forward_pair
+    lp, rp = torch.from_numpy(synth.lidar_batch(2, sweeps=3)).cuda(), torch.from_numpy(synth.radar_batch(2)).cuda()
+    outs = []
+    for paired in (False, True):
+        lid, rad = _shipped_module("lidar", train=True), _shipped_module("radar", train=True)
+        bd = {"points": lp, "radar_points": rp, "batch_size": 2}
+        bd = forward_pair(lid, rad, bd) if paired else rad(lid(bd))
+        assert bd["pillar_features"].requires_grad and bd["radar_pillar_features"].requires_grad
+        loss = bd["radar_pillar_features"].square().sum()
+        if use_both:
+            loss = loss + (bd["pillar_features"] * 0.5).sum()
+        loss.backward()
+        torch.cuda.synchronize()
+        gl = lid.pfn_layers[0].linear.weight.grad
+        assert (gl is not None) == use_both
+        outs.append((bd["pillar_features"].detach().clone(), bd["pillar_coords"].clone(), bd["radar_pillar_features"].detach().clone(),
+                     rad.pfn_layers[0].linear.weight.grad.clone(), rad.pfn_layers[0].norm.weight.grad.clone(),
+                     gl.clone() if gl is not None else torch.zeros(1), lid.pfn_layers[0].norm.running_var.clone(),
+                     lid.pfn_layers[0].norm.num_batches_tracked.clone()))
+    for a, b in zip(*outs):
+        if a.dtype.is_floating_point:
+            assert H.norm_rel_err(b.cpu().numpy(), a.cpu().numpy()) <= 1e-6
+        else:
+            assert torch.equal(a, b)
