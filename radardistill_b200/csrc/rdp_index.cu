@@ -292,6 +292,7 @@ count_scan_kernel(const int32_t *__restrict__ counts, uint64_t *__restrict__ sta
 // ----------------------------------------------------------------------------- K5
 // Grouped row layout: RS = grouped_row_floats(cols) floats = [row | pad | original row id | pillar id], written with
 // 16-byte stores only (the scatter is bound by store requests, not bytes).
+template <bool FRAMES>   // FRAMES: rows without the batch column + frame offsets (compiled apart: the padded-row path stays as it was)
 __global__ void __launch_bounds__(kIndexThreads)
 group_rows_kernel(const float *__restrict__ pts, const int32_t *__restrict__ ranks, long long n0, int cols,
                   int32_t *__restrict__ ends, float *__restrict__ grows, const int32_t *__restrict__ offsets, int batch) {
@@ -301,13 +302,13 @@ group_rows_kernel(const float *__restrict__ pts, const int32_t *__restrict__ ran
     const int rs = grouped_row_floats(cols);
     const long long row0 = (long long)blockIdx.x * kIndexTileRows;
     const int rows = (int)min((long long)kIndexTileRows, n0 - row0);
-    const int in_cols = offsets ? cols - 1 : cols;   // without a batch column the grouped row gets the frame id written in
+    const int in_cols = FRAMES ? cols - 1 : cols;   // without a batch column the grouped row gets the frame id written in
     const int floats = rows * in_cols;
     const uint32_t bulk_bytes = (uint32_t)(floats * 4) & ~15u;
     const float *src = pts + row0 * in_cols;
     __shared__ int s_b0;
     if (tid == 0) {
-        s_b0 = offsets ? frame_of(offsets, batch, row0) : 0;
+        s_b0 = FRAMES ? frame_of(offsets, batch, row0) : 0;
         mbar_init(&bar, 1);
         fence_mbar_init();
     }
@@ -320,11 +321,17 @@ group_rows_kernel(const float *__restrict__ pts, const int32_t *__restrict__ ran
     if (blockIdx.x == 0 && tid == 0) grows[rs - 1] = __int_as_float(-1);  // sentinel row: "no pillar" before position 0
     // claim the grouped positions while the tile is in flight
     int pos[kIndexTileRows / kIndexThreads], rk[kIndexTileRows / kIndexThreads];
+    float fbv[kIndexTileRows / kIndexThreads] = {};
 #pragma unroll
     for (int k = 0; k < kIndexTileRows / kIndexThreads; ++k) {
         const int r = k * kIndexThreads + tid;
         rk[k] = (r < rows) ? ranks[row0 + r] : -1;
         pos[k] = (rk[k] >= 0) ? atomicAdd(ends + rk[k], 1) : -1;
+        if (FRAMES) {   // frame id of the row, resolved here so that nothing but smem reads sits between the scattered stores below
+            int b = s_b0;
+            while (b + 1 < batch && row0 + r >= (long long)offsets[b + 1]) ++b;
+            fbv[k] = (float)b;
+        }
     }
     if (bulk_bytes) mbar_wait(&bar, 0);
     __syncthreads();
@@ -332,20 +339,14 @@ group_rows_kernel(const float *__restrict__ pts, const int32_t *__restrict__ ran
     for (int k = 0; k < kIndexTileRows / kIndexThreads; ++k) {
         if (pos[k] < 0) continue;
         const int r = k * kIndexThreads + tid;
-        float fb = 0.0f;
-        const float *p = tile + r * in_cols;
-        if (offsets) {
-            int b = s_b0;
-            while (b + 1 < batch && row0 + r >= (long long)offsets[b + 1]) ++b;
-            fb = (float)b;
-            p -= 1;   // logical column c >= 1 is input column c - 1; column 0 is fb
-        }
+        const float fb = fbv[k];
+        const float *p = tile + r * in_cols - (FRAMES ? 1 : 0);   // FRAMES: logical column c >= 1 is input column c - 1, column 0 is fb
         if (rs == 8) {
             // one 256-bit store (STG.256) = one full 32-byte sector per row: the scatter is bound by store requests
             float v[8];
 #pragma unroll
             for (int c = 0; c < 8; ++c)
-                v[c] = c < cols ? ((offsets && c == 0) ? fb : p[c]) : (c == 6 ? __int_as_float((int)(row0 + r)) : (c == 7 ? __int_as_float(rk[k]) : 0.0f));
+                v[c] = c < cols ? ((FRAMES && c == 0) ? fb : p[c]) : (c == 6 ? __int_as_float((int)(row0 + r)) : (c == 7 ? __int_as_float(rk[k]) : 0.0f));
             asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(grows + ((size_t)pos[k] + 1) * 8), "f"(v[0]),
                          "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
                          : "memory");
@@ -357,7 +358,7 @@ group_rows_kernel(const float *__restrict__ pts, const int32_t *__restrict__ ran
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const int c = c4 + i;
-                v[i] = c < cols ? ((offsets && c == 0) ? fb : p[c]) : (c == rs - 2 ? __int_as_float((int)(row0 + r)) : (c == rs - 1 ? __int_as_float(rk[k]) : 0.0f));
+                v[i] = c < cols ? ((FRAMES && c == 0) ? fb : p[c]) : (c == rs - 2 ? __int_as_float((int)(row0 + r)) : (c == rs - 1 ? __int_as_float(rk[k]) : 0.0f));
             }
             d[c4 >> 2] = make_float4(v[0], v[1], v[2], v[3]);
         }
@@ -466,7 +467,8 @@ extern "C" int rdp_index_fwd_frames(const float *points, const int32_t *frame_of
     if (smem > 200 * 1024) return RDP_ERR_UNSUPPORTED;
     if (smem > 48 * 1024) {
         RDP_CUDA_OK(cudaFuncSetAttribute(quantize_mark_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        RDP_CUDA_OK(cudaFuncSetAttribute(group_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        RDP_CUDA_OK(cudaFuncSetAttribute(group_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        RDP_CUDA_OK(cudaFuncSetAttribute(group_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
     const int tiles = (int)ws.index_tiles;
     quantize_mark_kernel<<<tiles, kIndexThreads, smem, stream>>>(points, n_points, g, ws.bitmap, ws.keys, ws.tile_keep, counters,
@@ -478,8 +480,12 @@ extern "C" int rdp_index_fwd_frames(const float *points, const int32_t *frame_of
     rank_count_kernel<<<tiles, kIndexThreads, 0, stream>>>(ws.keys, n_points, ws.bitmap, ws.word_prefix, ws.tile_keep,
                                                          inverse, counts, counters, ws.orig2kept, ws.kept2orig);
     count_scan_kernel<<<kScanGrid, kScanThreads, 0, stream>>>(counts, ws.scan_state_b, ws.ends, ws.tile_first, counters);
-    group_rows_kernel<<<tiles, kIndexThreads, smem, stream>>>(points, ws.keys, n_points, geom->cols, ws.ends, ws.grows, frame_offsets,
-                                                              geom->batch_size);
+    if (frame_offsets)
+        group_rows_kernel<true><<<tiles, kIndexThreads, smem, stream>>>(points, ws.keys, n_points, geom->cols, ws.ends, ws.grows,
+                                                                        frame_offsets, geom->batch_size);
+    else
+        group_rows_kernel<false><<<tiles, kIndexThreads, smem, stream>>>(points, ws.keys, n_points, geom->cols, ws.ends, ws.grows,
+                                                                         nullptr, geom->batch_size);
     pillar_table_kernel<<<(unsigned)((ws.pcap + 255) / 256), 256, 0, stream>>>(ws.grows, ws.ends, counters,
                                                                                grouped_row_floats(geom->cols), g, ws.aux, coord_cols, coords);
     RDP_CUDA_OK(cudaGetLastError());

@@ -156,6 +156,13 @@ __device__ __forceinline__ void fold_bn(double gamma, double beta, double mean, 
     *shift = (float)__dsub_rn(beta, __dmul_rn(mean, s));
 }
 
+// (lo, hi) -> one 64-bit register pair, for lexicographic compares that cost two ISETPs
+__device__ __forceinline__ unsigned long long pack64(uint32_t lo, uint32_t hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+    return r;
+}
+
 __device__ __forceinline__ int warp_min(int v) { return __reduce_min_sync(0xffffffffu, v); }
 __device__ __forceinline__ int warp_max(int v) { return __reduce_max_sync(0xffffffffu, v); }
 
@@ -305,7 +312,7 @@ __global__ void __launch_bounds__(kPfnThreads, (MODE == PFN_MODE_APPLY) ? 5 : 4)
     int mk[WN], mp[WN];
     auto reset_max = [&]() {
 #pragma unroll
-        for (int cc = 0; cc < WN; ++cc) { m[cc] = want_arg ? -1.0f : 0.0f; mk[cc] = INF; mp[cc] = 0; }
+        for (int cc = 0; cc < WN; ++cc) { m[cc] = 0.0f; mk[cc] = INF; mp[cc] = 0; }   // (0, INF) loses to every real row
     };
     float *fout = nullptr;
     int32_t *aout = nullptr;
@@ -320,8 +327,12 @@ __global__ void __launch_bounds__(kPfnThreads, (MODE == PFN_MODE_APPLY) ? 5 : 4)
             if (!want_arg) {
                 m[cc] = fmaxf(m[cc], y);  // ReLU folds into the max with 0
             } else {
+                // larger z wins, ties go to the lower kept index: z >= 0, so (float bits of z, ~index) orders correctly as one
+                // unsigned 64-bit key (two compares instead of three)
                 const float z = fmaxf(y, 0.0f);
-                if (z > m[cc] || (z == m[cc] && kj < mk[cc])) { m[cc] = z; mk[cc] = kj; mp[cc] = gb + j; }
+                if (pack64(~(uint32_t)kj, __float_as_uint(z)) > pack64(~(uint32_t)mk[cc], __float_as_uint(m[cc]))) {
+                    m[cc] = z; mk[cc] = kj; mp[cc] = gb + j;
+                }
             }
         }
         if (meta & 1) {
