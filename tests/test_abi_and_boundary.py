@@ -127,3 +127,46 @@ def test_torch_library_ops_are_registered_with_fake_kernels():
         g = torch.ops.rdp.pillar_encode_backward(pts, feats, feats, argpos, bn_state, out[6], out[7], w, None, v(), v(), v(), v(),
                                                  ints, floats, 2, True)
         assert [tuple(t.shape) for t in g] == [(32, 15), (32,), (32,)]
+
+
+def test_plan_carves_one_scratch_allocation():
+    """ops._plan: librdp workspace | counters | BN state | inverse | counts in ONE buffer, 256-byte aligned regions."""
+    spec = ops.make_spec(6, synth.VOXEL_SIZE, synth.grid_size_of(), synth.PC_RANGE, _lib.LAYOUT_SIMPLE2D, True, True, True, False, 32)
+    for train in (False, True):
+        pl = ops._plan(spec, 8, 21_827, train)
+        assert pl is ops._plan(spec, 8, 21_827, train)            # cached
+        offs = [0, pl.off_counters, pl.off_bn, pl.off_inverse, pl.off_counts, pl.total_bytes]
+        assert offs == sorted(offs) and all(o % 256 == 0 for o in offs)
+        assert pl.off_bn - pl.off_counters >= 4 * _lib.RDP_NUM_COUNTERS
+        assert pl.off_inverse - pl.off_bn >= 8 * pl.bn_doubles
+        assert pl.off_counts - pl.off_inverse >= 4 * (pl.cap + 4) and pl.total_bytes - pl.off_counts >= 4 * (pl.cap + 4)
+        assert pl.bn_doubles == (4 * 32 + 1 + 15 + 15 * 15 if train else 0)
+    assert ops._plan(spec, 8, 21_827, True) is not ops._plan(spec, 8, 21_827, False)
+
+
+def test_collate_frames_is_collate_without_the_batch_column():
+    frames = [synth.radar_frame(s, n_points=50 + 7 * s) for s in range(4)]
+    frames[2] = frames[2][:0]
+    padded = synth.collate(frames)
+    raw, offs = synth.collate_frames(frames)
+    assert offs.dtype == np.int32 and offs[0] == 0 and offs[-1] == len(raw) == len(padded)
+    np.testing.assert_array_equal(raw, padded[:, 1:])
+    for b in range(4):
+        assert np.all(padded[offs[b]:offs[b + 1], 0] == b)
+
+
+def test_pin_cpus_partitions_the_allowed_cores():
+    import bench
+    before = os.sched_getaffinity(0)
+    try:
+        n = 2 if len(before) >= 2 else 1
+        sets = []
+        for r in range(n):
+            os.sched_setaffinity(0, before)
+            got = bench.pin_cpus(r, n)
+            assert got and set(got) <= before and os.sched_getaffinity(0) == set(got)
+            sets.append(set(got))
+        if n == 2:
+            assert not (sets[0] & sets[1])
+    finally:
+        os.sched_setaffinity(0, before)
