@@ -394,3 +394,42 @@ def test_forward_pair_single_autograd_node_matches_sequential(use_both):
             assert H.norm_rel_err(b.cpu().numpy(), a.cpu().numpy()) <= 1e-6
         else:
             assert torch.equal(a, b)
+
+
+def test_full_size_properties_batch_of_eight():
+    """BASELINE configs[2] at full size (8 LiDAR frames, 2.7 M rows): size-independent properties instead of the oracle.
+    Sortedness of the merged keys, count / inverse consistency against a numpy re-quantisation, permutation invariance of
+    the pillar set and of the max-pooled features (bit-exact in eval mode)."""
+    from radardistill_b200 import synth
+    pts = synth.lidar_batch(8)
+    m = _shipped_module("lidar", train=False)
+    lo, vs, nx, ny = np.float32(synth.PC_RANGE[:2]), np.float32(synth.VOXEL_SIZE[:2]), m.spec.nx, m.spec.ny
+
+    def run(p):
+        with torch.no_grad():
+            out = m({"points": torch.from_numpy(p).cuda(), "batch_size": 8})
+        r = m.last_result
+        return (out["pillar_features"].cpu().numpy(), out["pillar_coords"].cpu().numpy().astype(np.int64), r.inverse.cpu().numpy(),
+                r.counts.cpu().numpy(), r.n_kept)
+
+    f, c, inv, cnt, n = run(pts)
+    # sortedness: rows are in ascending merged-key order, no duplicates (torch.unique, :212)
+    key = (c[:, 0] * nx + c[:, 2]) * ny + c[:, 1]
+    assert np.all(np.diff(key) > 0)
+    # counts / inverse against an independent numpy quantisation (:201-210)
+    q = np.floor((pts[:, 1:3] - lo) / vs).astype(np.int64)
+    keep = (q[:, 0] >= 0) & (q[:, 0] < nx) & (q[:, 1] >= 0) & (q[:, 1] < ny)
+    assert n == int(keep.sum()) and cnt.sum() == n and cnt.min() >= 1
+    pk = (pts[keep, 0].astype(np.int64) * nx + q[keep, 0]) * ny + q[keep, 1]
+    np.testing.assert_array_equal(key[inv], pk)
+    np.testing.assert_array_equal(np.bincount(inv, minlength=len(cnt)), cnt)
+    # permutation invariance: another row order gives the same pillars and bit-identical features
+    perm = np.random.default_rng(3).permutation(len(pts))
+    f2, c2, inv2, cnt2, n2 = run(np.ascontiguousarray(pts[perm]))
+    np.testing.assert_array_equal(c2, c)
+    np.testing.assert_array_equal(cnt2, cnt)
+    np.testing.assert_array_equal(f2, f)
+    kept_perm = keep[perm]   # the inverse follows the rows: point j of the permuted input still lands in its own pillar
+    np.testing.assert_array_equal(key[inv2], ((pts[perm][kept_perm, 0].astype(np.int64) * nx + q[perm][kept_perm, 0]) * ny + q[perm][kept_perm, 1]))
+    # features are a max over each pillar's rows of a ReLU: non-negative and finite
+    assert np.isfinite(f).all() and f.min() >= 0.0
