@@ -4,22 +4,23 @@
 // PFNLayerV2.forward :35-46: scatter_mean, f_center / f_cluster / f_relative, concat,
 // Linear(no bias)+BatchNorm1d+ReLU, scatter_max (+argmax), and the autograd of that chain.
 //
-// Input is the pillar-grouped row array written by group_rows_kernel (rdp_index.cu): rows of one pillar are
-// contiguous and pillars are in key order.  One persistent CTA (128 threads) walks a contiguous range of
-// tiles; tile t owns the pillars that START in grouped rows [128 t, 128 t + 128) and reads rows
-// [128 t, 128 t + 192) -- a fixed-size, 16-byte aligned window that is prefetched one tile ahead with 1-D TMA
-// bulk copies (rows + pillar ids + original-row ids) onto an mbarrier, double buffered.  A pillar that runs
-// past the staged window (> 64 rows of overhang) takes the "big pillar" path straight from global memory.
+// Input is the pillar-grouped row array written by group_rows_kernel and the pillar table written by
+// pillar_table_kernel (rdp_index.cu): rows of one pillar are contiguous, pillars are in key order, and the table
+// holds every pillar's mean, centre, first row and row count.  One persistent CTA (128 threads) takes tiles
+// b, b + grid, b + 2 grid, ...; tile t owns the pillars that START in grouped rows [128 t, 128 t + 128) and stages
+// rows [128 t - 1, 128 t + 192) plus the table slice of its pillars -- fixed-size, 16-byte aligned windows -- one
+// tile ahead with two 1-D TMA bulk copies onto an mbarrier, double buffered.  A pillar that runs past the staged
+// window (> 64 rows of overhang) takes the "big pillar" path straight from global memory.
 //
-//   P0  head flags from the pillar ids -> first/last pillar of the tile                (thread = row)
-//   P1  row -> pillar slot, pillar start table                                         (thread = row)
-//   P2  per-pillar fp64 xyz sum -> mean (one rounding), pillar centre                  (thread = pillar)
-//   C1  decorated features (same op order / roundings as the reference) -> smem        (thread = row)
-//   ST  lane = output channel, its weight row in registers; each warp streams a pillar-aligned quarter of the
-//       tile's rows: x = W f as a k-ascending fmaf chain (feature row broadcast from smem), y = fma(x, scale,
-//       shift), running max (+ lowest-index argmax), one coalesced 128 B store when a pillar's last row is in.
-//       STATS: fp64 sum x, sum x^2 per lane and the Gram matrix of the features (4x4 register blocks)
-//       BWD  : per (pillar, channel) route the gradient to the winning row and accumulate dbeta, G, A
+//   C1  decorated features (same op order / roundings as the reference) -> smem; slot / last-row flags (thread = row)
+//   ST  APPLY / APPLY_ARG: sub-groups of 16 lanes stream pillar-aligned eighths of the tile's rows, each lane
+//       owning two output channels with their weight rows in registers: x = W f as a k-ascending fmaf chain (feature
+//       row broadcast from smem), y = fma(x, scale, shift), running max (+ lowest-index argmax as one packed 64-bit
+//       key), one coalesced 128 B store when a pillar's last row is in; argpos < 0 marks a ReLU-clamped maximum
+//       STATS: the fp64 Gram matrix of [features | 1] only (4x4 register blocks) -- the batch statistics of x = W f and
+//              the moments the backward needs both follow from it (bn_finalize_kernel), no linear layer in this pass
+//       BWD  : (grad, argpos) rows of 24 pillars at a time through a double buffer requested one chunk ahead; per
+//              (pillar, channel) route the gradient to the winning row, accumulate dbeta and A (G = w . A)
 // Arithmetic is the canonical form of oracle/pillar_oracle.c (ORC_MEAN_F64): outputs are bit-identical to it.
 #pragma once
 
