@@ -35,6 +35,11 @@ class VFETemplate(nn.Module):
         raise NotImplementedError
 
 
+def _world_size() -> int:
+    import torch.distributed as dist
+    return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+
 def _cfg_get(cfg, key, default=None):
     if hasattr(cfg, "get"):
         return cfg.get(key, default)
@@ -126,6 +131,11 @@ class _FusedDynamicPillarVFE(VFETemplate):
         pfn = self.pfn_layers[0]
         norm = pfn.norm if self.use_norm else None
         train_bn = bool(self.use_norm and norm.training)
+        if train_bn and isinstance(norm, nn.SyncBatchNorm) and _world_size() > 1:
+            # tools/train.py --sync_bn (:34,144-145) converts the PFN's BatchNorm1d; the fused kernels compute per-rank batch
+            # statistics (the reference default), so refuse loudly instead of silently training with different semantics
+            raise NotImplementedError("SyncBatchNorm in the fused pillar encoder is not implemented yet (per-rank batch statistics "
+                                      "only, the reference default); run without --sync_bn or keep this module's norm a BatchNorm1d")
         bs = (int(offsets.shape[0]) - 1) if offsets is not None else self._batch_size(batch_dict, points)
         pm = ops.encode_async(points, self.spec, bs, pfn.linear.weight,
                               bias=None if self.use_norm else pfn.linear.bias,
