@@ -4,6 +4,10 @@
 
 #include "rdp_pfn_host.h"
 
+#ifndef RDP_PFN_APPLY_PER_SM
+#define RDP_PFN_APPLY_PER_SM 5
+#endif
+
 namespace rdp {
 
 static const PfnLaunch *lookup(const rdp_geom_t *g, const rdp_layout_t *l) {
@@ -121,7 +125,10 @@ extern "C" int rdp_pfn_fwd(const float *points, int64_t n_points, const rdp_geom
     static const bool use_rows = getenv("RDP_PFN_ROWS") != nullptr;
     const bool aligned32 = !(reinterpret_cast<uintptr_t>(features) & 31u) && !(reinterpret_cast<uintptr_t>(argpos) & 31u);
     if (!use_rows || !aligned32) {
-        RDP_CUDA_OK(L->tile(a, argpos ? PFN_MODE_APPLY_ARG : PFN_MODE_APPLY, grid, st));
+        // the eval kernel is compiled for 5 resident CTAs per SM (no partial-sum slots involved): let it have them
+        const int64_t tiles_ = (n_points + kPfnWin - 1) / kPfnWin;
+        const int agrid = argpos ? grid : (int)(tiles_ < 148 * RDP_PFN_APPLY_PER_SM ? (tiles_ < 1 ? 1 : tiles_) : 148 * RDP_PFN_APPLY_PER_SM);
+        RDP_CUDA_OK(L->tile(a, argpos ? PFN_MODE_APPLY_ARG : PFN_MODE_APPLY, agrid, st));
     } else {
         const int64_t tiles = (n_points + kPfnWin - 1) / kPfnWin;
         const int rgrid = (int)(tiles < kRowsGridCap ? (tiles < 1 ? 1 : tiles) : kRowsGridCap);
