@@ -381,10 +381,14 @@ pillar_table_kernel(const float *__restrict__ grows, const int32_t *__restrict__
     if (p >= counters[RDP_CNT_P]) return;
     const int s = p ? ends[p - 1] : 0, e = ends[p];
     double sx = 0.0, sy = 0.0, sz = 0.0;
-    const float *r = grows + ((size_t)s + 1) * rs;
-    const float x0 = r[1], y0 = r[2];
-    const int b0 = __float2int_rz(r[0]);
-    for (int i = s; i < e; ++i, r += rs) { sx += (double)r[1]; sy += (double)r[2]; sz += (double)r[3]; }
+    const float *r = grows + ((size_t)s + 1) * rs;   // rows are 16-byte aligned: [b, x, y, z] is one 128-bit load
+    const float4 v0 = __ldg(reinterpret_cast<const float4 *>(r));
+    const float x0 = v0.y, y0 = v0.z;
+    const int b0 = __float2int_rz(v0.x);
+    for (int i = s; i < e; ++i, r += rs) {
+        const float4 v = __ldg(reinterpret_cast<const float4 *>(r));
+        sx += (double)v.y; sy += (double)v.z; sz += (double)v.w;
+    }
     float mx, my, mz;
     mean3(sx, sy, sz, e - s, &mx, &my, &mz);
     // centre of the cell: cx*vx + x_off with separate mul / add roundings (:215-216); the quantisation repeats
