@@ -204,7 +204,8 @@ RDP_API int rdp_pillar_lookup(int64_t n_points, const rdp_geom_t *geom, void *wo
                               int32_t *lookup, void *stream);
 
 /*
- * Copies counters[] to `host_mapped` (pinned, device-visible host memory: cudaHostAlloc / torch pin_memory under UVA)
+ * The one read-back of the path: N and P (the sizes the reference learns through the boolean-mask index at
+ * dynamic_pillar_vfe.py:204-206 and torch.unique at :212).  Copies counters[] to `host_mapped` (pinned, device-visible host memory: cudaHostAlloc / torch pin_memory under UVA)
  * from a one-warp kernel instead of a DMA transfer, so the 64-byte read-back never queues behind bulk copies on the
  * copy engines.  The values are visible on the host once `stream` has been synchronised.
  */
@@ -212,7 +213,9 @@ RDP_API int rdp_publish_counters(const int32_t *counters, int32_t *host_mapped, 
 
 /*
  * Host-buffer convenience (what a non-torch caller binds): uploads `points` (host), runs
- * rdp_index_fwd + rdp_pfn_fwd in eval mode, downloads the results and synchronises.
+ * rdp_index_fwd + rdp_pfn_fwd in eval mode, downloads the results and synchronises -- the whole eval-mode
+ * forward of dynamic_pillar_vfe.py:195-252 (and :90-142, :255-373) including load_data_to_gpu
+ * (pcdet/models/__init__.py:23-36) on the way in.
  * Host output buffers must hold n_points rows; *n_kept / *n_pillars receive N and P.
  * Parameters in `params` are HOST pointers here.
  */
