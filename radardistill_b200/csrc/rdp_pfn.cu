@@ -153,6 +153,8 @@ extern "C" int rdp_pfn_bwd(const float *points, int64_t n_points, const rdp_geom
     }
     (void)features;   // the ReLU mask travels in the sign of argpos; kept in the signature for ABI stability
     if (!points || !workspace || !grad_features || !argpos) return RDP_ERR_INVALID_ARG;
+    // both are sources of 16-byte bulk (TMA) copies
+    if ((reinterpret_cast<uintptr_t>(grad_features) & 15u) || (reinterpret_cast<uintptr_t>(argpos) & 15u)) return RDP_ERR_INVALID_ARG;
     if (train && !bn_state) return RDP_ERR_INVALID_ARG;
     const PfnLaunch *L = lookup(geom, layout);
     if (!L) return RDP_ERR_UNSUPPORTED;

@@ -251,13 +251,16 @@ def _params_struct(spec: "EncoderSpec", weight, bias, gamma, beta, running_mean,
     return p
 
 
-def _check_param(t: Optional[torch.Tensor], shape, name: str):
+def _check_param(t: Optional[torch.Tensor], shape, name: str, device=None):
     if t is None:
         return None
+    # no silent copies: the kernels keep raw addresses (the train-mode forward updates the running statistics in place and
+    # the backward re-reads the parameters), so a temporary contiguous copy would be updated / read instead of the module's tensor
     if not t.is_cuda or t.dtype != torch.float32 or tuple(t.shape) != tuple(shape) or not t.is_contiguous():
-        if t.is_cuda and t.dtype == torch.float32 and tuple(t.shape) == tuple(shape):
-            return t.detach().contiguous()
-        raise ValueError(f"{name}: expected a CUDA float32 tensor of shape {tuple(shape)}, got {t.dtype} {tuple(t.shape)} on {t.device}")
+        raise ValueError(f"{name}: expected a contiguous CUDA float32 tensor of shape {tuple(shape)}, got {t.dtype} "
+                         f"{tuple(t.shape)} (contiguous={t.is_contiguous()}) on {t.device}")
+    if device is not None and t.device != device:
+        raise ValueError(f"{name} lives on {t.device} but the points are on {device}")
     return t
 
 
@@ -310,12 +313,12 @@ def encode_launch(points: torch.Tensor, spec: EncoderSpec, batch_size: int, weig
     dev = pts.device
     n0 = pts.shape[0]
     use_norm = gamma is not None
-    weight = _check_param(weight, (spec.c_out, spec.c_in), "linear.weight")
-    bias = _check_param(bias, (spec.c_out,), "linear.bias")
-    gamma = _check_param(gamma, (spec.c_out,), "norm.weight")
-    beta = _check_param(beta, (spec.c_out,), "norm.bias")
-    running_mean = _check_param(running_mean, (spec.c_out,), "norm.running_mean")
-    running_var = _check_param(running_var, (spec.c_out,), "norm.running_var")
+    weight = _check_param(weight, (spec.c_out, spec.c_in), "linear.weight", dev)
+    bias = _check_param(bias, (spec.c_out,), "linear.bias", dev)
+    gamma = _check_param(gamma, (spec.c_out,), "norm.weight", dev)
+    beta = _check_param(beta, (spec.c_out,), "norm.bias", dev)
+    running_mean = _check_param(running_mean, (spec.c_out,), "norm.running_mean", dev)
+    running_var = _check_param(running_var, (spec.c_out,), "norm.running_var", dev)
     train_bn = bool(train_bn and use_norm)
     batch_size = int(batch_size)
     pl = _plan(spec, batch_size, int(n0), train_bn)
@@ -391,6 +394,8 @@ def encode_backward(points: torch.Tensor, spec: EncoderSpec, batch_size: int, re
         g = grad_features
         if g.dtype != torch.float32 or not g.is_contiguous():
             g = g.contiguous().float()
+        if g.data_ptr() % 16:   # the backward stages gradient rows with 16-byte bulk copies (a view into a flat buffer may be offset)
+            g = g.clone()
         prm = res.params_struct
         if prm is None or bool(prm.train_bn) != train_bn:
             prm = _params_struct(spec, weight, bias, gamma, beta, running_mean, running_var, train_bn)

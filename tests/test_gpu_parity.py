@@ -433,3 +433,106 @@ def test_full_size_properties_batch_of_eight():
     np.testing.assert_array_equal(key[inv2], ((pts[perm][kept_perm, 0].astype(np.int64) * nx + q[perm][kept_perm, 0]) * ny + q[perm][kept_perm, 1]))
     # features are a max over each pillar's rows of a ReLU: non-negative and finite
     assert np.isfinite(f).all() and f.min() >= 0.0
+
+
+def _train_step_against_oracle(kind, pts, batch, grad_seed):
+    """Train-mode forward + backward of a shipped encoder on `pts`, every output compared with the C oracle."""
+    import os
+    c, key = (5, "points") if kind == "lidar" else (6, "radar_points")
+    m = _shipped_module(kind, train=True)
+    o = _oracle_of(m, c)
+    orc.set_threads(os.cpu_count() or 8)
+    r = o.forward(pts, training=True)
+    out = m({key: torch.from_numpy(pts).cuda(), "batch_size": batch})
+    res = m.last_result
+    fk = [k for k in out if k.endswith("pillar_features")][0]
+    ck = [k for k in out if k.endswith("_coords")][0]
+    assert res.n_kept == r["n"] and res.n_pillars == r["p"]
+    np.testing.assert_array_equal(out[ck].cpu().numpy(), r["coords"])
+    np.testing.assert_array_equal(res.inverse.cpu().numpy(), r["inverse"])
+    np.testing.assert_array_equal(res.counts.cpu().numpy(), r["counts"])
+    np.testing.assert_array_equal(res.argmax.cpu().numpy(), r["argmax"])
+    f = out[fk]
+    assert H.norm_rel_err(f.detach().cpu().numpy(), r["features"]) <= 1e-6
+    gout = torch.randn(f.shape, generator=torch.Generator().manual_seed(grad_seed)).cuda()
+    f.backward(gout)
+    b = o.backward(r, gout.cpu().numpy())
+    pfn = m.pfn_layers[0]
+    assert H.norm_rel_err(pfn.linear.weight.grad.cpu().numpy(), b["d_weight"]) <= H.RTOL_GRADS
+    assert H.norm_rel_err(pfn.norm.weight.grad.cpu().numpy(), b["d_gamma"]) <= H.RTOL_GRADS
+    assert H.norm_rel_err(pfn.norm.bias.grad.cpu().numpy(), b["d_beta"]) <= H.RTOL_GRADS
+    assert H.norm_rel_err(pfn.norm.running_mean.cpu().numpy(), r["new_running_mean"]) <= 1e-6
+    assert H.norm_rel_err(pfn.norm.running_var.cpu().numpy(), r["new_running_var"]) <= 1e-6
+    return r
+
+
+def test_full_size_train_step_vs_oracle_batch_of_eight():
+    """BASELINE configs[2] exactly as bench.py's mode B times it: 8 LiDAR frames (2.7 M rows) and 8 radar frames, both
+    encoders train-mode BN, forward + backward, against the C oracle: coords / inverse / counts / argmax bit-exact,
+    features <= 1e-6, dW / dgamma / dbeta <= 1e-5 (dynamic_pillar_vfe.py:195-252)."""
+    from radardistill_b200 import synth
+    r = _train_step_against_oracle("lidar", synth.lidar_batch(8), 8, 21)
+    assert r["n"] > 2_500_000 and r["p"] > 1_000_000
+    _train_step_against_oracle("radar", synth.radar_batch(8), 8, 22)
+
+
+def test_stress_spec_size_one_million_points_per_frame():
+    """BASELINE configs[4] at the specified size: 1 M points per frame (2 frames = one GPU's share of batch 16 over 8
+    GPUs), 0.05 m pillars: eval forward bit-exact and a train step against the oracle."""
+    import os
+    from oracle.ref_loader import Cfg
+    from radardistill_b200 import synth, vfe
+    grid = synth.grid_size_of(synth.PC_RANGE, synth.STRESS_VOXEL_SIZE)
+    pts = synth.stress_batch(2, n_points=1_000_000)
+    cfg = Cfg(USE_NORM=True, WITH_DISTANCE=False, USE_ABSLOTE_XYZ=True, USE_CLUSTER_XYZ=True, NUM_FILTERS=[32])
+    torch.manual_seed(12)
+    m = vfe.DynamicPillarVFESimple2D(model_cfg=cfg, num_point_features=5, voxel_size=synth.STRESS_VOXEL_SIZE, grid_size=grid,
+                                     point_cloud_range=synth.PC_RANGE).cuda()
+    n = m.pfn_layers[0].norm
+    with torch.no_grad():
+        n.weight.uniform_(0.5, 1.5); n.bias.normal_(0, 0.2); n.running_mean.normal_(0, 1); n.running_var.uniform_(0.5, 4)
+    pfn = m.pfn_layers[0]
+    ocfg = orc.OracleConfig(num_point_features=5, voxel_size=tuple(synth.STRESS_VOXEL_SIZE), grid_size=tuple(grid),
+                            point_cloud_range=tuple(synth.PC_RANGE))
+    cp = lambda t: t.detach().cpu().numpy().copy()
+    o = orc.PillarOracle(ocfg, cp(pfn.linear.weight), cp(n.weight), cp(n.bias), cp(n.running_mean), cp(n.running_var))
+    orc.set_threads(os.cpu_count() or 8)
+    dev = torch.from_numpy(pts).cuda()
+    m.eval()
+    r = o.forward(pts, training=False, keep_intermediates=False)
+    assert r["n0"] == 2_000_000 and r["counts"].max() > 1000
+    with torch.no_grad():
+        out = m({"points": dev, "batch_size": 2})
+    np.testing.assert_array_equal(out["pillar_coords"].cpu().numpy(), r["coords"])
+    np.testing.assert_array_equal(m.last_result.counts.cpu().numpy(), r["counts"])
+    np.testing.assert_array_equal(m.last_result.inverse.cpu().numpy(), r["inverse"])
+    np.testing.assert_array_equal(out["pillar_features"].cpu().numpy(), r["features"])
+    m.train()
+    r = o.forward(pts, training=True)
+    out = m({"points": dev, "batch_size": 2})
+    np.testing.assert_array_equal(m.last_result.argmax.cpu().numpy(), r["argmax"])
+    f = out["pillar_features"]
+    assert H.norm_rel_err(f.detach().cpu().numpy(), r["features"]) <= 1e-6
+    gout = torch.randn(f.shape, generator=torch.Generator().manual_seed(6)).cuda()
+    f.backward(gout)
+    b = o.backward(r, gout.cpu().numpy())
+    assert H.norm_rel_err(pfn.linear.weight.grad.cpu().numpy(), b["d_weight"]) <= H.RTOL_GRADS
+    assert H.norm_rel_err(n.weight.grad.cpu().numpy(), b["d_gamma"]) <= H.RTOL_GRADS
+    assert H.norm_rel_err(n.bias.grad.cpu().numpy(), b["d_beta"]) <= H.RTOL_GRADS
+
+
+def test_backward_accepts_a_misaligned_upstream_gradient():
+    """a contiguous upstream gradient whose storage offset is not a multiple of 16 bytes (a view into a flat
+    buffer) must give the same parameter gradients as an aligned copy (the kernels stage gradient rows with 16-byte bulk copies)."""
+    from radardistill_b200 import synth
+    pts = torch.from_numpy(synth.radar_batch(2)).cuda()
+    grads = []
+    for misaligned in (False, True):
+        m = _shipped_module("radar", train=True)
+        f = m({"radar_points": pts, "batch_size": 2})["radar_pillar_features"]
+        g = torch.randn(f.numel() + 1, generator=torch.Generator().manual_seed(4)).cuda()
+        gv = g[1:].view_as(f) if misaligned else g[1:].clone().view_as(f)
+        assert (gv.data_ptr() % 16 != 0) == misaligned
+        f.backward(gv)
+        grads.append(m.pfn_layers[0].linear.weight.grad.clone())
+    assert H.norm_rel_err(grads[1].cpu().numpy(), grads[0].cpu().numpy()) <= 1e-6
