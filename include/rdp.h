@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define RDP_ABI_VERSION 4
+#define RDP_ABI_VERSION 5
 
 #if defined(__GNUC__)
 #define RDP_API __attribute__((visibility("default")))
@@ -62,6 +62,9 @@ typedef struct rdp_geom {
     int32_t nx, ny;     /* grid_size[0], grid_size[1]                                        */
     int32_t batch_size; /* frames in this call; rows carry their frame index in column 0     */
     int32_t cols;       /* floats per row = 1 + num_point_features                           */
+    int32_t nz;         /* <= 1: pillars (z neither quantised nor masked, dynamic_pillar_vfe.py:201-206);
+                           > 1: voxels, grid_size[2] (dynamic_voxel_vfe.py:57-66, dynamic_mean_vfe.py:52-60): z is
+                           quantised and masked too, the key gains cz and coords are [b, z, y, x]          */
 } rdp_geom_t;
 
 /* Feature layout + PFN shape: model_cfg of the reference classes (:53-62, :150-166). */
@@ -88,6 +91,16 @@ typedef struct rdp_pfn_params {
     int32_t train_bn;     /* 1: batch statistics + running-stat update; 0: running stats     */
     int64_t *num_batches_tracked; /* norm.num_batches_tracked (device, int64): += 1 by a train-mode forward over more
                                      than one point, as BatchNorm1d does; may be NULL                               */
+    /* SyncBatchNorm (tools/train.py:34,144-145): batch statistics over the points of ALL ranks.  The library issues no
+       collective; the caller all-reduces two small fp64 vectors of the workspace (rdp_stats_buffers) between phases:
+         forward : phase 1 = index + feature moments, stop;  all-reduce(SUM) the stats vector (keep a copy of the local one);
+                   phase 2 = fold the (global) moments into bn_state + the rest of the forward, `local_stats` = the copy
+         backward: phase 1 = the backward sums, stop;  all-reduce(SUM) a COPY of the bwd vector;
+                   phase 2 = closed-form epilogue with `global_bwd` = that all-reduced copy
+       0 = everything in one call (per-rank statistics, the reference default).                                    */
+    int32_t stats_phase;
+    const double *local_stats;    /* forward phase 2: this rank's moments (device), as left by phase 1              */
+    const double *global_bwd;     /* backward phase 2: the all-reduced backward sums (device)                        */
 } rdp_pfn_params_t;
 
 RDP_API int rdp_abi_version(void);
@@ -155,6 +168,16 @@ RDP_API int rdp_pfn_fwd(const float *points, int64_t n_points, const rdp_geom_t 
                         double *bn_state, void *stream);
 
 RDP_API int64_t rdp_bn_state_doubles(const rdp_layout_t *layout);
+
+/* 1 if the fused kernels are compiled for this (row width, distance feature, c_out, feature layout), else 0: constructors
+   validate their configuration with this instead of failing at the first forward. */
+RDP_API int rdp_config_supported(const rdp_geom_t *geom, const rdp_layout_t *layout);
+
+/* Byte offsets (inside the workspace) and lengths (in doubles) of the two fp64 vectors a SyncBatchNorm caller all-reduces
+   between the phases described at rdp_pfn_params_t.stats_phase: the feature moments (+ the point count in the last slot)
+   and the backward sums. */
+RDP_API int rdp_stats_buffers(int64_t n_points, const rdp_geom_t *geom, const rdp_layout_t *layout, size_t *stats_offset,
+                              int64_t *stats_doubles, size_t *bwd_offset, int64_t *bwd_doubles);
 
 /*
  * rdp_index_fwd_publish followed by rdp_pfn_fwd in one call (one trip through the host binding per forward).

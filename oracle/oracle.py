@@ -19,7 +19,9 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "libpillar_oracle.so")
 
 MEAN_SEQ_F32 = 0   # torch_scatter CPU semantics (pinning against the reference)
-MEAN_F64 = 1       # canonical, order-independent (what the CUDA path implements)
+MEAN_F64 = 1       # round-1 canonical form: fp64 mean, k-ascending fmaf chain over the reference's feature order
+FOLDED = 2         # round-2 canonical form, what the CUDA kernels implement: fp64 mean + affine-folded linear layer
+MAX_G = 14
 LAYOUT_SIMPLE2D = 0
 LAYOUT_DYNPILLAR = 1
 
@@ -48,7 +50,7 @@ def lib():
         build()
         _lib = C.CDLL(_SO)
         _lib.orc_abi_version.restype = C.c_int
-        assert _lib.orc_abi_version() == 1
+        assert _lib.orc_abi_version() == 2
     return _lib
 
 
@@ -115,7 +117,7 @@ class PillarOracle:
     """CPU oracle with the module's state: W (Cout,Cin), gamma, beta, running stats."""
 
     def __init__(self, cfg: OracleConfig, weight, gamma=None, beta=None, running_mean=None,
-                 running_var=None, bias=None, mean_mode: int = MEAN_F64):
+                 running_var=None, bias=None, mean_mode: int = FOLDED):
         self.cfg, self.mean_mode = cfg, mean_mode
         f32 = lambda a, d: np.ascontiguousarray(d if a is None else a, dtype=np.float32)
         co = cfg.c_out
@@ -153,7 +155,9 @@ class PillarOracle:
             raise ValueError("Expected more than 1 value per channel when training")  # torch BN behaviour
         mean = np.zeros((max(p, 1), 3), np.float32)
         L.orc_pillar_mean(_p(r["points"]), C.byref(self._cs), _p(r["keep"]), _p(r["inverse"]), _p(r["counts"]),
-                          C.c_int64(n), C.c_int64(p), C.c_int(self.mean_mode), _p(mean))
+                          C.c_int64(n), C.c_int64(p), C.c_int(min(self.mean_mode, MEAN_F64)), _p(mean))
+        if self.mean_mode == FOLDED:
+            return self._forward_folded(r, mean, training, keep_intermediates)
         f = np.empty((max(n, 1), cin), np.float32)
         L.orc_features(_p(r["points"]), C.byref(self._cs), _p(r["keep"]), _p(r["pcoord"]), _p(r["inverse"]), _p(mean),
                        C.c_int64(n), _p(f))
@@ -177,6 +181,52 @@ class PillarOracle:
         r.update(features=out[:p], argmax=arg[:p], pillar_mean=mean[:p], scale=scale, shift=shift,
                  batch_mean=bmean, batch_var=bvar, training=training)
         if keep_intermediates:
+            r.update(f=f[:n], x=x[:n])
+        if training and cfg.use_norm and n > 0:
+            m = cfg.momentum
+            unbiased = bvar * (n / (n - 1.0)) if n > 1 else bvar
+            r["new_running_mean"] = ((1 - m) * self.running_mean + m * bmean).astype(np.float32)
+            r["new_running_var"] = ((1 - m) * self.running_var + m * unbiased).astype(np.float32)
+        return r
+
+    def _forward_folded(self, r, mean, training, keep_intermediates):
+        """ORC_FOLDED: the canonical arithmetic of the CUDA kernels (see the section header in pillar_oracle.c)."""
+        L, cfg = lib(), self.cfg
+        n, p, cin, co = r["n"], r["p"], cfg.c_in, cfg.c_out
+        T = np.zeros((max(cin, 1), MAX_G + 1), np.float32)
+        kin, g = C.c_int32(0), C.c_int32(0)
+        if L.orc_build_T(C.byref(self._cs), _p(T), C.byref(kin), C.byref(g)) != cin:
+            raise ValueError("oracle: layout does not fit the folded basis")
+        kin, g = kin.value, g.value
+        wg, cst = np.empty((co, g), np.float32), np.empty(co, np.float32)
+        L.orc_fold_weights(_p(self.weight), None if cfg.use_norm else _p(self.bias), _p(T), C.c_int(cin), C.c_int(co), C.c_int(g),
+                           _p(wg), _p(cst))
+        q = np.zeros((max(p, 1), 5), np.float32)
+        L.orc_pillar_consts(C.byref(self._cs), _p(r["unq"]), _p(mean), C.c_int64(p), _p(q))
+        rin = np.empty((max(n, 1), kin), np.float32)
+        v, x = np.empty((max(n, 1), co), np.float32), np.empty((max(n, 1), co), np.float32)
+        L.orc_forward_folded(_p(r["points"]), C.byref(self._cs), _p(r["keep"]), _p(r["inverse"]), _p(q), _p(wg), _p(cst),
+                             C.c_int(kin), C.c_int(g), C.c_int64(n), _p(rin), _p(v), _p(x))
+        bmean, bvar = np.zeros(co, np.float64), np.ones(co, np.float64)
+        scale, shift = np.ones(co, np.float32), np.zeros(co, np.float32)
+        if cfg.use_norm:
+            if training:
+                S1, S2 = np.zeros(g, np.float64), np.zeros((g, g), np.float64)
+                L.orc_moments_folded(_p(rin), _p(q), _p(r["inverse"]), C.c_int64(n), C.c_int(kin), C.c_int(g), _p(S1), _p(S2))
+                L.orc_bn_stats_from_moments(_p(S1), _p(S2), C.c_int64(n), C.c_int(g), _p(wg), _p(cst), C.c_int(co), _p(bmean), _p(bvar))
+            else:
+                bmean, bvar = self.running_mean.astype(np.float64), self.running_var.astype(np.float64)
+            L.orc_bn_fold(_p(self.gamma), _p(self.beta), _p(bmean), _p(bvar), C.c_double(cfg.eps), C.c_int(co), _p(scale), _p(shift))
+        out = np.empty((max(p, 1), co), np.float32); arg = np.empty((max(p, 1), co), np.int32)
+        L.orc_act_max_folded(_p(x), _p(v), C.c_int64(n), C.c_int(co), _p(scale), _p(shift), _p(r["inverse"]), C.c_int64(p),
+                             _p(out), _p(arg))
+        r.update(features=out[:p], argmax=arg[:p], pillar_mean=mean[:p], scale=scale, shift=shift, batch_mean=bmean,
+                 batch_var=bvar, training=training)
+        if keep_intermediates:
+            # the backward oracle works on the reference's own decorated features (orc_features) and the folded x
+            f = np.empty((max(n, 1), cin), np.float32)
+            L.orc_features(_p(r["points"]), C.byref(self._cs), _p(r["keep"]), _p(r["pcoord"]), _p(r["inverse"]), _p(mean),
+                           C.c_int64(n), _p(f))
             r.update(f=f[:n], x=x[:n])
         if training and cfg.use_norm and n > 0:
             m = cfg.momentum

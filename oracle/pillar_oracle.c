@@ -79,7 +79,7 @@ typedef struct {
     int32_t c_in, c_out;
 } orc_cfg;
 
-int orc_abi_version(void) { return 1; }
+int orc_abi_version(void) { return 2; }
 
 /* ------------------------------------------------------------------ a1-a4: index part */
 
@@ -446,4 +446,181 @@ void orc_backward(const float *g, const float *f, const float *x, const float *o
     free(dw);
     free(mu);
     free(gy);
+}
+
+/* ====================================================================================================================
+ * ORC_FOLDED (mean_mode 2): the canonical arithmetic of the round-2 CUDA kernels (radardistill_b200/csrc/rdp_pfn.cuh).
+ *
+ * Every decorated feature of the reference (:214-237, :105-121) is affine in the row's centre offsets
+ * d = xyz - centre (exactly f_center, :215-217) and in per-pillar constants:
+ *     xyz = d + centre,   f_cluster = xyz - mean = d + (centre - mean),   f_rel = xyz - lo = d + (centre - lo).
+ * With T the (c_in x (G+1)) matrix that writes the layout's features in the reduced basis
+ *     g = [dx, dy, dz, raw features 4.., (dist) | cx, cy, cx - mx, cy - my, cz - mz | 1]        (KIN row inputs, 5 pillar constants)
+ * the linear layer is  x_c = W_c . f = wg_c . g + const_c  with [wg_c | const_c] = W_c T (fp64, rounded once), evaluated as
+ *     v_ic = k-ascending fmaf chain over the KIN row inputs            (first term a plain product)
+ *     u_pc = fmaf chain over the 5 pillar constants, starting from const_c
+ *     x_ic = v_ic + u_pc  (one rounding);   y = fma(x, scale, shift);   z = max(y, 0);   out_pc = max_i z_ic.
+ * Train-mode batch statistics come from the fp64 moments of g (S1 = sum g, S2 = sum g g^T):
+ *     mean_c = wg_c . S1 / n + const_c,   var_c = wg_c^T S2 wg_c / n - (wg_c . S1 / n)^2.
+ * argmax rule: the row of the pillar with the largest s_c v_ic (s_c = sign(scale_c): the row that maximises the BatchNorm
+ * output), lowest kept index on exact ties; a (pillar, channel) whose maximum the ReLU clamped to 0 reports the pillar's
+ * lowest kept index (every row ties at 0 -- torch_scatter's CPU rule, :40) and receives no gradient.
+ * Against the reference arithmetic this differs by fp32 rounding only (features <= 1e-5 norm-relative on every golden).
+ * ==================================================================================================================== */
+#define ORC_MAX_G 14
+
+/* T (c_in rows, stride ORC_MAX_G + 1).  Returns c_in, or -1.  Mirrors build_T in radardistill_b200/csrc/rdp_pfn.cu. */
+int orc_build_T(const orc_cfg *g, float *T, int32_t *kin_out, int32_t *g_out) {
+    const int C = g->cols - 1, KIN = C + (g->with_distance ? 1 : 0), G = KIN + 5, S = ORC_MAX_G + 1;
+    if (G > ORC_MAX_G) return -1;
+    int j = 0;
+#define ROW() (memset(T + (size_t)j * S, 0, sizeof(float) * S), T + (size_t)(j++) * S)
+    float *r;
+    const float off_z = g->off[2];
+    for (int pass = 0; pass < 5; ++pass) {
+        /* block order: Simple2D = center, points, cluster, dist, relative ; DynamicPillarVFE = points, cluster, center, dist */
+        int what;
+        if (g->layout == ORC_LAYOUT_SIMPLE2D) { static const int o[5] = {0, 1, 2, 3, 4}; what = o[pass]; }
+        else { static const int o[5] = {1, 2, 0, 3, -1}; what = o[pass]; }
+        if (what == 0) {
+            for (int a = 0; a < 3; ++a) { r = ROW(); r[a] = 1.0f; }
+        } else if (what == 1) {
+            if (g->use_abs) {
+                r = ROW(); r[0] = 1.0f; r[KIN] = 1.0f;
+                r = ROW(); r[1] = 1.0f; r[KIN + 1] = 1.0f;
+                r = ROW(); r[2] = 1.0f; r[G] = off_z;
+            }
+            for (int c = 4; c <= C; ++c) { r = ROW(); r[c - 1] = 1.0f; }
+        } else if (what == 2) {
+            if (g->layout != ORC_LAYOUT_SIMPLE2D || g->use_cluster)
+                for (int a = 0; a < 3; ++a) { r = ROW(); r[a] = 1.0f; r[KIN + 2 + a] = 1.0f; }
+        } else if (what == 3) {
+            if (g->with_distance) { r = ROW(); r[C] = 1.0f; }
+        } else if (what == 4) {
+            if (g->use_relative) {
+                r = ROW(); r[0] = 1.0f; r[KIN] = 1.0f; r[G] = -g->lo[0];
+                r = ROW(); r[1] = 1.0f; r[KIN + 1] = 1.0f; r[G] = -g->lo[1];
+                r = ROW(); r[2] = 1.0f; r[G] = (float)((double)off_z - (double)g->lo[2]);
+            }
+        }
+    }
+#undef ROW
+    *kin_out = KIN; *g_out = G;
+    return j == g->c_in ? j : -1;
+}
+
+/* [wg_c | const_c] = W_c T (+ bias): fp64 products (exact) and sums in feature order, one rounding to fp32. */
+void orc_fold_weights(const float *W, const float *bias, const float *T, int cin, int cout, int G, float *wg, float *cst) {
+    const int S = ORC_MAX_G + 1;
+    for (int c = 0; c < cout; ++c) {
+        double acc[ORC_MAX_G + 1] = {0.0};
+        for (int j = 0; j < cin; ++j) {
+            const double w = (double)W[c * cin + j];
+            for (int m = 0; m <= G; ++m) { const double pr = w * (double)T[(size_t)j * S + m]; acc[m] = acc[m] + pr; }
+        }
+        if (bias) acc[G] = acc[G] + (double)bias[c];
+        for (int m = 0; m < G; ++m) wg[c * G + m] = (float)acc[m];
+        cst[c] = (float)acc[G];
+    }
+}
+
+/* Per-pillar constants q[p] = [cx, cy, cx - mx, cy - my, cz - mz] (cz = z_offset: pillars) from the merged key and the mean. */
+void orc_pillar_consts(const orc_cfg *g, const int32_t *unq, const float *mean, int64_t P, float *q) {
+    const int32_t sxy = g->nx * g->ny, sy = g->ny;
+    for (int64_t p = 0; p < P; ++p) {
+        const int32_t u = unq[p], cx = (u % sxy) / sy, cy = u % sy;
+        const float cenx = (float)cx * g->vsz[0] + g->off[0], ceny = (float)cy * g->vsz[1] + g->off[1];   /* (:215-216) */
+        q[5 * p] = cenx; q[5 * p + 1] = ceny;
+        q[5 * p + 2] = cenx - mean[3 * p]; q[5 * p + 3] = ceny - mean[3 * p + 1]; q[5 * p + 4] = g->off[2] - mean[3 * p + 2];
+    }
+}
+
+typedef struct { const float *pts; const orc_cfg *g; const int32_t *keep, *inv; const float *q, *wg, *cst; int KIN, G;
+                 float *rin, *v, *x; } fold_ctx;
+static void fold_range(int64_t lo, int64_t hi, void *p) {
+    fold_ctx *c = (fold_ctx *)p;
+    const int cols = c->g->cols, KIN = c->KIN, G = c->G, cout = c->g->c_out;
+    for (int64_t j = lo; j < hi; ++j) {
+        const float *r = c->pts + (int64_t)c->keep[j] * cols, *qp = c->q + 5 * (int64_t)c->inv[j];
+        float *rin = c->rin + j * KIN;
+        const float x = r[1], y = r[2], z = r[3];
+        rin[0] = x - qp[0]; rin[1] = y - qp[1]; rin[2] = z - c->g->off[2];
+        for (int k = 4; k < cols; ++k) rin[k - 1] = r[k];
+        if (c->g->with_distance) rin[cols - 1] = sqrtf(fmaf(z, z, fmaf(y, y, x * x)));
+        for (int o = 0; o < cout; ++o) {
+            const float *w = c->wg + o * G;
+            float v = w[0] * rin[0];
+            for (int k = 1; k < KIN; ++k) v = fmaf(w[k], rin[k], v);
+            float u = c->cst[o];
+            for (int k = 0; k < 5; ++k) u = fmaf(w[KIN + k], qp[k], u);
+            c->v[j * cout + o] = v;
+            c->x[j * cout + o] = v + u;
+        }
+    }
+}
+/* rin (n x KIN), v (n x cout), x = v + u (n x cout) */
+void orc_forward_folded(const float *pts, const orc_cfg *g, const int32_t *keep, const int32_t *inv, const float *q, const float *wg,
+                        const float *cst, int KIN, int G, int64_t n, float *rin, float *v, float *x) {
+    fold_ctx c = {pts, g, keep, inv, q, wg, cst, KIN, G, rin, v, x};
+    parallel_for(n, fold_range, &c);
+}
+
+/* S1 (G), S2 (G x G) of g_i = [rin_i | q_inv[i]] in fp64 (products of two fp32 values are exact). */
+void orc_moments_folded(const float *rin, const float *q, const int32_t *inv, int64_t n, int KIN, int G, double *S1, double *S2) {
+    for (int k = 0; k < G; ++k) S1[k] = 0.0;
+    for (int k = 0; k < G * G; ++k) S2[k] = 0.0;
+    for (int64_t j = 0; j < n; ++j) {
+        double gv[ORC_MAX_G];
+        for (int k = 0; k < KIN; ++k) gv[k] = (double)rin[j * KIN + k];
+        for (int k = 0; k < 5; ++k) gv[KIN + k] = (double)q[5 * (int64_t)inv[j] + k];
+        for (int k = 0; k < G; ++k) {
+            S1[k] += gv[k];
+            for (int l = k; l < G; ++l) S2[k * G + l] += gv[k] * gv[l];
+        }
+    }
+    for (int k = 0; k < G; ++k)
+        for (int l = 0; l < k; ++l) S2[k * G + l] = S2[l * G + k];
+}
+
+void orc_bn_stats_from_moments(const double *S1, const double *S2, int64_t n, int G, const float *wg, const float *cst, int cout,
+                               double *mean, double *var) {
+    for (int c = 0; c < cout; ++c) {
+        const float *w = wg + c * G;
+        double m1 = 0.0, e2 = 0.0;
+        for (int k = 0; k < G; ++k) {
+            m1 += (double)w[k] * S1[k];
+            double row = 0.0;
+            for (int l = 0; l < G; ++l) row += S2[k * G + l] * (double)w[l];
+            e2 += (double)w[k] * row;
+        }
+        double mc = n > 0 ? m1 / (double)n : 0.0;
+        double vv = n > 0 ? e2 / (double)n - mc * mc : 0.0;
+        mean[c] = n > 0 ? mc + (double)cst[c] : 0.0;
+        var[c] = vv > 0.0 ? vv : 0.0;
+    }
+}
+
+/* out / arg under the folded argmax rule (see the header of this section). */
+void orc_act_max_folded(const float *x, const float *v, int64_t n, int cout, const float *scale, const float *shift,
+                        const int32_t *inv, int64_t P, float *out, int32_t *arg) {
+    float *best = (float *)malloc(sizeof(float) * (size_t)(P * cout + 1));
+    int32_t *first = (int32_t *)malloc(sizeof(int32_t) * (size_t)(P + 1));
+    for (int64_t q = 0; q < P * cout; ++q) { out[q] = -1.0f; arg[q] = (int32_t)n; best[q] = -INFINITY; }
+    for (int64_t p = 0; p < P; ++p) first[p] = -1;
+    for (int64_t j = 0; j < n; ++j) {
+        const int64_t p = inv[j];
+        if (first[p] < 0) first[p] = (int32_t)j;
+        for (int c = 0; c < cout; ++c) {
+            const float y = fmaf(x[j * cout + c], scale[c], shift[c]);
+            const float z = y > 0.0f ? y : 0.0f;
+            if (z > out[p * cout + c]) out[p * cout + c] = z;
+            const float sv = scale[c] < 0.0f ? -v[j * cout + c] : v[j * cout + c];
+            if (sv > best[p * cout + c]) { best[p * cout + c] = sv; arg[p * cout + c] = (int32_t)j; } /* strict: first index */
+        }
+    }
+    for (int64_t p = 0; p < P; ++p)
+        for (int c = 0; c < cout; ++c)
+            if (!(out[p * cout + c] > 0.0f)) arg[p * cout + c] = first[p];
+    free(best);
+    free(first);
 }

@@ -8,19 +8,19 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("RDP_LIB_PATH", os.path.join(_HERE, "librdp.so"))  # override: kernel-variant experiments
 
-RDP_ABI_VERSION = 4
+RDP_ABI_VERSION = 5
 RDP_NUM_COUNTERS = 16
 CNT_N, CNT_P, CNT_ERRFLAGS = 0, 1, 2
 LAYOUT_SIMPLE2D, LAYOUT_DYNPILLAR = 0, 1
 
 EXPORTS = ["rdp_abi_version", "rdp_status_string", "rdp_last_cuda_error", "rdp_workspace_bytes", "rdp_index_fwd", "rdp_index_fwd_publish", "rdp_index_fwd_frames", "rdp_encode_fwd_frames",
            "rdp_pfn_fwd", "rdp_encode_fwd", "rdp_bn_state_doubles", "rdp_pfn_bwd", "rdp_argmax_kept", "rdp_pillar_lookup", "rdp_publish_counters",
-           "rdp_encode_host"]
+           "rdp_encode_host", "rdp_config_supported", "rdp_stats_buffers"]
 
 
 class Geom(C.Structure):
     _fields_ = [("lo", C.c_float * 3), ("vsz", C.c_float * 3), ("off", C.c_float * 3),
-                ("nx", C.c_int32), ("ny", C.c_int32), ("batch_size", C.c_int32), ("cols", C.c_int32)]
+                ("nx", C.c_int32), ("ny", C.c_int32), ("batch_size", C.c_int32), ("cols", C.c_int32), ("nz", C.c_int32)]
 
 
 class Layout(C.Structure):
@@ -31,7 +31,8 @@ class Layout(C.Structure):
 class PfnParams(C.Structure):
     _fields_ = [("weight", C.c_void_p), ("bias", C.c_void_p), ("gamma", C.c_void_p), ("beta", C.c_void_p),
                 ("running_mean", C.c_void_p), ("running_var", C.c_void_p), ("eps", C.c_double), ("momentum", C.c_double),
-                ("train_bn", C.c_int32), ("num_batches_tracked", C.c_void_p)]
+                ("train_bn", C.c_int32), ("num_batches_tracked", C.c_void_p),
+                ("stats_phase", C.c_int32), ("local_stats", C.c_void_p), ("global_bwd", C.c_void_p)]
 
 
 class RdpError(RuntimeError):
@@ -85,6 +86,11 @@ def load() -> C.CDLL:
     lib.rdp_pillar_lookup.argtypes = [C.c_int64, C.POINTER(Geom), vp, C.c_size_t, vp, vp]
     lib.rdp_publish_counters.restype = C.c_int
     lib.rdp_publish_counters.argtypes = [vp, vp, vp]
+    lib.rdp_config_supported.restype = C.c_int
+    lib.rdp_config_supported.argtypes = [C.POINTER(Geom), C.POINTER(Layout)]
+    lib.rdp_stats_buffers.restype = C.c_int
+    lib.rdp_stats_buffers.argtypes = [C.c_int64, C.POINTER(Geom), C.POINTER(Layout), C.POINTER(C.c_size_t), C.POINTER(C.c_int64),
+                                      C.POINTER(C.c_size_t), C.POINTER(C.c_int64)]
     lib.rdp_encode_host.restype = C.c_int
     lib.rdp_encode_host.argtypes = [vp, C.c_int64, C.POINTER(Geom), C.POINTER(Layout), C.POINTER(PfnParams), vp, vp, vp, vp,
                                     C.POINTER(C.c_int64), C.POINTER(C.c_int64)]

@@ -30,7 +30,7 @@ FLAGS = [*EXTRA, "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcom
 
 def _config_ids():
     txt = open(os.path.join(CSRC, "rdp_pfn_host.h")).read()
-    return [int(m) for m in re.findall(r"^\s*X\((\d+),", txt, flags=re.M)]
+    return sorted({int(m) for m in re.findall(r"\bX\((\d+),", txt)})
 
 
 def _units():

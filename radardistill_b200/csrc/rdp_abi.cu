@@ -15,9 +15,10 @@ void set_last_cuda_error(cudaError_t e, const char *where) {
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 int carve_workspace(void *base, int64_t n_points, const rdp_geom_t *geom, const rdp_layout_t *layout, Workspace *ws) {
+    (void)layout;
     if (!geom || !ws || n_points < 0) return RDP_ERR_INVALID_ARG;
     if (geom->nx <= 0 || geom->ny <= 0 || geom->batch_size <= 0 || geom->cols < 4) return RDP_ERR_INVALID_ARG;
-    const int64_t cells = (int64_t)geom->batch_size * geom->nx * geom->ny;
+    const int64_t cells = (int64_t)geom->batch_size * geom->nx * geom->ny * (geom->nz > 1 ? geom->nz : 1);
     if (cells >= (1ll << 31)) return RDP_ERR_KEYSPACE;
     memset(ws, 0, sizeof(*ws));
     const int64_t n = n_points > 0 ? n_points : 1;
@@ -26,14 +27,6 @@ int carve_workspace(void *base, int64_t n_points, const rdp_geom_t *geom, const 
     ws->pcap = n < cells ? n : cells;
     ws->index_tiles = (n + kIndexTileRows - 1) / kIndexTileRows;
     ws->pfn_tiles = (n + kPfnWin - 1) / kPfnWin;
-    ws->partial_blocks = kPfnGridCap;
-    int cin = kMaxCin, cout = kMaxCout;
-    if (layout) { cin = layout->c_in; cout = layout->c_out; }
-    const int64_t cs = cin + 9;  // super-feature count upper bound (unused layout options carry zero weights)
-    const int64_t t4 = (cs + 1 + 3) / 4;       // 4x4 blocks of the (features + ones column) Gram matrix
-    const int64_t stats_d = 2 * cout + 16 * t4 * (t4 + 1) / 2;
-    const int64_t bwd_d = (int64_t)cout * (cs + 2);
-    ws->partial_doubles_per_block = stats_d > bwd_d ? stats_d : bwd_d;
 
     char *p = static_cast<char *>(base);
     size_t off = 0;
@@ -46,12 +39,15 @@ int carve_workspace(void *base, int64_t n_points, const rdp_geom_t *geom, const 
     ws->zero_begin = take(0);
     ws->scan_state_a = reinterpret_cast<uint64_t *>(take(sizeof(uint64_t) * kScanGrid));
     ws->scan_state_b = reinterpret_cast<uint64_t *>(take(sizeof(uint64_t) * kScanGrid));
+    ws->acc_stats = reinterpret_cast<double *>(take(sizeof(double) * kMaxAcc));
+    ws->acc_bwd = reinterpret_cast<double *>(take(sizeof(double) * kMaxCout * (kMaxG + 1)));
     ws->bitmap = reinterpret_cast<uint32_t *>(take(sizeof(uint32_t) * words_pad));
     ws->zero_bytes = off;
-    ws->word_prefix = reinterpret_cast<uint32_t *>(take(sizeof(uint32_t) * words_pad));
+    ws->wordrank = reinterpret_cast<uint2 *>(take(sizeof(uint2) * words_pad));
     ws->keys = reinterpret_cast<int32_t *>(take(sizeof(int32_t) * (size_t)(n + 4)));
+    ws->slots = reinterpret_cast<int32_t *>(take(sizeof(int32_t) * (size_t)(n + 4)));
     ws->tile_keep = reinterpret_cast<int32_t *>(take(sizeof(int32_t) * (size_t)ws->index_tiles));
-    ws->ends = reinterpret_cast<int32_t *>(take(sizeof(int32_t) * (size_t)(ws->pcap + 4)));
+    ws->starts = reinterpret_cast<int32_t *>(take(sizeof(int32_t) * (size_t)(ws->pcap + 8)));
     const size_t pad = kPfnCap + 8;
     ws->grows = reinterpret_cast<float *>(take(sizeof(float) * (size_t)(n + pad + 1) * grouped_row_floats(geom->cols)));
     ws->aux = reinterpret_cast<float *>(take(sizeof(float) * 8 * (size_t)(ws->pcap + kPfnWin + 8)));
@@ -59,8 +55,6 @@ int carve_workspace(void *base, int64_t n_points, const rdp_geom_t *geom, const 
     ws->orig2kept = reinterpret_cast<int32_t *>(take(sizeof(int32_t) * (size_t)(n + 4)));
     ws->kept2orig = reinterpret_cast<int32_t *>(take(sizeof(int32_t) * (size_t)(n + 4)));
     ws->index_bytes = off;
-    ws->partials = reinterpret_cast<double *>(take(sizeof(double) * (size_t)ws->partial_blocks * ws->partial_doubles_per_block));
-    ws->totals = reinterpret_cast<double *>(take(sizeof(double) * (size_t)ws->partial_doubles_per_block));
     ws->total_bytes = off;
     return RDP_OK;
 }
@@ -96,30 +90,8 @@ extern "C" int rdp_workspace_bytes(int64_t n_points, const rdp_geom_t *geom, con
 
 extern "C" int64_t rdp_bn_state_doubles(const rdp_layout_t *layout) {
     if (!layout) return 0;
-    const int64_t cin = layout->c_in, cout = layout->c_out;
-    // [mean(cout) | var(cout) | scale(cout) | shift(cout) | n | S1(cin) | S2(cin*cin)]
-    return 4 * cout + 1 + cin + cin * cin;
-}
-
-extern "C" int rdp_encode_fwd(const float *points, int64_t n_points, const rdp_geom_t *geom, const rdp_layout_t *layout,
-                              const rdp_pfn_params_t *params, void *workspace, size_t workspace_bytes, int32_t *coords,
-                              int32_t *inverse, int32_t *counts, int32_t *counters, float *features, int32_t *argpos,
-                              double *bn_state, int32_t *host_mapped, void *event, void *stream) {
-    return rdp_encode_fwd_frames(points, nullptr, n_points, geom, layout, params, workspace, workspace_bytes, coords, inverse, counts,
-                                 counters, features, argpos, bn_state, host_mapped, event, stream);
-}
-
-extern "C" int rdp_encode_fwd_frames(const float *points, const int32_t *frame_offsets, int64_t n_points, const rdp_geom_t *geom,
-                                     const rdp_layout_t *layout, const rdp_pfn_params_t *params, void *workspace,
-                                     size_t workspace_bytes, int32_t *coords, int32_t *inverse, int32_t *counts, int32_t *counters,
-                                     float *features, int32_t *argpos, double *bn_state, int32_t *host_mapped, void *event,
-                                     void *stream) {
-    if (!layout) return RDP_ERR_INVALID_ARG;
-    int rc = rdp_index_fwd_frames(points, frame_offsets, n_points, geom, layout->coord_cols, workspace, workspace_bytes, coords,
-                                  inverse, counts, counters, host_mapped, event, stream);
-    if (rc != RDP_OK) return rc;
-    return rdp_pfn_fwd(points, n_points, geom, layout, params, workspace, workspace_bytes, counters, features, argpos, nullptr,
-                       bn_state, stream);
+    // [mean(cout) | var(cout) | scale(cout) | shift(cout) | n | S1(G) | S2(G*G)] in the reduced basis (G <= kMaxG)
+    return 4 * (int64_t)layout->c_out + 1 + kMaxG + kMaxG * kMaxG;
 }
 
 extern "C" int rdp_encode_host(const float *points, int64_t n_points, const rdp_geom_t *geom, const rdp_layout_t *layout,

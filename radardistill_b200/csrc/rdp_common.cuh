@@ -37,45 +37,47 @@ constexpr int kPfnCap = RDP_PFN_CAP;          // rows staged per tile: the windo
 #ifndef RDP_PFN_GRID_PER_SM
 #define RDP_PFN_GRID_PER_SM 4
 #endif
-constexpr int kPfnGridCap = 148 * RDP_PFN_GRID_PER_SM;  // persistent PFN CTAs (also the number of partial-sum slots)
+constexpr int kPfnGridCap = 148 * RDP_PFN_GRID_PER_SM;  // persistent PFN CTAs of the backward tile kernel
 __host__ __device__ constexpr int grouped_row_floats(int cols) { return (cols + 2 + 3) / 4 * 4; }
 constexpr int kMaxCin = 24;
-constexpr int kMaxCout = 64;
+constexpr int kMaxCout = 128;
+constexpr int kMaxG = 14;             // reduced basis [row inputs (<= 8) | pillar constants (5)] upper bound (+1 spare)
+constexpr int kMaxAcc = kMaxG + kMaxG * kMaxG + 2;   // first + second moments of the reduced basis, the point count
 
 // extra counter slots (after the public ones of rdp.h)
 constexpr int kCntTicketA = 4;   // bitmap scan ticket
 constexpr int kCntTicketB = 5;   // count scan ticket
 constexpr int kCntPfnBlocks = 6; // blocks used by the last stats launch
-constexpr int kCntDoneStats = 8; // CTAs of bn_finalize_kernel that have reduced their chunk (reset by the last one)
-constexpr int kCntDoneBwd = 9;   // same for bwd_finalize_kernel
+constexpr int kCntDoneStats = 8; // CTAs of the moments pass that have added their sums (the last one runs the BN epilogue)
+constexpr int kCntDoneBwd = 9;   // same for the backward tile kernel
+constexpr int kCntStatsTag = 10; // != 0: acc_stats holds the moments of this workspace's rows for layout tag (value)
 
 // ----------------------------------------------------------------------------- workspace layout
 struct Workspace {
     // zeroed by one memset at the start of rdp_index_fwd: [zero_begin, zero_begin + zero_bytes)
     uint64_t *scan_state_a;  // kScanGrid
     uint64_t *scan_state_b;  // kScanGrid
+    double *acc_stats;       // kMaxAcc        : fp64 totals of the train-mode feature moments (atomics; last CTA folds them)
+    double *acc_bwd;         // kMaxCout*(kMaxG+1) : fp64 totals of the backward sums
     uint32_t *bitmap;        // words
     // not zeroed
-    uint32_t *word_prefix;   // words
+    uint2 *wordrank;         // words : {bitmap word, exclusive pillar rank of the word} -- one 8-byte gather per point
     int32_t *keys;           // n  (merged key, then overwritten by the pillar rank; -1 = dropped)
+    int32_t *slots;          // n  position of the row inside its pillar (arrival order of rank_count_kernel's atomics)
     int32_t *tile_keep;      // index tiles
-    int32_t *ends;           // pcap  (exclusive starts -> after fill: inclusive ends)
+    int32_t *starts;         // pcap + 1  exclusive start of every pillar in the grouped order; starts[P] = N
     float *grows;            // (1 + n + pad) * RS : rows physically grouped by pillar (pillar order == key order);
                              // RS floats per row = [row | pad | original row id | pillar id]; row 0 is a sentinel
                              // (pillar id -1) in front of grouped position 0
-    double *partials;        // per-CTA partial sums of the train-mode statistics / backward
-    double *totals;          // their fixed-order sum (reduce_partials_kernel)
     char *zero_begin;
     size_t zero_bytes;
-    float *aux;              // (pcap + pad) * 8 : per-pillar table [mean xyz | centre xy | first grouped row | rows | 0]
+    float *aux;              // (pcap + pad) * 8 : per-pillar table [centre xy | centre - mean xyz | first grouped row | rows | lowest original row id]
     int32_t *tile_first;     // PFN tiles + 2   : first pillar that starts at or after grouped row 128 t
     int32_t *orig2kept;      // n     (only written / read when the range mask dropped rows)
     int32_t *kept2orig;      // n
     int64_t words, n, pcap, index_tiles, pfn_tiles;
-    size_t index_bytes;      // bytes rdp_index_fwd needs (everything before `partials`)
+    size_t index_bytes;      // bytes rdp_index_fwd needs
     size_t total_bytes;
-    int64_t partial_doubles_per_block;
-    int partial_blocks;
 };
 
 // Carves the workspace; `base` may be null to only compute total_bytes.
@@ -167,14 +169,24 @@ __device__ __forceinline__ uint32_t chunk_exclusive_prefix(uint64_t *state, int 
         atomicExch(reinterpret_cast<unsigned long long *>(state + ticket), (1ull << 63) | aggregate);
     }
     if (threadIdx.x < 32) {
+        // all look-back loads go out together (one L2 round trip when the predecessors have published); only the entries
+        // that were not ready are polled again
+        constexpr int Q = (kScanGrid + 31) / 32;
+        unsigned long long v[Q];
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+            const int j = (int)threadIdx.x + 32 * q;
+            v[q] = (j < ticket) ? *reinterpret_cast<volatile unsigned long long *>(state + j) : (1ull << 63);
+        }
         uint32_t sum = 0;
-        for (int j = threadIdx.x; j < ticket; j += 32) {
-            unsigned long long v;
-            do {
-                v = *reinterpret_cast<volatile unsigned long long *>(state + j);
-                if (!(v >> 63)) __nanosleep(40);
-            } while (!(v >> 63));
-            sum += static_cast<uint32_t>(v);
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+            const int j = (int)threadIdx.x + 32 * q;
+            while (!(v[q] >> 63)) {
+                __nanosleep(20);
+                v[q] = *reinterpret_cast<volatile unsigned long long *>(state + j);
+            }
+            sum += static_cast<uint32_t>(v[q]);
         }
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);

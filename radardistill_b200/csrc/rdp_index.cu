@@ -9,24 +9,21 @@
 // torch.unique's ascending order falls out of a popcount prefix scan over the bitmap -- a counting
 // sort with one-bit counters; no comparison sort, no ordering of floats, fully deterministic.
 //
-//   K1 quantize_mark   points (TMA bulk tile -> smem) -> key[i], bitmap |= bit(key)          [HBM: read rows]
-//   K2 bitmap_rank     popcount scan of the bitmap -> word_prefix, P; publishes (N, P) to the host
-//   K2b zero_counts    counts[0, P) = 0
-//   K3 rank_count      key[i] -> rank = word_prefix + popc(below) ; inverse[j] ; counts[rank]++
-//   K4 count_scan      exclusive scan of counts -> pillar start offsets
+//   K1 quantize_mark   points (TMA bulk tile -> smem) -> key[i], bitmap |= bit(key); counts[] = 0   [HBM: read rows]
+//   K2 bitmap_rank     popcount scan of the bitmap -> {word, rank of word} pairs, P; publishes (N, P) to the host
+//   K3 rank_count      key[i] -> rank = wordrank.rank + popc(below) ; inverse[j] ; slot[i] = counts[rank]++
+//   K4 count_scan      exclusive scan of counts -> pillar start offsets (starts[P] = N), tile_first
+//   K5 group_rows      grouped_rows[starts[rank] + slot] = row i | original row id | rank   (no atomics; the order
+//                      inside a pillar is the arrival order of K3's atomics -- every consumer is order independent).
+//                      The PFN kernels then stream contiguous, pillar-aligned row tiles with TMA.
 //   K6 pillar_table    thread = pillar: fp64 mean of its grouped rows, pillar centre, first row, row count; coords
-//   K5 group_rows      pos = start[rank]++ ; grouped_rows[pos] = row i, gpid[pos] = rank, gorder[pos] = i
-//                      (counting-sort fill; the order inside a pillar is arbitrary, every consumer is order
-//                      independent).  The PFN kernels then stream contiguous, pillar-aligned row tiles with TMA.
-#include "rdp_common.cuh"
+//                      (rdp_table.cuh; in train mode the fused call runs the variant that also sums the feature moments)
+// nz > 1 (DynamicVoxelVFE / DynamicMeanVFE, dynamic_voxel_vfe.py:57-71, dynamic_mean_vfe.py:52-60): z is quantised and
+// masked too and the key is ((b*nx + cx)*ny + cy)*nz + cz.
+#include "rdp_index_host.h"
 
 namespace rdp {
 
-struct GeomDev {
-    float lo_x, lo_y, vx, vy;
-    int nx, ny, batch, cols;
-    float off_x, off_y;
-};
 
 // Frame of input row i when the rows carry no batch column: offsets[b] <= i < offsets[b + 1] (offsets has batch + 1 entries).
 __device__ __forceinline__ int frame_of(const int32_t *__restrict__ offsets, int batch, long long i) {
@@ -42,7 +39,7 @@ __device__ __forceinline__ int frame_of(const int32_t *__restrict__ offsets, int
 __global__ void __launch_bounds__(kIndexThreads)
 quantize_mark_kernel(const float *__restrict__ pts, long long n0, GeomDev g, uint32_t *__restrict__ bitmap,
                      int32_t *__restrict__ keys, int32_t *__restrict__ tile_keep, int32_t *__restrict__ counters,
-                     const int32_t *__restrict__ offsets) {
+                     const int32_t *__restrict__ offsets, int32_t *__restrict__ counts) {
     extern __shared__ __align__(128) float tile[];
     __shared__ __align__(8) uint64_t bar;
     __shared__ int s_keep;
@@ -70,10 +67,17 @@ quantize_mark_kernel(const float *__restrict__ pts, long long n0, GeomDev g, uin
         tma_bulk_g2s(tile, src, bulk_bytes, &bar);  // one 1-D TMA copy of the whole row tile
     }
     for (int f = (int)(bulk_bytes >> 2) + tid; f < floats; f += kIndexThreads) tile[f] = src[f];  // <16 B tail
+    // counts[0, P) must be zero for K3's atomics and P <= n0: every tile clears its own stretch while its rows are in flight
+    if (row0 + tid * 4 + 3 < n0) {
+        *reinterpret_cast<int4 *>(counts + row0 + tid * 4) = make_int4(0, 0, 0, 0);
+    } else {
+        for (int q = 0; q < 4; ++q) if (row0 + tid * 4 + q < n0) counts[row0 + tid * 4 + q] = 0;
+    }
     if (bulk_bytes) mbar_wait(&bar, 0);
     __syncthreads();
 
-    const int sxy = g.nx * g.ny;
+    const bool vox = g.nz > 1;
+    const int sxy = g.nx * g.ny * (vox ? g.nz : 1);
     int kept = 0;
     bool bad_batch = false;
 #pragma unroll
@@ -85,6 +89,11 @@ quantize_mark_kernel(const float *__restrict__ pts, long long n0, GeomDev g, uin
             const float qx = floorf(__fdiv_rn(__fsub_rn(p[xc], g.lo_x), g.vx));
             const float qy = floorf(__fdiv_rn(__fsub_rn(p[xc + 1], g.lo_y), g.vy));
             bool ok = (qx >= 0.0f) && (qx < (float)g.nx) && (qy >= 0.0f) && (qy < (float)g.ny);  // NaN/inf fail
+            float qz = 0.0f;
+            if (vox) {   // dynamic_voxel_vfe.py:57-58: z is quantised and masked as well
+                qz = floorf(__fdiv_rn(__fsub_rn(p[xc + 2], g.lo_z), g.vz));
+                ok = ok && (qz >= 0.0f) && (qz < (float)g.nz);
+            }
             int b;
             if (offsets) {
                 b = s_b0;
@@ -95,7 +104,8 @@ quantize_mark_kernel(const float *__restrict__ pts, long long n0, GeomDev g, uin
             if (ok && (b < 0 || b >= g.batch)) { ok = false; bad_batch = true; }
             int key = -1;
             if (ok) {
-                key = b * sxy + (int)qx * g.ny + (int)qy;  // (:208-210)
+                key = vox ? b * sxy + ((int)qx * g.ny + (int)qy) * g.nz + (int)qz   // dynamic_voxel_vfe.py:63-66
+                          : b * sxy + (int)qx * g.ny + (int)qy;                     // (:208-210)
                 atomicOr(bitmap + (key >> 5), 1u << (key & 31));
                 ++kept;
             }
@@ -118,7 +128,7 @@ quantize_mark_kernel(const float *__restrict__ pts, long long n0, GeomDev g, uin
 // the exclusive rank of every word.
 __global__ void __launch_bounds__(kScanThreads)
 bitmap_rank_kernel(const uint32_t *__restrict__ bitmap, long long words,
-                   uint64_t *__restrict__ state, uint32_t *__restrict__ word_prefix, int32_t *__restrict__ counters,
+                   uint64_t *__restrict__ state, uint2 *__restrict__ wordrank, int32_t *__restrict__ counters,
                    volatile int32_t *host_mapped) {
     __shared__ int s_scan[9];
     __shared__ uint32_t s_u32;
@@ -160,29 +170,21 @@ bitmap_rank_kernel(const uint32_t *__restrict__ bitmap, long long words,
         uint32_t rank = base + (uint32_t)block_excl_scan_256(c, s_scan, &tile_total);
         base += (uint32_t)tile_total;
         if (w < w1) {
-            uint4 pre;
-            pre.x = rank;
-            pre.y = pre.x + __popc(v.x);
-            pre.z = pre.y + __popc(v.y);
-            pre.w = pre.z + __popc(v.z);
-            *reinterpret_cast<uint4 *>(word_prefix + w) = pre;
+            // {word, rank of the word's first pillar} pairs: K3 needs both per point -- one 8-byte gather instead of two
+            const uint32_t r1 = rank + __popc(v.x), r2 = r1 + __popc(v.y), r3 = r2 + __popc(v.z);
+            uint4 *dst = reinterpret_cast<uint4 *>(wordrank + w);
+            dst[0] = make_uint4(v.x, rank, v.y, r1);
+            dst[1] = make_uint4(v.z, r2, v.w, r3);
         }
     }
 }
 
-// ----------------------------------------------------------------------------- K2b
-// counts[0, P) = 0 for K3's atomics (P is only known on the device).
-__global__ void __launch_bounds__(256) zero_counts_kernel(int32_t *__restrict__ counts, const int32_t *__restrict__ counters) {
-    const int P = counters[RDP_CNT_P];
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P; i += gridDim.x * blockDim.x) counts[i] = 0;
-}
-
 // ----------------------------------------------------------------------------- K3
 __global__ void __launch_bounds__(kIndexThreads)
-rank_count_kernel(int32_t *__restrict__ keys, long long n0, const uint32_t *__restrict__ bitmap,
-                  const uint32_t *__restrict__ word_prefix, const int32_t *__restrict__ tile_keep,
-                  int32_t *__restrict__ inverse, int32_t *__restrict__ counts, const int32_t *__restrict__ counters,
-                  int32_t *__restrict__ orig2kept, int32_t *__restrict__ kept2orig) {
+rank_count_kernel(int32_t *__restrict__ keys, long long n0, const uint2 *__restrict__ wordrank,
+                  const int32_t *__restrict__ tile_keep, int32_t *__restrict__ inverse, int32_t *__restrict__ counts,
+                  const int32_t *__restrict__ counters, int32_t *__restrict__ orig2kept, int32_t *__restrict__ kept2orig,
+                  int32_t *__restrict__ slots) {
     __shared__ int s_scan[9];
     __shared__ long long s_base;
     const int tid = threadIdx.x;
@@ -203,8 +205,8 @@ rank_count_kernel(int32_t *__restrict__ keys, long long n0, const uint32_t *__re
     for (int q = 0; q < 4; ++q) {
         r[q] = -1;
         if (k[q] >= 0) {
-            const uint32_t w = bitmap[k[q] >> 5];
-            r[q] = (int)(word_prefix[k[q] >> 5] + __popc(w & ((1u << (k[q] & 31)) - 1u)));
+            const uint2 wr = __ldg(wordrank + (k[q] >> 5));
+            r[q] = (int)(wr.y + __popc(wr.x & ((1u << (k[q] & 31)) - 1u)));
             ++c;
         }
     }
@@ -233,9 +235,17 @@ rank_count_kernel(int32_t *__restrict__ keys, long long n0, const uint32_t *__re
                 inverse[j++] = r[q];
             }
     }
+    // the value the count had before this row arrived is the row's slot inside its pillar: K5 then needs no atomics
+    int sl[4] = {0, 0, 0, 0};
 #pragma unroll
     for (int q = 0; q < 4; ++q)
-        if (r[q] >= 0) atomicAdd(counts + r[q], 1);
+        if (r[q] >= 0) sl[q] = atomicAdd(counts + r[q], 1);
+    if (i0 + 3 < n0) {
+        *reinterpret_cast<int4 *>(slots + i0) = make_int4(sl[0], sl[1], sl[2], sl[3]);
+    } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) if (i0 + q < n0) slots[i0 + q] = sl[q];
+    }
     if (i0 + 3 < n0) {
         *reinterpret_cast<int4 *>(keys + i0) = make_int4(r[0], r[1], r[2], r[3]);  // key -> rank, in place
     } else {
@@ -246,7 +256,7 @@ rank_count_kernel(int32_t *__restrict__ keys, long long n0, const uint32_t *__re
 
 // ----------------------------------------------------------------------------- K4
 __global__ void __launch_bounds__(kScanThreads)
-count_scan_kernel(const int32_t *__restrict__ counts, uint64_t *__restrict__ state, int32_t *__restrict__ ends,
+count_scan_kernel(const int32_t *__restrict__ counts, uint64_t *__restrict__ state, int32_t *__restrict__ starts,
                   int32_t *__restrict__ tile_first, int32_t *__restrict__ counters) {
     __shared__ int s_scan[9];
     __shared__ uint32_t s_u32;
@@ -276,13 +286,16 @@ count_scan_kernel(const int32_t *__restrict__ counts, uint64_t *__restrict__ sta
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             if (p + q < p1) {
-                ends[p + q] = (int)s;  // exclusive start; K5 advances it to the inclusive end
+                starts[p + q] = (int)s;  // exclusive start of the pillar in the grouped order
                 const uint32_t e = s + (uint32_t)c[q];
                 // PFN tile t owns the pillars that start in grouped rows [128 t, 128 t + 128): pillar p+q+1 is the first
                 // pillar starting at or after every tile boundary in (s, e]
                 for (uint32_t t = s / kPfnWin + 1; t * (uint32_t)kPfnWin <= e; ++t) tile_first[t] = (int)(p + q + 1);
                 if (p + q == 0) tile_first[0] = 0;
-                if (p + q == P - 1 && e % kPfnWin != 0) tile_first[e / kPfnWin + 1] = (int)P;
+                if (p + q == P - 1) {
+                    starts[P] = (int)e;   // == N
+                    if (e % kPfnWin != 0) tile_first[e / kPfnWin + 1] = (int)P;
+                }
                 s = e;
             }
         }
@@ -294,8 +307,9 @@ count_scan_kernel(const int32_t *__restrict__ counts, uint64_t *__restrict__ sta
 // 16-byte stores only (the scatter is bound by store requests, not bytes).
 template <bool FRAMES>   // FRAMES: rows without the batch column + frame offsets (compiled apart: the padded-row path stays as it was)
 __global__ void __launch_bounds__(kIndexThreads)
-group_rows_kernel(const float *__restrict__ pts, const int32_t *__restrict__ ranks, long long n0, int cols,
-                  int32_t *__restrict__ ends, float *__restrict__ grows, const int32_t *__restrict__ offsets, int batch) {
+group_rows_kernel(const float *__restrict__ pts, const int32_t *__restrict__ ranks, const int32_t *__restrict__ slots, long long n0,
+                  int cols, const int32_t *__restrict__ starts, float *__restrict__ grows, const int32_t *__restrict__ offsets,
+                  int batch) {
     extern __shared__ __align__(128) float tile[];
     __shared__ __align__(8) uint64_t bar;
     const int tid = threadIdx.x;
@@ -319,14 +333,14 @@ group_rows_kernel(const float *__restrict__ pts, const int32_t *__restrict__ ran
     }
     for (int f = (int)(bulk_bytes >> 2) + tid; f < floats; f += kIndexThreads) tile[f] = src[f];
     if (blockIdx.x == 0 && tid == 0) grows[rs - 1] = __int_as_float(-1);  // sentinel row: "no pillar" before position 0
-    // claim the grouped positions while the tile is in flight
+    // grouped positions (pillar start + slot inside the pillar) are gathered while the tile is in flight
     int pos[kIndexTileRows / kIndexThreads], rk[kIndexTileRows / kIndexThreads];
     float fbv[kIndexTileRows / kIndexThreads] = {};
 #pragma unroll
     for (int k = 0; k < kIndexTileRows / kIndexThreads; ++k) {
         const int r = k * kIndexThreads + tid;
         rk[k] = (r < rows) ? ranks[row0 + r] : -1;
-        pos[k] = (rk[k] >= 0) ? atomicAdd(ends + rk[k], 1) : -1;
+        pos[k] = (rk[k] >= 0) ? __ldg(starts + rk[k]) + slots[row0 + r] : -1;
         if (FRAMES) {   // frame id of the row, resolved here so that nothing but smem reads sits between the scattered stores below
             int b = s_b0;
             while (b + 1 < batch && row0 + r >= (long long)offsets[b + 1]) ++b;
@@ -370,41 +384,9 @@ __global__ void publish_counters_kernel(const int32_t *__restrict__ counters, vo
     __threadfence_system();
 }
 
-// ----------------------------------------------------------------------------- K6
-// Per-pillar table for the PFN kernels: thread = pillar reads its (contiguous) grouped rows once and writes
-// [mean x, y, z | centre x, y | first grouped row | rows | 0] -- scatter_mean (:226) and the pillar centre (:215-216).
-// Mean: fp64 sum of the fp32 coordinates (order independent), correctly rounded quotient, one rounding to fp32.
-__global__ void __launch_bounds__(256)
-pillar_table_kernel(const float *__restrict__ grows, const int32_t *__restrict__ ends, const int32_t *__restrict__ counters,
-                    int rs, GeomDev g, float *__restrict__ aux, int coord_cols, int32_t *__restrict__ coords) {
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= counters[RDP_CNT_P]) return;
-    const int s = p ? ends[p - 1] : 0, e = ends[p];
-    double sx = 0.0, sy = 0.0, sz = 0.0;
-    const float *r = grows + ((size_t)s + 1) * rs;   // rows are 16-byte aligned: [b, x, y, z] is one 128-bit load
-    const float4 v0 = __ldg(reinterpret_cast<const float4 *>(r));
-    const float x0 = v0.y, y0 = v0.z;
-    const int b0 = __float2int_rz(v0.x);
-    for (int i = s; i < e; ++i, r += rs) {
-        const float4 v = __ldg(reinterpret_cast<const float4 *>(r));
-        sx += (double)v.y; sy += (double)v.z; sz += (double)v.w;
-    }
-    float mx, my, mz;
-    mean3(sx, sy, sz, e - s, &mx, &my, &mz);
-    // centre of the cell: cx*vx + x_off with separate mul / add roundings (:215-216); the quantisation repeats
-    // quantize_mark_kernel's IEEE ops, so cx / cy equal the emitted coords
-    const float qx = floorf(__fdiv_rn(__fsub_rn(x0, g.lo_x), g.vx)), qy = floorf(__fdiv_rn(__fsub_rn(y0, g.lo_y), g.vy));
-    const float cenx = __fadd_rn(__fmul_rn((float)(int)qx, g.vx), g.off_x), ceny = __fadd_rn(__fmul_rn((float)(int)qy, g.vy), g.off_y);
-    // pillar coords (:243-248): the pillars are in key order, and key = b*nx*ny + cx*ny + cy decodes to exactly these
-    if (coord_cols == 3) {
-        int32_t *o = coords + (size_t)p * 3;
-        o[0] = b0; o[1] = (int)qy; o[2] = (int)qx;   // [b, y, x]  (:248)
-    } else {
-        *reinterpret_cast<int4 *>(coords + (size_t)p * 4) = make_int4(b0, 0, (int)qy, (int)qx);  // (:138)
-    }
-    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(aux + (size_t)p * 8), "f"(mx), "f"(my), "f"(mz), "f"(cenx),
-                 "f"(ceny), "f"(__int_as_float(s)), "f"(__int_as_float(e - s)), "f"(0.0f)
-                 : "memory");
+// ----------------------------------------------------------------------------- K6 (rdp_table.cuh), generic form
+__global__ void __launch_bounds__(256) pillar_table_kernel(const __grid_constant__ TableArgs t) {
+    pillar_table_body(t);
 }
 
 // ----------------------------------------------------------------------------- pillar-id lookup
@@ -412,7 +394,7 @@ pillar_table_kernel(const float *__restrict__ grows, const int32_t *__restrict__
 // book (spconv_backbone_2d.py:262-271) without a hash pass of its own -- the occupancy bitmap + rank prefix already are
 // that table.  32 x 32 tiles: keys are x-major (b*nx*ny + cx*ny + cy), the output is y-major, so the tile is transposed
 // through shared memory and both sides stay coalesced.
-__global__ void __launch_bounds__(256) pillar_lookup_kernel(const uint32_t *__restrict__ bitmap, const uint32_t *__restrict__ word_prefix,
+__global__ void __launch_bounds__(256) pillar_lookup_kernel(const uint2 *__restrict__ wordrank,
                                                             int nx, int ny, int32_t *__restrict__ lookup) {
     __shared__ int tile[32][33];
     const int b = blockIdx.z, x0 = blockIdx.x * 32, y0 = blockIdx.y * 32;
@@ -422,8 +404,9 @@ __global__ void __launch_bounds__(256) pillar_lookup_kernel(const uint32_t *__re
         int v = -1;
         if (x < nx && y < ny) {
             const long long key = ((long long)b * nx + x) * ny + y;
-            const uint32_t w = bitmap[key >> 5], bit = 1u << (key & 31);
-            if (w & bit) v = (int)(word_prefix[key >> 5] + __popc(w & (bit - 1u)));
+            const uint2 wr = wordrank[key >> 5];
+            const uint32_t bit = 1u << (key & 31);
+            if (wr.x & bit) v = (int)(wr.y + __popc(wr.x & (bit - 1u)));
         }
         tile[j][tx] = v;
     }
@@ -440,10 +423,21 @@ static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t
 
 using namespace rdp;
 
-extern "C" int rdp_index_fwd_frames(const float *points, const int32_t *frame_offsets, int64_t n_points, const rdp_geom_t *geom,
-                                    int32_t coord_cols, void *workspace, size_t workspace_bytes, int32_t *coords, int32_t *inverse,
-                                    int32_t *counts, int32_t *counters, int32_t *host_mapped, void *event_v, void *stream_v) {
-    cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+namespace rdp {
+
+GeomDev make_geom_dev(const rdp_geom_t *geom) {
+    GeomDev g;
+    g.lo_x = geom->lo[0]; g.lo_y = geom->lo[1]; g.lo_z = geom->lo[2];
+    g.vx = geom->vsz[0]; g.vy = geom->vsz[1]; g.vz = geom->vsz[2];
+    g.nx = geom->nx; g.ny = geom->ny; g.nz = geom->nz > 1 ? geom->nz : 1;
+    g.batch = geom->batch_size; g.cols = geom->cols;
+    g.off_x = geom->off[0]; g.off_y = geom->off[1]; g.off_z = geom->off[2];
+    return g;
+}
+
+int index_fwd_impl(const float *points, const int32_t *frame_offsets, int64_t n_points, const rdp_geom_t *geom, int32_t coord_cols,
+                   void *workspace, size_t workspace_bytes, int32_t *coords, int32_t *inverse, int32_t *counts, int32_t *counters,
+                   int32_t *host_mapped, void *event_v, cudaStream_t stream, TableLaunchFn table_fn, void *table_ctx) {
     cudaEvent_t event = static_cast<cudaEvent_t>(event_v);
     // N, P and the error flags are final after the bitmap scan (K2): publish them there, so the host learns the output
     // sizes ~50 us into the call and can enqueue whatever follows while the remaining kernels run.
@@ -453,8 +447,9 @@ extern "C" int rdp_index_fwd_frames(const float *points, const int32_t *frame_of
         return RDP_OK;
     };
     if (!geom || !counters || n_points < 0 || (coord_cols != 3 && coord_cols != 4)) return RDP_ERR_INVALID_ARG;
+    if (geom->nz > 1 && coord_cols != 4) return RDP_ERR_INVALID_ARG;   // voxel coords are [b, z, y, x]
     if (n_points > 0 && (!points || !workspace || !coords || !inverse || !counts)) return RDP_ERR_INVALID_ARG;
-    if (!aligned16(points) || !aligned16(coords) || !aligned16(inverse) || !aligned16(workspace)) return RDP_ERR_INVALID_ARG;
+    if (!aligned16(points) || !aligned16(coords) || !aligned16(inverse) || !aligned16(counts) || !aligned16(workspace)) return RDP_ERR_INVALID_ARG;
     if (n_points >= (1ll << 31) - 8) return RDP_ERR_UNSUPPORTED;
     Workspace ws;
     int rc = carve_workspace(workspace, n_points, geom, nullptr, &ws);
@@ -465,8 +460,7 @@ extern "C" int rdp_index_fwd_frames(const float *points, const int32_t *frame_of
     if (n_points == 0) return publish();
     RDP_CUDA_OK(cudaMemsetAsync(ws.zero_begin, 0, ws.zero_bytes, stream));
 
-    GeomDev g{geom->lo[0], geom->lo[1], geom->vsz[0], geom->vsz[1], geom->nx, geom->ny, geom->batch_size, geom->cols,
-              geom->off[0], geom->off[1]};
+    const GeomDev g = make_geom_dev(geom);
     const size_t smem = (size_t)kIndexTileRows * geom->cols * sizeof(float);
     if (smem > 200 * 1024) return RDP_ERR_UNSUPPORTED;
     if (smem > 48 * 1024) {
@@ -476,24 +470,39 @@ extern "C" int rdp_index_fwd_frames(const float *points, const int32_t *frame_of
     }
     const int tiles = (int)ws.index_tiles;
     quantize_mark_kernel<<<tiles, kIndexThreads, smem, stream>>>(points, n_points, g, ws.bitmap, ws.keys, ws.tile_keep, counters,
-                                                                 frame_offsets);
-    bitmap_rank_kernel<<<kScanGrid, kScanThreads, 0, stream>>>(ws.bitmap, ws.words, ws.scan_state_a, ws.word_prefix, counters,
+                                                                 frame_offsets, counts);
+    bitmap_rank_kernel<<<kScanGrid, kScanThreads, 0, stream>>>(ws.bitmap, ws.words, ws.scan_state_a, ws.wordrank, counters,
                                                               host_mapped);
     if (event) RDP_CUDA_OK(cudaEventRecord(event, stream));
-    zero_counts_kernel<<<148 * 2, 256, 0, stream>>>(counts, counters);
-    rank_count_kernel<<<tiles, kIndexThreads, 0, stream>>>(ws.keys, n_points, ws.bitmap, ws.word_prefix, ws.tile_keep,
-                                                         inverse, counts, counters, ws.orig2kept, ws.kept2orig);
-    count_scan_kernel<<<kScanGrid, kScanThreads, 0, stream>>>(counts, ws.scan_state_b, ws.ends, ws.tile_first, counters);
+    rank_count_kernel<<<tiles, kIndexThreads, 0, stream>>>(ws.keys, n_points, ws.wordrank, ws.tile_keep, inverse, counts, counters,
+                                                         ws.orig2kept, ws.kept2orig, ws.slots);
+    count_scan_kernel<<<kScanGrid, kScanThreads, 0, stream>>>(counts, ws.scan_state_b, ws.starts, ws.tile_first, counters);
     if (frame_offsets)
-        group_rows_kernel<true><<<tiles, kIndexThreads, smem, stream>>>(points, ws.keys, n_points, geom->cols, ws.ends, ws.grows,
-                                                                        frame_offsets, geom->batch_size);
+        group_rows_kernel<true><<<tiles, kIndexThreads, smem, stream>>>(points, ws.keys, ws.slots, n_points, geom->cols, ws.starts,
+                                                                        ws.grows, frame_offsets, geom->batch_size);
     else
-        group_rows_kernel<false><<<tiles, kIndexThreads, smem, stream>>>(points, ws.keys, n_points, geom->cols, ws.ends, ws.grows,
-                                                                         nullptr, geom->batch_size);
-    pillar_table_kernel<<<(unsigned)((ws.pcap + 255) / 256), 256, 0, stream>>>(ws.grows, ws.ends, counters,
-                                                                               grouped_row_floats(geom->cols), g, ws.aux, coord_cols, coords);
+        group_rows_kernel<false><<<tiles, kIndexThreads, smem, stream>>>(points, ws.keys, ws.slots, n_points, geom->cols, ws.starts,
+                                                                         ws.grows, nullptr, geom->batch_size);
+    TableArgs t;
+    t.grows = ws.grows; t.starts = ws.starts; t.counters = counters; t.aux = ws.aux; t.coords = coords;
+    t.rs = grouped_row_floats(geom->cols); t.coord_cols = coord_cols; t.g = g;
+    const int tgrid = table_grid(ws.pcap);
+    if (table_fn) {
+        RDP_CUDA_OK(table_fn(t, table_ctx, tgrid, stream));
+    } else {
+        pillar_table_kernel<<<tgrid, 256, 0, stream>>>(t);
+    }
     RDP_CUDA_OK(cudaGetLastError());
     return RDP_OK;
+}
+
+}  // namespace rdp
+
+extern "C" int rdp_index_fwd_frames(const float *points, const int32_t *frame_offsets, int64_t n_points, const rdp_geom_t *geom,
+                                    int32_t coord_cols, void *workspace, size_t workspace_bytes, int32_t *coords, int32_t *inverse,
+                                    int32_t *counts, int32_t *counters, int32_t *host_mapped, void *event_v, void *stream_v) {
+    return index_fwd_impl(points, frame_offsets, n_points, geom, coord_cols, workspace, workspace_bytes, coords, inverse, counts,
+                          counters, host_mapped, event_v, static_cast<cudaStream_t>(stream_v), nullptr, nullptr);
 }
 
 extern "C" int rdp_index_fwd_publish(const float *points, int64_t n_points, const rdp_geom_t *geom, int32_t coord_cols,
@@ -524,7 +533,8 @@ extern "C" int rdp_pillar_lookup(int64_t n_points, const rdp_geom_t *geom, void 
     if (!workspace || ws.index_bytes > workspace_bytes) return RDP_ERR_WORKSPACE;
     dim3 grid((geom->nx + 31) / 32, (geom->ny + 31) / 32, geom->batch_size);
     if (grid.y > 65535 || grid.z > 65535) return RDP_ERR_UNSUPPORTED;
-    pillar_lookup_kernel<<<grid, 256, 0, stream>>>(ws.bitmap, ws.word_prefix, geom->nx, geom->ny, lookup);
+    if (geom->nz > 1) return RDP_ERR_UNSUPPORTED;   // the dense lookup is a 2-D (pillar) table
+    pillar_lookup_kernel<<<grid, 256, 0, stream>>>(ws.wordrank, geom->nx, geom->ny, lookup);
     RDP_CUDA_OK(cudaGetLastError());
     return RDP_OK;
 }

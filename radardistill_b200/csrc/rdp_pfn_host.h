@@ -1,39 +1,34 @@
 // rdp_pfn_host.h -- host-side table of the compiled PFN configurations.
 #pragma once
+#include "rdp_index_host.h"
 #include "rdp_pfn.cuh"
-#include "rdp_pfn_rows.cuh"
-#include "rdp_pfn_bwd.cuh"
 
 namespace rdp {
 
 struct PfnLaunch {
-    int cols, layout, dist, cout, cs;
-    int stats_partial_doubles, bwd_partial_doubles;
-    cudaError_t (*tile)(const PfnArgs &a, int mode, int grid, cudaStream_t st);
-    cudaError_t (*rows)(const PfnArgs &a, int want_arg, int grid, cudaStream_t st);   // pfn_rows_kernel (rdp_pfn_rows.cuh)
-    cudaError_t (*bwd_stream)(const PfnArgs &a, int grid, cudaStream_t st);            // pfn_bwd_stream_kernel (rdp_pfn_bwd.cuh)
-    // one launch each: fixed-order reduction of the per-CTA partials, then (last CTA) the closed-form epilogue
-    cudaError_t (*bn_finalize)(const PfnArgs &a, const double *partials, int nblocks, double *totals, int32_t *done, double *bn_state,
-                               float *rm, float *rv, double momentum, long long *num_batches_tracked, cudaStream_t st);
-    cudaError_t (*bwd_finalize)(const PfnArgs &a, const double *partials, int nblocks, double *totals, int32_t *done,
-                                const double *bn_state, int train_bn, float *dW, float *dg, float *db, cudaStream_t st);
+    int cols, dist, cout, g;
+    cudaError_t (*apply)(const PfnArgs &a, int want_arg, int grid, cudaStream_t st);
+    cudaError_t (*bwd)(const PfnArgs &a, int grid, cudaStream_t st);
+    cudaError_t (*moments)(const PfnArgs &a, int grid, cudaStream_t st);   // train-mode feature moments (+ BN epilogue in the last CTA)
+    cudaError_t (*bn_finalize)(const PfnArgs &a, cudaStream_t st);                       // SyncBatchNorm phase 2
+    cudaError_t (*bwd_finalize)(const PfnArgs &a, const double *glob, cudaStream_t st);  // SyncBatchNorm backward phase 2
 };
 
-// (id, cols, layout, with_distance, c_out) -- one translation unit each (rdp_pfn_inst.cu, -DRDP_CFG_ID=id)
-#define RDP_PFN_CONFIGS(X)                         \
-    X(0, 6, RDP_LAYOUT_SIMPLE2D, false, 32)        \
-    X(1, 7, RDP_LAYOUT_SIMPLE2D, false, 32)        \
-    X(2, 5, RDP_LAYOUT_DYNPILLAR, false, 64)       \
-    X(3, 5, RDP_LAYOUT_DYNPILLAR, true, 32)        \
-    X(4, 6, RDP_LAYOUT_SIMPLE2D, true, 32)         \
-    X(5, 5, RDP_LAYOUT_SIMPLE2D, false, 32)        \
-    X(6, 5, RDP_LAYOUT_DYNPILLAR, false, 32)       \
-    X(7, 6, RDP_LAYOUT_SIMPLE2D, false, 64)        \
-    X(8, 7, RDP_LAYOUT_SIMPLE2D, false, 64)        \
-    X(9, 6, RDP_LAYOUT_DYNPILLAR, false, 64)       \
-    X(10, 6, RDP_LAYOUT_DYNPILLAR, false, 32)
+// (id, cols, with_distance, c_out) -- one translation unit each (rdp_pfn_inst.cu, -DRDP_CFG_ID=id).  cols = 1 + raw point
+// features (4..8); the feature layout and the USE_* flags of model_cfg are runtime data (the matrix T), not instantiations.
+#define RDP_PFN_CONFIGS(X)   \
+    X(0, 4, false, 32)  X(1, 4, false, 64)  X(2, 4, false, 128)   \
+    X(3, 5, false, 32)  X(4, 5, false, 64)  X(5, 5, false, 128)   \
+    X(6, 6, false, 32)  X(7, 6, false, 64)  X(8, 6, false, 128)   \
+    X(9, 7, false, 32)  X(10, 7, false, 64) X(11, 7, false, 128)  \
+    X(12, 8, false, 32) X(13, 8, false, 64) X(14, 8, false, 128)  \
+    X(15, 4, true, 32)  X(16, 4, true, 64)  X(17, 4, true, 128)   \
+    X(18, 5, true, 32)  X(19, 5, true, 64)  X(20, 5, true, 128)   \
+    X(21, 6, true, 32)  X(22, 6, true, 64)  X(23, 6, true, 128)   \
+    X(24, 7, true, 32)  X(25, 7, true, 64)  X(26, 7, true, 128)   \
+    X(27, 8, true, 32)  X(28, 8, true, 64)  X(29, 8, true, 128)
 
-#define RDP_DECLARE_CFG(id, cols, layout, dist, cout) const PfnLaunch *rdp_pfn_cfg_##id();
+#define RDP_DECLARE_CFG(id, cols, dist, cout) const PfnLaunch *rdp_pfn_cfg_##id();
 RDP_PFN_CONFIGS(RDP_DECLARE_CFG)
 #undef RDP_DECLARE_CFG
 

@@ -43,7 +43,7 @@ class EncoderSpec:
         g = Geom()
         for k in range(3):
             g.lo[k], g.vsz[k], g.off[k] = self.lo[k], self.vsz[k], self.off[k]
-        g.nx, g.ny, g.batch_size, g.cols = self.nx, self.ny, int(batch_size), self.cols
+        g.nx, g.ny, g.batch_size, g.cols, g.nz = self.nx, self.ny, int(batch_size), self.cols, 0
         return g
 
     def layout_struct(self) -> Layout:
@@ -245,6 +245,7 @@ def _params_struct(spec: "EncoderSpec", weight, bias, gamma, beta, running_mean,
         p.running_mean, p.running_var = key[4] or None, key[5] or None
         p.eps, p.momentum, p.train_bn = spec.eps, spec.momentum, int(train_bn)
         p.num_batches_tracked = key[7] or None
+        p.stats_phase, p.local_stats, p.global_bwd = 0, None, None
         if len(_prm_cache) > 512:
             _prm_cache.clear()
         _prm_cache[key] = p

@@ -68,7 +68,7 @@ def _(points, weight, bias, gamma, beta, running_mean, running_var, spec_ints, s
     f32 = lambda *s: points.new_empty(s, dtype=torch.float32)
     i32 = lambda *s: points.new_empty(s, dtype=torch.int32)
     argpos = i32(n_pillars, c_out) if want_argmax else i32(0)
-    bn = points.new_empty((4 * c_out + 1 + c_in + c_in * c_in,) if (train_bn and gamma is not None) else (0,), dtype=torch.float64)
+    bn = points.new_empty((4 * c_out + 1 + 14 + 14 * 14,) if (train_bn and gamma is not None) else (0,), dtype=torch.float64)
     ws = points.new_empty((ctx.new_dynamic_size(),), dtype=torch.uint8)
     stat = f32(c_out) if running_mean is not None else f32(0)
     return (f32(n_pillars, c_out), i32(n_pillars, kc), i32(n_kept), i32(n_pillars), argpos, bn, ws, i32(16), stat,

@@ -36,7 +36,7 @@ def grid_of(g):
     return synth.grid_size_of(synth.PC_RANGE, g["voxel_size"])
 
 
-def oracle_from_golden(g, mean_mode=orc.MEAN_F64):
+def oracle_from_golden(g, mean_mode=orc.FOLDED):
     from radardistill_b200 import synth
     cfg = orc.config_for(g["class_name"], int(g["num_point_features"]), g["voxel_size"], grid_of(g),
                          synth.PC_RANGE, g["model_cfg"])

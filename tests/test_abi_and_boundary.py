@@ -123,7 +123,7 @@ def test_torch_library_ops_are_registered_with_fake_kernels():
         feats, coords, inverse, counts, argpos, bn_state = out[:6]
         assert feats.shape[1] == 32 and coords.shape[1] == 3 and feats.dtype == torch.float32 and coords.dtype == torch.int32
         assert feats.shape[0] == coords.shape[0] == counts.shape[0] == argpos.shape[0]      # one symbol: P
-        assert bn_state.shape[0] == 4 * 32 + 1 + 15 + 15 * 15
+        assert bn_state.shape[0] == 4 * 32 + 1 + 14 + 14 * 14   # reduced basis, upper bound G = 14
         g = torch.ops.rdp.pillar_encode_backward(pts, feats, feats, argpos, bn_state, out[6], out[7], w, None, v(), v(), v(), v(),
                                                  ints, floats, 2, True)
         assert [tuple(t.shape) for t in g] == [(32, 15), (32,), (32,)]
@@ -140,7 +140,7 @@ def test_plan_carves_one_scratch_allocation():
         assert pl.off_bn - pl.off_counters >= 4 * _lib.RDP_NUM_COUNTERS
         assert pl.off_inverse - pl.off_bn >= 8 * pl.bn_doubles
         assert pl.off_counts - pl.off_inverse >= 4 * (pl.cap + 4) and pl.total_bytes - pl.off_counts >= 4 * (pl.cap + 4)
-        assert pl.bn_doubles == (4 * 32 + 1 + 15 + 15 * 15 if train else 0)
+        assert pl.bn_doubles == (4 * 32 + 1 + 14 + 14 * 14 if train else 0)
     assert ops._plan(spec, 8, 21_827, True) is not ops._plan(spec, 8, 21_827, False)
 
 

@@ -29,7 +29,7 @@ def run_module(m, g, pts_np, key, batch_size=None):
 @pytest.mark.parametrize("path", FILES, ids=lambda p: p.split("/")[-1][:-4])
 def test_cuda_matches_oracle_and_reference(path):
     g = H.load_golden(path)
-    o = H.oracle_from_golden(g, orc.MEAN_F64)
+    o = H.oracle_from_golden(g, orc.FOLDED)
     m = H.module_from_golden(g)
     m.train(g["training"])
     r = o.forward(g["points"], training=g["training"])

@@ -19,7 +19,7 @@ def test_goldens_present():
 
 
 @pytest.mark.parametrize("path", FILES, ids=lambda p: p.split("/")[-1][:-4])
-@pytest.mark.parametrize("mean_mode", [orc.MEAN_SEQ_F32, orc.MEAN_F64], ids=["seqf32", "f64"])
+@pytest.mark.parametrize("mean_mode", [orc.MEAN_SEQ_F32, orc.MEAN_F64, orc.FOLDED], ids=["seqf32", "f64", "folded"])
 def test_oracle_matches_reference(path, mean_mode):
     g = H.load_golden(path)
     o = H.oracle_from_golden(g, mean_mode)
@@ -62,9 +62,12 @@ def test_mean_modes_agree_within_one_ulp():
     g = H.load_golden([f for f in FILES if "dense_cell__eval" in f][0])
     a = H.oracle_from_golden(g, orc.MEAN_SEQ_F32).forward(g["points"])
     b = H.oracle_from_golden(g, orc.MEAN_F64).forward(g["points"])
+    c = H.oracle_from_golden(g, orc.FOLDED).forward(g["points"])
     d = np.abs(a["pillar_mean"] - b["pillar_mean"])
     assert d.max() <= 64 * np.spacing(np.float32(54.0))  # 700-point pillar: sequential fp32 drift
     assert H.norm_rel_err(a["features"], b["features"]) <= H.RTOL_FEATURES
+    np.testing.assert_array_equal(b["pillar_mean"], c["pillar_mean"])      # the folded form keeps the fp64 mean
+    assert H.norm_rel_err(c["features"], b["features"]) <= H.RTOL_FEATURES
 
 
 def test_single_point_train_raises():

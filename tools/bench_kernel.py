@@ -5,7 +5,7 @@ import torch
 import bench
 from radardistill_b200 import _lib, ops
 
-def main(frames=8, reps=15):
+def main(frames=8, reps=int(os.environ.get("RDP_BENCH_REPS", "15"))):
     dev = torch.device("cuda", 0)
     lidar, _ = bench.make_clouds(0, frames)
     lid, rad, call = bench.build_modules(dev, "B", False)
@@ -20,7 +20,7 @@ def main(frames=8, reps=15):
     feats = torch.empty((len(lidar), spec.c_out), dtype=torch.float32, device=dev)
     argp = torch.empty((len(lidar), spec.c_out), dtype=torch.int32, device=dev)
     grad = torch.ones((res.n_pillars, spec.c_out), dtype=torch.float32, device=dev)
-    dw, dg, db = (torch.empty(s, device=dev) for s in ((32, 14), (32,), (32,)))
+    dw, dg, db = (torch.empty(s, device=dev) for s in ((spec.c_out, spec.c_in), (spec.c_out,), (spec.c_out,)))
     out = {}
     def timeit(name, fn):
         ts = []
