@@ -142,7 +142,7 @@ static int pfn_fwd_impl(const PfnLaunch *L, PfnArgs &a, const rdp_pfn_params_t *
     if (train) {
         if (prm->stats_phase != 2) {
             a.defer_finalize = prm->stats_phase == 1;
-            RDP_CUDA_OK(L->moments(a, 148 * (L->g <= 10 ? 3 : 2), st));
+            RDP_CUDA_OK(L->moments(a, 148 * 4, st));
         }
         if (prm->stats_phase == 1) return RDP_OK;   // SyncBatchNorm: the caller all-reduces the totals, then phase 2
         if (prm->stats_phase == 2) {

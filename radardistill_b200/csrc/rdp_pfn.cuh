@@ -70,6 +70,7 @@ struct PfnCfg {
     static constexpr int KIN = B::KIN, G = B::G, NACC = B::NACC, RS = B::RS;
     static constexpr int CPL = COUT / 32;                              // channels per lane
     static constexpr int BWD_PER = G + 1;                              // per channel: A(G) | dbeta
+    static constexpr int FW = (KIN + 1 + 3) / 4 * 4;                   // floats per row record in shared memory: row inputs | last-row flag
     static constexpr uint32_t ROW_BYTES = (kPfnCap + 1) * RS * 4;      // the window plus the row in front of it
     static constexpr uint32_t AUX_BYTES = kPfnWin * 8 * 4;
     static_assert(G <= kMaxG && COUT % 32 == 0 && COUT <= kMaxCout, "shape");
@@ -130,6 +131,7 @@ struct TileSmem {
     alignas(8) uint64_t pre[2];                    // BWD: arrival of a chunk's (grad, argpos) rows, double buffered
     alignas(16) float pre_grad[2][PCH > 0 ? PCH * Cfg::COUT : 4];
     alignas(16) int pre_arg[2][PCH > 0 ? PCH * Cfg::COUT : 4];
+    alignas(16) float frec[kPfnCap * Cfg::FW];     // per staged row: the KIN row inputs + last-row-of-pillar flag (tile_c1)
     int tf[2][2];                                  // per stage: first pillar of the tile, first pillar of the next
     float carry_v[4][Cfg::COUT];                   // big-pillar path: per-warp maxima, combined in warp order
     int carry_p[4][Cfg::COUT], carry_o[4][Cfg::COUT];
@@ -160,12 +162,40 @@ __device__ __forceinline__ TileBounds tile_bounds(const PfnStage<Cfg> &T, int ps
 }
 
 // ------------------------------------------------------------------------------------------- forward
+// Per tile:  C1 (thread = row) turns every staged row into its KIN row inputs + a last-row-of-pillar flag in shared
+// memory, so that the redundant per-lane work of the stream is two shared loads per row;  ST (lane = channel) walks the
+// rows of a pillar-aligned quarter of the tile per warp in one flat loop: KIN FMAs and a max per row, the pillar epilogue
+// (pillar term, BatchNorm, ReLU, one coalesced 128-byte store per 32 channels) when a row carries the flag.
+template <class Cfg>
+__device__ __forceinline__ void tile_c1(const PfnStage<Cfg> &T, const TileBounds &tb, float off_z, float *frec) {
+    constexpr int COLS = Cfg::COLS, RS = Cfg::RS, KIN = Cfg::KIN, FW = Cfg::FW;
+    for (int j = tb.j0 + (int)threadIdx.x; j < tb.jstop; j += kPfnThreads) {
+        const float *src = T.row(j);
+        float row[RS], rin[FW];
+#pragma unroll
+        for (int c4 = 0; c4 < RS; c4 += 4) {   // whole row incl. the pillar id in its last slot
+            const float4 q = *reinterpret_cast<const float4 *>(src + c4);
+            row[c4] = q.x; row[c4 + 1] = q.y; row[c4 + 2] = q.z; row[c4 + 3] = q.w;
+        }
+        const int gid = __float_as_int(row[RS - 1]);
+        const float2 cen = *reinterpret_cast<const float2 *>(&T.aux[(gid - tb.ps) * 8]);
+        row_inputs<COLS, Cfg::DIST>(row, cen.x, cen.y, off_z, rin);
+        const int last = (j == tb.jstop - 1) || (T.gid(j + 1) != gid);
+        rin[KIN] = __int_as_float(last);
+#pragma unroll
+        for (int k = KIN + 1; k < FW; ++k) rin[k] = 0.0f;
+        float4 *dst = reinterpret_cast<float4 *>(frec + j * FW);
+#pragma unroll
+        for (int k4 = 0; k4 < FW / 4; ++k4) dst[k4] = make_float4(rin[4 * k4], rin[4 * k4 + 1], rin[4 * k4 + 2], rin[4 * k4 + 3]);
+    }
+}
+
 template <class Cfg, bool ARG>
-__global__ void __launch_bounds__(kPfnThreads, Cfg::CPL == 1 ? (ARG ? 6 : 8) : (Cfg::CPL == 2 ? 4 : 2)) pfn_apply_kernel(const __grid_constant__ PfnArgs a) {
+__global__ void __launch_bounds__(kPfnThreads, Cfg::CPL == 1 ? (ARG ? 6 : 7) : (Cfg::CPL == 2 ? 4 : 2)) pfn_apply_kernel(const __grid_constant__ PfnArgs a) {
     extern __shared__ __align__(32) unsigned char smem_raw[];
     using Smem = TileSmem<Cfg, 0>;
     Smem &S = *reinterpret_cast<Smem *>(smem_raw);
-    constexpr int COUT = Cfg::COUT, COLS = Cfg::COLS, RS = Cfg::RS, CPL = Cfg::CPL, KIN = Cfg::KIN, G = Cfg::G;
+    constexpr int COUT = Cfg::COUT, COLS = Cfg::COLS, RS = Cfg::RS, CPL = Cfg::CPL, KIN = Cfg::KIN, G = Cfg::G, FW = Cfg::FW;
     constexpr int WIN = kPfnWin, NW = kPfnThreads / 32;
     constexpr bool DIST = Cfg::DIST;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -208,15 +238,8 @@ __global__ void __launch_bounds__(kPfnThreads, Cfg::CPL == 1 ? (ARG ? 6 : 8) : (
         tma_bulk_g2s(T.aux, a.aux + (size_t)pf * 8, Cfg::AUX_BYTES, &S.full[s]);
     };
 
-    // v[cc] = flipped linear value of one row (k-ascending fmaf chain over the row inputs)
-    auto row_v = [&](const float *src, float cenx, float ceny, float *v) {
-        float row[RS], rin[KIN];
-#pragma unroll
-        for (int c4 = 0; c4 < (COLS + 3) / 4 * 4; c4 += 4) {
-            const float4 q = *reinterpret_cast<const float4 *>(src + c4);
-            row[c4] = q.x; row[c4 + 1] = q.y; row[c4 + 2] = q.z; row[c4 + 3] = q.w;
-        }
-        row_inputs<COLS, DIST>(row, cenx, ceny, a.off_z, rin);
+    // v[cc] = flipped linear value of the row inputs (k-ascending fmaf chain)
+    auto chain = [&](const float *rin, float *v) {
 #pragma unroll
         for (int cc = 0; cc < CPL; ++cc) {
             float acc = __fmul_rn(wv[cc][0], rin[0]);
@@ -224,6 +247,24 @@ __global__ void __launch_bounds__(kPfnThreads, Cfg::CPL == 1 ? (ARG ? 6 : 8) : (
             for (int k = 1; k < KIN; ++k) acc = fmaf(wv[cc][k], rin[k], acc);
             v[cc] = acc;
         }
+    };
+    auto load_rec = [&](const float *rec, float *rin) {
+#pragma unroll
+        for (int k4 = 0; k4 < FW / 4; ++k4) {
+            const float4 q = *reinterpret_cast<const float4 *>(rec + 4 * k4);
+            rin[4 * k4] = q.x; rin[4 * k4 + 1] = q.y; rin[4 * k4 + 2] = q.z; rin[4 * k4 + 3] = q.w;
+        }
+    };
+    // big-pillar path: row straight from global memory
+    auto row_v_global = [&](const float *src, float cenx, float ceny, float *v) {
+        float row[RS], rin[KIN];
+#pragma unroll
+        for (int c4 = 0; c4 < (COLS + 3) / 4 * 4; c4 += 4) {
+            const float4 q = *reinterpret_cast<const float4 *>(src + c4);
+            row[c4] = q.x; row[c4 + 1] = q.y; row[c4 + 2] = q.z; row[c4 + 3] = q.w;
+        }
+        row_inputs<COLS, DIST>(row, cenx, ceny, a.off_z, rin);
+        chain(rin, v);
     };
     // pillar epilogue: x = s m + u (one rounding), BatchNorm, ReLU
     auto pillar_z = [&](const float *m, const float4 &a0, float ndz, float *z) {
@@ -265,6 +306,8 @@ __global__ void __launch_bounds__(kPfnThreads, Cfg::CPL == 1 ? (ARG ? 6 : 8) : (
         const int np = tb.jstop - tb.j0;
 
         if (np > 0) {
+            tile_c1<Cfg>(T, tb, a.off_z, S.frec);
+            __syncthreads();
             // warp `warp` streams a pillar-aligned quarter of the rows
             auto cut = [&](int q) -> int {
                 if (q <= 0) return tb.j0;
@@ -274,71 +317,72 @@ __global__ void __launch_bounds__(kPfnThreads, Cfg::CPL == 1 ? (ARG ? 6 : 8) : (
             };
             int w = cut(warp);
             const int wb = cut(warp + 1);
-            int slot = (w < wb) ? T.gid(w) - ps : 0;
-            float *fout = a.features + (size_t)(ps + slot) * COUT + lane;
-            int32_t *aout = ARG ? a.argpos + (size_t)(ps + slot) * COUT + lane : nullptr;
-            while (w < wb) {
-                const float4 a0 = *reinterpret_cast<const float4 *>(&T.aux[slot * 8]);       // centre xy, (centre - mean) xy
-                const float2 a1 = *reinterpret_cast<const float2 *>(&T.aux[slot * 8 + 4]);   // (centre - mean) z, first row
-                const int rows = __float_as_int(T.aux[slot * 8 + 6]);
+            if (w < wb) {
+                const int slot0 = T.gid(w) - ps;
+                const float *ax = T.aux + slot0 * 8;
+                float *fout = a.features + (size_t)(ps + slot0) * COUT + lane;
+                int32_t *aout = ARG ? a.argpos + (size_t)(ps + slot0) * COUT + lane : nullptr;
                 float m[CPL];
                 int mp[CPL];
                 bool tie = false;
+                int wfirst = w;   // first row of the pillar being streamed
 #pragma unroll
                 for (int cc = 0; cc < CPL; ++cc) { m[cc] = NEG_INF; mp[cc] = w; }
-                int r = 0;
-                for (; r + 1 < rows; r += 2) {   // two rows in flight: independent fmaf chains
-                    float v0[CPL], v1[CPL];
-                    row_v(T.row(w + r), a0.x, a0.y, v0);
-                    row_v(T.row(w + r + 1), a0.x, a0.y, v1);
+                // one row folded into the running maxima; closes the pillar when the row carries the last-row flag
+                auto fold = [&](const float *v, int last, int wr) {
 #pragma unroll
                     for (int cc = 0; cc < CPL; ++cc) {
                         if (!ARG) {
-                            m[cc] = fmaxf(m[cc], fmaxf(v0[cc], v1[cc]));
+                            m[cc] = fmaxf(m[cc], v[cc]);
                         } else {
-                            tie = tie || (v0[cc] == m[cc]);
-                            if (v0[cc] > m[cc]) { m[cc] = v0[cc]; mp[cc] = w + r; }
-                            tie = tie || (v1[cc] == m[cc]);
-                            if (v1[cc] > m[cc]) { m[cc] = v1[cc]; mp[cc] = w + r + 1; }
+                            tie = tie || (v[cc] == m[cc]);
+                            if (v[cc] > m[cc]) { m[cc] = v[cc]; mp[cc] = wr; }
                         }
                     }
-                }
-                if (r < rows) {
-                    float v0[CPL];
-                    row_v(T.row(w + r), a0.x, a0.y, v0);
+                    if (last) {
+                        if (ARG && __any_sync(0xffffffffu, tie)) {
+                            // exact ties (duplicate points): the winner is the tied row with the lowest original (== kept) index
+                            int mo[CPL];
 #pragma unroll
-                    for (int cc = 0; cc < CPL; ++cc) {
-                        if (!ARG) {
-                            m[cc] = fmaxf(m[cc], v0[cc]);
-                        } else {
-                            tie = tie || (v0[cc] == m[cc]);
-                            if (v0[cc] > m[cc]) { m[cc] = v0[cc]; mp[cc] = w + r; }
+                            for (int cc = 0; cc < CPL; ++cc) mo[cc] = 0x7fffffff;
+                            for (int rr = wfirst; rr <= wr; ++rr) {
+                                float rin[FW], v2[CPL];
+                                load_rec(S.frec + rr * FW, rin);
+                                chain(rin, v2);
+                                const int o = T.orig(rr);
+#pragma unroll
+                                for (int cc = 0; cc < CPL; ++cc)
+                                    if (v2[cc] == m[cc] && o < mo[cc]) { mo[cc] = o; mp[cc] = rr; }
+                            }
                         }
+                        const float4 a0 = *reinterpret_cast<const float4 *>(ax);   // centre xy, (centre - mean) xy
+                        float z[CPL];
+                        pillar_z(m, a0, ax[4], z);
+#pragma unroll
+                        for (int cc = 0; cc < CPL; ++cc) {
+                            fout[32 * cc] = z[cc];
+                            if (ARG) aout[32 * cc] = (z[cc] > 0.0f) ? (int)base + mp[cc] : -1;   // -1: ReLU clamped, no gradient
+                            m[cc] = NEG_INF;
+                        }
+                        ax += 8; fout += COUT;
+                        if (ARG) { aout += COUT; tie = false; wfirst = wr + 1; }
                     }
+                };
+                for (; w + 1 < wb; w += 2) {   // two rows in flight: independent load + fmaf chains
+                    float r0[FW], r1[FW], v0[CPL], v1[CPL];
+                    load_rec(S.frec + w * FW, r0);
+                    load_rec(S.frec + (w + 1) * FW, r1);
+                    chain(r0, v0);
+                    chain(r1, v1);
+                    fold(v0, __float_as_int(r0[KIN]), w);
+                    fold(v1, __float_as_int(r1[KIN]), w + 1);
                 }
-                if (ARG && __any_sync(0xffffffffu, tie)) {
-                    // exact ties (duplicate points): the winner is the tied row with the lowest original (== kept) index
-                    int mo[CPL];
-#pragma unroll
-                    for (int cc = 0; cc < CPL; ++cc) mo[cc] = 0x7fffffff;
-                    for (int rr = 0; rr < rows; ++rr) {
-                        float v0[CPL];
-                        row_v(T.row(w + rr), a0.x, a0.y, v0);
-                        const int o = T.orig(w + rr);
-#pragma unroll
-                        for (int cc = 0; cc < CPL; ++cc)
-                            if (v0[cc] == m[cc] && o < mo[cc]) { mo[cc] = o; mp[cc] = w + rr; }
-                    }
+                if (w < wb) {
+                    float r0[FW], v0[CPL];
+                    load_rec(S.frec + w * FW, r0);
+                    chain(r0, v0);
+                    fold(v0, __float_as_int(r0[KIN]), w);
                 }
-                float z[CPL];
-                pillar_z(m, a0, a1.x, z);
-#pragma unroll
-                for (int cc = 0; cc < CPL; ++cc) {
-                    fout[32 * cc] = z[cc];
-                    if (ARG) aout[32 * cc] = (z[cc] > 0.0f) ? (int)base + mp[cc] : -1;   // -1: ReLU clamped, no gradient
-                }
-                w += rows; ++slot; fout += COUT;
-                if (ARG) aout += COUT;
             }
         }
 
@@ -358,7 +402,7 @@ __global__ void __launch_bounds__(kPfnThreads, Cfg::CPL == 1 ? (ARG ? 6 : 8) : (
             for (long long i = ra; i < rb; ++i) {
                 const float *src = a.grows + ((size_t)i + 1) * RS;
                 float v0[CPL];
-                row_v(src, a0.x, a0.y, v0);
+                row_v_global(src, a0.x, a0.y, v0);
                 const int o = ARG ? __float_as_int(src[RS - 2]) : 0;
 #pragma unroll
                 for (int cc = 0; cc < CPL; ++cc) {
@@ -392,7 +436,7 @@ __global__ void __launch_bounds__(kPfnThreads, Cfg::CPL == 1 ? (ARG ? 6 : 8) : (
                 }
             }
         }
-        __syncthreads();   // every warp is done with stage s before the TMA of tile k + 2 lands in it
+        __syncthreads();   // every warp is done with stage s (and the row records) before the next tile overwrites them
     }
 }
 
@@ -463,28 +507,53 @@ __device__ __forceinline__ void bn_epilogue(const PfnArgs &a, const double *tota
 }
 
 // Feature moments S1 = sum g, S2 = sum g g^T over all kept rows (train-mode BatchNorm; oracle: orc_moments_folded): one
-// row-parallel pass over the grouped rows, thread = row, the next row's loads issued before the current row's arithmetic.
+// row-parallel pass over the grouped rows, lane = row, the next row's loads issued before the current row's arithmetic.
 // The sums are fp64 from the first product on (products of two fp32 values are exact in fp64), so the totals agree with
 // the oracle's sequential fp64 sums to ~1e-13 and the folded fp32 scale / shift -- hence every train-mode feature and the
 // ReLU mask the backward routes through -- come out bit-identical in practice.  (fp32 partial sums were tried first: 1e-8
 // agreement of scale / shift, but on 33 M (pillar, channel) pairs that flips a handful of pre-activations across zero and
-// each flip moves dbeta by one upstream gradient value.)  Per-warp shuffle reduction, one fp64 atomic per CTA and
-// element into the workspace totals (upper triangle of S2); the CTA that finishes last folds them into bn_state.
+// each flip moves dbeta by one upstream gradient value.)  The upper triangle of S2 is split between the two warps of a
+// pair that walk the same rows (rows k < KH of the triangle | the rest: balanced halves), which halves the fp64
+// accumulators a thread carries -- one thread owning all of them sat at 168 registers / 12 warps per SM, latency bound
+// at 70 us (ncu, profiles/r02b).  Per-warp shuffle reduction, fp64 atomics into the workspace totals; the CTA that
+// finishes last folds them into bn_state (no finalize launch).
+template <int G>
+struct MomentSplit {
+    static constexpr int tri(int k0, int k1) { int n = 0; for (int k = k0; k < k1; ++k) n += G - k + 1; return n; }   // S1[k] + row k of the triangle
+    static constexpr int kh() { int k = 1; while (tri(0, k) * 2 < tri(0, G)) ++k; return k; }
+    static constexpr int KH = kh();
+    static constexpr int NA = tri(0, KH), NB = tri(KH, G), NMAX = NA > NB ? NA : NB;
+};
+
+template <int G, int K0, int K1>
+__device__ __forceinline__ void moments_rows(const float *g, double *acc) {
+    double gd[G];
+#pragma unroll
+    for (int k = K0; k < G; ++k) gd[k] = (double)g[k];
+    int e = 0;
+#pragma unroll
+    for (int k = K0; k < K1; ++k) {
+        acc[e++] += gd[k];
+#pragma unroll
+        for (int l = k; l < G; ++l, ++e) acc[e] = fma(gd[k], gd[l], acc[e]);
+    }
+}
+
 template <class Cfg>
-__global__ void __launch_bounds__(128, Cfg::G <= 10 ? 3 : 2) pfn_moments_kernel(const __grid_constant__ PfnArgs a) {
+__global__ void __launch_bounds__(128, 4) pfn_moments_kernel(const __grid_constant__ PfnArgs a) {
     constexpr int G = Cfg::G, KIN = Cfg::KIN, RS = Cfg::RS, COLS = Cfg::COLS, NACC = Cfg::NACC;
-    constexpr int NT = G + G * (G + 1) / 2;   // S1 | upper triangle of S2, row-major
+    using MS = MomentSplit<G>;
     constexpr int LW = (COLS + 3) / 4 * 4;
-    __shared__ double red[4][NT];
+    __shared__ double red[4][MS::NMAX];
     __shared__ double sm[G + G * G];
     __shared__ int s_last;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, half = warp & 1;
     const long long N = a.counters[RDP_CNT_N];
-    double acc[NT];
+    double acc[MS::NMAX];
 #pragma unroll
-    for (int e = 0; e < NT; ++e) acc[e] = 0.0;
-    const long long stride = (long long)gridDim.x * 128;
-    long long row = (long long)blockIdx.x * 128 + tid;
+    for (int e = 0; e < MS::NMAX; ++e) acc[e] = 0.0;
+    const long long stride = (long long)gridDim.x * 64;
+    long long row = (long long)blockIdx.x * 64 + (warp >> 1) * 32 + lane;
     float r[LW], nr[LW];
     float4 q0 = make_float4(0.f, 0.f, 0.f, 0.f), nq0 = q0;
     float q1 = 0.0f, nq1 = 0.0f;
@@ -502,16 +571,8 @@ __global__ void __launch_bounds__(128, Cfg::G <= 10 ? 3 : 2) pfn_moments_kernel(
         float g[G];
         row_inputs<COLS, Cfg::DIST>(r, q0.x, q0.y, a.off_z, g);
         g[KIN] = q0.x; g[KIN + 1] = q0.y; g[KIN + 2] = q0.z; g[KIN + 3] = q0.w; g[KIN + 4] = q1;
-        double gd[G];
-#pragma unroll
-        for (int k = 0; k < G; ++k) gd[k] = (double)g[k];
-        int e = G;
-#pragma unroll
-        for (int k = 0; k < G; ++k) {
-            acc[k] += gd[k];
-#pragma unroll
-            for (int l = k; l < G; ++l, ++e) acc[e] = fma(gd[k], gd[l], acc[e]);
-        }
+        if (half == 0) moments_rows<G, 0, MS::KH>(g, acc);
+        else moments_rows<G, MS::KH, G>(g, acc);
         if (more) {
 #pragma unroll
             for (int c = 0; c < LW; ++c) r[c] = nr[c];
@@ -519,22 +580,21 @@ __global__ void __launch_bounds__(128, Cfg::G <= 10 ? 3 : 2) pfn_moments_kernel(
         }
     }
 #pragma unroll
-    for (int e = 0; e < NT; ++e) {
+    for (int e = 0; e < MS::NMAX; ++e) {
         double v = acc[e];
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
         if (lane == 0) red[warp][e] = v;
     }
     __syncthreads();
-    for (int e = tid; e < NT; e += 128) {
-        const double sacc = red[0][e] + red[1][e] + red[2][e] + red[3][e];
+    for (int e = tid; e < MS::NA + MS::NB; e += 128) {
+        // e enumerates half A's values, then half B's: [S1[k], S2[k][k..G-1]] for k in the half's range
+        const int h = e >= MS::NA, idx = h ? e - MS::NA : e;
+        const double sacc = red[h][idx] + red[h + 2][idx];
         if (sacc == 0.0) continue;
-        int dst = e;   // S1 entry
-        if (e >= G) {  // e - G = index in the row-major upper triangle -> (k, l) -> full-matrix slot
-            int k = 0, rem = e - G;
-            while (rem >= G - k) { rem -= G - k; ++k; }
-            dst = G + k * G + (k + rem);
-        }
+        int k = h ? MS::KH : 0, rem = idx;
+        while (rem >= G - k + 1) { rem -= G - k + 1; ++k; }
+        const int dst = rem == 0 ? k : G + k * G + (k + rem - 1);   // S1 entry | slot of S2[k][l] in the full matrix (upper triangle)
         atomicAdd(a.acc_stats + dst, sacc);
     }
     __threadfence();
@@ -695,14 +755,7 @@ __global__ void __launch_bounds__(kPfnThreads, Cfg::CPL == 1 ? 5 : (Cfg::CPL == 
         tma_bulk_g2s(S.pre_arg[b], a.argpos + (size_t)p0 * COUT, bytes, &S.pre[b]);
     };
     // gy * [row inputs | pillar constants | 1] of the winning row into the fp32 tile sums
-    auto route = [&](const float *src, const float4 &a0, float ndz, float gy, float *tA) {
-        float row[RS], rin[KIN];
-#pragma unroll
-        for (int c4 = 0; c4 < (COLS + 3) / 4 * 4; c4 += 4) {
-            const float4 q = *reinterpret_cast<const float4 *>(src + c4);
-            row[c4] = q.x; row[c4 + 1] = q.y; row[c4 + 2] = q.z; row[c4 + 3] = q.w;
-        }
-        row_inputs<COLS, DIST>(row, a0.x, a0.y, a.off_z, rin);
+    auto route_rin = [&](const float *rin, const float4 &a0, float ndz, float gy, float *tA) {
 #pragma unroll
         for (int k = 0; k < KIN; ++k) tA[k] = fmaf(gy, rin[k], tA[k]);
         tA[KIN] = fmaf(gy, a0.x, tA[KIN]);
@@ -711,6 +764,27 @@ __global__ void __launch_bounds__(kPfnThreads, Cfg::CPL == 1 ? 5 : (Cfg::CPL == 
         tA[KIN + 3] = fmaf(gy, a0.w, tA[KIN + 3]);
         tA[KIN + 4] = fmaf(gy, ndz, tA[KIN + 4]);
         tA[G] += gy;
+    };
+    // winner row given by its record in shared memory (tile_c1)
+    auto route = [&](const float *rec, const float4 &a0, float ndz, float gy, float *tA) {
+        float rin[Cfg::FW];
+#pragma unroll
+        for (int k4 = 0; k4 < (KIN + 3) / 4; ++k4) {
+            const float4 q = *reinterpret_cast<const float4 *>(rec + 4 * k4);
+            rin[4 * k4] = q.x; rin[4 * k4 + 1] = q.y; rin[4 * k4 + 2] = q.z; rin[4 * k4 + 3] = q.w;
+        }
+        route_rin(rin, a0, ndz, gy, tA);
+    };
+    // big-pillar path: winner row straight from global memory
+    auto route_global = [&](const float *src, const float4 &a0, float ndz, float gy, float *tA) {
+        float row[RS], rin[KIN];
+#pragma unroll
+        for (int c4 = 0; c4 < (COLS + 3) / 4 * 4; c4 += 4) {
+            const float4 q = *reinterpret_cast<const float4 *>(src + c4);
+            row[c4] = q.x; row[c4 + 1] = q.y; row[c4 + 2] = q.z; row[c4 + 3] = q.w;
+        }
+        row_inputs<COLS, DIST>(row, a0.x, a0.y, a.off_z, rin);
+        route_rin(rin, a0, ndz, gy, tA);
     };
 
     int nfa = 0, nfb = 0;
@@ -748,6 +822,8 @@ __global__ void __launch_bounds__(kPfnThreads, Cfg::CPL == 1 ? 5 : (Cfg::CPL == 
         pending = false;
 
         if (nb > 0) {
+            tile_c1<Cfg>(T, tb, a.off_z, S.frec);
+            __syncthreads();
             float tA[CPL][PER];
 #pragma unroll
             for (int cc = 0; cc < CPL; ++cc)
@@ -777,7 +853,7 @@ __global__ void __launch_bounds__(kPfnThreads, Cfg::CPL == 1 ? 5 : (Cfg::CPL == 
                     for (int cc = 0; cc < CPL; ++cc) {
                         const int o = q * COUT + lane + 32 * cc;
                         const int ap = S.pre_arg[b][o];   // -1: the forward marked the pillar as ReLU-clamped (:38)
-                        if (ap >= 0) route(T.row(ap - (int)base), a0, ndz, S.pre_grad[b][o], tA[cc]);
+                        if (ap >= 0) route(S.frec + (ap - (int)base) * Cfg::FW, a0, ndz, S.pre_grad[b][o], tA[cc]);
                     }
                 }
             }
@@ -800,7 +876,7 @@ __global__ void __launch_bounds__(kPfnThreads, Cfg::CPL == 1 ? 5 : (Cfg::CPL == 
                 float tB[PER];
 #pragma unroll
                 for (int m = 0; m < PER; ++m) tB[m] = 0.0f;
-                if (ap >= 0) route(a.grows + ((size_t)ap + 1) * RS, a0, ndz, a.grad[o], tB);
+                if (ap >= 0) route_global(a.grows + ((size_t)ap + 1) * RS, a0, ndz, a.grad[o], tB);
 #pragma unroll
                 for (int m = 0; m < PER; ++m) dA[cc][m] += (double)tB[m];
             }
