@@ -202,7 +202,8 @@ class PillarOracle:
         L.orc_fold_weights(_p(self.weight), None if cfg.use_norm else _p(self.bias), _p(T), C.c_int(cin), C.c_int(co), C.c_int(g),
                            _p(wg), _p(cst))
         q = np.zeros((max(p, 1), 5), np.float32)
-        L.orc_pillar_consts(C.byref(self._cs), _p(r["unq"]), _p(mean), C.c_int64(p), _p(q))
+        L.orc_pillar_consts(_p(r["points"]), C.byref(self._cs), _p(r["keep"]), _p(r["inverse"]), _p(r["unq"]), _p(r["counts"]),
+                            C.c_int64(n), C.c_int64(p), _p(q))
         rin = np.empty((max(n, 1), kin), np.float32)
         v, x = np.empty((max(n, 1), co), np.float32), np.empty((max(n, 1), co), np.float32)
         L.orc_forward_folded(_p(r["points"]), C.byref(self._cs), _p(r["keep"]), _p(r["inverse"]), _p(q), _p(wg), _p(cst),

@@ -456,6 +456,7 @@ void orc_backward(const float *g, const float *f, const float *x, const float *o
  *     xyz = d + centre,   f_cluster = xyz - mean = d + (centre - mean),   f_rel = xyz - lo = d + (centre - lo).
  * With T the (c_in x (G+1)) matrix that writes the layout's features in the reduced basis
  *     g = [dx, dy, dz, raw features 4.., (dist) | cx, cy, cx - mx, cy - my, cz - mz | 1]        (KIN row inputs, 5 pillar constants)
+ * (cx - mx etc. are evaluated as -mean(d): fp64 sum of the rows' fp32 offsets d, one division, one rounding -- see orc_pillar_consts)
  * the linear layer is  x_c = W_c . f = wg_c . g + const_c  with [wg_c | const_c] = W_c T (fp64, rounded once), evaluated as
  *     v_ic = k-ascending fmaf chain over the KIN row inputs            (first term a plain product)
  *     u_pc = fmaf chain over the 5 pillar constants, starting from const_c
@@ -524,15 +525,31 @@ void orc_fold_weights(const float *W, const float *bias, const float *T, int cin
     }
 }
 
-/* Per-pillar constants q[p] = [cx, cy, cx - mx, cy - my, cz - mz] (cz = z_offset: pillars) from the merged key and the mean. */
-void orc_pillar_consts(const orc_cfg *g, const int32_t *unq, const float *mean, int64_t P, float *q) {
+/* Per-pillar constants q[p] = [cx, cy, -mean(dx), -mean(dy), -mean(dz)]: the pillar centre (:215-216) and the negated
+ * mean of the rows' centre offsets d = xyz - centre -- i.e. centre - mean(xyz), evaluated on the small, exactly summable
+ * offsets: fp64 sum of the fp32 d values (exact, order independent), one division, one rounding to fp32.
+ * f_cluster = xyz - mean (:226-227) then is d + q[2:5]. */
+void orc_pillar_consts(const float *pts, const orc_cfg *g, const int32_t *keep, const int32_t *inv, const int32_t *unq,
+                       const int32_t *cnt, int64_t n, int64_t P, float *q) {
     const int32_t sxy = g->nx * g->ny, sy = g->ny;
+    const int cols = g->cols;
+    double *acc = (double *)calloc((size_t)(3 * P + 1), sizeof(double));
     for (int64_t p = 0; p < P; ++p) {
         const int32_t u = unq[p], cx = (u % sxy) / sy, cy = u % sy;
-        const float cenx = (float)cx * g->vsz[0] + g->off[0], ceny = (float)cy * g->vsz[1] + g->off[1];   /* (:215-216) */
-        q[5 * p] = cenx; q[5 * p + 1] = ceny;
-        q[5 * p + 2] = cenx - mean[3 * p]; q[5 * p + 3] = ceny - mean[3 * p + 1]; q[5 * p + 4] = g->off[2] - mean[3 * p + 2];
+        q[5 * p] = (float)cx * g->vsz[0] + g->off[0];       /* (:215-216): separate mul and add roundings */
+        q[5 * p + 1] = (float)cy * g->vsz[1] + g->off[1];
     }
+    for (int64_t j = 0; j < n; ++j) {
+        const float *r = pts + (int64_t)keep[j] * cols;
+        const int64_t p = inv[j];
+        const float dx = r[1] - q[5 * p], dy = r[2] - q[5 * p + 1], dz = r[3] - g->off[2];
+        acc[3 * p] += (double)dx; acc[3 * p + 1] += (double)dy; acc[3 * p + 2] += (double)dz;
+    }
+    for (int64_t p = 0; p < P; ++p) {
+        const double c = (double)(cnt[p] < 1 ? 1 : cnt[p]);
+        for (int k = 0; k < 3; ++k) q[5 * p + 2 + k] = (float)(-(acc[3 * p + k] / c));
+    }
+    free(acc);
 }
 
 typedef struct { const float *pts; const orc_cfg *g; const int32_t *keep, *inv; const float *q, *wg, *cst; int KIN, G;
@@ -546,7 +563,10 @@ static void fold_range(int64_t lo, int64_t hi, void *p) {
         const float x = r[1], y = r[2], z = r[3];
         rin[0] = x - qp[0]; rin[1] = y - qp[1]; rin[2] = z - c->g->off[2];
         for (int k = 4; k < cols; ++k) rin[k - 1] = r[k];
-        if (c->g->with_distance) rin[cols - 1] = sqrtf(fmaf(z, z, fmaf(y, y, x * x)));
+        if (c->g->with_distance) {   /* the grouped rows carry d, not xyz: the norm (:230-231) is taken of d + centre */
+            const float xr = rin[0] + qp[0], yr = rin[1] + qp[1], zr = rin[2] + c->g->off[2];
+            rin[cols - 1] = sqrtf(fmaf(zr, zr, fmaf(yr, yr, xr * xr)));
+        }
         for (int o = 0; o < cout; ++o) {
             const float *w = c->wg + o * G;
             float v = w[0] * rin[0];

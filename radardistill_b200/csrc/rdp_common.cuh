@@ -38,6 +38,7 @@ constexpr int kPfnCap = RDP_PFN_CAP;          // rows staged per tile: the windo
 #define RDP_PFN_GRID_PER_SM 4
 #endif
 constexpr int kPfnGridCap = 148 * RDP_PFN_GRID_PER_SM;  // persistent PFN CTAs of the backward tile kernel
+constexpr int kSliceInts = 136;       // ints staged per tile from starts[] / unq[]: 128 pillars + 1, from a 16-byte aligned address
 __host__ __device__ constexpr int grouped_row_floats(int cols) { return (cols + 2 + 3) / 4 * 4; }
 constexpr int kMaxCin = 24;
 constexpr int kMaxCout = 128;
@@ -64,11 +65,12 @@ struct Workspace {
     uint2 *wordrank;         // words : {bitmap word, exclusive pillar rank of the word} -- one 8-byte gather per point
     int32_t *keys;           // n  (merged key, then overwritten by the pillar rank; -1 = dropped)
     int32_t *slots;          // n  position of the row inside its pillar (arrival order of rank_count_kernel's atomics)
+    int32_t *unq;            // pcap  merged key of every pillar (torch.unique's first output, :212)
     int32_t *tile_keep;      // index tiles
     int32_t *starts;         // pcap + 1  exclusive start of every pillar in the grouped order; starts[P] = N
     float *grows;            // (1 + n + pad) * RS : rows physically grouped by pillar (pillar order == key order);
-                             // RS floats per row = [row | pad | original row id | pillar id]; row 0 is a sentinel
-                             // (pillar id -1) in front of grouped position 0
+                             // RS floats per row = [b | xyz - pillar centre | features | pad | original row id | pillar id];
+                             // row 0 is a sentinel (pillar id -1) in front of grouped position 0
     char *zero_begin;
     size_t zero_bytes;
     float *aux;              // (pcap + pad) * 8 : per-pillar table [centre xy | centre - mean xyz | first grouped row | rows | lowest original row id]

@@ -13,11 +13,12 @@
 //   K2 bitmap_rank     popcount scan of the bitmap -> {word, rank of word} pairs, P; publishes (N, P) to the host
 //   K3 rank_count      key[i] -> rank = wordrank.rank + popc(below) ; inverse[j] ; slot[i] = counts[rank]++
 //   K4 count_scan      exclusive scan of counts -> pillar start offsets (starts[P] = N), tile_first
-//   K5 group_rows      grouped_rows[starts[rank] + slot] = row i | original row id | rank   (no atomics; the order
+//   K5 group_rows      grouped_rows[starts[rank] + slot] = [b | xyz - centre | features | original row id | rank]   (no atomics; the order
 //                      inside a pillar is the arrival order of K3's atomics -- every consumer is order independent).
 //                      The PFN kernels then stream contiguous, pillar-aligned row tiles with TMA.
-//   K6 pillar_table    thread = pillar: fp64 mean of its grouped rows, pillar centre, first row, row count; coords
-//                      (rdp_table.cuh; in train mode the fused call runs the variant that also sums the feature moments)
+//   K6 pillar_table    thread = pillar: fp64 mean of its grouped rows' centre offsets, pillar centre, first row, row count; coords
+//                      (rdp_table.cuh; only for the split-call ABI -- the fused forward builds the same entries tile by tile
+//                      inside its PFN kernels and skips this launch)
 // nz > 1 (DynamicVoxelVFE / DynamicMeanVFE, dynamic_voxel_vfe.py:57-71, dynamic_mean_vfe.py:52-60): z is quantised and
 // masked too and the key is ((b*nx + cx)*ny + cy)*nz + cz.
 #include "rdp_index_host.h"
@@ -184,7 +185,7 @@ __global__ void __launch_bounds__(kIndexThreads)
 rank_count_kernel(int32_t *__restrict__ keys, long long n0, const uint2 *__restrict__ wordrank,
                   const int32_t *__restrict__ tile_keep, int32_t *__restrict__ inverse, int32_t *__restrict__ counts,
                   const int32_t *__restrict__ counters, int32_t *__restrict__ orig2kept, int32_t *__restrict__ kept2orig,
-                  int32_t *__restrict__ slots) {
+                  int32_t *__restrict__ slots, int32_t *__restrict__ unq) {
     __shared__ int s_scan[9];
     __shared__ long long s_base;
     const int tid = threadIdx.x;
@@ -239,7 +240,10 @@ rank_count_kernel(int32_t *__restrict__ keys, long long n0, const uint2 *__restr
     int sl[4] = {0, 0, 0, 0};
 #pragma unroll
     for (int q = 0; q < 4; ++q)
-        if (r[q] >= 0) sl[q] = atomicAdd(counts + r[q], 1);
+        if (r[q] >= 0) {
+            sl[q] = atomicAdd(counts + r[q], 1);
+            if (sl[q] == 0) unq[r[q]] = k[q];   // exactly one row per pillar arrives first: it records the pillar's merged key
+        }
     if (i0 + 3 < n0) {
         *reinterpret_cast<int4 *>(slots + i0) = make_int4(sl[0], sl[1], sl[2], sl[3]);
     } else {
@@ -309,7 +313,7 @@ template <bool FRAMES>   // FRAMES: rows without the batch column + frame offset
 __global__ void __launch_bounds__(kIndexThreads)
 group_rows_kernel(const float *__restrict__ pts, const int32_t *__restrict__ ranks, const int32_t *__restrict__ slots, long long n0,
                   int cols, const int32_t *__restrict__ starts, float *__restrict__ grows, const int32_t *__restrict__ offsets,
-                  int batch) {
+                  int batch, GeomDev g) {
     extern __shared__ __align__(128) float tile[];
     __shared__ __align__(8) uint64_t bar;
     const int tid = threadIdx.x;
@@ -355,26 +359,40 @@ group_rows_kernel(const float *__restrict__ pts, const int32_t *__restrict__ ran
         const int r = k * kIndexThreads + tid;
         const float fb = fbv[k];
         const float *p = tile + r * in_cols - (FRAMES ? 1 : 0);   // FRAMES: logical column c >= 1 is input column c - 1, column 0 is fb
+        // The grouped copy stores the centre offsets d = xyz - centre (exactly f_center, :215-217) in place of xyz: every
+        // later pass works on d, and the pillar mean is taken over these small, exactly summable values.  The centre repeats
+        // quantize_mark_kernel's IEEE ops on this row, so it equals the pillar's centre bit for bit.
+        float d[3];
+        {
+            const float x = p[1], y = p[2], z = p[3];
+            const float qx = floorf(__fdiv_rn(__fsub_rn(x, g.lo_x), g.vx)), qy = floorf(__fdiv_rn(__fsub_rn(y, g.lo_y), g.vy));
+            d[0] = __fsub_rn(x, __fadd_rn(__fmul_rn((float)(int)qx, g.vx), g.off_x));
+            d[1] = __fsub_rn(y, __fadd_rn(__fmul_rn((float)(int)qy, g.vy), g.off_y));
+            float cenz = g.off_z;
+            if (g.nz > 1) cenz = __fadd_rn(__fmul_rn((float)(int)floorf(__fdiv_rn(__fsub_rn(z, g.lo_z), g.vz)), g.vz), g.off_z);
+            d[2] = __fsub_rn(z, cenz);
+        }
+        auto col = [&](int c) -> float { return (c >= 1 && c <= 3) ? d[c - 1] : ((FRAMES && c == 0) ? fb : p[c]); };
         if (rs == 8) {
             // one 256-bit store (STG.256) = one full 32-byte sector per row: the scatter is bound by store requests
             float v[8];
 #pragma unroll
             for (int c = 0; c < 8; ++c)
-                v[c] = c < cols ? ((FRAMES && c == 0) ? fb : p[c]) : (c == 6 ? __int_as_float((int)(row0 + r)) : (c == 7 ? __int_as_float(rk[k]) : 0.0f));
+                v[c] = c < cols ? col(c) : (c == 6 ? __int_as_float((int)(row0 + r)) : (c == 7 ? __int_as_float(rk[k]) : 0.0f));
             asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(grows + ((size_t)pos[k] + 1) * 8), "f"(v[0]),
                          "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
                          : "memory");
             continue;
         }
-        float4 *d = reinterpret_cast<float4 *>(grows + ((size_t)pos[k] + 1) * rs);
+        float4 *dst = reinterpret_cast<float4 *>(grows + ((size_t)pos[k] + 1) * rs);
         for (int c4 = 0; c4 < rs; c4 += 4) {
             float v[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const int c = c4 + i;
-                v[i] = c < cols ? ((FRAMES && c == 0) ? fb : p[c]) : (c == rs - 2 ? __int_as_float((int)(row0 + r)) : (c == rs - 1 ? __int_as_float(rk[k]) : 0.0f));
+                v[i] = c < cols ? col(c) : (c == rs - 2 ? __int_as_float((int)(row0 + r)) : (c == rs - 1 ? __int_as_float(rk[k]) : 0.0f));
             }
-            d[c4 >> 2] = make_float4(v[0], v[1], v[2], v[3]);
+            dst[c4 >> 2] = make_float4(v[0], v[1], v[2], v[3]);
         }
     }
 }
@@ -437,7 +455,7 @@ GeomDev make_geom_dev(const rdp_geom_t *geom) {
 
 int index_fwd_impl(const float *points, const int32_t *frame_offsets, int64_t n_points, const rdp_geom_t *geom, int32_t coord_cols,
                    void *workspace, size_t workspace_bytes, int32_t *coords, int32_t *inverse, int32_t *counts, int32_t *counters,
-                   int32_t *host_mapped, void *event_v, cudaStream_t stream, TableLaunchFn table_fn, void *table_ctx) {
+                   int32_t *host_mapped, void *event_v, cudaStream_t stream, bool skip_table) {
     cudaEvent_t event = static_cast<cudaEvent_t>(event_v);
     // N, P and the error flags are final after the bitmap scan (K2): publish them there, so the host learns the output
     // sizes ~50 us into the call and can enqueue whatever follows while the remaining kernels run.
@@ -475,22 +493,19 @@ int index_fwd_impl(const float *points, const int32_t *frame_offsets, int64_t n_
                                                               host_mapped);
     if (event) RDP_CUDA_OK(cudaEventRecord(event, stream));
     rank_count_kernel<<<tiles, kIndexThreads, 0, stream>>>(ws.keys, n_points, ws.wordrank, ws.tile_keep, inverse, counts, counters,
-                                                         ws.orig2kept, ws.kept2orig, ws.slots);
+                                                         ws.orig2kept, ws.kept2orig, ws.slots, ws.unq);
     count_scan_kernel<<<kScanGrid, kScanThreads, 0, stream>>>(counts, ws.scan_state_b, ws.starts, ws.tile_first, counters);
     if (frame_offsets)
         group_rows_kernel<true><<<tiles, kIndexThreads, smem, stream>>>(points, ws.keys, ws.slots, n_points, geom->cols, ws.starts,
-                                                                        ws.grows, frame_offsets, geom->batch_size);
+                                                                        ws.grows, frame_offsets, geom->batch_size, g);
     else
         group_rows_kernel<false><<<tiles, kIndexThreads, smem, stream>>>(points, ws.keys, ws.slots, n_points, geom->cols, ws.starts,
-                                                                         ws.grows, nullptr, geom->batch_size);
-    TableArgs t;
-    t.grows = ws.grows; t.starts = ws.starts; t.counters = counters; t.aux = ws.aux; t.coords = coords;
-    t.rs = grouped_row_floats(geom->cols); t.coord_cols = coord_cols; t.g = g;
-    const int tgrid = table_grid(ws.pcap);
-    if (table_fn) {
-        RDP_CUDA_OK(table_fn(t, table_ctx, tgrid, stream));
-    } else {
-        pillar_table_kernel<<<tgrid, 256, 0, stream>>>(t);
+                                                                         ws.grows, nullptr, geom->batch_size, g);
+    if (!skip_table) {   // the fused forward builds the table (and the coords) inside its tile kernels instead
+        TableArgs t;
+        t.grows = ws.grows; t.starts = ws.starts; t.unq = ws.unq; t.counters = counters; t.aux = ws.aux; t.coords = coords;
+        t.rs = grouped_row_floats(geom->cols); t.coord_cols = coord_cols; t.g = g;
+        pillar_table_kernel<<<table_grid(ws.pcap), 256, 0, stream>>>(t);
     }
     RDP_CUDA_OK(cudaGetLastError());
     return RDP_OK;
@@ -502,7 +517,7 @@ extern "C" int rdp_index_fwd_frames(const float *points, const int32_t *frame_of
                                     int32_t coord_cols, void *workspace, size_t workspace_bytes, int32_t *coords, int32_t *inverse,
                                     int32_t *counts, int32_t *counters, int32_t *host_mapped, void *event_v, void *stream_v) {
     return index_fwd_impl(points, frame_offsets, n_points, geom, coord_cols, workspace, workspace_bytes, coords, inverse, counts,
-                          counters, host_mapped, event_v, static_cast<cudaStream_t>(stream_v), nullptr, nullptr);
+                          counters, host_mapped, event_v, static_cast<cudaStream_t>(stream_v), false);
 }
 
 extern "C" int rdp_index_fwd_publish(const float *points, int64_t n_points, const rdp_geom_t *geom, int32_t coord_cols,

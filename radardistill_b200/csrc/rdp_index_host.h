@@ -4,15 +4,11 @@
 
 namespace rdp {
 
-// Launches the pillar-table kernel.  The fused train-mode forward passes a hook that launches the per-configuration
-// variant which also accumulates the feature moments (rdp_pfn.cuh); nullptr = the generic table-only kernel.
-typedef cudaError_t (*TableLaunchFn)(const TableArgs &t, void *ctx, int grid, cudaStream_t st);
-
 GeomDev make_geom_dev(const rdp_geom_t *geom);
 
 int index_fwd_impl(const float *points, const int32_t *frame_offsets, int64_t n_points, const rdp_geom_t *geom, int32_t coord_cols,
                    void *workspace, size_t workspace_bytes, int32_t *coords, int32_t *inverse, int32_t *counts, int32_t *counters,
-                   int32_t *host_mapped, void *event, cudaStream_t stream, TableLaunchFn table_fn, void *table_ctx);
+                   int32_t *host_mapped, void *event, cudaStream_t stream, bool skip_table);
 
 inline int table_grid(int64_t pcap) {
     const int64_t blocks = (pcap + 255) / 256;

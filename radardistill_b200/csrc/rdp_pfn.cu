@@ -227,7 +227,7 @@ extern "C" int rdp_encode_fwd_frames(const float *points, const int32_t *frame_o
     a.bn_state = bn_state;
     if (prm->stats_phase != 2) {
         rc = index_fwd_impl(points, frame_offsets, n_points, geom, layout->coord_cols, workspace, workspace_bytes, coords, inverse,
-                            counts, counters, host_mapped, event, st, nullptr, nullptr);
+                            counts, counters, host_mapped, event, st, false);
         if (rc != RDP_OK || n_points == 0) return rc;
     }
     if (n_points == 0) return RDP_OK;

@@ -30,6 +30,7 @@ struct GeomDev {
 struct TableArgs {
     const float *grows;
     const int32_t *starts;
+    const int32_t *unq;
     int32_t *counters;
     float *aux;
     int32_t *coords;
@@ -45,17 +46,17 @@ struct RowBasis {
     static constexpr int RS = (COLS + 2 + 3) / 4 * 4;
 };
 
-// Row inputs of the folded linear layer: centre offsets (exactly f_center of the reference, :215-217), the raw feature
-// columns after xyz, and the distance feature (:230-231) when the layout has one.
+// Row inputs of the folded linear layer from a grouped row [b, dx, dy, dz, f...]: the centre offsets (exactly f_center of
+// the reference, :215-217), the raw feature columns after xyz, and the distance feature (:230-231) when the layout has one
+// (the absolute coordinates it needs are d + centre; see DESIGN.md for the rounding this adds to that one feature).
 template <int COLS, bool DIST>
-__device__ __forceinline__ void row_inputs(const float *r /* [b,x,y,z,f...] */, float cenx, float ceny, float cenz, float *out) {
-    const float x = r[1], y = r[2], z = r[3];
-    out[0] = __fsub_rn(x, cenx);
-    out[1] = __fsub_rn(y, ceny);
-    out[2] = __fsub_rn(z, cenz);
+__device__ __forceinline__ void row_inputs(const float *r, float cenx, float ceny, float cenz, float *out) {
 #pragma unroll
-    for (int c = 4; c < COLS; ++c) out[c - 1] = r[c];
-    if (DIST) out[COLS - 1] = sqrtf(fmaf(z, z, fmaf(y, y, __fmul_rn(x, x))));
+    for (int c = 1; c < COLS; ++c) out[c - 1] = r[c];
+    if (DIST) {
+        const float x = __fadd_rn(r[1], cenx), y = __fadd_rn(r[2], ceny), z = __fadd_rn(r[3], cenz);
+        out[COLS - 1] = sqrtf(fmaf(z, z, fmaf(y, y, __fmul_rn(x, x))));
+    }
 }
 
 template <int RSF>
@@ -67,12 +68,60 @@ __device__ __forceinline__ void load_row(const float *src, float *r) {
     }
 }
 
+// Pillar centre and coords from the merged key (:243-248, :132-138; voxels dynamic_voxel_vfe.py:94-100).
+__device__ __forceinline__ void decode_key(const GeomDev &g, int key, float *cenx, float *ceny, float *cenz, int4 *bzyx) {
+    const int nz = g.nz > 1 ? g.nz : 1;
+    const int sxy = g.nx * g.ny * nz;
+    const int b = key / sxy, rem = key - b * sxy;
+    const int cx = rem / (g.ny * nz), rem2 = rem - cx * (g.ny * nz);
+    const int cy = rem2 / nz, cz = rem2 - cy * nz;
+    *cenx = __fadd_rn(__fmul_rn((float)cx, g.vx), g.off_x);   // cx*vx + x_off with separate mul / add roundings (:215-216)
+    *ceny = __fadd_rn(__fmul_rn((float)cy, g.vy), g.off_y);
+    *cenz = g.nz > 1 ? __fadd_rn(__fmul_rn((float)cz, g.vz), g.off_z) : g.off_z;   // dynamic_voxel_vfe.py:79
+    *bzyx = make_int4(b, cz, cy, cx);
+}
+
+// One table entry [centre xy | -mean(d) xyz | start | rows | centre z] from the exact fp64 sums of the pillar's centre offsets d
+// (the grouped rows store d = xyz - centre): -mean(d) = centre - mean(xyz), the pillar part of f_cluster (:226-227).
+__device__ __forceinline__ void pillar_entry(float cenx, float ceny, float cenz, double sx, double sy, double sz, int start, int rows,
+                                             float *entry) {
+    float mx, my, mz;
+    mean3(sx, sy, sz, rows, &mx, &my, &mz);
+    entry[0] = cenx; entry[1] = ceny;
+    entry[2] = -mx; entry[3] = -my; entry[4] = -mz;
+    entry[5] = __int_as_float(start); entry[6] = __int_as_float(rows); entry[7] = cenz;
+}
+
+// fp64 sums of the offsets of grouped rows [s, e) by a whole warp (lane-strided, shuffle reduction; exact, so any order gives the same bits)
+__device__ __forceinline__ void warp_sum_rows(const float *grows, int rs, int s, int e, double *sx, double *sy, double *sz) {
+    const int lane = threadIdx.x & 31;
+    double ax = 0.0, ay = 0.0, az = 0.0;
+    for (int i = s + lane; i < e; i += 32) {
+        const float4 v = __ldg(reinterpret_cast<const float4 *>(grows + ((size_t)i + 1) * rs));
+        ax += (double)v.y; ay += (double)v.z; az += (double)v.w;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        ax += __shfl_xor_sync(0xffffffffu, ax, d);
+        ay += __shfl_xor_sync(0xffffffffu, ay, d);
+        az += __shfl_xor_sync(0xffffffffu, az, d);
+    }
+    *sx = ax; *sy = ay; *sz = az;
+}
+
+__device__ __forceinline__ void store_coords(int32_t *coords, int coord_cols, size_t p, const int4 &c) {
+    if (coord_cols == 3) {
+        int32_t *o = coords + p * 3;
+        o[0] = c.x; o[1] = c.z; o[2] = c.w;   // [b, y, x]  (:248)
+    } else {
+        *reinterpret_cast<int4 *>(coords + p * 4) = c;   // [b, 0, y, x] (:138) / [b, z, y, x]
+    }
+}
+
 __device__ __forceinline__ void pillar_table_body(const TableArgs &t) {
     const int lane = threadIdx.x & 31;
     const int P = t.counters[RDP_CNT_P];
     const int rs = t.rs;
-    const GeomDev &g = t.g;
-    const bool vox = g.nz > 1;
     const int stride = gridDim.x * blockDim.x;
     for (int pb = blockIdx.x * blockDim.x + (threadIdx.x & ~31); pb < P; pb += stride) {
         const int p = pb + lane;
@@ -81,65 +130,30 @@ __device__ __forceinline__ void pillar_table_body(const TableArgs &t) {
         if (valid) { s = t.starts[p]; e = t.starts[p + 1]; }
         const bool big = valid && (e - s) > kBigRows;
         double sx = 0.0, sy = 0.0, sz = 0.0;
-        float x0 = 0.0f, y0 = 0.0f, z0 = 0.0f, b0 = 0.0f;
-        if (valid) {
-            const float *r = t.grows + ((size_t)s + 1) * rs;   // rows are 16-byte aligned: [b, x, y, z] is one 128-bit load
-            const float4 v0 = __ldg(reinterpret_cast<const float4 *>(r));
-            b0 = v0.x; x0 = v0.y; y0 = v0.z; z0 = v0.w;
-            if (!big) {
-                sx = (double)x0; sy = (double)y0; sz = (double)z0;
-                r += rs;
-                for (int i = s + 1; i < e; ++i, r += rs) {
-                    const float4 v = __ldg(reinterpret_cast<const float4 *>(r));
-                    sx += (double)v.y; sy += (double)v.z; sz += (double)v.w;
-                }
+        if (valid && !big) {
+            const float *r = t.grows + ((size_t)s + 1) * rs;   // rows are 16-byte aligned: [b, dx, dy, dz] is one 128-bit load
+            for (int i = s; i < e; ++i, r += rs) {
+                const float4 v = __ldg(reinterpret_cast<const float4 *>(r));
+                sx += (double)v.y; sy += (double)v.z; sz += (double)v.w;
             }
         }
         unsigned bigmask = __ballot_sync(0xffffffffu, big);
-        while (bigmask) {   // whole-warp sum of one long pillar (exact in fp64: any order gives the same bits)
+        while (bigmask) {   // whole-warp sum of one long pillar
             const int src = __ffs(bigmask) - 1;
             bigmask &= bigmask - 1;
             const int sb = __shfl_sync(0xffffffffu, s, src), eb = __shfl_sync(0xffffffffu, e, src);
-            double ax = 0.0, ay = 0.0, az = 0.0;
-            for (int i = sb + lane; i < eb; i += 32) {
-                const float4 v = __ldg(reinterpret_cast<const float4 *>(t.grows + ((size_t)i + 1) * rs));
-                ax += (double)v.y; ay += (double)v.z; az += (double)v.w;
-            }
-#pragma unroll
-            for (int d = 16; d > 0; d >>= 1) {
-                ax += __shfl_xor_sync(0xffffffffu, ax, d);
-                ay += __shfl_xor_sync(0xffffffffu, ay, d);
-                az += __shfl_xor_sync(0xffffffffu, az, d);
-            }
+            double ax, ay, az;
+            warp_sum_rows(t.grows, rs, sb, eb, &ax, &ay, &az);
             if (lane == src) { sx = ax; sy = ay; sz = az; }
         }
-        float cenx = 0.0f, ceny = 0.0f, cenz = g.off_z, ndx = 0.0f, ndy = 0.0f, ndz = 0.0f;
         if (valid) {
-            float mx, my, mz;
-            mean3(sx, sy, sz, e - s, &mx, &my, &mz);
-            // centre of the cell: cx*vx + x_off with separate mul / add roundings (:215-216); the quantisation repeats
-            // quantize_mark_kernel's IEEE ops on a row of the pillar, so cx / cy (/ cz) equal the emitted coords
-            const float qx = floorf(__fdiv_rn(__fsub_rn(x0, g.lo_x), g.vx)), qy = floorf(__fdiv_rn(__fsub_rn(y0, g.lo_y), g.vy));
-            cenx = __fadd_rn(__fmul_rn((float)(int)qx, g.vx), g.off_x);
-            ceny = __fadd_rn(__fmul_rn((float)(int)qy, g.vy), g.off_y);
-            int cz = 0;
-            if (vox) {
-                const float qz = floorf(__fdiv_rn(__fsub_rn(z0, g.lo_z), g.vz));
-                cz = (int)qz;
-                cenz = __fadd_rn(__fmul_rn((float)cz, g.vz), g.off_z);   // dynamic_voxel_vfe.py:79
-            }
-            ndx = __fsub_rn(cenx, mx); ndy = __fsub_rn(ceny, my); ndz = __fsub_rn(cenz, mz);
-            const int bi = __float2int_rz(b0);
-            if (!t.coords) {
-                // table only (a caller that already has the coords)
-            } else if (t.coord_cols == 3) {
-                int32_t *o = t.coords + (size_t)p * 3;
-                o[0] = bi; o[1] = (int)qy; o[2] = (int)qx;   // [b, y, x]  (:248)
-            } else {
-                *reinterpret_cast<int4 *>(t.coords + (size_t)p * 4) = make_int4(bi, cz, (int)qy, (int)qx);  // (:138) / [b,z,y,x]
-            }
-            asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(t.aux + (size_t)p * 8), "f"(cenx), "f"(ceny), "f"(ndx),
-                         "f"(ndy), "f"(ndz), "f"(__int_as_float(s)), "f"(__int_as_float(e - s)), "f"(cenz)
+            float cenx, ceny, cenz, entry[8];
+            int4 c;
+            decode_key(t.g, t.unq[p], &cenx, &ceny, &cenz, &c);
+            pillar_entry(cenx, ceny, cenz, sx, sy, sz, s, e - s, entry);
+            if (t.coords) store_coords(t.coords, t.coord_cols, (size_t)p, c);
+            asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(t.aux + (size_t)p * 8), "f"(entry[0]), "f"(entry[1]),
+                         "f"(entry[2]), "f"(entry[3]), "f"(entry[4]), "f"(entry[5]), "f"(entry[6]), "f"(entry[7])
                          : "memory");
         }
     }
