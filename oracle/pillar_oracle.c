@@ -563,10 +563,7 @@ static void fold_range(int64_t lo, int64_t hi, void *p) {
         const float x = r[1], y = r[2], z = r[3];
         rin[0] = x - qp[0]; rin[1] = y - qp[1]; rin[2] = z - c->g->off[2];
         for (int k = 4; k < cols; ++k) rin[k - 1] = r[k];
-        if (c->g->with_distance) {   /* the grouped rows carry d, not xyz: the norm (:230-231) is taken of d + centre */
-            const float xr = rin[0] + qp[0], yr = rin[1] + qp[1], zr = rin[2] + c->g->off[2];
-            rin[cols - 1] = sqrtf(fmaf(zr, zr, fmaf(yr, yr, xr * xr)));
-        }
+        if (c->g->with_distance) rin[cols - 1] = sqrtf(fmaf(z, z, fmaf(y, y, x * x)));   /* (:230-231) */
         for (int o = 0; o < cout; ++o) {
             const float *w = c->wg + o * G;
             float v = w[0] * rin[0];

@@ -45,10 +45,10 @@ int carve_workspace(void *base, int64_t n_points, const rdp_geom_t *geom, const 
     ws->zero_bytes = off;
     ws->wordrank = reinterpret_cast<uint2 *>(take(sizeof(uint2) * words_pad));
     ws->keys = reinterpret_cast<int32_t *>(take(sizeof(int32_t) * (size_t)(n + 4)));
+    ws->ranks = reinterpret_cast<int32_t *>(take(sizeof(int32_t) * (size_t)(n + 4)));
     ws->slots = reinterpret_cast<int32_t *>(take(sizeof(int32_t) * (size_t)(n + 4)));
     ws->tile_keep = reinterpret_cast<int32_t *>(take(sizeof(int32_t) * (size_t)ws->index_tiles));
     ws->starts = reinterpret_cast<int32_t *>(take(sizeof(int32_t) * (size_t)(ws->pcap + kSliceInts + 8)));
-    ws->unq = reinterpret_cast<int32_t *>(take(sizeof(int32_t) * (size_t)(ws->pcap + kSliceInts + 8)));
     const size_t pad = kPfnCap + 8;
     ws->grows = reinterpret_cast<float *>(take(sizeof(float) * (size_t)(n + pad + 1) * grouped_row_floats(geom->cols)));
     ws->aux = reinterpret_cast<float *>(take(sizeof(float) * 8 * (size_t)(ws->pcap + kPfnWin + 8)));

@@ -63,13 +63,13 @@ struct Workspace {
     uint32_t *bitmap;        // words
     // not zeroed
     uint2 *wordrank;         // words : {bitmap word, exclusive pillar rank of the word} -- one 8-byte gather per point
-    int32_t *keys;           // n  (merged key, then overwritten by the pillar rank; -1 = dropped)
+    int32_t *keys;           // n  merged key (-1 = dropped)
+    int32_t *ranks;          // n  pillar rank of the row (-1 = dropped)
     int32_t *slots;          // n  position of the row inside its pillar (arrival order of rank_count_kernel's atomics)
-    int32_t *unq;            // pcap  merged key of every pillar (torch.unique's first output, :212)
     int32_t *tile_keep;      // index tiles
     int32_t *starts;         // pcap + 1  exclusive start of every pillar in the grouped order; starts[P] = N
     float *grows;            // (1 + n + pad) * RS : rows physically grouped by pillar (pillar order == key order);
-                             // RS floats per row = [b | xyz - pillar centre | features | pad | original row id | pillar id];
+                             // RS floats per row = [merged key | xyz | features | pad | original row id | pillar id];
                              // row 0 is a sentinel (pillar id -1) in front of grouped position 0
     char *zero_begin;
     size_t zero_bytes;

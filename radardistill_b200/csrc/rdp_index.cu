@@ -11,9 +11,9 @@
 //
 //   K1 quantize_mark   points (TMA bulk tile -> smem) -> key[i], bitmap |= bit(key); counts[] = 0   [HBM: read rows]
 //   K2 bitmap_rank     popcount scan of the bitmap -> {word, rank of word} pairs, P; publishes (N, P) to the host
-//   K3 rank_count      key[i] -> rank = wordrank.rank + popc(below) ; inverse[j] ; slot[i] = counts[rank]++
+//   K3 rank_count      key[i] -> rank[i] = wordrank.rank + popc(below) ; inverse[j] ; slot[i] = counts[rank]++
 //   K4 count_scan      exclusive scan of counts -> pillar start offsets (starts[P] = N), tile_first
-//   K5 group_rows      grouped_rows[starts[rank] + slot] = [b | xyz - centre | features | original row id | rank]   (no atomics; the order
+//   K5 group_rows      grouped_rows[starts[rank] + slot] = [merged key | xyz | features | original row id | rank]   (no atomics; the order
 //                      inside a pillar is the arrival order of K3's atomics -- every consumer is order independent).
 //                      The PFN kernels then stream contiguous, pillar-aligned row tiles with TMA.
 //   K6 pillar_table    thread = pillar: fp64 mean of its grouped rows' centre offsets, pillar centre, first row, row count; coords
@@ -182,10 +182,10 @@ bitmap_rank_kernel(const uint32_t *__restrict__ bitmap, long long words,
 
 // ----------------------------------------------------------------------------- K3
 __global__ void __launch_bounds__(kIndexThreads)
-rank_count_kernel(int32_t *__restrict__ keys, long long n0, const uint2 *__restrict__ wordrank,
+rank_count_kernel(const int32_t *__restrict__ keys, int32_t *__restrict__ ranks, long long n0, const uint2 *__restrict__ wordrank,
                   const int32_t *__restrict__ tile_keep, int32_t *__restrict__ inverse, int32_t *__restrict__ counts,
                   const int32_t *__restrict__ counters, int32_t *__restrict__ orig2kept, int32_t *__restrict__ kept2orig,
-                  int32_t *__restrict__ slots, int32_t *__restrict__ unq) {
+                  int32_t *__restrict__ slots) {
     __shared__ int s_scan[9];
     __shared__ long long s_base;
     const int tid = threadIdx.x;
@@ -240,10 +240,7 @@ rank_count_kernel(int32_t *__restrict__ keys, long long n0, const uint2 *__restr
     int sl[4] = {0, 0, 0, 0};
 #pragma unroll
     for (int q = 0; q < 4; ++q)
-        if (r[q] >= 0) {
-            sl[q] = atomicAdd(counts + r[q], 1);
-            if (sl[q] == 0) unq[r[q]] = k[q];   // exactly one row per pillar arrives first: it records the pillar's merged key
-        }
+        if (r[q] >= 0) sl[q] = atomicAdd(counts + r[q], 1);
     if (i0 + 3 < n0) {
         *reinterpret_cast<int4 *>(slots + i0) = make_int4(sl[0], sl[1], sl[2], sl[3]);
     } else {
@@ -251,10 +248,10 @@ rank_count_kernel(int32_t *__restrict__ keys, long long n0, const uint2 *__restr
         for (int q = 0; q < 4; ++q) if (i0 + q < n0) slots[i0 + q] = sl[q];
     }
     if (i0 + 3 < n0) {
-        *reinterpret_cast<int4 *>(keys + i0) = make_int4(r[0], r[1], r[2], r[3]);  // key -> rank, in place
+        *reinterpret_cast<int4 *>(ranks + i0) = make_int4(r[0], r[1], r[2], r[3]);
     } else {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) if (i0 + q < n0) keys[i0 + q] = r[q];
+        for (int q = 0; q < 4; ++q) if (i0 + q < n0) ranks[i0 + q] = r[q];
     }
 }
 
@@ -311,22 +308,19 @@ count_scan_kernel(const int32_t *__restrict__ counts, uint64_t *__restrict__ sta
 // 16-byte stores only (the scatter is bound by store requests, not bytes).
 template <bool FRAMES>   // FRAMES: rows without the batch column + frame offsets (compiled apart: the padded-row path stays as it was)
 __global__ void __launch_bounds__(kIndexThreads)
-group_rows_kernel(const float *__restrict__ pts, const int32_t *__restrict__ ranks, const int32_t *__restrict__ slots, long long n0,
-                  int cols, const int32_t *__restrict__ starts, float *__restrict__ grows, const int32_t *__restrict__ offsets,
-                  int batch, GeomDev g) {
+group_rows_kernel(const float *__restrict__ pts, const int32_t *__restrict__ keys, const int32_t *__restrict__ ranks,
+                  const int32_t *__restrict__ slots, long long n0, int cols, const int32_t *__restrict__ starts, float *__restrict__ grows) {
     extern __shared__ __align__(128) float tile[];
     __shared__ __align__(8) uint64_t bar;
     const int tid = threadIdx.x;
     const int rs = grouped_row_floats(cols);
     const long long row0 = (long long)blockIdx.x * kIndexTileRows;
     const int rows = (int)min((long long)kIndexTileRows, n0 - row0);
-    const int in_cols = FRAMES ? cols - 1 : cols;   // without a batch column the grouped row gets the frame id written in
+    const int in_cols = FRAMES ? cols - 1 : cols;
     const int floats = rows * in_cols;
     const uint32_t bulk_bytes = (uint32_t)(floats * 4) & ~15u;
     const float *src = pts + row0 * in_cols;
-    __shared__ int s_b0;
     if (tid == 0) {
-        s_b0 = FRAMES ? frame_of(offsets, batch, row0) : 0;
         mbar_init(&bar, 1);
         fence_mbar_init();
     }
@@ -338,18 +332,13 @@ group_rows_kernel(const float *__restrict__ pts, const int32_t *__restrict__ ran
     for (int f = (int)(bulk_bytes >> 2) + tid; f < floats; f += kIndexThreads) tile[f] = src[f];
     if (blockIdx.x == 0 && tid == 0) grows[rs - 1] = __int_as_float(-1);  // sentinel row: "no pillar" before position 0
     // grouped positions (pillar start + slot inside the pillar) are gathered while the tile is in flight
-    int pos[kIndexTileRows / kIndexThreads], rk[kIndexTileRows / kIndexThreads];
-    float fbv[kIndexTileRows / kIndexThreads] = {};
+    int pos[kIndexTileRows / kIndexThreads], rk[kIndexTileRows / kIndexThreads], ky[kIndexTileRows / kIndexThreads];
 #pragma unroll
     for (int k = 0; k < kIndexTileRows / kIndexThreads; ++k) {
         const int r = k * kIndexThreads + tid;
         rk[k] = (r < rows) ? ranks[row0 + r] : -1;
+        ky[k] = (r < rows) ? keys[row0 + r] : -1;
         pos[k] = (rk[k] >= 0) ? __ldg(starts + rk[k]) + slots[row0 + r] : -1;
-        if (FRAMES) {   // frame id of the row, resolved here so that nothing but smem reads sits between the scattered stores below
-            int b = s_b0;
-            while (b + 1 < batch && row0 + r >= (long long)offsets[b + 1]) ++b;
-            fbv[k] = (float)b;
-        }
     }
     if (bulk_bytes) mbar_wait(&bar, 0);
     __syncthreads();
@@ -357,40 +346,30 @@ group_rows_kernel(const float *__restrict__ pts, const int32_t *__restrict__ ran
     for (int k = 0; k < kIndexTileRows / kIndexThreads; ++k) {
         if (pos[k] < 0) continue;
         const int r = k * kIndexThreads + tid;
-        const float fb = fbv[k];
-        const float *p = tile + r * in_cols - (FRAMES ? 1 : 0);   // FRAMES: logical column c >= 1 is input column c - 1, column 0 is fb
-        // The grouped copy stores the centre offsets d = xyz - centre (exactly f_center, :215-217) in place of xyz: every
-        // later pass works on d, and the pillar mean is taken over these small, exactly summable values.  The centre repeats
-        // quantize_mark_kernel's IEEE ops on this row, so it equals the pillar's centre bit for bit.
-        float d[3];
-        {
-            const float x = p[1], y = p[2], z = p[3];
-            const float qx = floorf(__fdiv_rn(__fsub_rn(x, g.lo_x), g.vx)), qy = floorf(__fdiv_rn(__fsub_rn(y, g.lo_y), g.vy));
-            d[0] = __fsub_rn(x, __fadd_rn(__fmul_rn((float)(int)qx, g.vx), g.off_x));
-            d[1] = __fsub_rn(y, __fadd_rn(__fmul_rn((float)(int)qy, g.vy), g.off_y));
-            float cenz = g.off_z;
-            if (g.nz > 1) cenz = __fadd_rn(__fmul_rn((float)(int)floorf(__fdiv_rn(__fsub_rn(z, g.lo_z), g.vz)), g.vz), g.off_z);
-            d[2] = __fsub_rn(z, cenz);
-        }
-        auto col = [&](int c) -> float { return (c >= 1 && c <= 3) ? d[c - 1] : ((FRAMES && c == 0) ? fb : p[c]); };
+        // FRAMES: the input rows have no batch column -- logical column c >= 1 is input column c - 1.  Column 0 of the grouped
+        // row carries the pillar's merged key (:208-210) instead of the frame index (= key / (nx ny nz)): the table kernel
+        // decodes the pillar centre and the coords from it.
+        const float *p = tile + r * in_cols - (FRAMES ? 1 : 0);
+        const float c0 = __int_as_float(ky[k]), tail0 = __int_as_float((int)(row0 + r)), tail1 = __int_as_float(rk[k]);
         if (rs == 8) {
             // one 256-bit store (STG.256) = one full 32-byte sector per row: the scatter is bound by store requests
             float v[8];
+            v[0] = c0;
 #pragma unroll
-            for (int c = 0; c < 8; ++c)
-                v[c] = c < cols ? col(c) : (c == 6 ? __int_as_float((int)(row0 + r)) : (c == 7 ? __int_as_float(rk[k]) : 0.0f));
+            for (int c = 1; c < 8; ++c) v[c] = c < cols ? p[c] : (c == 6 ? tail0 : (c == 7 ? tail1 : 0.0f));
             asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(grows + ((size_t)pos[k] + 1) * 8), "f"(v[0]),
                          "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
                          : "memory");
             continue;
         }
         float4 *dst = reinterpret_cast<float4 *>(grows + ((size_t)pos[k] + 1) * rs);
-        for (int c4 = 0; c4 < rs; c4 += 4) {
+        dst[0] = make_float4(c0, p[1], p[2], p[3]);
+        for (int c4 = 4; c4 < rs; c4 += 4) {
             float v[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const int c = c4 + i;
-                v[i] = c < cols ? col(c) : (c == rs - 2 ? __int_as_float((int)(row0 + r)) : (c == rs - 1 ? __int_as_float(rk[k]) : 0.0f));
+                v[i] = c < cols ? p[c] : (c == rs - 2 ? tail0 : (c == rs - 1 ? tail1 : 0.0f));
             }
             dst[c4 >> 2] = make_float4(v[0], v[1], v[2], v[3]);
         }
@@ -492,18 +471,18 @@ int index_fwd_impl(const float *points, const int32_t *frame_offsets, int64_t n_
     bitmap_rank_kernel<<<kScanGrid, kScanThreads, 0, stream>>>(ws.bitmap, ws.words, ws.scan_state_a, ws.wordrank, counters,
                                                               host_mapped);
     if (event) RDP_CUDA_OK(cudaEventRecord(event, stream));
-    rank_count_kernel<<<tiles, kIndexThreads, 0, stream>>>(ws.keys, n_points, ws.wordrank, ws.tile_keep, inverse, counts, counters,
-                                                         ws.orig2kept, ws.kept2orig, ws.slots, ws.unq);
+    rank_count_kernel<<<tiles, kIndexThreads, 0, stream>>>(ws.keys, ws.ranks, n_points, ws.wordrank, ws.tile_keep, inverse, counts, counters,
+                                                         ws.orig2kept, ws.kept2orig, ws.slots);
     count_scan_kernel<<<kScanGrid, kScanThreads, 0, stream>>>(counts, ws.scan_state_b, ws.starts, ws.tile_first, counters);
     if (frame_offsets)
-        group_rows_kernel<true><<<tiles, kIndexThreads, smem, stream>>>(points, ws.keys, ws.slots, n_points, geom->cols, ws.starts,
-                                                                        ws.grows, frame_offsets, geom->batch_size, g);
+        group_rows_kernel<true><<<tiles, kIndexThreads, smem, stream>>>(points, ws.keys, ws.ranks, ws.slots, n_points, geom->cols,
+                                                                        ws.starts, ws.grows);
     else
-        group_rows_kernel<false><<<tiles, kIndexThreads, smem, stream>>>(points, ws.keys, ws.slots, n_points, geom->cols, ws.starts,
-                                                                         ws.grows, nullptr, geom->batch_size, g);
+        group_rows_kernel<false><<<tiles, kIndexThreads, smem, stream>>>(points, ws.keys, ws.ranks, ws.slots, n_points, geom->cols,
+                                                                         ws.starts, ws.grows);
     if (!skip_table) {   // the fused forward builds the table (and the coords) inside its tile kernels instead
         TableArgs t;
-        t.grows = ws.grows; t.starts = ws.starts; t.unq = ws.unq; t.counters = counters; t.aux = ws.aux; t.coords = coords;
+        t.grows = ws.grows; t.starts = ws.starts; t.counters = counters; t.aux = ws.aux; t.coords = coords;
         t.rs = grouped_row_floats(geom->cols); t.coord_cols = coord_cols; t.g = g;
         pillar_table_kernel<<<table_grid(ws.pcap), 256, 0, stream>>>(t);
     }

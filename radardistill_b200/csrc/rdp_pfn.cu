@@ -107,7 +107,7 @@ __global__ void argpos_to_kept_kernel(const int32_t *__restrict__ argpos, const 
     }
 }
 
-// scatter_mean's (P, 3) output (:226) for callers that want it: thread = pillar re-sums its rows (fp64, exact)
+// scatter_mean's (P, 3) output (:226) for callers that want it: thread = pillar re-sums its rows (fp64: exact, one rounding)
 __global__ void pillar_mean_kernel(const float *__restrict__ grows, int rs, const int32_t *__restrict__ starts,
                                    const int32_t *__restrict__ counters, float *__restrict__ out) {
     const int P = counters[RDP_CNT_P];
@@ -134,15 +134,20 @@ static int env_int(const char *name, int dflt) {
 }
 
 // PFN forward behind a finished index pass.
+// `coords` (may be null) / `coord_cols`: the train-mode statistics kernel rebuilds the pillar table on its way and writes the
+// coords when it stands in for the index pass's table kernel (rdp_encode_fwd).
 static int pfn_fwd_impl(const PfnLaunch *L, PfnArgs &a, const rdp_pfn_params_t *prm, const rdp_geom_t *geom, const Workspace &ws,
-                        int64_t n_points, float *pillar_mean, cudaStream_t st) {
+                        int64_t n_points, float *pillar_mean, int32_t *coords, int coord_cols, cudaStream_t st) {
     const bool train = a.train_bn != 0;
     if (pillar_mean)
         pillar_mean_kernel<<<148 * 4, 256, 0, st>>>(ws.grows, grouped_row_floats(geom->cols), ws.starts, a.counters, pillar_mean);
     if (train) {
         if (prm->stats_phase != 2) {
             a.defer_finalize = prm->stats_phase == 1;
-            RDP_CUDA_OK(L->moments(a, 148 * 4, st));
+            TableArgs t;
+            t.grows = ws.grows; t.starts = ws.starts; t.counters = a.counters; t.aux = ws.aux; t.coords = coords;
+            t.rs = grouped_row_floats(geom->cols); t.coord_cols = coord_cols; t.g = make_geom_dev(geom);
+            RDP_CUDA_OK(L->table_stats(t, a, ws.pcap, st));
         }
         if (prm->stats_phase == 1) return RDP_OK;   // SyncBatchNorm: the caller all-reduces the totals, then phase 2
         if (prm->stats_phase == 2) {
@@ -202,7 +207,7 @@ extern "C" int rdp_pfn_fwd(const float *points, int64_t n_points, const rdp_geom
     a.features = features;
     a.argpos = argpos;
     a.bn_state = bn_state;
-    return pfn_fwd_impl(L, a, prm, geom, ws, n_points, pillar_mean, st);
+    return pfn_fwd_impl(L, a, prm, geom, ws, n_points, pillar_mean, nullptr, layout->coord_cols, st);
 }
 
 extern "C" int rdp_encode_fwd_frames(const float *points, const int32_t *frame_offsets, int64_t n_points, const rdp_geom_t *geom,
@@ -226,12 +231,13 @@ extern "C" int rdp_encode_fwd_frames(const float *points, const int32_t *frame_o
     a.argpos = argpos;
     a.bn_state = bn_state;
     if (prm->stats_phase != 2) {
+        // train mode: the statistics kernel builds the pillar table (and the coords) itself
         rc = index_fwd_impl(points, frame_offsets, n_points, geom, layout->coord_cols, workspace, workspace_bytes, coords, inverse,
-                            counts, counters, host_mapped, event, st, false);
+                            counts, counters, host_mapped, event, st, a.train_bn != 0);
         if (rc != RDP_OK || n_points == 0) return rc;
     }
     if (n_points == 0) return RDP_OK;
-    return pfn_fwd_impl(L, a, prm, geom, ws, n_points, nullptr, st);
+    return pfn_fwd_impl(L, a, prm, geom, ws, n_points, nullptr, coords, layout->coord_cols, st);
 }
 
 extern "C" int rdp_encode_fwd(const float *points, int64_t n_points, const rdp_geom_t *geom, const rdp_layout_t *layout,

@@ -506,95 +506,179 @@ __device__ __forceinline__ void bn_epilogue(const PfnArgs &a, const double *tota
     for (int e = tid; e < G + G * G; e += blockDim.x) st[4 * COUT + 1 + e] = sm[e];
 }
 
-// Feature moments S1 = sum g, S2 = sum g g^T over all kept rows (train-mode BatchNorm; oracle: orc_moments_folded): one
-// row-parallel pass over the grouped rows, lane = row, the next row's loads issued before the current row's arithmetic.
-// The sums are fp64 from the first product on (products of two fp32 values are exact in fp64), so the totals agree with
-// the oracle's sequential fp64 sums to ~1e-13 and the folded fp32 scale / shift -- hence every train-mode feature and the
-// ReLU mask the backward routes through -- come out bit-identical in practice.  (fp32 partial sums were tried first: 1e-8
-// agreement of scale / shift, but on 33 M (pillar, channel) pairs that flips a handful of pre-activations across zero and
-// each flip moves dbeta by one upstream gradient value.)  The upper triangle of S2 is split between the two warps of a
-// pair that walk the same rows (rows k < KH of the triangle | the rest: balanced halves), which halves the fp64
-// accumulators a thread carries -- one thread owning all of them sat at 168 registers / 12 warps per SM, latency bound
-// at 70 us (ncu, profiles/r02b).  Per-warp shuffle reduction, fp64 atomics into the workspace totals; the CTA that
-// finishes last folds them into bn_state (no finalize launch).
-template <int G>
-struct MomentSplit {
-    static constexpr int tri(int k0, int k1) { int n = 0; for (int k = k0; k < k1; ++k) n += G - k + 1; return n; }   // S1[k] + row k of the triangle
-    static constexpr int kh() { int k = 1; while (tri(0, k) * 2 < tri(0, G)) ++k; return k; }
-    static constexpr int KH = kh();
-    static constexpr int NA = tri(0, KH), NB = tri(KH, G), NMAX = NA > NB ? NA : NB;
+// Pillar table + feature moments in one pass (train-mode BatchNorm; oracle: orc_moments_folded).  The moments
+// S1 = sum g, S2 = sum g g^T of the reduced basis g = [row inputs (KIN) | pillar constants q (5)] over all kept rows split
+// by where their factors live:
+//   row x row     sum_i r_i r_i^T             thread-local fp64 accumulators while the thread walks its pillar's rows
+//   row x pillar  sum_p (sum_{i in p} r_i) q_p^T     } per pillar, from the row sums the mean needs anyway
+//   pillar^2      sum_p n_p q_p q_p^T, S1     } -- staged per warp in shared memory as the vector
+//                                               e_p = [row sums | n_p q_p | q_p | 1]; lane j owns products e[a_j] e[b_j]
+// so the separate moments pass over the rows (and its dependent row -> table gathers) is gone: the statistics cost
+// KIN (KIN + 1) / 2 DFMAs per row inside the table kernel plus ~2 per (pillar, lane).  Products of two fp32 values are
+// exact in fp64; the row sums are exact; the totals agree with the oracle's sequential fp64 sums to ~1e-13, so the folded
+// fp32 scale / shift come out bit-identical in practice (train-mode tolerance: 1e-6).
+// Per-warp reduction, fp64 atomics into the workspace totals; the CTA that finishes last folds them into bn_state.
+template <class Cfg>
+struct StatMap {
+    static constexpr int KIN = Cfg::KIN, G = Cfg::G;
+    static constexpr int NV = KIN + 11;                       // e = [row sums (KIN) | n q (5) | q (5) | 1]
+    static constexpr int ONE = KIN + 10;
+    static constexpr int NE = KIN + 5 + 5 * KIN + 15;         // S1 row | S1 pillar | row x pillar | pillar^2 (upper triangle)
+    static constexpr int NRR = KIN * (KIN + 1) / 2;           // row x row (upper triangle), thread-local
+    static constexpr int EPL = (NE + 31) / 32;                // staged products per lane
+    // staged product i = e[a] * e[b], added to totals[dst]   (totals = [S1(G) | S2(G x G, upper triangle)])
+    __device__ static void entry(int i, int *a, int *b, int *dst) {
+        if (i < KIN) { *a = i; *b = ONE; *dst = i; return; }
+        i -= KIN;
+        if (i < 5) { *a = KIN + i; *b = ONE; *dst = KIN + i; return; }
+        i -= 5;
+        if (i < 5 * KIN) { const int k = i / 5, l = i % 5; *a = k; *b = KIN + 5 + l; *dst = G + k * G + KIN + l; return; }
+        i -= 5 * KIN;
+        int l = 0;
+        while (i >= 5 - l) { i -= 5 - l; ++l; }
+        *a = KIN + l; *b = KIN + 5 + l + i; *dst = G + (KIN + l) * G + KIN + l + i;
+    }
+    __device__ static int rr_dst(int e) {   // e-th element of the row x row upper triangle, row-major
+        int k = 0;
+        while (e >= KIN - k) { e -= KIN - k; ++k; }
+        return G + k * G + k + e;
+    }
 };
 
-template <int G, int K0, int K1>
-__device__ __forceinline__ void moments_rows(const float *g, double *acc) {
-    double gd[G];
-#pragma unroll
-    for (int k = K0; k < G; ++k) gd[k] = (double)g[k];
-    int e = 0;
-#pragma unroll
-    for (int k = K0; k < K1; ++k) {
-        acc[e++] += gd[k];
-#pragma unroll
-        for (int l = k; l < G; ++l, ++e) acc[e] = fma(gd[k], gd[l], acc[e]);
-    }
-}
+constexpr int kTableStatsThreads = 128;
 
 template <class Cfg>
-__global__ void __launch_bounds__(128, 4) pfn_moments_kernel(const __grid_constant__ PfnArgs a) {
-    constexpr int G = Cfg::G, KIN = Cfg::KIN, RS = Cfg::RS, COLS = Cfg::COLS, NACC = Cfg::NACC;
-    using MS = MomentSplit<G>;
+__global__ void __launch_bounds__(kTableStatsThreads, 4) pillar_table_stats_kernel(const __grid_constant__ TableArgs t,
+                                                                                const __grid_constant__ PfnArgs a) {
+    constexpr int KIN = Cfg::KIN, G = Cfg::G, RS = Cfg::RS, COLS = Cfg::COLS, NACC = Cfg::NACC;
+    using SM = StatMap<Cfg>;
+    constexpr int NV = SM::NV, NE = SM::NE, NRR = SM::NRR, EPL = SM::EPL, NW = kTableStatsThreads / 32;
+    constexpr int VS = NV | 1;                       // odd stride (in doubles): the lanes' vectors start in different banks
     constexpr int LW = (COLS + 3) / 4 * 4;
-    __shared__ double red[4][MS::NMAX];
-    __shared__ double sm[G + G * G];
+    __shared__ double vec[NW][32][VS];
+    __shared__ double red[NW][NE + NRR];
+    __shared__ double sm_ep[G + G * G];
     __shared__ int s_last;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, half = warp & 1;
-    const long long N = a.counters[RDP_CNT_N];
-    double acc[MS::NMAX];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int P = t.counters[RDP_CNT_P];
+    int ia[EPL], ib[EPL];
 #pragma unroll
-    for (int e = 0; e < MS::NMAX; ++e) acc[e] = 0.0;
-    const long long stride = (long long)gridDim.x * 64;
-    long long row = (long long)blockIdx.x * 64 + (warp >> 1) * 32 + lane;
-    float r[LW], nr[LW];
-    float4 q0 = make_float4(0.f, 0.f, 0.f, 0.f), nq0 = q0;
-    float q1 = 0.0f, nq1 = 0.0f;
-    auto fetch = [&](long long i, float *dst, float4 *a0, float *ndz) {
-        const float *src = a.grows + ((size_t)i + 1) * RS;
-        load_row<LW>(src, dst);
-        const int gid = __float_as_int(LW == RS ? dst[RS - 1] : __ldg(src + RS - 1));
-        *a0 = __ldg(reinterpret_cast<const float4 *>(a.aux + (size_t)gid * 8));
-        *ndz = __ldg(a.aux + (size_t)gid * 8 + 4);
-    };
-    if (row < N) fetch(row, r, &q0, &q1);
-    for (; row < N; row += stride) {
-        const bool more = row + stride < N;
-        if (more) fetch(row + stride, nr, &nq0, &nq1);
-        float g[G];
-        row_inputs<COLS, Cfg::DIST>(r, q0.x, q0.y, a.off_z, g);
-        g[KIN] = q0.x; g[KIN + 1] = q0.y; g[KIN + 2] = q0.z; g[KIN + 3] = q0.w; g[KIN + 4] = q1;
-        if (half == 0) moments_rows<G, 0, MS::KH>(g, acc);
-        else moments_rows<G, MS::KH, G>(g, acc);
-        if (more) {
-#pragma unroll
-            for (int c = 0; c < LW; ++c) r[c] = nr[c];
-            q0 = nq0; q1 = nq1;
-        }
+    for (int j = 0; j < EPL; ++j) {
+        int d;
+        ia[j] = ib[j] = 0;
+        if (lane + 32 * j < NE) SM::entry(lane + 32 * j, &ia[j], &ib[j], &d);
     }
+    double accs[EPL], rr[NRR];
 #pragma unroll
-    for (int e = 0; e < MS::NMAX; ++e) {
-        double v = acc[e];
+    for (int j = 0; j < EPL; ++j) accs[j] = 0.0;
+#pragma unroll
+    for (int e = 0; e < NRR; ++e) rr[e] = 0.0;
+
+    // one row into the thread's sums: rsum += r, rr += r r^T (upper triangle)
+    auto add_row = [&](const float *src, float cenx, float ceny, float cenz, double *rsum) {
+        float r[LW], g[KIN];
+        load_row<LW>(src, r);
+        row_inputs<COLS, Cfg::DIST>(r, cenx, ceny, cenz, g);
+        double gd[KIN];
+#pragma unroll
+        for (int k = 0; k < KIN; ++k) { gd[k] = (double)g[k]; rsum[k] += gd[k]; }
+        int e = 0;
+#pragma unroll
+        for (int k = 0; k < KIN; ++k)
+#pragma unroll
+            for (int l = k; l < KIN; ++l, ++e) rr[e] = fma(gd[k], gd[l], rr[e]);
+    };
+
+    const int stride = gridDim.x * kTableStatsThreads;
+    for (int pb = blockIdx.x * kTableStatsThreads + (tid & ~31); pb < P; pb += stride) {
+        const int p = pb + lane;
+        const bool valid = p < P;
+        int s = 0, e = 0, key = 0;
+        if (valid) {
+            s = t.starts[p]; e = t.starts[p + 1];
+            key = __float_as_int(__ldg(t.grows + ((size_t)s + 1) * RS));
+        }
+        float cenx = 0.f, ceny = 0.f, cenz = 0.f;
+        int4 c = make_int4(0, 0, 0, 0);
+        if (valid) decode_key(t.g, key, &cenx, &ceny, &cenz, &c);
+        const bool big = valid && (e - s) > kBigRows;
+        double rsum[KIN];
+#pragma unroll
+        for (int k = 0; k < KIN; ++k) rsum[k] = 0.0;
+        if (valid && !big) {
+            const float *r = t.grows + ((size_t)s + 1) * RS;
+            for (int i = s; i < e; ++i, r += RS) add_row(r, cenx, ceny, cenz, rsum);
+        }
+        unsigned bigmask = __ballot_sync(0xffffffffu, big);
+        while (bigmask) {   // one long pillar: the whole warp walks its rows (any lane may own any row's products)
+            const int src = __ffs(bigmask) - 1;
+            bigmask &= bigmask - 1;
+            const int sb = __shfl_sync(0xffffffffu, s, src), eb = __shfl_sync(0xffffffffu, e, src);
+            const float bx = __shfl_sync(0xffffffffu, cenx, src), by = __shfl_sync(0xffffffffu, ceny, src),
+                        bz = __shfl_sync(0xffffffffu, cenz, src);
+            double part[KIN];
+#pragma unroll
+            for (int k = 0; k < KIN; ++k) part[k] = 0.0;
+            for (int i = sb + lane; i < eb; i += 32) add_row(t.grows + ((size_t)i + 1) * RS, bx, by, bz, part);
+#pragma unroll
+            for (int k = 0; k < KIN; ++k) {
+                double v = part[k];
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+                if (lane == src) rsum[k] = v;
+            }
+        }
+        double *ev = vec[warp][lane];
+        if (valid) {
+            float entry[8];
+            pillar_entry(cenx, ceny, cenz, rsum[0], rsum[1], rsum[2], s, e - s, entry);
+            if (t.coords) store_coords(t.coords, t.coord_cols, (size_t)p, c);
+            asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(t.aux + (size_t)p * 8), "f"(entry[0]), "f"(entry[1]),
+                         "f"(entry[2]), "f"(entry[3]), "f"(entry[4]), "f"(entry[5]), "f"(entry[6]), "f"(entry[7])
+                         : "memory");
+            const double n = (double)(e - s);
+#pragma unroll
+            for (int k = 0; k < KIN; ++k) ev[k] = rsum[k];
+#pragma unroll
+            for (int l = 0; l < 5; ++l) {
+                const double q = (double)entry[l];
+                ev[KIN + l] = n * q;          // exact: n < 2^31, q has 24 significant bits
+                ev[KIN + 5 + l] = q;
+            }
+            ev[SM::ONE] = 1.0;
+        } else {
+#pragma unroll
+            for (int k = 0; k < NV; ++k) ev[k] = 0.0;
+        }
+        __syncwarp();
+#pragma unroll 4
+        for (int q = 0; q < 32; ++q) {
+            const double *w = vec[warp][q];
+#pragma unroll
+            for (int j = 0; j < EPL; ++j) accs[j] = fma(w[ia[j]], w[ib[j]], accs[j]);
+        }
+        __syncwarp();
+    }
+
+    // ---- per-CTA sums -> fp64 totals (atomics); the CTA that finishes last runs the BatchNorm epilogue
+#pragma unroll
+    for (int j = 0; j < EPL; ++j)
+        if (lane + 32 * j < NE) red[warp][lane + 32 * j] = accs[j];
+#pragma unroll
+    for (int e = 0; e < NRR; ++e) {
+        double v = rr[e];
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
-        if (lane == 0) red[warp][e] = v;
+        if (lane == 0) red[warp][NE + e] = v;
     }
     __syncthreads();
-    for (int e = tid; e < MS::NA + MS::NB; e += 128) {
-        // e enumerates half A's values, then half B's: [S1[k], S2[k][k..G-1]] for k in the half's range
-        const int h = e >= MS::NA, idx = h ? e - MS::NA : e;
-        const double sacc = red[h][idx] + red[h + 2][idx];
+    for (int e = tid; e < NE + NRR; e += kTableStatsThreads) {
+        double sacc = 0.0;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) sacc += red[w][e];
         if (sacc == 0.0) continue;
-        int k = h ? MS::KH : 0, rem = idx;
-        while (rem >= G - k + 1) { rem -= G - k + 1; ++k; }
-        const int dst = rem == 0 ? k : G + k * G + (k + rem - 1);   // S1 entry | slot of S2[k][l] in the full matrix (upper triangle)
+        int dst;
+        if (e < NE) { int x, y; SM::entry(e, &x, &y, &dst); } else dst = SM::rr_dst(e - NE);
         atomicAdd(a.acc_stats + dst, sacc);
     }
     __threadfence();
@@ -609,12 +693,12 @@ __global__ void __launch_bounds__(128, 4) pfn_moments_kernel(const __grid_consta
     if (!s_last) return;
     __threadfence();
     if (a.defer_finalize) {   // SyncBatchNorm: the totals (and the point count beside them) are all-reduced over the ranks first
-        if (tid == 0) a.acc_stats[NACC] = (double)N;
+        if (tid == 0) a.acc_stats[NACC] = (double)a.counters[RDP_CNT_N];
         return;
     }
-    bn_epilogue<Cfg>(a, a.acc_stats, sm);
+    bn_epilogue<Cfg>(a, a.acc_stats, sm_ep);
     __syncthreads();
-    for (int e = tid; e <= NACC; e += 128) a.acc_stats[e] = 0.0;   // ready for the next launch on this workspace
+    for (int e = tid; e <= NACC; e += kTableStatsThreads) a.acc_stats[e] = 0.0;   // ready for the next launch on this workspace
 }
 
 // Stand-alone epilogue: SyncBatchNorm (after the all-reduce of the totals).  One CTA.

@@ -9,7 +9,8 @@ struct PfnLaunch {
     int cols, dist, cout, g;
     cudaError_t (*apply)(const PfnArgs &a, int want_arg, int grid, cudaStream_t st);
     cudaError_t (*bwd)(const PfnArgs &a, int grid, cudaStream_t st);
-    cudaError_t (*moments)(const PfnArgs &a, int grid, cudaStream_t st);   // train-mode feature moments (+ BN epilogue in the last CTA)
+    // pillar table + train-mode feature moments (+ BN epilogue in the last CTA): replaces the generic table kernel
+    cudaError_t (*table_stats)(const TableArgs &t, const PfnArgs &a, int64_t pcap, cudaStream_t st);
     cudaError_t (*bn_finalize)(const PfnArgs &a, cudaStream_t st);                       // SyncBatchNorm phase 2
     cudaError_t (*bwd_finalize)(const PfnArgs &a, const double *glob, cudaStream_t st);  // SyncBatchNorm backward phase 2
 };

@@ -52,8 +52,9 @@ static cudaError_t bwd(const PfnArgs &a, int grid, cudaStream_t st) {
     return cudaGetLastError();
 }
 
-static cudaError_t moments(const PfnArgs &a, int grid, cudaStream_t st) {
-    pfn_moments_kernel<Cfg><<<grid, 128, 0, st>>>(a);
+static cudaError_t table_stats(const TableArgs &t, const PfnArgs &a, int64_t pcap, cudaStream_t st) {
+    const int64_t blocks = (pcap + kTableStatsThreads - 1) / kTableStatsThreads, cap = 148 * 8;
+    pillar_table_stats_kernel<Cfg><<<(int)(blocks < 1 ? 1 : (blocks < cap ? blocks : cap)), kTableStatsThreads, 0, st>>>(t, a);
     return cudaGetLastError();
 }
 
@@ -71,7 +72,7 @@ static cudaError_t bwd_finalize(const PfnArgs &a, const double *glob, cudaStream
 #define RDP_CAT2(a, b) a##b
 #define RDP_CAT(a, b) RDP_CAT2(a, b)
 const PfnLaunch *RDP_CAT(rdp_pfn_cfg_, RDP_CFG_ID)() {
-    static const PfnLaunch L = {Cfg::COLS, Cfg::DIST ? 1 : 0, Cfg::COUT, Cfg::G, apply, bwd, moments, bn_finalize, bwd_finalize};
+    static const PfnLaunch L = {Cfg::COLS, Cfg::DIST ? 1 : 0, Cfg::COUT, Cfg::G, apply, bwd, table_stats, bn_finalize, bwd_finalize};
     return &L;
 }
 

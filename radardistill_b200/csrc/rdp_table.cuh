@@ -30,7 +30,6 @@ struct GeomDev {
 struct TableArgs {
     const float *grows;
     const int32_t *starts;
-    const int32_t *unq;
     int32_t *counters;
     float *aux;
     int32_t *coords;
@@ -46,17 +45,18 @@ struct RowBasis {
     static constexpr int RS = (COLS + 2 + 3) / 4 * 4;
 };
 
-// Row inputs of the folded linear layer from a grouped row [b, dx, dy, dz, f...]: the centre offsets (exactly f_center of
-// the reference, :215-217), the raw feature columns after xyz, and the distance feature (:230-231) when the layout has one
-// (the absolute coordinates it needs are d + centre; see DESIGN.md for the rounding this adds to that one feature).
+// Row inputs of the folded linear layer from a grouped row [key, x, y, z, f...]: the centre offsets d = xyz - centre (exactly
+// f_center of the reference, :215-217), the raw feature columns after xyz, and the distance feature (:230-231) when the
+// layout has one.
 template <int COLS, bool DIST>
 __device__ __forceinline__ void row_inputs(const float *r, float cenx, float ceny, float cenz, float *out) {
+    const float x = r[1], y = r[2], z = r[3];
+    out[0] = __fsub_rn(x, cenx);
+    out[1] = __fsub_rn(y, ceny);
+    out[2] = __fsub_rn(z, cenz);
 #pragma unroll
-    for (int c = 1; c < COLS; ++c) out[c - 1] = r[c];
-    if (DIST) {
-        const float x = __fadd_rn(r[1], cenx), y = __fadd_rn(r[2], ceny), z = __fadd_rn(r[3], cenz);
-        out[COLS - 1] = sqrtf(fmaf(z, z, fmaf(y, y, __fmul_rn(x, x))));
-    }
+    for (int c = 4; c < COLS; ++c) out[c - 1] = r[c];
+    if (DIST) out[COLS - 1] = sqrtf(fmaf(z, z, fmaf(y, y, __fmul_rn(x, x))));
 }
 
 template <int RSF>
@@ -82,7 +82,7 @@ __device__ __forceinline__ void decode_key(const GeomDev &g, int key, float *cen
 }
 
 // One table entry [centre xy | -mean(d) xyz | start | rows | centre z] from the exact fp64 sums of the pillar's centre offsets d
-// (the grouped rows store d = xyz - centre): -mean(d) = centre - mean(xyz), the pillar part of f_cluster (:226-227).
+// d = xyz - centre: -mean(d) = centre - mean(xyz), the pillar part of f_cluster (:226-227).
 __device__ __forceinline__ void pillar_entry(float cenx, float ceny, float cenz, double sx, double sy, double sz, int start, int rows,
                                              float *entry) {
     float mx, my, mz;
@@ -92,13 +92,14 @@ __device__ __forceinline__ void pillar_entry(float cenx, float ceny, float cenz,
     entry[5] = __int_as_float(start); entry[6] = __int_as_float(rows); entry[7] = cenz;
 }
 
-// fp64 sums of the offsets of grouped rows [s, e) by a whole warp (lane-strided, shuffle reduction; exact, so any order gives the same bits)
-__device__ __forceinline__ void warp_sum_rows(const float *grows, int rs, int s, int e, double *sx, double *sy, double *sz) {
+// fp64 sums of the centre offsets of grouped rows [s, e) by a whole warp (lane-strided, shuffle reduction; exact, so any order gives the same bits)
+__device__ __forceinline__ void warp_sum_rows(const float *grows, int rs, int s, int e, float cenx, float ceny, float cenz, double *sx,
+                                              double *sy, double *sz) {
     const int lane = threadIdx.x & 31;
     double ax = 0.0, ay = 0.0, az = 0.0;
     for (int i = s + lane; i < e; i += 32) {
         const float4 v = __ldg(reinterpret_cast<const float4 *>(grows + ((size_t)i + 1) * rs));
-        ax += (double)v.y; ay += (double)v.z; az += (double)v.w;
+        ax += (double)__fsub_rn(v.y, cenx); ay += (double)__fsub_rn(v.z, ceny); az += (double)__fsub_rn(v.w, cenz);
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) {
@@ -130,11 +131,20 @@ __device__ __forceinline__ void pillar_table_body(const TableArgs &t) {
         if (valid) { s = t.starts[p]; e = t.starts[p + 1]; }
         const bool big = valid && (e - s) > kBigRows;
         double sx = 0.0, sy = 0.0, sz = 0.0;
-        if (valid && !big) {
-            const float *r = t.grows + ((size_t)s + 1) * rs;   // rows are 16-byte aligned: [b, dx, dy, dz] is one 128-bit load
-            for (int i = s; i < e; ++i, r += rs) {
-                const float4 v = __ldg(reinterpret_cast<const float4 *>(r));
-                sx += (double)v.y; sy += (double)v.z; sz += (double)v.w;
+        float cenx = 0.f, ceny = 0.f, cenz = 0.f;
+        int4 c = make_int4(0, 0, 0, 0);
+        if (valid) {
+            const float *r = t.grows + ((size_t)s + 1) * rs;   // rows are 16-byte aligned: [key, x, y, z] is one 128-bit load
+            const float4 v0 = __ldg(reinterpret_cast<const float4 *>(r));
+            decode_key(t.g, __float_as_int(v0.x), &cenx, &ceny, &cenz, &c);
+            if (!big) {
+                // the mean is taken over the centre offsets d = xyz - centre (f_center, :215-217): small, exactly summable
+                sx = (double)__fsub_rn(v0.y, cenx); sy = (double)__fsub_rn(v0.z, ceny); sz = (double)__fsub_rn(v0.w, cenz);
+                r += rs;
+                for (int i = s + 1; i < e; ++i, r += rs) {
+                    const float4 v = __ldg(reinterpret_cast<const float4 *>(r));
+                    sx += (double)__fsub_rn(v.y, cenx); sy += (double)__fsub_rn(v.z, ceny); sz += (double)__fsub_rn(v.w, cenz);
+                }
             }
         }
         unsigned bigmask = __ballot_sync(0xffffffffu, big);
@@ -142,14 +152,14 @@ __device__ __forceinline__ void pillar_table_body(const TableArgs &t) {
             const int src = __ffs(bigmask) - 1;
             bigmask &= bigmask - 1;
             const int sb = __shfl_sync(0xffffffffu, s, src), eb = __shfl_sync(0xffffffffu, e, src);
+            const float bx = __shfl_sync(0xffffffffu, cenx, src), by = __shfl_sync(0xffffffffu, ceny, src),
+                        bz = __shfl_sync(0xffffffffu, cenz, src);
             double ax, ay, az;
-            warp_sum_rows(t.grows, rs, sb, eb, &ax, &ay, &az);
+            warp_sum_rows(t.grows, rs, sb, eb, bx, by, bz, &ax, &ay, &az);
             if (lane == src) { sx = ax; sy = ay; sz = az; }
         }
         if (valid) {
-            float cenx, ceny, cenz, entry[8];
-            int4 c;
-            decode_key(t.g, t.unq[p], &cenx, &ceny, &cenz, &c);
+            float entry[8];
             pillar_entry(cenx, ceny, cenz, sx, sy, sz, s, e - s, entry);
             if (t.coords) store_coords(t.coords, t.coord_cols, (size_t)p, c);
             asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(t.aux + (size_t)p * 8), "f"(entry[0]), "f"(entry[1]),
