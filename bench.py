@@ -2,6 +2,7 @@
 """bench.py -- pillar-encoder throughput on B200 (BASELINE.json metric), one JSON line on stdout.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--mode B|A]
+                    [--scaling weak|strong] [--config paired|stress]
 
 Workload (BASELINE.json configs[2]/[3]): paired radar + LiDAR pillar encoding, forward + backward,
 8 frames per GPU with the radar_distill_train.yaml grid; synthetic nuScenes-shaped clouds
@@ -15,9 +16,14 @@ value  = points/s over all ranks with inputs resident in HBM (CUDA events per st
 e2e    = the same through the module API from pinned HOST buffers: every step uploads its points (H2D) and reads the
          step's result -- the parameter gradients -- back (D2H); "e2e_host_outputs" additionally downloads the
          pillar features / coords (what a host-side consumer of rdp_encode_host would receive)
---impl reference: the CPU oracle port (oracle/pillar_oracle.c, all host threads) on the same workload.
-Multi-GPU: frames shard over ranks (weak scaling, 8 frames per GPU); the only collective is DDP's gradient
-all-reduce of the PFN parameters.
+roofline = the dominant kernel of the timed step (mode B: pfn_apply_kernel<ARG>, the train-mode forward tile kernel), timed
+         live with CUDA events; roofline.whole_step = algorithmic bytes of fwd+bwd of both encoders / the step time
+         (the north_star quantity); "configs" = the other BASELINE.json configurations, measured briefly at N = 1
+--impl reference: the CPU port of the path (oracle/pillar_oracle.c, all host threads) on the same workload, same frame
+         count and warm-up; when build() staged the reference's own torch files (oracle/_ref/) its rows are listed too.
+--scaling strong: BASELINE.json configs[3] -- global batch 64, 64 / N frames per rank.   --config stress: configs[4] --
+         1 M-point clouds at 0.05 m pillars, global batch 16, 16 / N frames per rank.
+Multi-GPU: frames shard over ranks; the only collective is the gradient all-reduce of the PFN parameters.
 """
 from __future__ import annotations
 
@@ -37,18 +43,37 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 FRAMES_PER_GPU = 8
+STRONG_GLOBAL_BATCH = 64      # BASELINE.json configs[3]
+STRESS_GLOBAL_BATCH = 16      # BASELINE.json configs[4]
 S2D_CFG = dict(USE_NORM=True, WITH_DISTANCE=False, USE_ABSLOTE_XYZ=True, USE_CLUSTER_XYZ=True, NUM_FILTERS=[32])
+DYN_CFG = dict(USE_NORM=True, WITH_DISTANCE=False, USE_ABSLOTE_XYZ=True, NUM_FILTERS=[64])   # DynamicPillarVFE 10 -> 64
 
 
 class Cfg(dict):
     __getattr__ = dict.__getitem__
 
 
-def make_clouds(rank: int, frames: int):
+def make_clouds(rank: int, frames: int, config: str = "paired"):
     from radardistill_b200 import synth
-    lidar = synth.collate([synth.lidar_frame(rank * frames + b) for b in range(frames)])
+    if config == "stress":   # configs[4]: dense 1 M-point clouds (skewed pillars, 20 % exact duplicates) + the usual radar frames
+        lidar = synth.collate([synth.stress_frame(rank * frames + b) for b in range(frames)])
+    else:
+        lidar = synth.collate([synth.lidar_frame(rank * frames + b) for b in range(frames)])
     radar = synth.collate([synth.radar_frame(rank * frames + b) for b in range(frames)])
     return lidar, radar
+
+
+def voxel_of(config: str):
+    from radardistill_b200 import synth
+    return synth.STRESS_VOXEL_SIZE if config == "stress" else synth.VOXEL_SIZE
+
+
+def frames_per_rank(args, world: int) -> int:
+    if args.config == "stress":
+        return max(STRESS_GLOBAL_BATCH // world, 1)
+    if args.scaling == "strong":
+        return max(STRONG_GLOBAL_BATCH // world, 1)
+    return FRAMES_PER_GPU
 
 
 def peaks():
@@ -100,13 +125,14 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm
-def oracle_pair(seed=0):
+def oracle_pair(seed=0, voxel=None):
     from oracle import oracle as orc
     from radardistill_b200 import synth
     rng = np.random.default_rng(seed)
+    voxel = list(voxel if voxel is not None else synth.VOXEL_SIZE)
     out = {}
     for kind, c in (("lidar", 5), ("radar", 6)):
-        cfg = orc.OracleConfig(num_point_features=c, voxel_size=tuple(synth.VOXEL_SIZE), grid_size=tuple(synth.grid_size_of()),
+        cfg = orc.OracleConfig(num_point_features=c, voxel_size=tuple(voxel), grid_size=tuple(synth.grid_size_of(voxel_size=voxel)),
                                point_cloud_range=tuple(synth.PC_RANGE))
         w = (rng.standard_normal((32, cfg.c_in)) * 0.2).astype(np.float32)
         out[kind] = orc.PillarOracle(cfg, w, rng.uniform(0.5, 1.5, 32), rng.normal(0, 0.2, 32), rng.normal(0, 1, 32),
@@ -125,10 +151,10 @@ def cpu_step(oracles, lidar, radar, mode):
             o.backward(r, g)
 
 
-def time_cpu(lidar, radar, mode, steps, warmup, threads):
+def time_cpu(lidar, radar, mode, steps, warmup, threads, voxel=None):
     from oracle import oracle as orc
     orc.set_threads(threads)
-    oracles = oracle_pair()
+    oracles = oracle_pair(voxel=voxel)
     for _ in range(warmup):
         cpu_step(oracles, lidar, radar, mode)
     t0 = time.perf_counter()
@@ -138,44 +164,121 @@ def time_cpu(lidar, radar, mode, steps, warmup, threads):
     return (len(lidar) + len(radar)) / dt, dt
 
 
+def time_torch_reference(mode, cores, frames=1):
+    """The reference's OWN torch path (DynamicPillarVFESimple2D + Radar_DynamicPillarVFESimple2D loaded from the files that
+    build() staged in oracle/_ref/, torch_scatter restated by oracle/ref_loader.py) on the host cores: `frames` paired
+    frames, one warm-up + two timed steps per row.  Two rows, as BASELINE.md section 3 plans: as-written, and with
+    `dim=0` dropped from the 1-D torch.unique call (bit-identical output, removes the aten::unique_dim pathology).
+    Returns [] when the files are not staged."""
+    try:
+        import torch
+        from oracle import ref_loader
+        if not ref_loader.reference_available():
+            return []
+        from radardistill_b200 import synth
+        torch.set_num_threads(cores)
+        lidar, radar = make_clouds(0, frames)
+        grid = synth.grid_size_of()
+        mods = {"lidar": ref_loader.build_reference("DynamicPillarVFESimple2D", S2D_CFG, 5, synth.VOXEL_SIZE, grid, synth.PC_RANGE, force_cpu=True),
+                "radar": ref_loader.build_reference("Radar_DynamicPillarVFESimple2D", S2D_CFG, 6, synth.VOXEL_SIZE, grid, synth.PC_RANGE, force_cpu=True)}
+        if mode == "A":
+            mods["lidar"].eval()
+        pts = {"lidar": torch.from_numpy(lidar), "radar": torch.from_numpy(radar)}
+
+        def step():
+            for kind, key, out_key in (("lidar", "points", "pillar_features"), ("radar", "radar_points", "radar_pillar_features")):
+                m = mods[kind]
+                train = mode == "B" or kind == "radar"
+                with ref_loader.cpu_cuda_identity(True), torch.set_grad_enabled(train):
+                    out = m({key: pts[kind]})
+                if train:
+                    out[out_key].backward(torch.ones_like(out[out_key]))
+                    m.zero_grad(set_to_none=True)
+
+        rows = []
+        orig_unique = torch.unique
+
+        def unique_1d(x, *a, **k):
+            if x.dim() == 1:
+                k.pop("dim", None)
+            return orig_unique(x, *a, **k)
+
+        for variant, patch in (("as written", None), ("dim=0 dropped from the 1-D torch.unique (same output)", unique_1d)):
+            if patch is not None:
+                torch.unique = patch
+            try:
+                step()
+                t0 = time.perf_counter()
+                for _ in range(2):
+                    step()
+                dt = (time.perf_counter() - t0) / 2
+            finally:
+                torch.unique = orig_unique
+            rows.append({"value": (len(lidar) + len(radar)) / dt, "unit": "points/s", "cores": cores, "kind": "reference",
+                         "variant": variant, "s_per_step": dt,
+                         "sample": f"{frames} paired frame(s) ({len(lidar)} LiDAR + {len(radar)} radar rows), mode {mode}, 1 warm-up + 2 timed "
+                                   f"steps, torch {torch.__version__} CPU, reference classes from oracle/_ref, torch_scatter restated"})
+        return rows
+    except Exception as e:   # the baseline rows are a report, never a reason to lose the bench line
+        return [{"kind": "reference", "unavailable": f"{type(e).__name__}: {e}"}]
+
+
 def run_reference(args):
-    """--impl reference: the CPU port of the reference path on the host cores (rank 0 only)."""
+    """--impl reference: the CPU port of the reference path on the host cores (rank 0 only), on the GPU arm's workload:
+    same frame count, same warm-up, same step count."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     cores = os.cpu_count() or 1
-    frames = 2  # bounded sample: 2 of the 8 paired frames per step (same generators, same per-frame shapes)
-    lidar, radar = make_clouds(0, frames)
-    value, dt = time_cpu(lidar, radar, args.mode, max(args.steps, 1), min(args.warmup, 1), cores)
+    frames = frames_per_rank(args, world)
+    if args.scaling == "strong" or args.config == "stress":
+        frames = min(frames, 8)   # bounded sample of the rank-0 shard: the rate is per point
+    lidar, radar = make_clouds(0, frames, args.config)
+    steps, warmup = max(args.steps, 1), max(args.warmup, 0)
+    value, dt = time_cpu(lidar, radar, args.mode, steps, warmup, cores, voxel_of(args.config))
+    torch_rows = time_torch_reference(args.mode, cores) if args.config == "paired" else []
     line = {"impl": "reference", "metric": "pillar-encoder points/s (fwd+bwd)", "value": value, "unit": "points/s",
-            "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args.mode, frames, len(lidar), len(radar)),
+            "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": dt * 1e3,
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, args.mode, frames, len(lidar), len(radar)),
             "cpu_baseline": {"value": value, "unit": "points/s", "cores": cores, "kind": "port",
-                             "sample": f"{frames} paired frames/step ({len(lidar)} LiDAR + {len(radar)} radar rows), C oracle, "
-                                       f"{cores} threads in the per-point loops"},
+                             "sample": f"{frames} paired frames/step ({len(lidar)} LiDAR + {len(radar)} radar rows), C oracle "
+                                       f"(oracle/pillar_oracle.c), {cores} threads in the per-point loops"},
+            "cpu_baseline_reference_torch": torch_rows,
             "e2e": {"value": value, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
-def workload_config(mode, frames, n_lidar, n_radar):
-    return {"workload": "paired radar+LiDAR pillar encoding fwd+bwd (BASELINE.json configs[2]; radar_distill_train.yaml grid 1440x1440, "
-                        "0.075 m pillars)", "mode": "B: both encoders train-BN fwd+bwd" if mode == "B" else
+def workload_config(args, mode, frames, n_lidar, n_radar):
+    from radardistill_b200 import synth
+    vox = voxel_of(args.config)
+    grid = synth.grid_size_of(voxel_size=vox)
+    what = ("paired radar+LiDAR pillar encoding fwd+bwd (BASELINE.json configs[2]; radar_distill_train.yaml grid 1440x1440, 0.075 m pillars)"
+            if args.config == "paired" else
+            "stress: 1 M-point dense clouds at 0.05 m pillars (2160x2160), skewed pillars + 20 % exact duplicates, paired with the radar "
+            "frames, fwd+bwd (BASELINE.json configs[4], global batch 16)")
+    if args.config == "paired" and args.scaling == "strong":
+        what += f"; strong scaling: global batch {STRONG_GLOBAL_BATCH} (configs[3])"
+    return {"workload": what, "mode": "B: both encoders train-BN fwd+bwd" if mode == "B" else
             "A: LiDAR frozen eval fwd, radar train fwd+bwd", "frames_per_gpu": frames, "lidar_rows_per_gpu": int(n_lidar),
-            "radar_rows_per_gpu": int(n_radar), "encoders": "DynamicPillarVFESimple2D 14->32 + Radar_DynamicPillarVFESimple2D 15->32",
+            "radar_rows_per_gpu": int(n_radar), "grid": [int(grid[0]), int(grid[1])],
+            "encoders": "DynamicPillarVFESimple2D 14->32 + Radar_DynamicPillarVFESimple2D 15->32",
             "l2": "256 MiB scratch written between timed steps (L2 flushed)"}
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
-def build_modules(device, mode, ddp):
+def build_modules(device, mode, ddp, voxel=None):
     import torch
     from radardistill_b200 import synth, vfe
     from radardistill_b200.vfe import forward_pair
     torch.manual_seed(1234)
-    lid = vfe.DynamicPillarVFESimple2D(model_cfg=Cfg(S2D_CFG), num_point_features=5, voxel_size=synth.VOXEL_SIZE,
-                                       grid_size=synth.grid_size_of(), point_cloud_range=synth.PC_RANGE).to(device)
-    rad = vfe.Radar_DynamicPillarVFESimple2D(model_cfg=Cfg(S2D_CFG), num_point_features=6, voxel_size=synth.VOXEL_SIZE,
-                                             grid_size=synth.grid_size_of(), point_cloud_range=synth.PC_RANGE).to(device)
+    voxel = list(voxel if voxel is not None else synth.VOXEL_SIZE)
+    grid = synth.grid_size_of(voxel_size=voxel)
+    lid = vfe.DynamicPillarVFESimple2D(model_cfg=Cfg(S2D_CFG), num_point_features=5, voxel_size=voxel,
+                                       grid_size=grid, point_cloud_range=synth.PC_RANGE).to(device)
+    rad = vfe.Radar_DynamicPillarVFESimple2D(model_cfg=Cfg(S2D_CFG), num_point_features=6, voxel_size=voxel,
+                                             grid_size=grid, point_cloud_range=synth.PC_RANGE).to(device)
     for m in (lid, rad):
         n = m.pfn_layers[0].norm
         with torch.no_grad():
@@ -279,10 +382,10 @@ def run_ours(args):
     if ddp:
         dist.init_process_group("nccl", device_id=device)
     _lib.load()
-    mode, frames = args.mode, FRAMES_PER_GPU
-    lidar, radar = make_clouds(rank, frames)
+    mode, frames = args.mode, frames_per_rank(args, world)
+    lidar, radar = make_clouds(rank, frames, args.config)
     n_rows = len(lidar) + len(radar)
-    lid, rad, call = build_modules(device, mode, args.dp if ddp else False)
+    lid, rad, call = build_modules(device, mode, args.dp if ddp else False, voxel_of(args.config))
     lidar_dev, radar_dev = torch.from_numpy(lidar).to(device), torch.from_numpy(radar).to(device)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
     upstream = make_upstream(device, len(lidar), len(radar), list(lid.parameters()) + list(rad.parameters()))
@@ -352,7 +455,7 @@ def run_ours(args):
     # ---- mode A beside it (reference-faithful step) when the headline is mode B, N == 1 only
     extra = {}
     if mode == "B" and not ddp:
-        lidA, radA, callA = build_modules(device, "A", False)
+        lidA, radA, callA = build_modules(device, "A", False, voxel_of(args.config))
         upstreamA = dict(upstream, params=list(lidA.parameters()) + list(radA.parameters()))
         for _ in range(3):
             gpu_step(callA, lidar_dev, radar_dev, "A", frames, upstreamA)
@@ -427,10 +530,11 @@ def run_ours(args):
                "d2h_bytes_per_step": out_d2h, "ms_per_step": out_dt * 1e3,
                "how": "as e2e, plus the D2H of the pillar features and coords of both encoders (PCIe bound)"}
 
-    # ---- roofline: the PFN kernels on the LiDAR batch, each timed live with CUDA events on the launching stream, L2
-    #      flushed before every launch.  Headline = pfn_tile_kernel<APPLY> (one launch per eval-mode rdp_pfn_fwd: the
-    #      kernel both step modes spend the most forward time in); the train-mode forward and the backward calls
-    #      (several launches each, dominated by one tile kernel) are listed beside it.
+    # ---- roofline: the librdp calls on the LiDAR batch, each timed live with CUDA events on the launching stream, L2
+    #      flushed before every launch.  Headline kernel = the dominant kernel of the timed step: mode B (train forward +
+    #      backward) spends its largest share in pfn_apply_kernel<ARG = true> -- the forward tile kernel that also writes the
+    #      argmax; an eval-BN rdp_pfn_fwd call that asks for the argmax launches exactly that kernel and nothing else.  Mode A
+    #      (frozen LiDAR) is dominated by the eval instantiation <ARG = false>.
     roof = None
     if rank == 0:
         import ctypes as C
@@ -441,6 +545,9 @@ def run_ours(args):
         w = lid.pfn_layers[0].linear.weight.detach()
         res = ops.encode_forward(lidar_dev, spec, frames, w, None, norm.weight, norm.bias, norm.running_mean.clone(),
                                  norm.running_var.clone(), True, True)   # train-mode state for the backward timing
+        rres = ops.encode_forward(radar_dev, rad.spec, frames, rad.pfn_layers[0].linear.weight.detach(), None,
+                                  rad.pfn_layers[0].norm.weight, rad.pfn_layers[0].norm.bias,
+                                  rad.pfn_layers[0].norm.running_mean.clone(), rad.pfn_layers[0].norm.running_var.clone(), True, True)
         torch.cuda.synchronize()
         P_ = ops._ptr
         feats = torch.empty((len(lidar), spec.c_out), dtype=torch.float32, device=device)
@@ -478,73 +585,204 @@ def run_ours(args):
 
         reps = max(args.steps, 10)
         idx = timed(call_index, reps)
-        dur = timed(lambda: call_fwd(prm_eval, None, None), reps)
-        dur_train = timed(lambda: call_fwd(prm_train, P_(argp), P_(res.bn_state)), reps)
+        dur_eval = timed(lambda: call_fwd(prm_eval, None, None), reps)            # pfn_apply_kernel<ARG = false> alone
+        dur_arg = timed(lambda: call_fwd(prm_eval, P_(argp), None), reps)          # pfn_apply_kernel<ARG = true> alone
+        dur_train = timed(lambda: call_fwd(prm_train, P_(argp), P_(res.bn_state)), reps)   # table+moments kernel, then <ARG = true>
         dur_bwd = timed(call_bwd, reps)
         n_kept, n_pil = res.n_kept, res.n_pillars
         row_bytes = 4 * spec.cols
-        alg = row_bytes * n_kept + 4 * spec.c_out * n_pil           # rows read once + feature rows written once
-        alg_fwd = row_bytes * len(lidar) + 4 * n_kept + n_pil * (4 * spec.c_out + 4 * spec.coord_cols + 4)  # SURVEY 8(d) B_fwd
-        alg_train = 2 * row_bytes * n_kept + 8 * spec.c_out * n_pil  # moments pass re-reads the rows; features + argmax written
-        alg_bwd = 8 * spec.c_out * n_pil + row_bytes * n_kept + 4 * n_kept   # SURVEY 8(d) B_bwd
         peak, peak_src = peaks()
-        traffic, traffic_src, tj_all = None, None, {}
-        tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
+
+        def alg_forward(sp, n0, nk, npil, train):   # SURVEY 8(d) B_fwd (+ the argmax in train mode)
+            return 4 * sp.cols * n0 + 4 * nk + npil * (4 * sp.c_out + 4 * sp.coord_cols + 4) + (4 * sp.c_out * npil if train else 0)
+
+        def alg_backward(sp, nk, npil):             # SURVEY 8(d) B_bwd
+            return 8 * sp.c_out * npil + 4 * sp.cols * nk + 4 * nk
+
+        alg_apply = row_bytes * n_kept + 4 * spec.c_out * n_pil           # rows read once + feature rows written once
+        alg_apply_arg = alg_apply + 4 * spec.c_out * n_pil                # + the argmax rows
+        alg_fwd = alg_forward(spec, len(lidar), n_kept, n_pil, False)
+        alg_train = 2 * row_bytes * n_kept + 8 * spec.c_out * n_pil       # the statistics pass re-reads the rows; features + argmax written
+        alg_bwd = alg_backward(spec, n_kept, n_pil)
+        # the whole timed step: forward (+ backward where the mode trains) of BOTH encoders
+        step_bytes = alg_forward(rad.spec, len(radar), rres.n_kept, rres.n_pillars, True) + alg_backward(rad.spec, rres.n_kept, rres.n_pillars)
+        step_bytes += alg_forward(spec, len(lidar), n_kept, n_pil, mode == "B") + (alg_bwd if mode == "B" else 0)
+        tj_all = {}
+        tp = os.path.join(ROOT, "profiles", "r02_traffic.json")
         if os.path.exists(tp):  # dram__bytes_read + dram__bytes_write per launch from the committed ncu --set full captures
             tj_all = json.load(open(tp))
-            tj = tj_all.get("pfn_tile_apply_eval", {})
-            if tj.get("rows") == n_kept and tj.get("pillars") == n_pil:
-                traffic, traffic_src = tj["dram_bytes_read"] + tj["dram_bytes_write"], tj["source"]
+
+        def traffic_of(key):
+            t = tj_all.get(key)
+            if t and t.get("rows") == n_kept and t.get("pillars") == n_pil:
+                return t["dram_bytes_read"] + t["dram_bytes_write"], t.get("source")
+            return None, None
 
         def entry(name, alg_bytes, ms, key=None):
             e = {"kernel": name, "algorithmic_bytes": int(alg_bytes), "ms": ms, "achieved": alg_bytes / (ms * 1e-3) / 1e9,
                  "frac": alg_bytes / (ms * 1e-3) / 1e9 / peak}
-            t = tj_all.get(key) if key else None
-            if t and t.get("rows") == n_kept and t.get("pillars") == n_pil:
-                e["traffic"] = t["dram_bytes_read"] + t["dram_bytes_write"]
+            t, _ = traffic_of(key) if key else (None, None)
+            if t is not None:
+                e["traffic"] = t
             return e
 
-        roof = {"bound": "hbm", "kernel": "pfn_tile_kernel<PfnCfg<6 cols, Simple2D, 32 ch>, APPLY> (LiDAR batch of 8 frames, eval BN)",
-                "achieved": alg / (dur * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": alg / (dur * 1e-3) / 1e9 / peak,
-                "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "kernel_ms": dur, "algorithmic_bytes": int(alg),
-                "frac_of_8000_nominal": alg / (dur * 1e-3) / 1e9 / 8000.0,
-                "whole_forward": {"algorithmic_bytes": int(alg_fwd), "ms": idx + dur, "index_ms": idx,
-                                  "achieved": alg_fwd / ((idx + dur) * 1e-3) / 1e9,
-                                  "frac": alg_fwd / ((idx + dur) * 1e-3) / 1e9 / peak},
+        if mode == "B":
+            head_name, head_alg, head_ms, head_key = ("pfn_apply_kernel<PfnCfg<6 cols, no distance, 32 ch>, ARG = true> (LiDAR batch, train forward: "
+                                                      "features + argmax)"), alg_apply_arg, dur_arg, "pfn_apply_arg"
+        else:
+            head_name, head_alg, head_ms, head_key = ("pfn_apply_kernel<PfnCfg<6 cols, no distance, 32 ch>, ARG = false> (LiDAR batch, eval BN "
+                                                      "forward)"), alg_apply, dur_eval, "pfn_apply_eval"
+        traffic, traffic_src = traffic_of(head_key)
+        roof = {"bound": "hbm", "kernel": head_name, "achieved": head_alg / (head_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                "frac": head_alg / (head_ms * 1e-3) / 1e9 / peak, "traffic": traffic, "traffic_source": traffic_src,
+                "peak_source": peak_src, "kernel_ms": head_ms, "algorithmic_bytes": int(head_alg),
+                "frac_of_8000_nominal": head_alg / (head_ms * 1e-3) / 1e9 / 8000.0,
+                "whole_step": {"what": f"mode {mode}: forward{' + backward' if mode == 'B' else ''} of the LiDAR encoder and forward + backward "
+                                       "of the radar encoder, SURVEY 8(d) algorithmic bytes / the timed step (ms_per_step)",
+                               "algorithmic_bytes": int(step_bytes), "ms": step_ms, "achieved": step_bytes / (step_ms * 1e-3) / 1e9,
+                               "frac": step_bytes / (step_ms * 1e-3) / 1e9 / peak,
+                               "frac_of_8000_nominal": step_bytes / (step_ms * 1e-3) / 1e9 / 8000.0},
+                "whole_forward": {"algorithmic_bytes": int(alg_fwd), "ms": idx + dur_eval, "index_ms": idx,
+                                  "achieved": alg_fwd / ((idx + dur_eval) * 1e-3) / 1e9,
+                                  "frac": alg_fwd / ((idx + dur_eval) * 1e-3) / 1e9 / peak},
                 "other_calls": [
-                    entry("rdp_index_fwd: 7 index kernels + publish", row_bytes * len(lidar) + 4 * n_kept + n_pil * (4 * spec.coord_cols + 4), idx),
-                    entry("rdp_pfn_fwd train: pfn_tile<STATS> + bn_finalize + pfn_tile<APPLY_ARG>", alg_train, dur_train, "pfn_train_fwd"),
-                    entry("rdp_pfn_bwd: pfn_tile<BWD> + bwd_finalize", alg_bwd, dur_bwd, "pfn_tile_bwd")]}
+                    entry("rdp_index_fwd: quantize_mark, bitmap_rank, rank_count, count_scan, group_rows, pillar_table",
+                          row_bytes * len(lidar) + 4 * n_kept + n_pil * (4 * spec.coord_cols + 4), idx, "index_call"),
+                    entry("pfn_apply_kernel<ARG = false> (eval forward)", alg_apply, dur_eval, "pfn_apply_eval"),
+                    entry("pfn_apply_kernel<ARG = true> (train forward)", alg_apply_arg, dur_arg, "pfn_apply_arg"),
+                    entry("rdp_pfn_fwd train: pillar_table_stats_kernel (table + BatchNorm moments) + pfn_apply_kernel<ARG = true>",
+                          alg_train, dur_train, "pfn_train_fwd"),
+                    entry("rdp_pfn_bwd: pfn_bwd_kernel (closed-form epilogue in its last CTA)", alg_bwd, dur_bwd, "pfn_bwd")]}
+
+    # ---- the other BASELINE.json configurations, measured briefly (N = 1, rank 0, default workload only)
+    others = None
+    if rank == 0 and not ddp and args.config == "paired" and args.scaling == "weak" and not args.no_configs:
+        others = other_configs(device, flush, max(min(args.steps, 10), 3))
 
     if rank == 0:
-        cpu = None
+        cpu, cpu_torch = None, []
         if not ddp:
             cores = os.cpu_count() or 1
-            fr = 2
-            l2, r2 = make_clouds(0, fr)
-            v, dt = time_cpu(l2, r2, mode, 3, 1, cores)
+            fr = min(frames, 8)
+            l2, r2 = (lidar, radar) if fr == frames else make_clouds(0, fr, args.config)
+            v, dt = time_cpu(l2, r2, mode, 3, 1, cores, voxel_of(args.config))
             cpu = {"value": v, "unit": "points/s", "cores": cores, "kind": "port",
-                   "sample": f"{fr} of the {frames} paired frames ({len(l2)} LiDAR + {len(r2)} radar rows) x 3 steps, C oracle "
+                   "sample": f"{fr} of the {frames} paired frames ({len(l2)} LiDAR + {len(r2)} radar rows) x 3 steps after 1 warm-up, C oracle "
                              f"(oracle/pillar_oracle.c), {cores} threads in the per-point loops, {dt:.2f} s/step"}
-        # librdp kernels per step: index 8 (quantise, scan, publish, zero, rank, scan, group, table); forward 3 in train mode
-        # (moments, finalize, apply) or 1; backward 2 (tile, finalize).  The radar encoder always trains.
-        launches_lidar = 8 + (3 + 2 if mode == "B" else 1)
-        launches = (launches_lidar + 13) * args.steps
+            if args.config == "paired":
+                cpu_torch = time_torch_reference(mode, cores)
+        # librdp kernels per step and encoder: index 5 (quantise, bitmap scan, rank, count scan, group) + table (train: table +
+        # moments) + apply = 7 per forward, + 1 backward tile kernel (its epilogue runs in its last CTA).  The radar encoder always trains.
+        launches_lidar = 7 + (1 if mode == "B" else 0)
+        launches = (launches_lidar + 8) * args.steps
         line = {"metric": "pillar-encoder points/s (fwd+bwd)", "value": value, "unit": "points/s", "n_gpus": world,
                 "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": step_ms, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": dict(workload_config(mode, frames, len(lidar), len(radar)),
+                "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": dict(workload_config(args, mode, frames, len(lidar), len(radar)),
                                cpus_pinned=(pinned if pinned is None else len(pinned)),
                                data_parallel=("none" if not ddp else ("GradientAllReduce: one NCCL all_reduce of the flat PFN gradients "
                                               "per step" if args.dp == "lean" else "torch DistributedDataParallel"))),
                 "e2e": e2e, "e2e_host_outputs": e2e_out,
                 "gpu_launches": launches,
-                "clocks": clk.summary(), "roofline": roof, "cpu_baseline": cpu, "wall_s_timed_region": wall}
+                "clocks": clk.summary(), "roofline": roof, "cpu_baseline": cpu, "cpu_baseline_reference_torch": cpu_torch,
+                "wall_s_timed_region": wall}
+        if others is not None:
+            line["configs"] = others
         line.update(extra)
         print(json.dumps(line), flush=True)
     if ddp:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def other_configs(device, flush, steps):
+    """BASELINE.json configs[0], [1] and [4] at N = 1, a few L2-flushed steps each (device-timed with CUDA events):
+    one radar frame (fwd+bwd), one LiDAR frame forward through DynamicPillarVFESimple2D 14->32 and DynamicPillarVFE 10->64
+    (us per frame), and the 1 M-point stress clouds at 0.05 m pillars (2 frames = one rank's share of the batch of 16)."""
+    import torch
+    from radardistill_b200 import synth, vfe
+    out = {}
+
+    def timed(fn):
+        ts = []
+        for i in range(steps + 3):
+            flush.fill_(1)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record()
+            torch.cuda.synchronize()
+            if i >= 3:
+                ts.append(e0.elapsed_time(e1))
+        return sum(ts) / len(ts)
+
+    def module(cls, cfg, c, voxel=synth.VOXEL_SIZE):
+        torch.manual_seed(7)
+        m = cls(model_cfg=Cfg(cfg), num_point_features=c, voxel_size=list(voxel), grid_size=synth.grid_size_of(voxel_size=list(voxel)),
+                point_cloud_range=synth.PC_RANGE).to(device)
+        n = m.pfn_layers[-1].norm
+        with torch.no_grad():
+            n.weight.uniform_(0.5, 1.5); n.bias.normal_(0, 0.2); n.running_mean.normal_(0, 1); n.running_var.uniform_(0.5, 4)
+        return m
+
+    # configs[1]: one 10-sweep LiDAR frame, eval forward
+    frame = synth.collate([synth.lidar_frame(0)])
+    pts = torch.from_numpy(frame).to(device)
+    m = module(vfe.DynamicPillarVFESimple2D, S2D_CFG, 5).eval()
+    with torch.no_grad():
+        ms = timed(lambda: m({"points": pts, "batch_size": 1}))
+        p = int(m({"points": pts, "batch_size": 1})["pillar_features"].shape[0])
+    out["lidar_frame_forward_simple2d_14to32"] = {"config": "configs[1]: LiDAR-teacher DynamicPillarVFESimple2D eval forward, one 10-sweep frame, batch 1",
+                                                  "us_per_frame": ms * 1e3, "points": int(len(frame)), "pillars": p,
+                                                  "points_per_s": len(frame) / (ms * 1e-3)}
+    pts4 = torch.from_numpy(np.ascontiguousarray(frame[:, :5])).to(device)     # b, x, y, z, intensity: DynamicPillarVFE 4 + 6 = 10 -> 64
+    m = module(vfe.DynamicPillarVFE, DYN_CFG, 4).eval()
+    with torch.no_grad():
+        ms = timed(lambda: m({"points": pts4, "batch_size": 1}))
+    out["lidar_frame_forward_dynpillar_10to64"] = {"config": "configs[1] with north_star's DynamicPillarVFE (PillarNet nuScenes 0.075 m grid) 10->64, eval forward, batch 1",
+                                                   "us_per_frame": ms * 1e3, "points": int(len(frame)), "points_per_s": len(frame) / (ms * 1e-3)}
+    # configs[0]: one radar frame (the reference's CPU-runnable case), train forward + backward
+    rframe = synth.collate([synth.radar_frame(0)])
+    rpts = torch.from_numpy(rframe).to(device)
+    m = module(vfe.Radar_DynamicPillarVFESimple2D, S2D_CFG, 6).train()
+    g = torch.randn((len(rframe), 32), device=device)
+
+    def radar_step():
+        for p_ in m.parameters():
+            p_.grad = None
+        f = m({"radar_points": rpts, "batch_size": 1})["radar_pillar_features"]
+        f.backward(g[:f.shape[0]])
+    ms = timed(radar_step)
+    from oracle import oracle as orc
+    orc.set_threads(os.cpu_count() or 1)
+    o = oracle_pair()["radar"]
+    t0 = time.perf_counter()
+    for _ in range(5):
+        r = o.forward(rframe, training=True, keep_intermediates=True)
+        o.backward(r, np.ones_like(r["features"]))
+    cpu_dt = (time.perf_counter() - t0) / 5
+    out["radar_frame_fwd_bwd"] = {"config": "configs[0]: radar-branch encoder, one radar frame, batch 1, train forward + backward",
+                                  "us_per_frame": ms * 1e3, "points": int(len(rframe)), "points_per_s": len(rframe) / (ms * 1e-3),
+                                  "cpu_port_us_per_frame": cpu_dt * 1e6, "note": "launch-latency bound on the GPU: 8 dependent kernels for 3 k points"}
+    # configs[4]: stress clouds, one rank's share (2 of 16 frames), train forward + backward
+    sframes = STRESS_GLOBAL_BATCH // 8
+    stress = synth.collate([synth.stress_frame(b) for b in range(sframes)])
+    spts = torch.from_numpy(stress).to(device)
+    m = module(vfe.DynamicPillarVFESimple2D, S2D_CFG, 5, synth.STRESS_VOXEL_SIZE).train()
+    g = torch.randn((len(stress), 32), device=device)
+    torch.cuda.reset_peak_memory_stats(device)
+    base_mem = torch.cuda.memory_allocated(device)
+
+    def stress_step():
+        for p_ in m.parameters():
+            p_.grad = None
+        f = m({"points": spts, "batch_size": sframes})["pillar_features"]
+        f.backward(g[:f.shape[0]])
+    ms = timed(stress_step)
+    out["stress_fwd_bwd"] = {"config": f"configs[4]: 1 M-point dense clouds, 0.05 m pillars (2160x2160), {sframes} frames = one of 8 ranks' share of "
+                                       "the batch of 16, train forward + backward",
+                             "ms_per_step": ms, "points": int(len(stress)), "pillars": int(m.last_result.n_pillars),
+                             "points_per_s": len(stress) / (ms * 1e-3),
+                             "peak_step_memory_bytes": int(torch.cuda.max_memory_allocated(device) - base_mem)}
+    return out
 
 
 def main():
@@ -554,6 +792,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default="B", choices=["A", "B"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: 8 frames per GPU (default); strong: global batch 64 split over the ranks (BASELINE.json configs[3])")
+    ap.add_argument("--config", default="paired", choices=["paired", "stress"],
+                    help="paired: configs[2]/[3] (default); stress: configs[4], 1 M-point clouds at 0.05 m pillars, global batch 16")
+    ap.add_argument("--no-configs", action="store_true", help="skip the brief runs of the other BASELINE.json configurations")
     ap.add_argument("--pin-cpus", type=int, default=1,
                     help="N > 1: give every rank its own physical cores (sched_setaffinity); 0 = leave the scheduler alone")
     ap.add_argument("--dp", default="lean", choices=["lean", "ddp"],

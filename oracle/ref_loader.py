@@ -32,8 +32,31 @@ import types
 
 import torch
 
+_REL = os.path.join("pcdet", "models", "backbones_3d", "vfe")
+# oracle/_ref/: git-ignored copy of the two reference files this path consists of, made by __graft_entry__.build() in the
+# build container so that bench.py's CPU-baseline legs can time the reference's own torch path on the GPU box (where
+# /root/reference does not exist).  Never committed, never imported by the product.
+STAGED_ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
 REF_ROOT = os.environ.get("RDP_REFERENCE_ROOT", "/root/reference")
-_VFE_DIR = os.path.join(REF_ROOT, "pcdet", "models", "backbones_3d", "vfe")
+if not os.path.isfile(os.path.join(REF_ROOT, _REL, "dynamic_pillar_vfe.py")) and \
+        os.path.isfile(os.path.join(STAGED_ROOT, _REL, "dynamic_pillar_vfe.py")):
+    REF_ROOT = STAGED_ROOT
+_VFE_DIR = os.path.join(REF_ROOT, _REL)
+REF_FILES = ("vfe_template.py", "dynamic_pillar_vfe.py", "dynamic_voxel_vfe.py", "dynamic_mean_vfe.py")
+
+
+def stage_reference(src_root: str = "/root/reference") -> bool:
+    """Copies the reference files of this path into oracle/_ref/ (build container only).  Returns True if staged."""
+    import shutil
+    src = os.path.join(src_root, _REL)
+    if not os.path.isfile(os.path.join(src, "dynamic_pillar_vfe.py")):
+        return os.path.isfile(os.path.join(STAGED_ROOT, _REL, "dynamic_pillar_vfe.py"))
+    dst = os.path.join(STAGED_ROOT, _REL)
+    os.makedirs(dst, exist_ok=True)
+    for fn in REF_FILES:
+        if os.path.isfile(os.path.join(src, fn)):
+            shutil.copyfile(os.path.join(src, fn), os.path.join(dst, fn))
+    return True
 
 
 def reference_available() -> bool:
@@ -99,9 +122,10 @@ _loaded = None
 
 
 @contextlib.contextmanager
-def cpu_cuda_identity():
-    """While active, ``Tensor.cuda()`` is the identity (the reference ctor calls it)."""
-    if torch.cuda.is_available():
+def cpu_cuda_identity(force: bool = False):
+    """While active, ``Tensor.cuda()`` is the identity (the reference ctor calls it).  ``force``: also on a box with a
+    GPU (the CPU-baseline legs of bench.py run the reference on the host cores there)."""
+    if torch.cuda.is_available() and not force:
         yield
         return
     orig = torch.Tensor.cuda
@@ -138,14 +162,14 @@ class Cfg(dict):
     __getattr__ = dict.__getitem__
 
 
-def build_reference(name, model_cfg, num_point_features, voxel_size, grid_size, point_cloud_range):
+def build_reference(name, model_cfg, num_point_features, voxel_size, grid_size, point_cloud_range, force_cpu=False):
     ref = load_reference()
     cls = {"DynPillarVFE": ref.DynamicPillarVFE,
            "DynamicPillarVFE": ref.DynamicPillarVFE,
            "DynamicPillarVFESimple2D": ref.DynamicPillarVFESimple2D,
            "Radar_DynamicPillarVFESimple2D": ref.Radar_DynamicPillarVFESimple2D,
            "Radar_DynamicPillarVFESimple2D_Test": ref.Radar_DynamicPillarVFESimple2D_Test}[name]
-    with cpu_cuda_identity():
+    with cpu_cuda_identity(force_cpu):
         return cls(model_cfg=Cfg(model_cfg), num_point_features=num_point_features, voxel_size=voxel_size,
                    grid_size=grid_size, point_cloud_range=point_cloud_range, depth_downsample_factor=None)
 
