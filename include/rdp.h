@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define RDP_ABI_VERSION 5
+#define RDP_ABI_VERSION 6
 
 #if defined(__GNUC__)
 #define RDP_API __attribute__((visibility("default")))
@@ -53,6 +53,8 @@ enum rdp_counter {
 
 #define RDP_LAYOUT_SIMPLE2D 0  /* DynamicPillarVFESimple2D + radar subclasses (:219-237): [center|pts|cluster|dist|rel] */
 #define RDP_LAYOUT_DYNPILLAR 1 /* DynamicPillarVFE (:113-121):                            [pts|cluster|center|dist]    */
+#define RDP_LAYOUT_DYNVOXEL 2  /* DynamicVoxelVFE (dynamic_voxel_vfe.py:73-91): as DYNPILLAR with a z-aware voxel centre;
+                                  rdp_decorate only (geom->nz > 1) -- the fused single-layer kernels are pillar-only     */
 
 /* Grid geometry: the constructor arguments of the reference classes (:73-85, :177-189). */
 typedef struct rdp_geom {
@@ -155,8 +157,8 @@ RDP_API int rdp_index_fwd_frames(const float *points, const int32_t *frame_offse
  *   features    (cap n_points, c_out) fp32      rows [0,P)
  *   argpos      (cap n_points, c_out) int32     winning row of every (pillar, channel) as a position in the
  *                                               workspace's pillar-grouped order (lowest kept index on ties),
- *                                               bit-complemented (negative) where the ReLU clamped the maximum to 0
- *                                               (no gradient flows, :38); input of rdp_pfn_bwd / rdp_argmax_kept.
+ *                                               -1 where the ReLU clamped the maximum to 0 (no gradient flows, :38);
+ *                                               input of rdp_pfn_bwd / rdp_argmax_kept.
  *                                               NULL if not wanted.
  *   pillar_mean (cap n_points, 3) fp32          per-pillar xyz mean (scatter_mean, :226); NULL if not wanted
  *   bn_state    (rdp_bn_state_doubles(layout)) fp64: batch mean/var, folded scale/shift and the feature
@@ -245,6 +247,47 @@ RDP_API int rdp_publish_counters(const int32_t *counters, int32_t *host_mapped, 
 RDP_API int rdp_encode_host(const float *points, int64_t n_points, const rdp_geom_t *geom, const rdp_layout_t *layout,
                     const rdp_pfn_params_t *params, float *features, int32_t *coords, int32_t *inverse,
                     int32_t *counts, int64_t *n_kept, int64_t *n_pillars);
+
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Stacked PFN layers and the sibling encoders.  All of them follow rdp_index_fwd (2-D key, or 3-D with
+ * geom->nz > 1) on the same workspace / stream and reuse its pillar-grouped rows and pillar table.
+ */
+
+/*
+ * The decorated per-point features the reference concatenates in front of its first PFNLayerV2, in KEPT-point order:
+ *   features (cap n_points, layout->c_in) fp32, rows [0, N)
+ * Replaces dynamic_pillar_vfe.py:214-237 (Simple2D), :105-121 (DynamicPillarVFE) and dynamic_voxel_vfe.py:73-91
+ * (RDP_LAYOUT_DYNVOXEL: voxel centre incl. z).  layout->c_out is ignored.
+ */
+RDP_API int rdp_decorate(int64_t n_points, const rdp_geom_t *geom, const rdp_layout_t *layout, void *workspace,
+                         size_t workspace_bytes, const int32_t *counters, float *features, void *stream);
+
+/*
+ * scatter_max over the pillars for the activations of a stacked layer (PFNLayerV2.forward :40):
+ *   x (N, channels) fp32 in kept-point order -> out (cap P, channels) fp32, argmax_kept (cap P, channels) int32 = kept index
+ *   of the winning row (lowest index on ties).  rdp_segment_max_bwd is its autograd: grad_x[argmax[p][c]][c] = grad_out[p][c]
+ *   into a ZEROED grad_x (N, channels).
+ */
+RDP_API int rdp_segment_max_fwd(const float *x, int32_t channels, int64_t n_points, const rdp_geom_t *geom, void *workspace,
+                                size_t workspace_bytes, const int32_t *counters, float *out, int32_t *argmax_kept, void *stream);
+RDP_API int rdp_segment_max_bwd(const float *grad_out, const int32_t *argmax_kept, int64_t n_pillars, int32_t channels,
+                                float *grad_x, void *stream);
+
+/* DynamicMeanVFE (dynamic_mean_vfe.py:63-65): mean (cap P, cols - 1) fp32 = per-voxel mean of every point column. */
+RDP_API int rdp_voxel_mean(int64_t n_points, const rdp_geom_t *geom, void *workspace, size_t workspace_bytes,
+                           const int32_t *counters, float *mean, void *stream);
+
+/*
+ * Device-side input preparation: the range mask of the data processor (mask_points_by_range,
+ * pcdet/datasets/processor/data_processor.py:80-86: lo <= x, y <= hi, inclusive) as a stable compaction, and, with
+ * shuffle_seed != 0, the shuffle of :99-114 as a fixed pseudo-random permutation of the kept rows.
+ *   points (n_points, cols) fp32, x in column x_col (y in x_col + 1); range_xy_lo_hi = {lo_x, lo_y, hi_x, hi_y} (host)
+ *   out (cap n_points, cols); n_out (device int32) = rows kept; scratch of rdp_prepare_scratch_bytes(n_points) bytes
+ */
+RDP_API size_t rdp_prepare_scratch_bytes(int64_t n_points);
+RDP_API int rdp_prepare_points(const float *points, int64_t n_points, int32_t cols, int32_t x_col, const float *range_xy_lo_hi,
+                               uint64_t shuffle_seed, void *scratch, size_t scratch_bytes, float *out, int32_t *n_out, void *stream);
 
 #ifdef __cplusplus
 }

@@ -148,7 +148,9 @@ def load_reference():
     pkg = types.ModuleType(_PKG)
     pkg.__path__ = [_VFE_DIR]
     sys.modules[_PKG] = pkg
-    for name in ("vfe_template", "dynamic_pillar_vfe"):
+    for name in ("vfe_template", "dynamic_pillar_vfe", "dynamic_voxel_vfe", "dynamic_mean_vfe"):
+        if not os.path.isfile(os.path.join(_VFE_DIR, f"{name}.py")):
+            continue
         spec = importlib.util.spec_from_file_location(f"{_PKG}.{name}", os.path.join(_VFE_DIR, f"{name}.py"))
         m = importlib.util.module_from_spec(spec)
         sys.modules[f"{_PKG}.{name}"] = m
@@ -164,6 +166,12 @@ class Cfg(dict):
 
 def build_reference(name, model_cfg, num_point_features, voxel_size, grid_size, point_cloud_range, force_cpu=False):
     ref = load_reference()
+    if name in ("DynamicVoxelVFE", "DynMeanVFE", "DynamicMeanVFE"):
+        mod = sys.modules[f"{_PKG}.dynamic_voxel_vfe" if name == "DynamicVoxelVFE" else f"{_PKG}.dynamic_mean_vfe"]
+        cls = mod.DynamicVoxelVFE if name == "DynamicVoxelVFE" else mod.DynamicMeanVFE
+        with cpu_cuda_identity(force_cpu):
+            return cls(model_cfg=Cfg(model_cfg), num_point_features=num_point_features, voxel_size=voxel_size,
+                       grid_size=grid_size, point_cloud_range=point_cloud_range)
     cls = {"DynPillarVFE": ref.DynamicPillarVFE,
            "DynamicPillarVFE": ref.DynamicPillarVFE,
            "DynamicPillarVFESimple2D": ref.DynamicPillarVFESimple2D,
@@ -174,7 +182,7 @@ def build_reference(name, model_cfg, num_point_features, voxel_size, grid_size, 
                    grid_size=grid_size, point_cloud_range=point_cloud_range, depth_downsample_factor=None)
 
 
-def run_reference(module, points: torch.Tensor, points_key="points", capture=None):
+def run_reference(module, points: torch.Tensor, points_key="points", capture=None, extra=None):
     """Runs the reference forward on CPU; ``capture`` (dict) receives inverse / argmax / counts.
 
     The reference does not expose ``unq_inv`` / ``unq_cnt`` / the scatter_max argmax, so
@@ -198,7 +206,7 @@ def run_reference(module, points: torch.Tensor, points_key="points", capture=Non
     ts.scatter_max, torch.unique = rec_max, rec_unique
     try:
         with cpu_cuda_identity():
-            out = module({points_key: points})
+            out = module(dict({points_key: points}, **(extra or {})))
     finally:
         ts.scatter_max, torch.unique = orig_max, orig_unique
     return out

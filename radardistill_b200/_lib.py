@@ -8,14 +8,15 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("RDP_LIB_PATH", os.path.join(_HERE, "librdp.so"))  # override: kernel-variant experiments
 
-RDP_ABI_VERSION = 5
+RDP_ABI_VERSION = 6
 RDP_NUM_COUNTERS = 16
 CNT_N, CNT_P, CNT_ERRFLAGS = 0, 1, 2
-LAYOUT_SIMPLE2D, LAYOUT_DYNPILLAR = 0, 1
+LAYOUT_SIMPLE2D, LAYOUT_DYNPILLAR, LAYOUT_DYNVOXEL = 0, 1, 2
 
 EXPORTS = ["rdp_abi_version", "rdp_status_string", "rdp_last_cuda_error", "rdp_workspace_bytes", "rdp_index_fwd", "rdp_index_fwd_publish", "rdp_index_fwd_frames", "rdp_encode_fwd_frames",
            "rdp_pfn_fwd", "rdp_encode_fwd", "rdp_bn_state_doubles", "rdp_pfn_bwd", "rdp_argmax_kept", "rdp_pillar_lookup", "rdp_publish_counters",
-           "rdp_encode_host", "rdp_config_supported", "rdp_stats_buffers"]
+           "rdp_encode_host", "rdp_config_supported", "rdp_stats_buffers", "rdp_decorate", "rdp_segment_max_fwd", "rdp_segment_max_bwd",
+           "rdp_voxel_mean", "rdp_prepare_scratch_bytes", "rdp_prepare_points"]
 
 
 class Geom(C.Structure):
@@ -94,6 +95,18 @@ def load() -> C.CDLL:
     lib.rdp_encode_host.restype = C.c_int
     lib.rdp_encode_host.argtypes = [vp, C.c_int64, C.POINTER(Geom), C.POINTER(Layout), C.POINTER(PfnParams), vp, vp, vp, vp,
                                     C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    lib.rdp_decorate.restype = C.c_int
+    lib.rdp_decorate.argtypes = [C.c_int64, C.POINTER(Geom), C.POINTER(Layout), vp, C.c_size_t, vp, vp, vp]
+    lib.rdp_segment_max_fwd.restype = C.c_int
+    lib.rdp_segment_max_fwd.argtypes = [vp, C.c_int32, C.c_int64, C.POINTER(Geom), vp, C.c_size_t, vp, vp, vp, vp]
+    lib.rdp_segment_max_bwd.restype = C.c_int
+    lib.rdp_segment_max_bwd.argtypes = [vp, vp, C.c_int64, C.c_int32, vp, vp]
+    lib.rdp_voxel_mean.restype = C.c_int
+    lib.rdp_voxel_mean.argtypes = [C.c_int64, C.POINTER(Geom), vp, C.c_size_t, vp, vp, vp]
+    lib.rdp_prepare_scratch_bytes.restype = C.c_size_t
+    lib.rdp_prepare_scratch_bytes.argtypes = [C.c_int64]
+    lib.rdp_prepare_points.restype = C.c_int
+    lib.rdp_prepare_points.argtypes = [vp, C.c_int64, C.c_int32, C.c_int32, C.POINTER(C.c_float), C.c_uint64, vp, C.c_size_t, vp, vp, vp]
     _lib = lib
     return lib
 

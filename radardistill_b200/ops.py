@@ -38,12 +38,13 @@ class EncoderSpec:
     ny: int
     eps: float = 1e-3
     momentum: float = 0.01
+    nz: int = 0                   # > 1: voxels (3-D key, z quantised and masked): DynamicVoxelVFE / DynamicMeanVFE
 
     def geom(self, batch_size: int) -> Geom:
         g = Geom()
         for k in range(3):
             g.lo[k], g.vsz[k], g.off[k] = self.lo[k], self.vsz[k], self.off[k]
-        g.nx, g.ny, g.batch_size, g.cols, g.nz = self.nx, self.ny, int(batch_size), self.cols, 0
+        g.nx, g.ny, g.batch_size, g.cols, g.nz = self.nx, self.ny, int(batch_size), self.cols, int(self.nz)
         return g
 
     def layout_struct(self) -> Layout:
@@ -54,12 +55,15 @@ class EncoderSpec:
 def make_spec(num_point_features: int, voxel_size, grid_size, point_cloud_range, layout: int, use_abs: bool,
               use_cluster: bool, use_relative: bool, with_distance: bool, c_out: int) -> EncoderSpec:
     c = int(num_point_features)
+    nz = 0
     if layout == _lib.LAYOUT_SIMPLE2D:
         c_in = 3 + (c if use_abs else c - 3) + (3 if use_cluster else 0) + (3 if use_relative else 0)
         coord_cols = 3
     else:
         c_in = (c if use_abs else c - 3) + 6
         use_cluster, use_relative, coord_cols = True, False, 4
+        if layout == _lib.LAYOUT_DYNVOXEL:
+            nz = int(grid_size[2])
     c_in += 1 if with_distance else 0
     pcr = np.asarray(point_cloud_range, dtype=np.float32)
     vs = np.asarray([float(v) for v in voxel_size], dtype=np.float64)
@@ -68,7 +72,7 @@ def make_spec(num_point_features: int, voxel_size, grid_size, point_cloud_range,
     off = tuple(float(np.float32(vs[k] / 2.0 + float(pcr[k]))) for k in range(3))   # (:180-182)
     return EncoderSpec(cols=c + 1, layout=layout, use_abs=bool(use_abs), use_cluster=bool(use_cluster),
                        use_relative=bool(use_relative), with_distance=bool(with_distance), c_in=c_in, c_out=int(c_out),
-                       coord_cols=coord_cols, lo=lo, vsz=vsz, off=off, nx=int(grid_size[0]), ny=int(grid_size[1]))
+                       coord_cols=coord_cols, lo=lo, vsz=vsz, off=off, nx=int(grid_size[0]), ny=int(grid_size[1]), nz=nz)
 
 
 class EncodeResult:
@@ -76,24 +80,25 @@ class EncodeResult:
     ``counts``, ``bn_state``, ``counters`` and ``workspace`` are views into the one scratch allocation of the call and
     are only materialised when somebody asks for them (they are inspection / backward state, not hot-path outputs)."""
     __slots__ = ("features", "coords", "argpos", "n_kept", "n_pillars", "spec", "batch_size", "n_points", "train_bn",
-                 "_buf", "_plan", "_argmax", "_views", "params_struct")
+                 "_buf", "_plan", "_argmax", "_views", "params_struct", "sync_group")
 
     def __init__(self, features, coords, argpos, n_kept, n_pillars, spec, batch_size, n_points, buf, plan, train_bn=False,
-                 params_struct=None):
+                 params_struct=None, sync_group=None):
         self.features, self.coords, self.argpos = features, coords, argpos
         self.n_kept, self.n_pillars, self.spec, self.batch_size, self.n_points = n_kept, n_pillars, spec, batch_size, n_points
         self._buf, self._plan, self.train_bn, self.params_struct = buf, plan, train_bn, params_struct
         self._argmax, self._views = None, {}
+        self.sync_group = sync_group   # SyncBatchNorm: process group of the batch statistics (None: per-rank statistics)
 
     def without_outputs(self):
         """Copy for the autograd node: must not reference the node's own outputs (reference cycle => ~1 GB waits for the GC)."""
         r = EncodeResult(None, None, self.argpos, self.n_kept, self.n_pillars, self.spec, self.batch_size, self.n_points,
-                         self._buf, self._plan, self.train_bn, self.params_struct)
+                         self._buf, self._plan, self.train_bn, self.params_struct, self.sync_group)
         return r
 
     def with_outputs(self, features, coords):
         r = EncodeResult(features, coords, self.argpos, self.n_kept, self.n_pillars, self.spec, self.batch_size,
-                         self.n_points, self._buf, self._plan, self.train_bn, self.params_struct)
+                         self.n_points, self._buf, self._plan, self.train_bn, self.params_struct, self.sync_group)
         r._views = self._views
         return r
 
@@ -198,7 +203,17 @@ class _Plan:
     geometry / layout structs, the workspace size and the carving of the call's single scratch allocation
     [ librdp workspace | counters | bn_state | inverse | counts ]."""
     __slots__ = ("spec", "geom", "layout", "ws_bytes", "cap", "bn_doubles", "off_counters", "off_bn", "off_inverse",
-                 "off_counts", "total_bytes")
+                 "off_counts", "total_bytes", "_stats")
+
+    def stats_buffers(self, n0: int):
+        """(stats offset, stats doubles, bwd offset, bwd doubles) inside the workspace: the two fp64 vectors a SyncBatchNorm
+        forward / backward all-reduces between its phases (rdp_stats_buffers)."""
+        if self._stats is None:
+            so, bo, sd, bd = C.c_size_t(0), C.c_size_t(0), C.c_int64(0), C.c_int64(0)
+            _lib.check(_lib.load().rdp_stats_buffers(n0, C.byref(self.geom), C.byref(self.layout), C.byref(so), C.byref(sd),
+                                                    C.byref(bo), C.byref(bd)), "rdp_stats_buffers")
+            self._stats = (so.value, sd.value, bo.value, bd.value)
+        return self._stats
 
 
 _plan_cache = {}
@@ -211,6 +226,7 @@ def _plan(spec: "EncoderSpec", batch_size: int, n0: int, train_bn: bool) -> _Pla
         return pl
     lib = _lib.load()
     pl = _Plan()
+    pl._stats = None
     pl.spec, pl.geom, pl.layout = spec, spec.geom(batch_size), spec.layout_struct()
     nbytes = C.c_size_t(0)
     _lib.check(lib.rdp_workspace_bytes(n0, C.byref(pl.geom), C.byref(pl.layout), C.byref(nbytes)), "rdp_workspace_bytes")
@@ -252,6 +268,16 @@ def _params_struct(spec: "EncoderSpec", weight, bias, gamma, beta, running_mean,
     return p
 
 
+def _phase_params(prm: PfnParams, phase: int, local_stats=None, global_bwd=None) -> PfnParams:
+    """A copy of a (cached) parameter struct for one phase of a SyncBatchNorm forward / backward."""
+    q = PfnParams()
+    C.memmove(C.byref(q), C.byref(prm), C.sizeof(PfnParams))
+    q.stats_phase = phase
+    q.local_stats = None if local_stats is None else local_stats.data_ptr()
+    q.global_bwd = None if global_bwd is None else global_bwd.data_ptr()
+    return q
+
+
 def _check_param(t: Optional[torch.Tensor], shape, name: str, device=None):
     if t is None:
         return None
@@ -268,7 +294,7 @@ def _check_param(t: Optional[torch.Tensor], shape, name: str, device=None):
 class PendingEncode:
     """Kernels of one forward have been enqueued on the current stream; `finish` waits for the early (N, P) publication."""
     __slots__ = ("spec", "batch_size", "n_points", "points", "coords", "features", "argpos", "buf", "plan", "host", "event",
-                 "train_bn", "prm")
+                 "train_bn", "prm", "sync_group", "keep")
 
 
 _host_pool = {}
@@ -288,7 +314,7 @@ def _take_host(dev_index: int, stream_handle: int):
 
 def encode_launch(points: torch.Tensor, spec: EncoderSpec, batch_size: int, weight, bias, gamma, beta, running_mean,
                   running_var, train_bn: bool, want_argmax: bool, num_batches_tracked=None,
-                  frame_offsets: Optional[torch.Tensor] = None) -> PendingEncode:
+                  frame_offsets: Optional[torch.Tensor] = None, sync_group=None) -> PendingEncode:
     """Enqueues index + PFN forward on the current stream (one call into librdp) and returns without synchronising.
 
     ``frame_offsets`` (int32 CUDA, ``batch_size + 1`` entries): ``points`` then holds the frames back to back WITHOUT the
@@ -340,19 +366,40 @@ def encode_launch(points: torch.Tensor, spec: EncoderSpec, batch_size: int, weig
         prm = _params_struct(spec, weight, bias, gamma, beta, running_mean, running_var, train_bn,
                              num_batches_tracked if train_bn else None)
         base = buf.data_ptr()
-        _lib.check(lib.rdp_encode_fwd_frames(pts.data_ptr(), None if frame_offsets is None else frame_offsets.data_ptr(), n0,
-                                             C.byref(pl.geom), C.byref(pl.layout), C.byref(prm), base, pl.ws_bytes,
-                                             coords.data_ptr(), base + pl.off_inverse, base + pl.off_counts,
-                                             base + pl.off_counters, features.data_ptr(),
-                                             None if argpos is None else argpos.data_ptr(),
-                                             (base + pl.off_bn) if train_bn else None, host.data_ptr(), event.cuda_event, st),
-                   "rdp_encode_fwd_frames")
+
+        def call(q):
+            _lib.check(lib.rdp_encode_fwd_frames(pts.data_ptr(), None if frame_offsets is None else frame_offsets.data_ptr(), n0,
+                                                 C.byref(pl.geom), C.byref(pl.layout), C.byref(q), base, pl.ws_bytes,
+                                                 coords.data_ptr(), base + pl.off_inverse, base + pl.off_counts,
+                                                 base + pl.off_counters, features.data_ptr(),
+                                                 None if argpos is None else argpos.data_ptr(),
+                                                 (base + pl.off_bn) if train_bn else None, host.data_ptr(), event.cuda_event, st),
+                       "rdp_encode_fwd_frames")
+
+        keep = None
+        if sync_group is not None and train_bn:
+            # SyncBatchNorm (tools/train.py:34,144-145): batch statistics over the points of every rank of the group.
+            # Phase 1 = index + feature moments; one all-reduce of the (<= 184)-double moment vector; phase 2 = the rest.
+            import torch.distributed as dist
+            if n0 == 0:
+                raise NotImplementedError("SyncBatchNorm with an empty local batch (this rank would skip the collectives)")
+            so, sd, _, _ = pl.stats_buffers(n0)
+            call(_phase_params(prm, 1))
+            stats = buf[so:so + 8 * sd].view(torch.float64)
+            local = stats.clone()
+            dist.all_reduce(stats, group=sync_group)
+            keep = (local, _phase_params(prm, 2, local_stats=local))
+            call(keep[1])
+        else:
+            sync_group = None
+            call(prm)
     finally:
         if switch:
             torch.cuda.set_device(prev)
     p = PendingEncode()
     p.spec, p.batch_size, p.n_points, p.points, p.coords, p.features, p.argpos = spec, batch_size, int(n0), pts, coords, features, argpos
     p.buf, p.plan, p.host, p.event, p.train_bn, p.prm = buf, pl, (host, host_np), event, train_bn, prm
+    p.sync_group, p.keep = sync_group, keep
     return p
 
 
@@ -366,7 +413,7 @@ def encode_finish(p: PendingEncode) -> EncodeResult:
     if err & 1:
         raise ValueError(f"points[:, 0] holds a batch index outside [0, {p.batch_size})")
     return EncodeResult(p.features[:n_pillars], p.coords[:n_pillars], None if p.argpos is None else p.argpos[:n_pillars],
-                        n_kept, n_pillars, p.spec, p.batch_size, p.n_points, p.buf, p.plan, p.train_bn, p.prm)
+                        n_kept, n_pillars, p.spec, p.batch_size, p.n_points, p.buf, p.plan, p.train_bn, p.prm, p.sync_group)
 
 
 def encode_forward(points: torch.Tensor, spec: EncoderSpec, batch_size: int, weight, bias, gamma, beta, running_mean,
@@ -401,14 +448,37 @@ def encode_backward(points: torch.Tensor, spec: EncoderSpec, batch_size: int, re
         if prm is None or bool(prm.train_bn) != train_bn:
             prm = _params_struct(spec, weight, bias, gamma, beta, running_mean, running_var, train_bn)
         ws_ptr, ws_bytes, cnt_ptr, bn_ptr = res._state_ptrs()
-        _lib.check(lib.rdp_pfn_bwd(points.data_ptr(), points.shape[0], C.byref(pl.geom), C.byref(pl.layout), C.byref(prm),
-                                   ws_ptr, ws_bytes, cnt_ptr, g.data_ptr(), None, res.argpos.data_ptr(), bn_ptr, d_w.data_ptr(),
-                                   None if d_g is None else d_g.data_ptr(), d_b.data_ptr(), _raw_stream(dev.index)),
-                   "rdp_pfn_bwd")
+
+        def call(q):
+            _lib.check(lib.rdp_pfn_bwd(points.data_ptr(), points.shape[0], C.byref(pl.geom), C.byref(pl.layout), C.byref(q),
+                                       ws_ptr, ws_bytes, cnt_ptr, g.data_ptr(), None, res.argpos.data_ptr(), bn_ptr, d_w.data_ptr(),
+                                       None if d_g is None else d_g.data_ptr(), d_b.data_ptr(), _raw_stream(dev.index)),
+                       "rdp_pfn_bwd")
+
+        sync_group = getattr(res, "sync_group", None)
+        if sync_group is not None and train_bn:
+            # SyncBatchNorm backward: the per-channel sums (dbeta, dgamma enter every rank's correction terms) are all-reduced
+            # between the tile kernel (phase 1) and the closed-form epilogue (phase 2)
+            import torch.distributed as dist
+            _, _, bo, bd = pl.stats_buffers(points.shape[0])
+            call(_phase_params(prm, 1))
+            glob = res._buf[bo:bo + 8 * bd].view(torch.float64).clone()
+            dist.all_reduce(glob, group=sync_group)
+            call(_phase_params(prm, 2, global_bwd=glob))
+        else:
+            call(prm)
     finally:
         if switch:
             torch.cuda.set_device(prev)
     return d_w, d_g, d_b
+
+
+class _Holder:
+    """Out-parameter of the autograd functions (a plain list would be copied by torch.amp.custom_fwd's argument casting)."""
+    __slots__ = ("items",)
+
+    def __init__(self):
+        self.items = []
 
 
 class _PillarEncodeFn(torch.autograd.Function):
@@ -416,9 +486,10 @@ class _PillarEncodeFn(torch.autograd.Function):
     were already enqueued (``pending``); this only waits for the (N, P) publication and wires up the backward."""
 
     @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)   # --use_amp (train_utils.py:57-64): the encoder stays fp32
     def forward(ctx, weight, bias, gamma, beta, running_mean, running_var, pending, holder):
         res = encode_finish(pending)
-        holder.append(res)
+        holder.items.append(res)
         # the node must not reference its own outputs (reference cycle => the ~1 GB of state would wait for the GC)
         ctx.res = res.without_outputs()
         ctx.spec, ctx.batch_size, ctx.train_bn = pending.spec, pending.batch_size, pending.train_bn
@@ -429,6 +500,7 @@ class _PillarEncodeFn(torch.autograd.Function):
         return res.features, res.coords
 
     @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
     def backward(ctx, grad_features, _grad_coords):
         weight, bias, gamma, beta = ctx.saved_tensors
         res = ctx.res
@@ -446,9 +518,10 @@ class _PairEncodeFn(torch.autograd.Function):
     streams.  Same gradients as two ``_PillarEncodeFn`` nodes."""
 
     @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
     def forward(ctx, wa, ba, ga, bea, wb, bb, gb, beb, pma, pmb, side, holder):
         ra, rb = encode_finish(pma.pending), encode_finish(pmb.pending)
-        holder.extend((ra, rb))
+        holder.items.extend((ra, rb))
         ctx.ra, ctx.rb = ra.without_outputs(), rb.without_outputs()
         ctx.pa, ctx.pb, ctx.side = pma, pmb, side
         ctx.save_for_backward(wa, ba, ga, bea, wb, bb, gb, beb)
@@ -457,6 +530,7 @@ class _PairEncodeFn(torch.autograd.Function):
         return ra.features, ra.coords, rb.features, rb.coords
 
     @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
     def backward(ctx, gfa, _gca, gfb, _gcb):
         wa, ba, ga, bea, wb, bb, gb, beb = ctx.saved_tensors
 
@@ -492,9 +566,9 @@ class _PairEncodeFn(torch.autograd.Function):
 
 def encode_wait_pair(pma: "PendingModuleEncode", pmb: "PendingModuleEncode", side):
     """``encode_wait`` for two pending encodes that both need gradients: one autograd node for the pair."""
-    holder = []
+    holder = _Holder()
     fa, ca, fb, cb = _PairEncodeFn.apply(*pma.params[:4], *pmb.params[:4], pma, pmb, side, holder)
-    return holder[0].with_outputs(fa, ca), holder[1].with_outputs(fb, cb)
+    return holder.items[0].with_outputs(fa, ca), holder.items[1].with_outputs(fb, cb)
 
 
 class PendingModuleEncode:
@@ -505,7 +579,8 @@ class PendingModuleEncode:
 
 
 def encode_async(points, spec: EncoderSpec, batch_size: int, weight, bias=None, gamma=None, beta=None, running_mean=None,
-                 running_var=None, train_bn: bool = False, num_batches_tracked=None, frame_offsets=None) -> PendingModuleEncode:
+                 running_var=None, train_bn: bool = False, num_batches_tracked=None, frame_offsets=None,
+                 sync_group=None) -> PendingModuleEncode:
     """Enqueues a (differentiable) encode on the current stream; pair with ``encode_wait``."""
     if points.requires_grad:
         raise NotImplementedError("gradients w.r.t. points are not produced (points are a leaf in the reference)")
@@ -513,15 +588,16 @@ def encode_async(points, spec: EncoderSpec, batch_size: int, weight, bias=None, 
                                               (gamma is not None and gamma.requires_grad) or
                                               (beta is not None and beta.requires_grad))
     pending = encode_launch(points, spec, batch_size, weight, bias, gamma, beta, running_mean, running_var, train_bn,
-                            want_argmax=needs_grad, num_batches_tracked=num_batches_tracked, frame_offsets=frame_offsets)
+                            want_argmax=needs_grad, num_batches_tracked=num_batches_tracked, frame_offsets=frame_offsets,
+                            sync_group=sync_group)
     return PendingModuleEncode(pending, (weight, bias, gamma, beta, running_mean, running_var), needs_grad)
 
 
 def encode_wait(pm: PendingModuleEncode) -> EncodeResult:
     if pm.needs_grad:
-        holder = []
+        holder = _Holder()
         feats, coords = _PillarEncodeFn.apply(*pm.params, pm.pending, holder)
-        return holder[0].with_outputs(feats, coords)
+        return holder.items[0].with_outputs(feats, coords)
     return encode_finish(pm.pending)
 
 

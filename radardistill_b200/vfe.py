@@ -18,7 +18,7 @@ from __future__ import annotations
 import torch
 import torch.nn as nn
 
-from . import _lib, ops
+from . import _lib, ops, stack_ops
 
 
 class VFETemplate(nn.Module):
@@ -54,8 +54,11 @@ def _cfg(cfg, key):
 
 
 class PFNLayerV2(nn.Module):
-    """Parameter holder with the reference's names (``dynamic_pillar_vfe.py:14-33``): ``linear`` and ``norm``.
-    The computation of its ``forward`` (:35-46) is fused into the encoder kernels."""
+    """``dynamic_pillar_vfe.py:14-46`` with the reference's parameter names (``linear``, ``norm``).
+
+    A single (last) layer over pillars is fused into the encoder kernels and never calls ``forward``.  Stacked layers
+    (``NUM_FILTERS`` longer than 1) and the voxel encoder run ``forward``: Linear + BatchNorm1d + ReLU as library calls,
+    ``scatter_max`` by ``rdp_segment_max_fwd`` over the pillar-grouped rows of the index pass."""
 
     def __init__(self, in_channels, out_channels, use_norm=True, last_layer=False):
         super().__init__()
@@ -70,8 +73,18 @@ class PFNLayerV2(nn.Module):
             self.linear = nn.Linear(in_channels, out_channels, bias=True)
         self.relu = nn.ReLU()
 
-    def forward(self, inputs, unq_inv):  # pragma: no cover
-        raise _lib.RdpError("PFNLayerV2 is fused into the pillar-encoder kernels; call the VFE module instead")
+    def forward(self, inputs, unq_inv):
+        """``unq_inv``: the ``stack_ops.IndexResult`` of the index pass (it carries ``inverse`` and the grouped rows the
+        pooling kernel walks).  There is no torch_scatter path."""
+        if not isinstance(unq_inv, stack_ops.IndexResult):
+            raise _lib.RdpError("PFNLayerV2.forward needs the IndexResult of the encoder's index pass; call the VFE module")
+        x = self.linear(inputs)                                        # (:36)
+        x = self.norm(x) if self.use_norm else x                       # (:37)
+        x = self.relu(x)                                               # (:38)
+        x_max = stack_ops.segment_max(x, unq_inv)[0]                   # (:40)
+        if self.last_vfe:
+            return x_max                                               # (:42-43)
+        return torch.cat([x, x_max[unq_inv.inverse.long(), :]], dim=1)  # (:44-46)
 
 
 class _FusedDynamicPillarVFE(VFETemplate):
@@ -93,14 +106,18 @@ class _FusedDynamicPillarVFE(VFETemplate):
             self.use_cluster_xyz, self.use_relative_xyz, self.double_flip = True, False, False
         self.num_filters = list(_cfg(model_cfg, "NUM_FILTERS"))
         assert len(self.num_filters) > 0
-        if len(self.num_filters) != 1:
-            raise NotImplementedError("fused encoder covers the single-PFN-layer configurations the reference ships "
-                                      "(NUM_FILTERS of length 1); multi-layer PFN stacks are listed as 'next' in DESIGN.md")
+        first_out = self.num_filters[0] if len(self.num_filters) == 1 else self.num_filters[0] // 2
         self.spec = ops.make_spec(num_point_features, voxel_size, grid_size, point_cloud_range, self._layout,
                                   bool(self.use_absolute_xyz), bool(self.use_cluster_xyz), bool(self.use_relative_xyz),
-                                  bool(self.with_distance), self.num_filters[-1])
+                                  bool(self.with_distance), first_out)
         self.num_point_features = self.spec.c_in
-        self.pfn_layers = nn.ModuleList([PFNLayerV2(self.spec.c_in, self.num_filters[0], self.use_norm, last_layer=True)])
+        filters = [self.spec.c_in] + self.num_filters                   # (:63-72)
+        self.pfn_layers = nn.ModuleList([PFNLayerV2(filters[i], filters[i + 1], self.use_norm, last_layer=(i >= len(filters) - 2))
+                                         for i in range(len(filters) - 1)])
+        # One PFN layer over pillars runs in the fused kernels when they are compiled for this row width / channel count;
+        # stacked layers, voxel grids and any other shape take the layer-stack path (index + rdp_decorate + PFNLayerV2.forward).
+        self.fused = (len(self.num_filters) == 1 and self.spec.nz <= 1 and
+                      bool(_lib.load().rdp_config_supported(ops.C.byref(self.spec.geom(1)), ops.C.byref(self.spec.layout_struct()))))
         self.voxel_x, self.voxel_y, self.voxel_z = voxel_size[0], voxel_size[1], voxel_size[2]
         self.x_offset, self.y_offset, self.z_offset = self.spec.off
         self.scale_xy = int(grid_size[0]) * int(grid_size[1])
@@ -128,26 +145,45 @@ class _FusedDynamicPillarVFE(VFETemplate):
         # optional device-side input prep: `<points key>_offsets` (int32, batch_size + 1) => `points` is (N, C) without the
         # batch column, frames back to back (what the dataset produces before collate_batch pads the frame index in)
         offsets = batch_dict.get(self._points_key + "_offsets", None)
+        bs = (int(offsets.shape[0]) - 1) if offsets is not None else self._batch_size(batch_dict, points)
+        if not self.fused:
+            return ("stack", points, offsets, bs), False
         pfn = self.pfn_layers[0]
         norm = pfn.norm if self.use_norm else None
         train_bn = bool(self.use_norm and norm.training)
+        sync_group = None
         if train_bn and isinstance(norm, nn.SyncBatchNorm) and _world_size() > 1:
-            # tools/train.py --sync_bn (:34,144-145) converts the PFN's BatchNorm1d; the fused kernels compute per-rank batch
-            # statistics (the reference default), so refuse loudly instead of silently training with different semantics
-            raise NotImplementedError("SyncBatchNorm in the fused pillar encoder is not implemented yet (per-rank batch statistics "
-                                      "only, the reference default); run without --sync_bn or keep this module's norm a BatchNorm1d")
-        bs = (int(offsets.shape[0]) - 1) if offsets is not None else self._batch_size(batch_dict, points)
+            # tools/train.py --sync_bn (:34,144-145) converts the PFN's BatchNorm1d: batch statistics over every rank's points --
+            # the fused forward / backward run in two phases around one small all-reduce each (ops.encode_launch)
+            import torch.distributed as dist
+            sync_group = norm.process_group if norm.process_group is not None else dist.group.WORLD
         pm = ops.encode_async(points, self.spec, bs, pfn.linear.weight,
                               bias=None if self.use_norm else pfn.linear.bias,
                               gamma=norm.weight if norm is not None else None, beta=norm.bias if norm is not None else None,
                               running_mean=norm.running_mean if norm is not None else None,
                               running_var=norm.running_var if norm is not None else None, train_bn=train_bn,
-                              num_batches_tracked=norm.num_batches_tracked if train_bn else None, frame_offsets=offsets)
+                              num_batches_tracked=norm.num_batches_tracked if train_bn else None, frame_offsets=offsets,
+                              sync_group=sync_group)
         return pm, train_bn
 
     def finish(self, batch_dict, token):
         pm, train_bn = token
+        if isinstance(pm, tuple) and pm[0] == "stack":
+            return self._forward_stack(batch_dict, *pm[1:])
         return self._publish(batch_dict, ops.encode_wait(pm), train_bn)
+
+    def _forward_stack(self, batch_dict, points, offsets, bs):
+        """Layer-stack path (``dynamic_pillar_vfe.py:93-140``, ``dynamic_voxel_vfe.py:55-105``): index kernels, decorated
+        per-point features, then the PFN layers as the reference chains them (:123-124)."""
+        idx = stack_ops.index_forward(points, self.spec, bs, offsets)
+        features = stack_ops.decorate(idx)
+        for pfn in self.pfn_layers:
+            features = pfn(features, idx)
+        object.__setattr__(self, "last_result", idx)
+        for k in self._feature_keys:
+            batch_dict[k] = features
+        batch_dict[self._coords_key] = idx.coords
+        return batch_dict
 
     def _publish(self, batch_dict, res, train_bn):
         if train_bn:
@@ -181,7 +217,8 @@ def forward_pair(first, second, batch_dict, side_stream=None, first_no_grad=Fals
         torch.cuda.set_stream(side)       # plain stream switches: the `with torch.cuda.stream(...)` manager costs ~25 us a time
         tok2 = second.launch(batch_dict)
         torch.cuda.set_stream(main)
-        if tok1[0].needs_grad and tok2[0].needs_grad:   # one autograd node for the pair
+        fused_pair = not isinstance(tok1[0], tuple) and not isinstance(tok2[0], tuple)
+        if fused_pair and tok1[0].needs_grad and tok2[0].needs_grad:   # one autograd node for the pair
             res1, res2 = ops.encode_wait_pair(tok1[0], tok2[0], side)
             batch_dict = first._publish(batch_dict, res1, tok1[1])
             batch_dict = second._publish(batch_dict, res2, tok2[1])
@@ -222,6 +259,39 @@ class DynamicPillarVFESimple2D(_FusedDynamicPillarVFE):
     pass
 
 
+class DynamicVoxelVFE(_FusedDynamicPillarVFE):
+    """``dynamic_voxel_vfe.py:15-106``: 3-D voxel key (z quantised and masked too), voxel centre incl. z, features
+    ``[points | f_cluster | f_center | dist]``, PFN layer stack, coords ``[b, z, y, x]``.  Layer-stack path."""
+    _layout = _lib.LAYOUT_DYNVOXEL
+    _feature_keys = ("pillar_features", "voxel_features")
+    _coords_key = "voxel_coords"
+
+
+class DynamicMeanVFE(VFETemplate):
+    """``dynamic_mean_vfe.py:14-76``: per-voxel mean of every point column; no parameters, no gradient."""
+
+    def __init__(self, model_cfg, num_point_features, voxel_size, grid_size, point_cloud_range, **kwargs):
+        super().__init__(model_cfg=model_cfg)
+        self.num_point_features = num_point_features
+        self.spec = ops.make_spec(num_point_features, voxel_size, grid_size, point_cloud_range, _lib.LAYOUT_DYNVOXEL,
+                                  True, True, False, False, num_point_features)
+        self.voxel_x, self.voxel_y, self.voxel_z = voxel_size[0], voxel_size[1], voxel_size[2]
+        self.x_offset, self.y_offset, self.z_offset = self.spec.off
+        object.__setattr__(self, "last_result", None)
+
+    def get_output_feature_dim(self):
+        return self.num_point_features
+
+    @torch.no_grad()
+    def forward(self, batch_dict, **kwargs):
+        points = batch_dict["points"]
+        idx = stack_ops.index_forward(points, self.spec, int(batch_dict["batch_size"]))
+        object.__setattr__(self, "last_result", idx)
+        batch_dict["voxel_features"] = stack_ops.voxel_mean(idx)
+        batch_dict["voxel_coords"] = idx.coords
+        return batch_dict
+
+
 class Radar_DynamicPillarVFESimple2D(DynamicPillarVFESimple2D):
     _points_key = "radar_points"
     _feature_keys = ("radar_pillar_features",)
@@ -238,6 +308,8 @@ REGISTRY = {
     "VFETemplate": VFETemplate,
     "DynPillarVFE": DynamicPillarVFE,
     "DynamicPillarVFESimple2D": DynamicPillarVFESimple2D,
+    "DynamicVoxelVFE": DynamicVoxelVFE,
+    "DynMeanVFE": DynamicMeanVFE,
     "Radar_DynamicPillarVFESimple2D": Radar_DynamicPillarVFESimple2D,
     "Radar_DynamicPillarVFESimple2D_Test": Radar_DynamicPillarVFESimple2D_Test,
 }
@@ -245,7 +317,7 @@ REGISTRY = {
 
 def register(vfe_all: dict) -> dict:
     """Overwrites the dynamic-pillar entries of ``pcdet.models.backbones_3d.vfe.__all__`` in place."""
-    for name in ("DynPillarVFE", "DynamicPillarVFESimple2D", "Radar_DynamicPillarVFESimple2D",
+    for name in ("DynPillarVFE", "DynamicPillarVFESimple2D", "DynamicVoxelVFE", "DynMeanVFE", "Radar_DynamicPillarVFESimple2D",
                  "Radar_DynamicPillarVFESimple2D_Test"):
         vfe_all[name] = REGISTRY[name]
     return vfe_all

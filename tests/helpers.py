@@ -18,7 +18,8 @@ RTOL_GRADS_REF = 1e-5    # oracle (fp64 reductions) vs the reference's fp32 auto
 
 
 def golden_files():
-    return sorted(glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+    """The single-layer pillar goldens (oracle/gen_golden.py); the layer-stack / voxel / mean ones are `stack__*.npz`."""
+    return sorted(f for f in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")) if not os.path.basename(f).startswith("stack__"))
 
 
 def load_golden(path):

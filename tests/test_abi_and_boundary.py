@@ -79,9 +79,19 @@ def test_modules_keep_reference_contract():
     reg = vfe.register({"MeanVFE": object})
     assert reg["DynPillarVFE"] is vfe.DynamicPillarVFE and reg["Radar_DynamicPillarVFESimple2D_Test"] is vfe.Radar_DynamicPillarVFESimple2D_Test
     assert reg["MeanVFE"] is object
-    with pytest.raises(NotImplementedError):
-        vfe.DynamicPillarVFESimple2D(model_cfg=Cfg(S2D, NUM_FILTERS=[32, 64]), num_point_features=5, voxel_size=synth.VOXEL_SIZE,
-                                     grid_size=grid, point_cloud_range=synth.PC_RANGE)
+    # stacked PFN layers (dynamic_pillar_vfe.py:63-72): non-last layers have out_channels // 2 outputs and feed a concat of 2x that
+    two = vfe.DynamicPillarVFESimple2D(model_cfg=Cfg(S2D, NUM_FILTERS=[32, 64]), num_point_features=5, voxel_size=synth.VOXEL_SIZE,
+                                       grid_size=grid, point_cloud_range=synth.PC_RANGE)
+    assert tuple(two.state_dict()["pfn_layers.0.linear.weight"].shape) == (16, 14)
+    assert tuple(two.state_dict()["pfn_layers.1.linear.weight"].shape) == (64, 32)
+    assert not two.fused and lid.fused and two.get_output_feature_dim() == 64
+    vox = vfe.DynamicVoxelVFE(model_cfg=Cfg(USE_NORM=True, WITH_DISTANCE=False, USE_ABSLOTE_XYZ=True, NUM_FILTERS=[128, 256]),
+                              num_point_features=4, voxel_size=[0.1, 0.1, 0.2], grid_size=[1080, 1080, 40], point_cloud_range=synth.PC_RANGE)
+    assert tuple(vox.state_dict()["pfn_layers.0.linear.weight"].shape) == (64, 10) and vox.spec.nz == 40 and not vox.fused
+    mean = vfe.DynamicMeanVFE(model_cfg=Cfg(), num_point_features=5, voxel_size=[0.1, 0.1, 0.2], grid_size=[1080, 1080, 40],
+                              point_cloud_range=synth.PC_RANGE)
+    assert mean.get_output_feature_dim() == 5 and len(mean.state_dict()) == 0
+    assert reg["DynamicVoxelVFE"] is vfe.DynamicVoxelVFE and reg["DynMeanVFE"] is vfe.DynamicMeanVFE
     flip = vfe.DynamicPillarVFESimple2D(model_cfg=Cfg(S2D, DOUBLE_FLIP=True), num_point_features=5, voxel_size=synth.VOXEL_SIZE,
                                         grid_size=grid, point_cloud_range=synth.PC_RANGE)
     with pytest.raises(NotImplementedError):
