@@ -507,36 +507,33 @@ __device__ __forceinline__ void bn_epilogue(const PfnArgs &a, const double *tota
 }
 
 // Pillar table + feature moments in one pass (train-mode BatchNorm; oracle: orc_moments_folded).  The moments
-// S1 = sum g, S2 = sum g g^T of the reduced basis g = [row inputs (KIN) | pillar constants q (5)] over all kept rows split
+// S1 = sum g, S2 = sum g g^T of the reduced basis g = [row inputs r (KIN) | pillar constants q (5)] over all kept rows split
 // by where their factors live:
-//   row x row     sum_i r_i r_i^T             thread-local fp64 accumulators while the thread walks its pillar's rows
-//   row x pillar  sum_p (sum_{i in p} r_i) q_p^T     } per pillar, from the row sums the mean needs anyway
-//   pillar^2      sum_p n_p q_p q_p^T, S1     } -- staged per warp in shared memory as the vector
-//                                               e_p = [row sums | n_p q_p | q_p | 1]; lane j owns products e[a_j] e[b_j]
-// so the separate moments pass over the rows (and its dependent row -> table gathers) is gone: the statistics cost
-// KIN (KIN + 1) / 2 DFMAs per row inside the table kernel plus ~2 per (pillar, lane).  Products of two fp32 values are
-// exact in fp64; the row sums are exact; the totals agree with the oracle's sequential fp64 sums to ~1e-13, so the folded
-// fp32 scale / shift come out bit-identical in practice (train-mode tolerance: 1e-6).
-// Per-warp reduction, fp64 atomics into the workspace totals; the CTA that finishes last folds them into bn_state.
+//   row x row     sum_i r_i r_i^T                     thread-local fp64 accumulators while the thread walks its pillar's rows
+//   row x pillar  sum_p (sum_{i in p} r_i) q_p^T      } per pillar, from the row sums the mean needs anyway: a rank-32 update
+//   pillar^2      sum_p n_p q_p q_p^T, S1             } per warp batch of 32 pillars,  [rs | n q]^T [q | 1]  (13 x 6), on the fp64
+//                                                       tensor pipe (mma.m8n8k4.f64) from per-warp staging in shared memory
+// so the separate moments pass over the rows (and its dependent row -> table gathers) is gone.  Products of two fp32
+// values are exact in fp64; the row sums are exact; the totals agree with the oracle's sequential fp64 sums to ~1e-13, so
+// the folded fp32 scale / shift come out bit-identical in practice (train-mode tolerance: 1e-6).
+// Per-CTA reduction, fp64 atomics into the workspace totals; the CTA that finishes last folds them into bn_state.
+__device__ __forceinline__ void dmma_m8n8k4(double &c0, double &c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
 template <class Cfg>
 struct StatMap {
     static constexpr int KIN = Cfg::KIN, G = Cfg::G;
-    static constexpr int NV = KIN + 11;                       // e = [row sums (KIN) | n q (5) | q (5) | 1]
-    static constexpr int ONE = KIN + 10;
-    static constexpr int NE = KIN + 5 + 5 * KIN + 15;         // S1 row | S1 pillar | row x pillar | pillar^2 (upper triangle)
-    static constexpr int NRR = KIN * (KIN + 1) / 2;           // row x row (upper triangle), thread-local
-    static constexpr int EPL = (NE + 31) / 32;                // staged products per lane
-    // staged product i = e[a] * e[b], added to totals[dst]   (totals = [S1(G) | S2(G x G, upper triangle)])
-    __device__ static void entry(int i, int *a, int *b, int *dst) {
-        if (i < KIN) { *a = i; *b = ONE; *dst = i; return; }
-        i -= KIN;
-        if (i < 5) { *a = KIN + i; *b = ONE; *dst = KIN + i; return; }
-        i -= 5;
-        if (i < 5 * KIN) { const int k = i / 5, l = i % 5; *a = k; *b = KIN + 5 + l; *dst = G + k * G + KIN + l; return; }
-        i -= 5 * KIN;
-        int l = 0;
-        while (i >= 5 - l) { i -= 5 - l; ++l; }
-        *a = KIN + l; *b = KIN + 5 + l + i; *dst = G + (KIN + l) * G + KIN + l + i;
+    static constexpr int NA = 16;                             // A operand per pillar: [row sums (KIN) | n q (5) | 0...]
+    static constexpr int NB = 8;                              // B operand per pillar: [q (5) | 1 | 0 0]
+    static constexpr int NRR = KIN * (KIN + 1) / 2;           // row x row (upper triangle), thread-local when RR
+    static_assert(KIN + 5 <= NA, "A operand rows");
+    // element (a, b) of the 16 x 8 product -> slot of totals = [S1(G) | S2(G x G, upper triangle)], or -1
+    __device__ static int dst(int a, int b) {
+        if (a >= KIN + 5 || b > 5) return -1;
+        if (b == 5) return a;                                               // S1: row sums | sum n q
+        if (a < KIN) return G + a * G + KIN + b;                            // row x pillar
+        return (a - KIN) <= b ? G + a * G + KIN + b : -1;                   // pillar^2, upper triangle
     }
     __device__ static int rr_dst(int e) {   // e-th element of the row x row upper triangle, row-major
         int k = 0;
@@ -549,35 +546,27 @@ constexpr int kTableStatsThreads = 128;
 
 template <class Cfg>
 __global__ void __launch_bounds__(kTableStatsThreads, 4) pillar_table_stats_kernel(const __grid_constant__ TableArgs t,
-                                                                                const __grid_constant__ PfnArgs a) {
+                                                                                         const __grid_constant__ PfnArgs a) {
     constexpr int KIN = Cfg::KIN, G = Cfg::G, RS = Cfg::RS, COLS = Cfg::COLS, NACC = Cfg::NACC;
     using SM = StatMap<Cfg>;
-    constexpr int NV = SM::NV, NE = SM::NE, NRR = SM::NRR, EPL = SM::EPL, NW = kTableStatsThreads / 32;
-    constexpr int VS = NV | 1;                       // odd stride (in doubles): the lanes' vectors start in different banks
+    constexpr int NA = SM::NA, NB = SM::NB, NRR = SM::NRR, NW = kTableStatsThreads / 32;
+    constexpr int VS = NA + NB + 1;                  // odd stride (in doubles): the lanes' vectors start in different banks
     constexpr int LW = (COLS + 3) / 4 * 4;
     __shared__ double vec[NW][32][VS];
-    __shared__ double red[NW][NE + NRR];
+    __shared__ double red[NW][3 * 64 + NRR];
     __shared__ double sm_ep[G + G * G];
     __shared__ int s_last;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int P = t.counters[RDP_CNT_P];
-    int ia[EPL], ib[EPL];
-#pragma unroll
-    for (int j = 0; j < EPL; ++j) {
-        int d;
-        ia[j] = ib[j] = 0;
-        if (lane + 32 * j < NE) SM::entry(lane + 32 * j, &ia[j], &ib[j], &d);
-    }
-    double accs[EPL], rr[NRR];
-#pragma unroll
-    for (int j = 0; j < EPL; ++j) accs[j] = 0.0;
+    double c00 = 0.0, c01 = 0.0, c10 = 0.0, c11 = 0.0;   // C fragments of the two 8 x 8 tiles (rows 0..7 | 8..15 of the A operand)
+    double rr[NRR];
 #pragma unroll
     for (int e = 0; e < NRR; ++e) rr[e] = 0.0;
 
     // one row into the thread's sums: rsum += r, rr += r r^T (upper triangle)
     auto add_row = [&](const float *src, float cenx, float ceny, float cenz, double *rsum) {
         float r[LW], g[KIN];
-        load_row<LW>(src, r);
+        load_row<LW, RS>(src, r);
         row_inputs<COLS, Cfg::DIST>(r, cenx, ceny, cenz, g);
         double gd[KIN];
 #pragma unroll
@@ -628,6 +617,7 @@ __global__ void __launch_bounds__(kTableStatsThreads, 4) pillar_table_stats_kern
                 if (lane == src) rsum[k] = v;
             }
         }
+        // stage the pillar's operands: A = [row sums | n q | 0], B = [q | 1 | 0 0]   (an invalid lane stages zeros)
         double *ev = vec[warp][lane];
         if (valid) {
             float entry[8];
@@ -643,43 +633,49 @@ __global__ void __launch_bounds__(kTableStatsThreads, 4) pillar_table_stats_kern
             for (int l = 0; l < 5; ++l) {
                 const double q = (double)entry[l];
                 ev[KIN + l] = n * q;          // exact: n < 2^31, q has 24 significant bits
-                ev[KIN + 5 + l] = q;
+                ev[NA + l] = q;
             }
-            ev[SM::ONE] = 1.0;
+#pragma unroll
+            for (int k = KIN + 5; k < NA; ++k) ev[k] = 0.0;
+            ev[NA + 5] = 1.0; ev[NA + 6] = 0.0; ev[NA + 7] = 0.0;
         } else {
 #pragma unroll
-            for (int k = 0; k < NV; ++k) ev[k] = 0.0;
+            for (int k = 0; k < NA + NB; ++k) ev[k] = 0.0;
         }
         __syncwarp();
-#pragma unroll 4
-        for (int q = 0; q < 32; ++q) {
-            const double *w = vec[warp][q];
+        // rank-32 update on the fp64 tensor pipe: k-step j covers pillars 4 j .. 4 j + 3 of the batch.  Fragment layout of
+        // mma.m8n8k4.f64: A[row = lane / 4][k = lane % 4], B[k = lane % 4][col = lane / 4], C[row = lane / 4][col = 2 (lane % 4) + {0, 1}]
 #pragma unroll
-            for (int j = 0; j < EPL; ++j) accs[j] = fma(w[ia[j]], w[ib[j]], accs[j]);
+        for (int j = 0; j < 8; ++j) {
+            const double *w = vec[warp][4 * j + (lane & 3)];
+            const double bq = w[NA + (lane >> 2)];
+            dmma_m8n8k4(c00, c01, w[lane >> 2], bq);
+            dmma_m8n8k4(c10, c11, w[8 + (lane >> 2)], bq);
         }
         __syncwarp();
     }
 
     // ---- per-CTA sums -> fp64 totals (atomics); the CTA that finishes last runs the BatchNorm epilogue
-#pragma unroll
-    for (int j = 0; j < EPL; ++j)
-        if (lane + 32 * j < NE) red[warp][lane + 32 * j] = accs[j];
+    {
+        const int row = lane >> 2, col = 2 * (lane & 3);
+        red[warp][row * 8 + col] = c00; red[warp][row * 8 + col + 1] = c01;
+        red[warp][64 + row * 8 + col] = c10; red[warp][64 + row * 8 + col + 1] = c11;
+    }
 #pragma unroll
     for (int e = 0; e < NRR; ++e) {
         double v = rr[e];
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
-        if (lane == 0) red[warp][NE + e] = v;
+        if (lane == 0) red[warp][128 + e] = v;
     }
     __syncthreads();
-    for (int e = tid; e < NE + NRR; e += kTableStatsThreads) {
+    for (int e = tid; e < 128 + NRR; e += kTableStatsThreads) {
         double sacc = 0.0;
 #pragma unroll
         for (int w = 0; w < NW; ++w) sacc += red[w][e];
         if (sacc == 0.0) continue;
-        int dst;
-        if (e < NE) { int x, y; SM::entry(e, &x, &y, &dst); } else dst = SM::rr_dst(e - NE);
-        atomicAdd(a.acc_stats + dst, sacc);
+        const int dst = e < 128 ? SM::dst(e >> 3, e & 7) : SM::rr_dst(e - 128);
+        if (dst >= 0) atomicAdd(a.acc_stats + dst, sacc);
     }
     __threadfence();
     __syncthreads();

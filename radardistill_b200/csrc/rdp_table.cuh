@@ -59,8 +59,14 @@ __device__ __forceinline__ void row_inputs(const float *r, float cenx, float cen
     if (DIST) out[COLS - 1] = sqrtf(fmaf(z, z, fmaf(y, y, __fmul_rn(x, x))));
 }
 
-template <int RSF>
+template <int RSF, int ROW_STRIDE = 0>   // RSF floats loaded; rows ROW_STRIDE floats apart (0 = unknown: 16-byte loads only)
 __device__ __forceinline__ void load_row(const float *src, float *r) {
+    if (RSF == 8 && ROW_STRIDE == 8) {   // a 32-byte grouped row is one aligned sector: one 256-bit load (sm_100 LDG.256) instead of two 128-bit ones
+        asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7])
+                     : "l"(src));
+        return;
+    }
 #pragma unroll
     for (int c4 = 0; c4 < RSF; c4 += 4) {
         const float4 v = __ldg(reinterpret_cast<const float4 *>(src + c4));

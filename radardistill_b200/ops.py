@@ -485,8 +485,11 @@ class _PillarEncodeFn(torch.autograd.Function):
     """Autograd node: saves (points, argpos, BN state, workspace) -- never the (N, C) activations.  The forward kernels
     were already enqueued (``pending``); this only waits for the (N, P) publication and wires up the backward."""
 
+    # --use_amp (tools/train.py:52, train_utils.py:57-64): the node opts out of autocast by construction -- nothing in its
+    # forward or backward is a torch op that autocast could re-type: the kernels read the fp32 master parameters and points
+    # through raw pointers and write fp32 (a half-precision upstream gradient is widened in encode_backward).  The
+    # torch.amp.custom_fwd / custom_bwd wrappers would add ~30 us of context-manager overhead per step for no effect.
     @staticmethod
-    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)   # --use_amp (train_utils.py:57-64): the encoder stays fp32
     def forward(ctx, weight, bias, gamma, beta, running_mean, running_var, pending, holder):
         res = encode_finish(pending)
         holder.items.append(res)
@@ -500,7 +503,6 @@ class _PillarEncodeFn(torch.autograd.Function):
         return res.features, res.coords
 
     @staticmethod
-    @torch.amp.custom_bwd(device_type="cuda")
     def backward(ctx, grad_features, _grad_coords):
         weight, bias, gamma, beta = ctx.saved_tensors
         res = ctx.res
@@ -518,7 +520,6 @@ class _PairEncodeFn(torch.autograd.Function):
     streams.  Same gradients as two ``_PillarEncodeFn`` nodes."""
 
     @staticmethod
-    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
     def forward(ctx, wa, ba, ga, bea, wb, bb, gb, beb, pma, pmb, side, holder):
         ra, rb = encode_finish(pma.pending), encode_finish(pmb.pending)
         holder.items.extend((ra, rb))
@@ -530,7 +531,6 @@ class _PairEncodeFn(torch.autograd.Function):
         return ra.features, ra.coords, rb.features, rb.coords
 
     @staticmethod
-    @torch.amp.custom_bwd(device_type="cuda")
     def backward(ctx, gfa, _gca, gfb, _gcb):
         wa, ba, ga, bea, wb, bb, gb, beb = ctx.saved_tensors
 

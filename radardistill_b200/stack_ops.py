@@ -79,9 +79,8 @@ class _SegmentMaxFn(torch.autograd.Function):
     """``torch_scatter.scatter_max(x, unq_inv, dim=0)`` (PFNLayerV2.forward :40) over the pillars of an IndexResult."""
 
     @staticmethod
-    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
     def forward(ctx, x, idx):
-        x = x.contiguous()
+        x = x.contiguous().float()   # autocast (--use_amp) hands over half-precision activations: the pooling runs and returns fp32
         n, c = x.shape
         if n != idx.n_kept:
             raise ValueError(f"activations have {n} rows, the index pass kept {idx.n_kept} points")
@@ -99,7 +98,6 @@ class _SegmentMaxFn(torch.autograd.Function):
         return out, arg
 
     @staticmethod
-    @torch.amp.custom_bwd(device_type="cuda")
     def backward(ctx, g_out, _g_arg):
         (arg,) = ctx.saved_tensors
         p, c = arg.shape
