@@ -84,5 +84,41 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+EXT_NAME = "rdp_torch_ext"
+EXT_DIR = os.path.join(HERE, "_build_ext")
+
+
+def ext_path():
+    """Path of the built host extension (rdp_torch_ext.so next to librdp.so), or None."""
+    p = os.path.join(HERE, EXT_NAME + ".so")
+    return p if os.path.exists(p) else None
+
+
+def build_ext(force: bool = False, verbose: bool = False):
+    """Builds the native host path (csrc/rdp_torch.cpp: torch C++ extension, g++ only -- the kernels stay in librdp.so) in-tree.
+    The .so is copied next to librdp.so so that it travels to the GPU box and is imported there without a rebuild."""
+    import shutil
+    src = os.path.join(CSRC, "rdp_torch.cpp")
+    h = hashlib.sha256()
+    for fn in (src, os.path.join(INCLUDE, "rdp.h")):
+        with open(fn, "rb") as f:
+            h.update(f.read())
+    import torch
+    h.update(torch.__version__.encode())
+    digest, stamp, out = h.hexdigest(), os.path.join(EXT_DIR, "digest.txt"), os.path.join(HERE, EXT_NAME + ".so")
+    if not force and os.path.exists(out) and os.path.exists(stamp) and open(stamp).read() == digest:
+        return out
+    os.makedirs(EXT_DIR, exist_ok=True)
+    from torch.utils import cpp_extension
+    cpp_extension.load(name=EXT_NAME, sources=[src], extra_include_paths=[INCLUDE, "/usr/local/cuda/include"],
+                       extra_cflags=["-O2", "-std=c++17"], extra_ldflags=[f"-L{HERE}", "-lrdp", "-Wl,-rpath,'$$ORIGIN'", f"-Wl,-rpath,{HERE}", "-L/usr/local/cuda/lib64", "-lcudart", "-lc10_cuda", "-ltorch_cuda"],
+                       build_directory=EXT_DIR, with_cuda=False, is_python_module=False, verbose=verbose)
+    shutil.copyfile(os.path.join(EXT_DIR, EXT_NAME + ".so"), out)
+    with open(stamp, "w") as f:
+        f.write(digest)
+    return out
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_ext(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -18,7 +18,7 @@ from __future__ import annotations
 import torch
 import torch.nn as nn
 
-from . import _lib, ops, stack_ops
+from . import _ext, _lib, ops, stack_ops
 
 
 class VFETemplate(nn.Module):
@@ -166,6 +166,41 @@ class _FusedDynamicPillarVFE(VFETemplate):
                               sync_group=sync_group)
         return pm, train_bn
 
+    def _native_args(self, batch_dict, grad_enabled):
+        """Descriptor of this encoder's call for the native host path (csrc/rdp_torch.cpp), or None when this call has to go
+        through the Python glue (layer-stack path, SyncBatchNorm, DOUBLE_FLIP error path)."""
+        if not self.fused or self.double_flip:
+            return None
+        pfn = self.pfn_layers[0]
+        norm = pfn.norm if self.use_norm else None
+        train_bn = bool(self.use_norm and norm.training)
+        if train_bn and isinstance(norm, nn.SyncBatchNorm) and _world_size() > 1:
+            return None
+        points = batch_dict[self._points_key]
+        if points.requires_grad:
+            return None
+        offsets = batch_dict.get(self._points_key + "_offsets", None)
+        bs = (int(offsets.shape[0]) - 1) if offsets is not None else self._batch_size(batch_dict, points)
+        spec = self.spec
+        pl = ops._plan(spec, bs, int(points.shape[0]), train_bn)
+        w = pfn.linear.weight
+        want_grad = grad_enabled and (w.requires_grad or (norm is not None and (norm.weight.requires_grad or norm.bias.requires_grad)) or
+                                      (norm is None and pfn.linear.bias.requires_grad))
+        geom = spec.lo + spec.vsz + spec.off + (spec.nx, spec.ny, bs, spec.cols, spec.nz)
+        lay = (spec.layout, int(spec.use_abs), int(spec.use_cluster), int(spec.use_relative), int(spec.with_distance), spec.c_in, spec.c_out,
+               spec.coord_cols)
+        plan = (pl.ws_bytes, pl.off_counters, pl.off_bn, pl.off_inverse, pl.off_counts, pl.total_bytes, pl.cap)
+        if norm is not None:
+            prm = (w, None, norm.weight, norm.bias, norm.running_mean, norm.running_var, norm.num_batches_tracked)
+        else:
+            prm = (w, pfn.linear.bias, None, None, None, None, None)
+        return (geom, lay, plan, spec.eps, spec.momentum, points, offsets) + prm + (train_bn, bool(want_grad)), pl, bs, train_bn
+
+    def _publish_native(self, batch_dict, out, pl, bs, train_bn, n_points):
+        feats, coords, argpos, buf, n_kept, n_pillars = out
+        res = ops.EncodeResult(feats, coords, argpos, n_kept, n_pillars, self.spec, bs, n_points, buf, pl, train_bn, None)
+        return self._publish(batch_dict, res, train_bn)
+
     def finish(self, batch_dict, token):
         pm, train_bn = token
         if isinstance(pm, tuple) and pm[0] == "stack":
@@ -205,10 +240,19 @@ class _FusedDynamicPillarVFE(VFETemplate):
 def forward_pair(first, second, batch_dict, side_stream=None, first_no_grad=False):
     """Runs two independent encoders (e.g. ``vfe`` and ``radar_vfe``, pillarnet.py:28-33) concurrently: ``second`` is
     enqueued on a side stream while ``first`` runs on the current one.  Results are identical to calling them in turn."""
+    grad_on = torch.is_grad_enabled()
+    ext = _ext.load() if side_stream is None else None
+    if ext is not None and isinstance(first, _FusedDynamicPillarVFE) and isinstance(second, _FusedDynamicPillarVFE):
+        # native host path: one call enqueues both encoders on two streams, waits for both (N, P) and wires one autograd node
+        na = first._native_args(batch_dict, grad_on and not first_no_grad)
+        nb = second._native_args(batch_dict, grad_on) if na is not None else None
+        if na is not None and nb is not None:
+            out = ext.pair_forward(na[0], nb[0])
+            batch_dict = first._publish_native(batch_dict, out[:6], na[1], na[2], na[3], int(na[0][5].shape[0]))
+            return second._publish_native(batch_dict, out[6:], nb[1], nb[2], nb[3], int(nb[0][5].shape[0]))
     main = torch.cuda.current_stream()
     side = side_stream if side_stream is not None else _side_stream(main.device)
     side.wait_stream(main)   # inputs of `second` were produced on the current stream
-    grad_on = torch.is_grad_enabled()
     try:
         if first_no_grad and grad_on:   # frozen teacher (FREEZE_PIPELINE)
             torch.set_grad_enabled(False)
