@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define RDP_ABI_VERSION 6
+#define RDP_ABI_VERSION 7
 
 #if defined(__GNUC__)
 #define RDP_API __attribute__((visibility("default")))
@@ -288,6 +288,21 @@ RDP_API int rdp_voxel_mean(int64_t n_points, const rdp_geom_t *geom, void *works
 RDP_API size_t rdp_prepare_scratch_bytes(int64_t n_points);
 RDP_API int rdp_prepare_points(const float *points, int64_t n_points, int32_t cols, int32_t x_col, const float *range_xy_lo_hi,
                                uint64_t shuffle_seed, void *scratch, size_t scratch_bytes, float *out, int32_t *n_out, void *stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * The step's one collective (DistributedDataParallel's gradient averaging of the PFN parameters, tools/train.py:175-176)
+ * as a one-shot all-reduce over NVLink peer memory: ONE kernel on the caller's stream packs this rank's gradient tensors
+ * into its peer-mapped staging buffer, signals every peer, waits for every peer and sums all ranks' slots in rank order
+ * (bit-identical results on all ranks), out = scale * sum.  The caller provides the mapping:
+ *   peer_staging  device array of `world` pointers: every rank's staging buffer of rdp_allreduce_staging_bytes(n, world) bytes
+ *                 as mapped into THIS process (CUDA IPC / torch symmetric memory), zero-filled before the first call
+ *   step          1, 2, 3, ... -- the same on every rank for the same collective (each call uses the next number)
+ * segments / counts: host arrays of n_segments (<= RDP_ALLREDUCE_MAX_SEGMENTS) device pointers and float counts.
+ */
+#define RDP_ALLREDUCE_MAX_SEGMENTS 16
+RDP_API size_t rdp_allreduce_staging_bytes(int64_t n_floats, int32_t world);
+RDP_API int rdp_allreduce_small(const float *const *segments, const int32_t *counts, int32_t n_segments, float *const *peer_staging,
+                                int32_t rank, int32_t world, uint32_t step, float scale, float *out, void *stream);
 
 #ifdef __cplusplus
 }

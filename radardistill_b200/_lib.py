@@ -8,7 +8,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("RDP_LIB_PATH", os.path.join(_HERE, "librdp.so"))  # override: kernel-variant experiments
 
-RDP_ABI_VERSION = 6
+RDP_ABI_VERSION = 7
 RDP_NUM_COUNTERS = 16
 CNT_N, CNT_P, CNT_ERRFLAGS = 0, 1, 2
 LAYOUT_SIMPLE2D, LAYOUT_DYNPILLAR, LAYOUT_DYNVOXEL = 0, 1, 2
@@ -16,7 +16,7 @@ LAYOUT_SIMPLE2D, LAYOUT_DYNPILLAR, LAYOUT_DYNVOXEL = 0, 1, 2
 EXPORTS = ["rdp_abi_version", "rdp_status_string", "rdp_last_cuda_error", "rdp_workspace_bytes", "rdp_index_fwd", "rdp_index_fwd_publish", "rdp_index_fwd_frames", "rdp_encode_fwd_frames",
            "rdp_pfn_fwd", "rdp_encode_fwd", "rdp_bn_state_doubles", "rdp_pfn_bwd", "rdp_argmax_kept", "rdp_pillar_lookup", "rdp_publish_counters",
            "rdp_encode_host", "rdp_config_supported", "rdp_stats_buffers", "rdp_decorate", "rdp_segment_max_fwd", "rdp_segment_max_bwd",
-           "rdp_voxel_mean", "rdp_prepare_scratch_bytes", "rdp_prepare_points"]
+           "rdp_voxel_mean", "rdp_prepare_scratch_bytes", "rdp_prepare_points", "rdp_allreduce_staging_bytes", "rdp_allreduce_small"]
 
 
 class Geom(C.Structure):
@@ -107,6 +107,10 @@ def load() -> C.CDLL:
     lib.rdp_prepare_scratch_bytes.argtypes = [C.c_int64]
     lib.rdp_prepare_points.restype = C.c_int
     lib.rdp_prepare_points.argtypes = [vp, C.c_int64, C.c_int32, C.c_int32, C.POINTER(C.c_float), C.c_uint64, vp, C.c_size_t, vp, vp, vp]
+    lib.rdp_allreduce_staging_bytes.restype = C.c_size_t
+    lib.rdp_allreduce_staging_bytes.argtypes = [C.c_int64, C.c_int32]
+    lib.rdp_allreduce_small.restype = C.c_int
+    lib.rdp_allreduce_small.argtypes = [vp, vp, C.c_int32, vp, C.c_int32, C.c_int32, C.c_uint32, C.c_float, vp, vp]
     _lib = lib
     return lib
 

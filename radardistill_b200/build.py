@@ -35,7 +35,8 @@ def _config_ids():
 
 def _units():
     units = [("rdp_abi", "rdp_abi.cu", []), ("rdp_index", "rdp_index.cu", []), ("rdp_pfn", "rdp_pfn.cu", []),
-             ("rdp_stack", "rdp_stack.cu", [])]
+             ("rdp_stack", "rdp_stack.cu", []),
+             ("rdp_allreduce", "rdp_allreduce.cu", [])]
     units += [(f"rdp_pfn_inst_{i}", "rdp_pfn_inst.cu", [f"-DRDP_CFG_ID={i}"]) for i in _config_ids()]
     return units
 

@@ -54,15 +54,21 @@ def aggregate_throughput(rows_per_rank, seconds_per_rank):
 
 
 class GradientAllReduce:
-    """Averages the gradients of ``params`` over the ranks of ``group`` with one all-reduce of a flat buffer.
+    """Averages the gradients of ``params`` over the ranks of ``group`` with one collective per step.
 
         reducer = GradientAllReduce(params)          # once
         loss.backward(); reducer.reduce()            # every step; p.grad then holds the average (views of the flat buffer)
 
-    ``reduce`` is asynchronous with respect to the host: the collective runs on the backend's stream and the current
-    stream waits for it (like DDP's finalize step), so the next kernels that read the gradients are ordered after it."""
+    Two data paths, same result layout:
+      * ``p2p`` (default on CUDA when torch's symmetric memory can map the ranks' buffers): ``rdp_allreduce_small`` -- ONE kernel
+        on the current stream packs the gradients into a peer-mapped staging buffer, signals the peers over NVLink, waits for
+        them and sums all ranks' buffers in rank order (~8 us on 8 B200s; bit-identical on every rank);
+      * ``nccl``: ``_foreach_copy_`` + ``all_reduce(AVG)`` of the flat buffer (~33 us + a pack kernel; NCCL runs on its own
+        stream).  Used when the mapping is unavailable, on CPU (gloo), or with ``RDP_ALLREDUCE=nccl``.
+    ``reduce`` never blocks the host: the next kernels on the current stream are ordered after the collective."""
 
-    def __init__(self, params, group=None):
+    def __init__(self, params, group=None, backend: str = "auto"):
+        import os
         import torch.distributed as dist
         self.dist, self.group = dist, group
         self.params = [p for p in params if p.requires_grad]
@@ -74,9 +80,26 @@ class GradientAllReduce:
         for p in self.params:
             self.views.append(self.flat[off:off + p.numel()].view_as(p))
             off += p.numel()
+        self.p2p = None
+        backend = os.environ.get("RDP_ALLREDUCE", backend)
+        if backend in ("auto", "p2p") and self.world > 1 and ref is not None and ref.is_cuda and ref.dtype == torch.float32 \
+                and len(self.params) <= 16:
+            try:
+                self.p2p = _PeerAllReduce(n, ref.device, group if group is not None else dist.group.WORLD, dist)
+            except Exception as e:   # no peer mapping on this box: NCCL does the same job
+                if backend == "p2p":
+                    raise
+                self.p2p = None
+                self.p2p_error = f"{type(e).__name__}: {e}"
 
     def reduce(self):
         if self.flat is None:
+            return None
+        if self.p2p is not None:
+            grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in self.params]
+            self.p2p(grads, self.flat)
+            for p, v in zip(self.params, self.views):
+                p.grad = v
             return None
         grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in self.params]
         torch._foreach_copy_(self.views, grads)          # pack (one fused kernel)
@@ -91,3 +114,38 @@ class GradientAllReduce:
         for p, v in zip(self.params, self.views):
             p.grad = v
         return work
+
+
+class _PeerAllReduce:
+    """Host side of ``rdp_allreduce_small``: a symmetric (peer-mapped) staging buffer per rank, the device table of the peers'
+    mappings and the step counter.  torch's symmetric memory does the CUDA IPC exchange; the data path is librdp's kernel."""
+
+    def __init__(self, n: int, device, group, dist):
+        import ctypes as C
+        import torch.distributed._symmetric_memory as symm
+        from . import _lib
+        self.C, self.lib, self._lib = C, _lib.load(), _lib
+        self.rank, self.world, self.n, self.device = dist.get_rank(group), dist.get_world_size(group), n, device
+        nbytes = int(self.lib.rdp_allreduce_staging_bytes(n, self.world))
+        self.staging = symm.empty(nbytes // 4, dtype=torch.float32, device=device)
+        self.staging.zero_()
+        self.handle = symm.rendezvous(self.staging, group)
+        self.peers = torch.tensor([int(p) for p in self.handle.buffer_ptrs], dtype=torch.int64, device=device)
+        torch.cuda.synchronize(device)
+        dist.barrier(group)          # every rank's signal words are zero before anybody's first step
+        self.step = 0
+        self.scale = 1.0 / self.world
+
+    def __call__(self, grads, out):
+        C = self.C
+        k = len(grads)
+        for g in grads:
+            if not g.is_contiguous() or g.dtype != torch.float32 or g.device != self.device:
+                raise ValueError("gradients must be contiguous float32 tensors on the reducer's device")
+        seg = (C.c_void_p * k)(*[g.data_ptr() for g in grads])
+        cnt = (C.c_int32 * k)(*[g.numel() for g in grads])
+        self.step += 1
+        with torch.cuda.device(self.device):
+            self._lib.check(self.lib.rdp_allreduce_small(seg, cnt, k, self.peers.data_ptr(), self.rank, self.world, self.step & 0xFFFFFFFF or 1,
+                                                          self.scale, out.data_ptr(), torch.cuda.current_stream(self.device).cuda_stream),
+                            "rdp_allreduce_small")
