@@ -399,18 +399,7 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     def timed_steps(m, k):
-        evs = []
-        # the step is within ~10 % of host bound and every step ends in a rendezvous of all ranks: a cyclic-GC pause on any
-        # one rank stalls all of them, so the collector is parked over the timed steps (as long-running training loops do:
-        # collect at a step boundary of your choosing, not in the middle of a launch sequence)
-        gc.collect()
-        gc.freeze()
-        gc.disable()
-        try:
-            return _timed_steps(m, k, evs)
-        finally:
-            gc.enable()
-            gc.unfreeze()
+        return _timed_steps(m, k, [])
 
     def _timed_steps(m, k, evs):
         for _ in range(k):
@@ -426,6 +415,14 @@ def run_ours(args):
     clk = ClockSampler(local)
     if rank == 0:     # one sampler per job: the step is host-bound, eight pollers would perturb what they measure
         clk.__enter__()   # started before the warm-up so that nvidia-smi is already streaming when the timed steps run
+    # Every step ends in a rendezvous of all ranks (the gradient all-reduce), so a cyclic-GC pause on any one rank stalls all of
+    # them: the collector is parked over the measurement (as long-running training loops do: collect at a step boundary of
+    # your choosing, not in the middle of a launch sequence).  It is parked BEFORE the warm-up and the barrier, so that the
+    # ranks enter the timed region aligned -- a collection of different length per rank right before the first timed step
+    # would be charged to that step on every rank.
+    gc.collect()
+    gc.freeze()
+    gc.disable()
     for _ in range(max(args.warmup, 3)):
         gpu_step(call, lidar_dev, radar_dev, mode, frames, upstream)
     barrier()
@@ -690,6 +687,8 @@ def run_ours(args):
             line["configs"] = others
         line.update(extra)
         print(json.dumps(line), flush=True)
+    gc.enable()
+    gc.unfreeze()
     if ddp:
         dist.barrier()
         dist.destroy_process_group()
