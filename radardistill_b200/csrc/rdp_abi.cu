@@ -1,5 +1,6 @@
 // rdp_abi.cu -- status strings, workspace carving and the host-buffer convenience entry point.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "rdp_common.cuh"
@@ -10,6 +11,11 @@ static thread_local char g_last_cuda_error[256] = "";
 
 void set_last_cuda_error(cudaError_t e, const char *where) {
     snprintf(g_last_cuda_error, sizeof(g_last_cuda_error), "%s: %s (%s)", cudaGetErrorName(e), cudaGetErrorString(e), where);
+}
+
+bool pdl_enabled() {
+    static const bool on = [] { const char *v = getenv("RDP_NO_PDL"); return !(v && v[0] == '1'); }();
+    return on;
 }
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }

@@ -131,6 +131,12 @@ __device__ __forceinline__ void mean3(double sx, double sy, double sz, int cnt, 
     *mz = (float)__fma_rn(__fma_rn(-qz, b, sz), y, qz);
 }
 
+// --- programmatic dependent launch (PDL): a kernel launched with launch_pdl() may be scheduled while its predecessor in the
+//     stream drains, so the launch latency and the ramp-up of its CTAs hide behind the predecessor's tail.  pdl_wait() -- the
+//     FIRST statement of every such kernel -- blocks until the predecessor grid has completed and its writes are visible, so
+//     ordering is exactly that of a plain stream (a no-op when the kernel was launched without the attribute).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // --- block-wide exclusive scan of one int per thread (blockDim.x == 256), returns exclusive prefix,
 //     *total receives the block sum.  `sm` needs 9 ints.
 __device__ __forceinline__ int block_excl_scan_256(int v, int *sm, int *total) {
@@ -201,5 +207,20 @@ __device__ __forceinline__ uint32_t chunk_exclusive_prefix(uint64_t *state, int 
 }
 
 #endif  // __CUDACC__
+
+// Launch with the programmatic-stream-serialization attribute (see pdl_wait).  RDP_NO_PDL=1 falls back to plain launches.
+bool pdl_enabled();
+#ifdef __CUDACC__
+template <class... KArgs, class... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args &&...args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
 
 }  // namespace rdp

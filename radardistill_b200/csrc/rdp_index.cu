@@ -131,6 +131,7 @@ __global__ void __launch_bounds__(kScanThreads)
 bitmap_rank_kernel(const uint32_t *__restrict__ bitmap, long long words,
                    uint64_t *__restrict__ state, uint2 *__restrict__ wordrank, int32_t *__restrict__ counters,
                    volatile int32_t *host_mapped) {
+    pdl_wait();
     __shared__ int s_scan[9];
     __shared__ uint32_t s_u32;
     __shared__ int s_ticket;
@@ -186,6 +187,7 @@ rank_count_kernel(const int32_t *__restrict__ keys, int32_t *__restrict__ ranks,
                   const int32_t *__restrict__ tile_keep, int32_t *__restrict__ inverse, int32_t *__restrict__ counts,
                   const int32_t *__restrict__ counters, int32_t *__restrict__ orig2kept, int32_t *__restrict__ kept2orig,
                   int32_t *__restrict__ slots) {
+    pdl_wait();
     __shared__ int s_scan[9];
     __shared__ long long s_base;
     const int tid = threadIdx.x;
@@ -259,6 +261,7 @@ rank_count_kernel(const int32_t *__restrict__ keys, int32_t *__restrict__ ranks,
 __global__ void __launch_bounds__(kScanThreads)
 count_scan_kernel(const int32_t *__restrict__ counts, uint64_t *__restrict__ state, int32_t *__restrict__ starts,
                   int32_t *__restrict__ tile_first, int32_t *__restrict__ counters) {
+    pdl_wait();
     __shared__ int s_scan[9];
     __shared__ uint32_t s_u32;
     __shared__ int s_ticket;
@@ -310,6 +313,7 @@ template <bool FRAMES>   // FRAMES: rows without the batch column + frame offset
 __global__ void __launch_bounds__(kIndexThreads)
 group_rows_kernel(const float *__restrict__ pts, const int32_t *__restrict__ keys, const int32_t *__restrict__ ranks,
                   const int32_t *__restrict__ slots, long long n0, int cols, const int32_t *__restrict__ starts, float *__restrict__ grows) {
+    pdl_wait();
     extern __shared__ __align__(128) float tile[];
     __shared__ __align__(8) uint64_t bar;
     const int tid = threadIdx.x;
@@ -383,6 +387,7 @@ __global__ void publish_counters_kernel(const int32_t *__restrict__ counters, vo
 
 // ----------------------------------------------------------------------------- K6 (rdp_table.cuh), generic form
 __global__ void __launch_bounds__(256) pillar_table_kernel(const __grid_constant__ TableArgs t) {
+    pdl_wait();
     pillar_table_body(t);
 }
 
@@ -468,23 +473,23 @@ int index_fwd_impl(const float *points, const int32_t *frame_offsets, int64_t n_
     const int tiles = (int)ws.index_tiles;
     quantize_mark_kernel<<<tiles, kIndexThreads, smem, stream>>>(points, n_points, g, ws.bitmap, ws.keys, ws.tile_keep, counters,
                                                                  frame_offsets, counts);
-    bitmap_rank_kernel<<<kScanGrid, kScanThreads, 0, stream>>>(ws.bitmap, ws.words, ws.scan_state_a, ws.wordrank, counters,
-                                                              host_mapped);
+    RDP_CUDA_OK(launch_pdl(bitmap_rank_kernel, kScanGrid, kScanThreads, 0, stream, ws.bitmap, ws.words, ws.scan_state_a, ws.wordrank, counters,
+                           host_mapped));
     if (event) RDP_CUDA_OK(cudaEventRecord(event, stream));
-    rank_count_kernel<<<tiles, kIndexThreads, 0, stream>>>(ws.keys, ws.ranks, n_points, ws.wordrank, ws.tile_keep, inverse, counts, counters,
-                                                         ws.orig2kept, ws.kept2orig, ws.slots);
-    count_scan_kernel<<<kScanGrid, kScanThreads, 0, stream>>>(counts, ws.scan_state_b, ws.starts, ws.tile_first, counters);
+    RDP_CUDA_OK(launch_pdl(rank_count_kernel, tiles, kIndexThreads, 0, stream, ws.keys, ws.ranks, n_points, ws.wordrank, ws.tile_keep, inverse,
+                           counts, counters, ws.orig2kept, ws.kept2orig, ws.slots));
+    RDP_CUDA_OK(launch_pdl(count_scan_kernel, kScanGrid, kScanThreads, 0, stream, counts, ws.scan_state_b, ws.starts, ws.tile_first, counters));
     if (frame_offsets)
-        group_rows_kernel<true><<<tiles, kIndexThreads, smem, stream>>>(points, ws.keys, ws.ranks, ws.slots, n_points, geom->cols,
-                                                                        ws.starts, ws.grows);
+        RDP_CUDA_OK(launch_pdl(group_rows_kernel<true>, tiles, kIndexThreads, smem, stream, points, ws.keys, ws.ranks, ws.slots, n_points,
+                               geom->cols, ws.starts, ws.grows));
     else
-        group_rows_kernel<false><<<tiles, kIndexThreads, smem, stream>>>(points, ws.keys, ws.ranks, ws.slots, n_points, geom->cols,
-                                                                         ws.starts, ws.grows);
+        RDP_CUDA_OK(launch_pdl(group_rows_kernel<false>, tiles, kIndexThreads, smem, stream, points, ws.keys, ws.ranks, ws.slots, n_points,
+                               geom->cols, ws.starts, ws.grows));
     if (!skip_table) {   // the fused forward builds the table (and the coords) inside its tile kernels instead
         TableArgs t;
         t.grows = ws.grows; t.starts = ws.starts; t.counters = counters; t.aux = ws.aux; t.coords = coords;
         t.rs = grouped_row_floats(geom->cols); t.coord_cols = coord_cols; t.g = g;
-        pillar_table_kernel<<<table_grid(ws.pcap), 256, 0, stream>>>(t);
+        RDP_CUDA_OK(launch_pdl(pillar_table_kernel, table_grid(ws.pcap), 256, 0, stream, t));
     }
     RDP_CUDA_OK(cudaGetLastError());
     return RDP_OK;

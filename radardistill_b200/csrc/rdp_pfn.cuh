@@ -192,6 +192,7 @@ __device__ __forceinline__ void tile_c1(const PfnStage<Cfg> &T, const TileBounds
 
 template <class Cfg, bool ARG>
 __global__ void __launch_bounds__(kPfnThreads, Cfg::CPL == 1 ? (ARG ? 6 : 7) : (Cfg::CPL == 2 ? 4 : 2)) pfn_apply_kernel(const __grid_constant__ PfnArgs a) {
+    pdl_wait();
     extern __shared__ __align__(32) unsigned char smem_raw[];
     using Smem = TileSmem<Cfg, 0>;
     Smem &S = *reinterpret_cast<Smem *>(smem_raw);
@@ -547,6 +548,7 @@ constexpr int kTableStatsThreads = 128;
 template <class Cfg>
 __global__ void __launch_bounds__(kTableStatsThreads, 4) pillar_table_stats_kernel(const __grid_constant__ TableArgs t,
                                                                                          const __grid_constant__ PfnArgs a) {
+    pdl_wait();
     constexpr int KIN = Cfg::KIN, G = Cfg::G, RS = Cfg::RS, COLS = Cfg::COLS, NACC = Cfg::NACC;
     using SM = StatMap<Cfg>;
     constexpr int NA = SM::NA, NB = SM::NB, NRR = SM::NRR, NW = kTableStatsThreads / 32;
@@ -791,6 +793,7 @@ __global__ void __launch_bounds__(256) bwd_finalize_kernel(const __grid_constant
 
 template <class Cfg>
 __global__ void __launch_bounds__(kPfnThreads, Cfg::CPL == 1 ? 5 : (Cfg::CPL == 2 ? 3 : 2)) pfn_bwd_kernel(const __grid_constant__ PfnArgs a) {
+    pdl_wait();
     extern __shared__ __align__(32) unsigned char smem_raw[];
     constexpr int PCH = 24;   // pillars per prefetch chunk of (grad, argpos) rows (two chunks in flight)
     using Smem = TileSmem<Cfg, PCH>;

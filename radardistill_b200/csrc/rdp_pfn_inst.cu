@@ -35,8 +35,7 @@ static cudaError_t launch_apply(const PfnArgs &a, int grid, cudaStream_t st) {
     static bool configured[64] = {false};
     cudaError_t e = ensure_smem(pfn_apply_kernel<Cfg, ARG>, smem, configured);
     if (e != cudaSuccess) return e;
-    pfn_apply_kernel<Cfg, ARG><<<grid, kPfnThreads, smem, st>>>(a);
-    return cudaGetLastError();
+    return launch_pdl(pfn_apply_kernel<Cfg, ARG>, grid, kPfnThreads, smem, st, a);
 }
 
 static cudaError_t apply(const PfnArgs &a, int want_arg, int grid, cudaStream_t st) {
@@ -48,14 +47,12 @@ static cudaError_t bwd(const PfnArgs &a, int grid, cudaStream_t st) {
     static bool configured[64] = {false};
     cudaError_t e = ensure_smem(pfn_bwd_kernel<Cfg>, smem, configured);
     if (e != cudaSuccess) return e;
-    pfn_bwd_kernel<Cfg><<<grid, kPfnThreads, smem, st>>>(a);
-    return cudaGetLastError();
+    return launch_pdl(pfn_bwd_kernel<Cfg>, grid, kPfnThreads, smem, st, a);
 }
 
 static cudaError_t table_stats(const TableArgs &t, const PfnArgs &a, int64_t pcap, cudaStream_t st) {
     const int64_t blocks = (pcap + kTableStatsThreads - 1) / kTableStatsThreads, cap = 148 * 8;
-    pillar_table_stats_kernel<Cfg><<<(int)(blocks < 1 ? 1 : (blocks < cap ? blocks : cap)), kTableStatsThreads, 0, st>>>(t, a);
-    return cudaGetLastError();
+    return launch_pdl(pillar_table_stats_kernel<Cfg>, (int)(blocks < 1 ? 1 : (blocks < cap ? blocks : cap)), kTableStatsThreads, 0, st, t, a);
 }
 
 static cudaError_t bn_finalize(const PfnArgs &a, cudaStream_t st) {
