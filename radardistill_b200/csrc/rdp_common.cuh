@@ -26,6 +26,7 @@ void set_last_cuda_error(cudaError_t e, const char *where);
 #endif
 constexpr int kIndexThreads = RDP_INDEX_THREADS;
 constexpr int kIndexTileRows = 4 * RDP_INDEX_THREADS;  // points per CTA in the quantise / rank / fill kernels
+constexpr int kRankSub = 2;            // index tiles per CTA of rank_count_kernel (8 rows per thread)
 constexpr int kScanThreads = 256;
 constexpr int kScanGrid = 296;        // 2 CTAs per SM: every CTA of a chunked scan is co-resident
 constexpr int kPfnThreads = 128;

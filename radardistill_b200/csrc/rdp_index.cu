@@ -191,69 +191,89 @@ rank_count_kernel(const int32_t *__restrict__ keys, int32_t *__restrict__ ranks,
     __shared__ int s_scan[9];
     __shared__ long long s_base;
     const int tid = threadIdx.x;
-    const long long row0 = (long long)blockIdx.x * kIndexTileRows;
-    const long long i0 = row0 + tid * 4;
-
-    int k[4] = {-1, -1, -1, -1};
-    if (i0 + 3 < n0) {
-        const int4 v = *reinterpret_cast<const int4 *>(keys + i0);
-        k[0] = v.x; k[1] = v.y; k[2] = v.z; k[3] = v.w;
-    } else {
+    // A CTA covers kRankSub index tiles (8 rows per thread): the kernel is bound by two dependent L2 round trips per row (the
+    // {word, rank} gather, then the slot atomic), so the rows in flight per SM set its speed.  All gathers are issued first,
+    // then all atomics; the stores follow.  Nothing below synchronises the CTA unless the range mask dropped a row.
+    const long long cta0 = (long long)blockIdx.x * kRankSub * kIndexTileRows;
+    int k[kRankSub][4], r[kRankSub][4], sl[kRankSub][4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) if (i0 + q < n0) k[q] = keys[i0 + q];
-    }
-    int r[4];
-    int c = 0;
+    for (int s = 0; s < kRankSub; ++s) {
+        const long long i0 = cta0 + (long long)s * kIndexTileRows + tid * 4;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        r[q] = -1;
-        if (k[q] >= 0) {
-            const uint2 wr = __ldg(wordrank + (k[q] >> 5));
-            r[q] = (int)(wr.y + __popc(wr.x & ((1u << (k[q] & 31)) - 1u)));
-            ++c;
+        for (int q = 0; q < 4; ++q) k[s][q] = -1;
+        if (i0 + 3 < n0) {
+            const int4 v = *reinterpret_cast<const int4 *>(keys + i0);
+            k[s][0] = v.x; k[s][1] = v.y; k[s][2] = v.z; k[s][3] = v.w;
+        } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) if (i0 + q < n0) k[s][q] = keys[i0 + q];
         }
     }
-    // position among the KEPT points (stable compaction of :204-206)
-    const bool none_dropped = (long long)counters[RDP_CNT_N] == n0;
-    if (!none_dropped) {
-        long long part = 0;
-        for (int t = tid; t < (int)blockIdx.x; t += kIndexThreads) part += tile_keep[t];
 #pragma unroll
-        for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
-        if (tid == 0) s_base = 0;
-        __syncthreads();
-        if ((tid & 31) == 0 && part) atomicAdd(reinterpret_cast<unsigned long long *>(&s_base), (unsigned long long)part);
-        __syncthreads();
+    for (int s = 0; s < kRankSub; ++s)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            r[s][q] = -1;
+            if (k[s][q] >= 0) {
+                const uint2 wr = __ldg(wordrank + (k[s][q] >> 5));
+                r[s][q] = (int)(wr.y + __popc(wr.x & ((1u << (k[s][q] & 31)) - 1u)));
+            }
+        }
+    // the value the count had before this row arrived is the row's slot inside its pillar: K5 then needs no atomics
+#pragma unroll
+    for (int s = 0; s < kRankSub; ++s)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            sl[s][q] = 0;
+            if (r[s][q] >= 0) sl[s][q] = atomicAdd(counts + r[s][q], 1);
+        }
+    const bool none_dropped = (long long)counters[RDP_CNT_N] == n0;
+#pragma unroll
+    for (int s = 0; s < kRankSub; ++s) {
+        const long long i0 = cta0 + (long long)s * kIndexTileRows + tid * 4;
+        if (i0 + 3 < n0) {
+            *reinterpret_cast<int4 *>(ranks + i0) = make_int4(r[s][0], r[s][1], r[s][2], r[s][3]);
+            *reinterpret_cast<int4 *>(slots + i0) = make_int4(sl[s][0], sl[s][1], sl[s][2], sl[s][3]);
+            if (none_dropped) *reinterpret_cast<int4 *>(inverse + i0) = make_int4(r[s][0], r[s][1], r[s][2], r[s][3]);
+        } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (i0 + q < n0) {
+                    ranks[i0 + q] = r[s][q];
+                    slots[i0 + q] = sl[s][q];
+                    if (none_dropped) inverse[i0 + q] = r[s][q];
+                }
+        }
     }
-    int tot;
-    const int excl = block_excl_scan_256(c, s_scan, &tot);
-    long long j = none_dropped ? i0 : s_base + excl;
-    if (none_dropped && i0 + 3 < n0) {
-        *reinterpret_cast<int4 *>(inverse + i0) = make_int4(r[0], r[1], r[2], r[3]);
-    } else {
+    if (none_dropped) return;
+    // position among the KEPT points (stable compaction of :204-206): kept rows of all earlier index tiles, then a block
+    // scan per tile of this CTA
+    long long part = 0;
+    for (int t = tid; t < (int)blockIdx.x * kRankSub; t += kIndexThreads) part += tile_keep[t];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
+    if (tid == 0) s_base = 0;
+    __syncthreads();
+    if ((tid & 31) == 0 && part) atomicAdd(reinterpret_cast<unsigned long long *>(&s_base), (unsigned long long)part);
+    __syncthreads();
+    long long base = s_base;
+#pragma unroll
+    for (int s = 0; s < kRankSub; ++s) {
+        const long long i0 = cta0 + (long long)s * kIndexTileRows + tid * 4;
+        int c = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) c += r[s][q] >= 0 ? 1 : 0;
+        int tot;
+        const int excl = block_excl_scan_256(c, s_scan, &tot);
+        long long j = base + excl;
 #pragma unroll
         for (int q = 0; q < 4; ++q)
-            if (r[q] >= 0) {
-                if (!none_dropped) { orig2kept[i0 + q] = (int)j; kept2orig[j] = (int)(i0 + q); }
-                inverse[j++] = r[q];
+            if (r[s][q] >= 0) {
+                orig2kept[i0 + q] = (int)j;
+                kept2orig[j] = (int)(i0 + q);
+                inverse[j++] = r[s][q];
             }
-    }
-    // the value the count had before this row arrived is the row's slot inside its pillar: K5 then needs no atomics
-    int sl[4] = {0, 0, 0, 0};
-#pragma unroll
-    for (int q = 0; q < 4; ++q)
-        if (r[q] >= 0) sl[q] = atomicAdd(counts + r[q], 1);
-    if (i0 + 3 < n0) {
-        *reinterpret_cast<int4 *>(slots + i0) = make_int4(sl[0], sl[1], sl[2], sl[3]);
-    } else {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) if (i0 + q < n0) slots[i0 + q] = sl[q];
-    }
-    if (i0 + 3 < n0) {
-        *reinterpret_cast<int4 *>(ranks + i0) = make_int4(r[0], r[1], r[2], r[3]);
-    } else {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) if (i0 + q < n0) ranks[i0 + q] = r[q];
+        base += tot;
     }
 }
 
@@ -476,7 +496,7 @@ int index_fwd_impl(const float *points, const int32_t *frame_offsets, int64_t n_
     RDP_CUDA_OK(launch_pdl(bitmap_rank_kernel, kScanGrid, kScanThreads, 0, stream, ws.bitmap, ws.words, ws.scan_state_a, ws.wordrank, counters,
                            host_mapped));
     if (event) RDP_CUDA_OK(cudaEventRecord(event, stream));
-    RDP_CUDA_OK(launch_pdl(rank_count_kernel, tiles, kIndexThreads, 0, stream, ws.keys, ws.ranks, n_points, ws.wordrank, ws.tile_keep, inverse,
+    RDP_CUDA_OK(launch_pdl(rank_count_kernel, (tiles + kRankSub - 1) / kRankSub, kIndexThreads, 0, stream, ws.keys, ws.ranks, n_points, ws.wordrank, ws.tile_keep, inverse,
                            counts, counters, ws.orig2kept, ws.kept2orig, ws.slots));
     RDP_CUDA_OK(launch_pdl(count_scan_kernel, kScanGrid, kScanThreads, 0, stream, counts, ws.scan_state_b, ws.starts, ws.tile_first, counters));
     if (frame_offsets)
