@@ -70,7 +70,7 @@ struct PfnCfg {
     static constexpr int KIN = B::KIN, G = B::G, NACC = B::NACC, RS = B::RS;
     static constexpr int CPL = COUT / 32;                              // channels per lane
     static constexpr int BWD_PER = G + 1;                              // per channel: A(G) | dbeta
-    static constexpr int FW = (KIN + 1 + 3) / 4 * 4;                   // floats per row record in shared memory: row inputs | last-row flag
+    static constexpr int FW = (KIN + 2 + 3) / 4 * 4;                   // floats per row record in shared memory: row inputs | last-row flag | grouped position
     static constexpr uint32_t ROW_BYTES = (kPfnCap + 1) * RS * 4;      // the window plus the row in front of it
     static constexpr uint32_t AUX_BYTES = kPfnWin * 8 * 4;
     static_assert(G <= kMaxG && COUT % 32 == 0 && COUT <= kMaxCout, "shape");
@@ -166,8 +166,12 @@ __device__ __forceinline__ TileBounds tile_bounds(const PfnStage<Cfg> &T, int ps
 // memory, so that the redundant per-lane work of the stream is two shared loads per row;  ST (lane = channel) walks the
 // rows of a pillar-aligned quarter of the tile per warp in one flat loop: KIN FMAs and a max per row, the pillar epilogue
 // (pillar term, BatchNorm, ReLU, one coalesced 128-byte store per 32 channels) when a row carries the flag.
-template <class Cfg>
-__device__ __forceinline__ void tile_c1(const PfnStage<Cfg> &T, const TileBounds &tb, float off_z, float *frec) {
+// SORT (train forward): the records of a pillar are written in the order of their ORIGINAL row ids instead of the arrival
+// order of the grouping pass, each carrying its grouped position.  The stream then needs no tie handling at all: "first
+// strict maximum wins" is the documented tie rule (lowest kept-point index among equal maxima).  The rank of a row inside
+// its pillar is a count over the pillar's staged rows -- 1 comparison for 2 of 3 pillars, ~6 on average for the others.
+template <class Cfg, bool SORT>
+__device__ __forceinline__ void tile_c1(const PfnStage<Cfg> &T, const TileBounds &tb, long long base, float off_z, float *frec) {
     constexpr int COLS = Cfg::COLS, RS = Cfg::RS, KIN = Cfg::KIN, FW = Cfg::FW;
     for (int j = tb.j0 + (int)threadIdx.x; j < tb.jstop; j += kPfnThreads) {
         const float *src = T.row(j);
@@ -178,13 +182,25 @@ __device__ __forceinline__ void tile_c1(const PfnStage<Cfg> &T, const TileBounds
             row[c4] = q.x; row[c4 + 1] = q.y; row[c4 + 2] = q.z; row[c4 + 3] = q.w;
         }
         const int gid = __float_as_int(row[RS - 1]);
-        const float2 cen = *reinterpret_cast<const float2 *>(&T.aux[(gid - tb.ps) * 8]);
+        const float *ax = &T.aux[(gid - tb.ps) * 8];
+        const float2 cen = *reinterpret_cast<const float2 *>(ax);
         row_inputs<COLS, Cfg::DIST>(row, cen.x, cen.y, off_z, rin);
-        const int last = (j == tb.jstop - 1) || (T.gid(j + 1) != gid);
+        int slot = j, last;
+        if (SORT) {
+            const int first = __float_as_int(ax[5]) - (int)base, n = __float_as_int(ax[6]);
+            const int o = __float_as_int(row[RS - 2]);
+            int idx = 0;
+            for (int r = first; r < first + n; ++r) idx += (T.orig(r) < o) ? 1 : 0;   // original row ids are unique
+            slot = first + idx;
+            last = (idx == n - 1);
+        } else {
+            last = (j == tb.jstop - 1) || (T.gid(j + 1) != gid);
+        }
         rin[KIN] = __int_as_float(last);
+        rin[KIN + 1] = __int_as_float((int)base + j);
 #pragma unroll
-        for (int k = KIN + 1; k < FW; ++k) rin[k] = 0.0f;
-        float4 *dst = reinterpret_cast<float4 *>(frec + j * FW);
+        for (int k = KIN + 2; k < FW; ++k) rin[k] = 0.0f;
+        float4 *dst = reinterpret_cast<float4 *>(frec + slot * FW);
 #pragma unroll
         for (int k4 = 0; k4 < FW / 4; ++k4) dst[k4] = make_float4(rin[4 * k4], rin[4 * k4 + 1], rin[4 * k4 + 2], rin[4 * k4 + 3]);
     }
@@ -307,7 +323,7 @@ __global__ void __launch_bounds__(kPfnThreads, Cfg::CPL == 1 ? (ARG ? 6 : 7) : (
         const int np = tb.jstop - tb.j0;
 
         if (np > 0) {
-            tile_c1<Cfg>(T, tb, a.off_z, S.frec);
+            tile_c1<Cfg, ARG>(T, tb, base, a.off_z, S.frec);
             __syncthreads();
             // warp `warp` streams a pillar-aligned quarter of the rows
             auto cut = [&](int q) -> int {
@@ -325,48 +341,32 @@ __global__ void __launch_bounds__(kPfnThreads, Cfg::CPL == 1 ? (ARG ? 6 : 7) : (
                 int32_t *aout = ARG ? a.argpos + (size_t)(ps + slot0) * COUT + lane : nullptr;
                 float m[CPL];
                 int mp[CPL];
-                bool tie = false;
-                int wfirst = w;   // first row of the pillar being streamed
 #pragma unroll
-                for (int cc = 0; cc < CPL; ++cc) { m[cc] = NEG_INF; mp[cc] = w; }
-                // one row folded into the running maxima; closes the pillar when the row carries the last-row flag
-                auto fold = [&](const float *v, int last, int wr) {
+                for (int cc = 0; cc < CPL; ++cc) { m[cc] = NEG_INF; mp[cc] = 0; }
+                // one row folded into the running maxima; closes the pillar when the row carries the last-row flag.  ARG: the
+                // records of a pillar arrive in original-row order (tile_c1<SORT>), so the first strict maximum is the winner
+                // of the documented tie rule and `pos` is its grouped position.
+                auto fold = [&](const float *v, int last, int pos) {
 #pragma unroll
                     for (int cc = 0; cc < CPL; ++cc) {
                         if (!ARG) {
                             m[cc] = fmaxf(m[cc], v[cc]);
-                        } else {
-                            tie = tie || (v[cc] == m[cc]);
-                            if (v[cc] > m[cc]) { m[cc] = v[cc]; mp[cc] = wr; }
+                        } else if (v[cc] > m[cc]) {
+                            m[cc] = v[cc]; mp[cc] = pos;
                         }
                     }
                     if (last) {
-                        if (ARG && __any_sync(0xffffffffu, tie)) {
-                            // exact ties (duplicate points): the winner is the tied row with the lowest original (== kept) index
-                            int mo[CPL];
-#pragma unroll
-                            for (int cc = 0; cc < CPL; ++cc) mo[cc] = 0x7fffffff;
-                            for (int rr = wfirst; rr <= wr; ++rr) {
-                                float rin[FW], v2[CPL];
-                                load_rec(S.frec + rr * FW, rin);
-                                chain(rin, v2);
-                                const int o = T.orig(rr);
-#pragma unroll
-                                for (int cc = 0; cc < CPL; ++cc)
-                                    if (v2[cc] == m[cc] && o < mo[cc]) { mo[cc] = o; mp[cc] = rr; }
-                            }
-                        }
                         const float4 a0 = *reinterpret_cast<const float4 *>(ax);   // centre xy, (centre - mean) xy
                         float z[CPL];
                         pillar_z(m, a0, ax[4], z);
 #pragma unroll
                         for (int cc = 0; cc < CPL; ++cc) {
                             fout[32 * cc] = z[cc];
-                            if (ARG) aout[32 * cc] = (z[cc] > 0.0f) ? (int)base + mp[cc] : -1;   // -1: ReLU clamped, no gradient
+                            if (ARG) aout[32 * cc] = (z[cc] > 0.0f) ? mp[cc] : -1;   // -1: ReLU clamped, no gradient
                             m[cc] = NEG_INF;
                         }
                         ax += 8; fout += COUT;
-                        if (ARG) { aout += COUT; tie = false; wfirst = wr + 1; }
+                        if (ARG) aout += COUT;
                     }
                 };
                 for (; w + 1 < wb; w += 2) {   // two rows in flight: independent load + fmaf chains
@@ -375,14 +375,14 @@ __global__ void __launch_bounds__(kPfnThreads, Cfg::CPL == 1 ? (ARG ? 6 : 7) : (
                     load_rec(S.frec + (w + 1) * FW, r1);
                     chain(r0, v0);
                     chain(r1, v1);
-                    fold(v0, __float_as_int(r0[KIN]), w);
-                    fold(v1, __float_as_int(r1[KIN]), w + 1);
+                    fold(v0, __float_as_int(r0[KIN]), __float_as_int(r0[KIN + 1]));
+                    fold(v1, __float_as_int(r1[KIN]), __float_as_int(r1[KIN + 1]));
                 }
                 if (w < wb) {
                     float r0[FW], v0[CPL];
                     load_rec(S.frec + w * FW, r0);
                     chain(r0, v0);
-                    fold(v0, __float_as_int(r0[KIN]), w);
+                    fold(v0, __float_as_int(r0[KIN]), __float_as_int(r0[KIN + 1]));
                 }
             }
         }
@@ -905,7 +905,7 @@ __global__ void __launch_bounds__(kPfnThreads, Cfg::CPL == 1 ? 5 : (Cfg::CPL == 
         pending = false;
 
         if (nb > 0) {
-            tile_c1<Cfg>(T, tb, a.off_z, S.frec);
+            tile_c1<Cfg, false>(T, tb, base, a.off_z, S.frec);
             __syncthreads();
             float tA[CPL][PER];
 #pragma unroll
