@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(1024) allreduce_oneshot_kernel(const __grid_co
         const uint32_t *my_signals = reinterpret_cast<const uint32_t *>(peers[rank] + 2 * (size_t)n_pad);
         const long long t0 = clock64();
         while ((int32_t)(ld_acquire_sys(my_signals + tid) - step) < 0) {   // wrap-safe "published step >= this step"
-            if (clock64() - t0 > 8000000000ll) { s_timeout = 1; break; }   // ~4 s: a peer died -- poison the result instead of hanging
+            if (clock64() - t0 > 240000000000ll) { s_timeout = 1; break; }   // ~2 min: a peer died -- poison the result instead of hanging forever
         }
     }
     __syncthreads();

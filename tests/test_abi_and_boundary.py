@@ -180,3 +180,67 @@ def test_pin_cpus_partitions_the_allowed_cores():
             assert not (sets[0] & sets[1])
     finally:
         os.sched_setaffinity(0, before)
+
+
+def test_host_extension_loads_and_matches_the_abi():
+    """rdp_torch_ext.so (csrc/rdp_torch.cpp, built by build_ext) is plumbing around the same librdp calls; it must load on a box
+    without a GPU and agree with the library's ABI version."""
+    from radardistill_b200 import _ext, build
+    if build.ext_path() is None:
+        pytest.skip("rdp_torch_ext.so has not been built (python -m radardistill_b200.build)")
+    mod = _ext.load()
+    assert mod is not None and mod.abi_version() == _lib.RDP_ABI_VERSION and hasattr(mod, "pair_forward")
+
+
+def test_round2_entry_points_validate_their_arguments_without_a_gpu():
+    import ctypes as C
+    lib = _lib.load()
+    spec = ops.make_spec(5, synth.VOXEL_SIZE, synth.grid_size_of(), synth.PC_RANGE, _lib.LAYOUT_SIMPLE2D, True, True, True, False, 32)
+    geom, layout = spec.geom(2), spec.layout_struct()
+    inv = _lib.RdpError
+    # n_points == 0 is a no-op everywhere; missing buffers are refused before anything is launched
+    assert lib.rdp_decorate(0, C.byref(geom), C.byref(layout), None, 0, 1, None, None) == 0
+    assert lib.rdp_decorate(10, C.byref(geom), C.byref(layout), None, 0, 1, None, None) == -1
+    bad = spec.layout_struct(); bad.c_in = 13
+    assert lib.rdp_decorate(10, C.byref(geom), C.byref(bad), 1, 1 << 30, 1, 1, None) == -1          # c_in does not match the layout
+    assert lib.rdp_segment_max_fwd(None, 32, 10, C.byref(geom), None, 0, 1, None, None, None) == -1
+    assert lib.rdp_segment_max_bwd(None, None, 0, 32, None, None) == 0
+    assert lib.rdp_voxel_mean(10, C.byref(geom), None, 0, 1, None, None) == -1
+    rng = (C.c_float * 4)(-54, -54, 54, 54)
+    assert lib.rdp_prepare_points(None, 10, 5, 4, rng, 0, None, 0, None, 1, None) == -1              # y column outside the row
+    assert lib.rdp_prepare_scratch_bytes(1000) >= 4 * 4
+    assert lib.rdp_allreduce_staging_bytes(1056, 8) >= 2 * 1056 * 4 + 8 * 4
+    assert lib.rdp_allreduce_small(None, None, 1, None, 0, 8, 1, 0.125, None, None) == -1
+    seg, cnt = (C.c_void_p * 1)(16), (C.c_int32 * 1)(4)
+    assert lib.rdp_allreduce_small(seg, cnt, 1, 16, 8, 8, 1, 0.125, 16, None) == -1                  # rank outside the world
+    assert lib.rdp_allreduce_small(seg, cnt, 1, 16, 0, 8, 0, 0.125, 16, None) == -1                  # step numbers start at 1
+    voxel = ops.make_spec(4, [0.1, 0.1, 0.2], [1080, 1080, 40], synth.PC_RANGE, _lib.LAYOUT_DYNVOXEL, True, True, False, False, 32)
+    assert voxel.nz == 40 and voxel.coord_cols == 4 and voxel.c_in == 10
+    assert lib.rdp_config_supported(C.byref(voxel.geom(1)), C.byref(voxel.layout_struct())) == 0      # voxels: layer-stack path
+    nbytes = C.c_size_t(0)
+    assert lib.rdp_workspace_bytes(1000, C.byref(voxel.geom(64)), C.byref(voxel.layout_struct()), C.byref(nbytes)) == -5   # key space > int32
+    del inv
+
+
+def test_shuffle_permutation_of_prepare_points_is_a_bijection():
+    """The seeded permutation of rdp_prepare_points (csrc/rdp_stack.cu: perm_index) restated in integers: an odd multiplier, an
+    xor-shift and an addition are bijections on [0, 2^k); cycle-walking restricts them to [0, n)."""
+    M = (1 << 64) - 1
+
+    def perm(j, n, seed):
+        k = 1
+        while (1 << k) < n:
+            k += 1
+        mask = (1 << k) - 1
+        v = j
+        while True:
+            v = (v * (((2 * seed + 0x9E3779B97F4A7C15) & M) | 1)) & mask
+            v ^= v >> (k // 2 + 1)
+            v = (v * 0xD6E8FEB86659FD93) & mask
+            v = (v + seed) & mask
+            if v < n:
+                return v
+
+    for n in (1, 2, 3, 17, 1000, 4097):
+        for seed in (1, 12345, (1 << 63) + 5):
+            assert sorted(perm(j, n, seed) for j in range(n)) == list(range(n))
