@@ -432,6 +432,7 @@ def run_ours(args):
     barrier()
     wall = time.perf_counter() - t_wall0
     step_ms = sum(ms) / len(ms)
+    step_stats = {"median": statistics.median(ms), "min": min(ms), "max": max(ms)}   # this rank's steps (rank 0 reports its own)
     if ddp:
         t = torch.tensor([step_ms], device=device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -681,7 +682,7 @@ def run_ours(args):
                                               "per step" if args.dp == "lean" else "torch DistributedDataParallel"))),
                 "e2e": e2e, "e2e_host_outputs": e2e_out,
                 "gpu_launches": launches,
-                "clocks": clk.summary(), "roofline": roof, "cpu_baseline": cpu, "cpu_baseline_reference_torch": cpu_torch,
+                "ms_per_step_rank0": step_stats, "clocks": clk.summary(), "roofline": roof, "cpu_baseline": cpu, "cpu_baseline_reference_torch": cpu_torch,
                 "wall_s_timed_region": wall}
         if others is not None:
             line["configs"] = others
