@@ -39,7 +39,7 @@ constexpr int kPfnCap = RDP_PFN_CAP;          // rows staged per tile: the windo
 #define RDP_PFN_GRID_PER_SM 4
 #endif
 constexpr int kPfnGridCap = 148 * RDP_PFN_GRID_PER_SM;  // persistent PFN CTAs of the backward tile kernel
-constexpr int kSliceInts = 136;       // ints staged per tile from starts[] / unq[]: 128 pillars + 1, from a 16-byte aligned address
+constexpr int kSliceInts = 136;       // slack (ints) behind starts[]: a 128-pillar slice + 1 can be read from any 16-byte aligned address
 __host__ __device__ constexpr int grouped_row_floats(int cols) { return (cols + 2 + 3) / 4 * 4; }
 constexpr int kMaxCin = 24;
 constexpr int kMaxCout = 128;
@@ -49,10 +49,10 @@ constexpr int kMaxAcc = kMaxG + kMaxG * kMaxG + 2;   // first + second moments o
 // extra counter slots (after the public ones of rdp.h)
 constexpr int kCntTicketA = 4;   // bitmap scan ticket
 constexpr int kCntTicketB = 5;   // count scan ticket
-constexpr int kCntPfnBlocks = 6; // blocks used by the last stats launch
+constexpr int kCntPfnBlocks = 6; // (reserved)
 constexpr int kCntDoneStats = 8; // CTAs of the moments pass that have added their sums (the last one runs the BN epilogue)
 constexpr int kCntDoneBwd = 9;   // same for the backward tile kernel
-constexpr int kCntStatsTag = 10; // != 0: acc_stats holds the moments of this workspace's rows for layout tag (value)
+constexpr int kCntStatsTag = 10; // (reserved)
 
 // ----------------------------------------------------------------------------- workspace layout
 struct Workspace {

@@ -16,9 +16,10 @@
 //   K5 group_rows      grouped_rows[starts[rank] + slot] = [merged key | xyz | features | original row id | rank]   (no atomics; the order
 //                      inside a pillar is the arrival order of K3's atomics -- every consumer is order independent).
 //                      The PFN kernels then stream contiguous, pillar-aligned row tiles with TMA.
-//   K6 pillar_table    thread = pillar: fp64 mean of its grouped rows' centre offsets, pillar centre, first row, row count; coords
-//                      (rdp_table.cuh; only for the split-call ABI -- the fused forward builds the same entries tile by tile
-//                      inside its PFN kernels and skips this launch)
+//   K6 pillar_table    thread = pillar: key decode (centre, coords), fp64 mean of its grouped rows' centre offsets, first row,
+//                      row count (rdp_table.cuh).  A train-mode fused forward skips this launch: its statistics kernel
+//                      (pillar_table_stats_kernel, rdp_pfn.cuh) writes the same table while it accumulates the moments.
+// K2..K6 are launched with programmatic dependent launch (rdp_common.cuh: pdl_wait is their first statement).
 // nz > 1 (DynamicVoxelVFE / DynamicMeanVFE, dynamic_voxel_vfe.py:57-71, dynamic_mean_vfe.py:52-60): z is quantised and
 // masked too and the key is ((b*nx + cx)*ny + cy)*nz + cz.
 #include "rdp_index_host.h"

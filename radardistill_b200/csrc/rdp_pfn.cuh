@@ -23,9 +23,11 @@
 // (rdp_table.cuh): rows of one pillar are contiguous, pillars are in key order.  One persistent CTA (128 threads) takes
 // tiles b, b + grid, ...; tile t owns the pillars that START in grouped rows [128 t, 128 t + 128) and stages rows
 // [128 t - 1, 128 t + 192) plus the table slice of its pillars -- fixed-size, 16-byte aligned windows -- one tile ahead
-// with two 1-D TMA bulk copies onto an mbarrier, double buffered.  Each warp streams a pillar-aligned quarter of the
-// tile's rows straight from the staged buffers (lane = channel): no intermediate feature tile, one block barrier per
-// tile.  A pillar that runs past the staged window (> 64 rows of overhang) is streamed from global memory by all warps.
+// with two 1-D TMA bulk copies onto an mbarrier, double buffered.  Per tile a thread = row phase turns the staged rows into
+// row records (row inputs, last-row flag, grouped position; in the train forward sorted by original row id inside each
+// pillar), then each warp streams a pillar-aligned quarter of the records (lane = channel): no intermediate feature tile,
+// two block barriers per tile.  A pillar that runs past the staged window (> 64 rows of overhang) is streamed from global
+// memory by all warps.
 #pragma once
 
 #include "rdp_table.cuh"

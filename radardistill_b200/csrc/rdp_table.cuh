@@ -1,4 +1,4 @@
-// rdp_table.cuh -- the per-pillar table kernel (K6) and, fused into it for train-mode BatchNorm, the feature moments.
+// rdp_table.cuh -- the per-pillar table kernel (K6) and the helpers it shares with the train-mode statistics kernel.
 //
 // Replaces scatter_mean (/root/reference/pcdet/models/backbones_3d/vfe/dynamic_pillar_vfe.py:226-227, :105-106), the
 // pillar centre of f_center (:214-217, :108-111; voxel form dynamic_voxel_vfe.py:75-79) and the coordinate decode
@@ -10,9 +10,9 @@
 // quotient, one rounding to fp32.  A pillar with more than kBigRows rows is summed by its whole warp (lane-strided rows,
 // shuffle reduction -- still exact), so one 3 500-point cell does not serialise 3 500 dependent loads on one thread.
 //
-// The train-mode feature moments are a separate row-parallel pass (pfn_moments_kernel, rdp_pfn.cuh): fused into this
-// thread = pillar kernel their ~70 accumulators per thread cut the occupancy of an already latency-bound kernel to 11 warps
-// per SM (178 registers; measured at compile time), which costs more than the second read of the rows.
+// Train-mode BatchNorm: pillar_table_stats_kernel (rdp_pfn.cuh, one instantiation per compiled shape) is this kernel plus
+// the feature moments -- row x row products thread-local, the pillar-level products as rank-32 updates on the fp64 tensor
+// pipe -- and the BatchNorm epilogue in its last CTA.
 #pragma once
 
 #include "rdp_common.cuh"
