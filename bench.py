@@ -672,14 +672,19 @@ def run_ours(args):
         # librdp kernels per step and encoder: index 5 (quantise, bitmap scan, rank, count scan, group) + table (train: table +
         # moments) + apply = 7 per forward, + 1 backward tile kernel (its epilogue runs in its last CTA).  The radar encoder always trains.
         launches_lidar = 7 + (1 if mode == "B" else 0)
-        launches = (launches_lidar + 8) * args.steps
+        red = upstream.get("reducer")
+        per_step = launches_lidar + 8 + (1 if red is not None and getattr(red, "p2p", None) is not None else 0)   # + rdp_allreduce_small
+        launches = per_step * args.steps
         line = {"metric": "pillar-encoder points/s (fwd+bwd)", "value": value, "unit": "points/s", "n_gpus": world,
                 "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": step_ms, "higher_is_better": True,
                 "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": dict(workload_config(args, mode, frames, len(lidar), len(radar)),
                                cpus_pinned=(pinned if pinned is None else len(pinned)),
-                               data_parallel=("none" if not ddp else ("GradientAllReduce: one NCCL all_reduce of the flat PFN gradients "
-                                              "per step" if args.dp == "lean" else "torch DistributedDataParallel"))),
+                               data_parallel=("none" if not ddp else (
+                                   ("GradientAllReduce: rdp_allreduce_small, one kernel per step over NVLink peer memory"
+                                    if getattr(upstream.get("reducer"), "p2p", None) is not None else
+                                    "GradientAllReduce: one NCCL all_reduce of the flat PFN gradients per step")
+                                   if args.dp == "lean" else "torch DistributedDataParallel"))),
                 "e2e": e2e, "e2e_host_outputs": e2e_out,
                 "gpu_launches": launches,
                 "ms_per_step_rank0": step_stats, "clocks": clk.summary(), "roofline": roof, "cpu_baseline": cpu, "cpu_baseline_reference_torch": cpu_torch,
