@@ -96,25 +96,41 @@ def ext_path():
 
 
 def build_ext(force: bool = False, verbose: bool = False):
-    """Builds the native host path (csrc/rdp_torch.cpp: torch C++ extension, g++ only -- the kernels stay in librdp.so) in-tree.
-    The .so is copied next to librdp.so so that it travels to the GPU box and is imported there without a rebuild."""
-    import shutil
+    """Builds the native host path (csrc/rdp_torch.cpp: a torch C++ extension, g++ only -- the kernels stay in librdp.so) in-tree,
+    next to librdp.so, so that it travels to the GPU box and is imported there without a rebuild.  Compiled and linked with
+    plain g++ invocations (torch's include / library paths from torch.utils.cpp_extension): `cpp_extension.load` would also
+    LOAD the result, and a second load of the same TORCH_LIBRARY from its installed path aborts the process."""
+    import sysconfig
+    import torch
+    from torch.utils import cpp_extension
     src = os.path.join(CSRC, "rdp_torch.cpp")
     h = hashlib.sha256()
     for fn in (src, os.path.join(INCLUDE, "rdp.h")):
         with open(fn, "rb") as f:
             h.update(f.read())
-    import torch
     h.update(torch.__version__.encode())
     digest, stamp, out = h.hexdigest(), os.path.join(EXT_DIR, "digest.txt"), os.path.join(HERE, EXT_NAME + ".so")
     if not force and os.path.exists(out) and os.path.exists(stamp) and open(stamp).read() == digest:
         return out
     os.makedirs(EXT_DIR, exist_ok=True)
-    from torch.utils import cpp_extension
-    cpp_extension.load(name=EXT_NAME, sources=[src], extra_include_paths=[INCLUDE, "/usr/local/cuda/include"],
-                       extra_cflags=["-O2", "-std=c++17"], extra_ldflags=[f"-L{HERE}", "-lrdp", "-Wl,-rpath,'$$ORIGIN'", f"-Wl,-rpath,{HERE}", "-L/usr/local/cuda/lib64", "-lcudart", "-lc10_cuda", "-ltorch_cuda"],
-                       build_directory=EXT_DIR, with_cuda=False, is_python_module=False, verbose=verbose)
-    shutil.copyfile(os.path.join(EXT_DIR, EXT_NAME + ".so"), out)
+    cxx = cpp_extension.get_cxx_compiler()   # what cpp_extension.load would use (CXX, else the toolchain torch was configured with)
+    obj = os.path.join(EXT_DIR, "rdp_torch.o")
+    inc = ["-I", INCLUDE, "-I", "/usr/local/cuda/include"]
+    for d in cpp_extension.include_paths() + [sysconfig.get_paths()["include"]]:
+        inc += ["-isystem", d]
+    compile_cmd = [cxx, f"-DTORCH_EXTENSION_NAME={EXT_NAME}", "-DTORCH_API_INCLUDE_EXTENSION_H", *inc, "-fPIC", "-std=c++17", "-O2",
+                   "-c", src, "-o", obj]
+    libdirs = []
+    for d in cpp_extension.library_paths():
+        libdirs += ["-L", d]
+    link_cmd = [cxx, obj, "-shared", "-L", HERE, "-lrdp", "-Wl,-rpath,$ORIGIN", f"-Wl,-rpath,{HERE}", "-L", "/usr/local/cuda/lib64", "-lcudart",
+                *libdirs, "-lc10", "-lc10_cuda", "-ltorch_cpu", "-ltorch_cuda", "-ltorch", "-ltorch_python", "-o", out]
+    for cmd in (compile_cmd, link_cmd):
+        if verbose:
+            print(" ".join(cmd))
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"building {EXT_NAME} failed:\n{' '.join(cmd)}\n{r.stdout}\n{r.stderr}")
     with open(stamp, "w") as f:
         f.write(digest)
     return out
